@@ -1,0 +1,130 @@
+/* osp_b200.h -- C ABI of the B200-native outer-product SpGEMM engine.
+ *
+ * Drop-in boundary for the functional multiply/merge path of anneouyang/OuterSPACE.
+ * The reference has no FFI layer: its boundary is the C++ surface
+ *
+ *     size_t simulateOuterSPACE(const CSRMatrix &lmatCSC, const CSRMatrix &rmatCSR)
+ *         (decl simulator/SimSpGEMM.cpp:816, def simulator/SimOuterSPACE.cpp:859)
+ *
+ * whose first act is `TaskProvider provider(lmatCSC, rmatCSR)` (SimOuterSPACE.cpp:860),
+ * i.e. multiplyPhase (:74-97) + mergePhase (:98-132).  Every entry point below cites the
+ * reference interface it replaces.  All pointers are plain pointers to the reference's
+ * own storage layouts:
+ *
+ *     pos   = CSRMatrix::pos.data()   -- uint64_t[n_slices+1]        (common.h:41)
+ *     data  = CSRMatrix::data.data()  -- packed 8-byte {uint32 idx; float val}[nnz]
+ *                                                                  (common.h:10-16,42)
+ *
+ * No C++ or torch types cross this boundary.  Functions return OSP_OK or an error code
+ * and never abort or throw (the reference asserts / throws the int 233 instead).
+ * The C++ shim that keeps the reference's own names (CSRMatrix, readcoo, coo2csr<>,
+ * TaskProvider) on top of this ABI is include/osp_b200.hpp.
+ */
+#ifndef OSP_B200_H
+#define OSP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------ */
+#define OSP_OK               0
+#define OSP_ERR_INVALID      1   /* bad argument / k-dimension mismatch (assert, SimOuterSPACE.cpp:47) */
+#define OSP_ERR_CUDA         2   /* CUDA runtime failure; osp_last_error() has the string */
+#define OSP_ERR_OOM          3   /* device or host allocation failed */
+#define OSP_ERR_INDEX        4   /* index out of range (assert rowId < NRow, SimOuterSPACE.cpp:68) */
+#define OSP_ERR_IO           5   /* file could not be opened */
+#define OSP_ERR_UNSUPPORTED  6   /* size beyond what this build handles (documented in DESIGN.md) */
+#define OSP_ERR_NO_DEVICE    7   /* no CUDA device: there is NO CPU fallback */
+#define OSP_ERR_DUPLICATE  233   /* duplicate (row,col); the reference throws 233 (SimSpGEMM.cpp:49) */
+
+/* ---- flags for osp_spgemm_args.flags ------------------------------------------------- */
+#define OSP_A_IS_CSR         1u  /* a_pos/a_data hold CSR(A) (a_slices = rows of A, idx = k): the engine
+                                    runs the device CSR->CSC conversion (coo2csr<true>, SimSpGEMM.cpp:878) */
+#define OSP_DEVICE_POINTERS  2u  /* all operand pointers are device pointers (HBM-resident operands) */
+#define OSP_ROWWISE_ORDER    4u  /* experiment knob: emit partial products in row order of A instead of
+                                    k-slice order (same bins, same result; see DESIGN.md "multiply order") */
+#define OSP_PROFILE_PHASES   8u  /* synchronise between phases so that stats.ms_* are per-phase times */
+
+typedef struct osp_ctx osp_ctx;        /* one per GPU; single owner, one call at a time */
+typedef struct osp_result osp_result;  /* C = A*B in HBM until freed */
+
+/* Operands of one C = A*B.  Replaces the two `const CSRMatrix &` of simulateOuterSPACE. */
+typedef struct osp_spgemm_args {
+    uint64_t        a_slices;  /* a_pos has a_slices+1 entries: n_k for CSC(A), rows(A) with OSP_A_IS_CSR */
+    const uint64_t *a_pos;
+    const void     *a_data;    /* CSC(A): idx = row id, ascending inside a column, no duplicates */
+    uint64_t        n_k;       /* inner dimension: b_pos has n_k+1 entries */
+    const uint64_t *b_pos;
+    const void     *b_data;    /* CSR(B): idx = col id, ascending inside a row, no duplicates */
+    uint64_t        rows_c;    /* 0 = reference semantics: max row id of A + 1 (SimOuterSPACE.cpp:49-53) */
+    uint64_t        cols_b;    /* 0 = derive as max col id of B + 1; otherwise every col id must be < cols_b */
+    uint32_t        flags;
+    uint32_t        reserved;
+} osp_spgemm_args;
+
+/* Counters of one call (all sizes in elements, times in milliseconds of device time). */
+typedef struct osp_stats {
+    uint64_t rows_c, cols_b, n_k;
+    uint64_t nnz_a, nnz_b, nnz_c;
+    uint64_t products;            /* P = sum_k nnz(A(:,k))*nnz(B(k,:)) = mulflops_ref, SimSpGEMM.cpp:884-891 */
+    uint64_t algorithmic_bytes;   /* 16P + 8nnzC + 24nnzA + 8nnzB + 8(2m+3n+5) */
+    uint64_t rows_short, rows_medium, rows_long; /* merge classes */
+    uint64_t kernel_launches;     /* kernels this call launched */
+    uint64_t row_chunks;          /* output-row blocks the call was split into */
+    float    ms_total;            /* first kernel to last kernel */
+    float    ms_convert;          /* CSR->CSC conversion + symbolic count/scan */
+    float    ms_multiply;
+    float    ms_merge;
+    float    ms_h2d, ms_d2h;      /* host-pointer calls only */
+} osp_stats;
+
+/* ---- context ------------------------------------------------------------------------- */
+int  osp_device_count(void);                        /* 0 when no usable GPU */
+int  osp_create(int device, osp_ctx **out);         /* binds to one GPU, creates its stream + workspace */
+void osp_destroy(osp_ctx *ctx);
+const char *osp_last_error(const osp_ctx *ctx);     /* message of the last failing call on ctx (or global) */
+int  osp_set_workspace_limit(osp_ctx *ctx, uint64_t bytes); /* cap on partial-product workspace; larger
+                                                       products are processed in output-row blocks */
+void *osp_stream(osp_ctx *ctx);                     /* the cudaStream_t every kernel of ctx runs on */
+
+/* ---- the hot path: TaskProvider(lmatCSC, rmatCSR) ------------------------------------- */
+int  osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out);
+int  osp_result_dims(const osp_result *r, uint64_t *rows, uint64_t *nnz);
+int  osp_result_copy(osp_result *r, uint64_t *pos, void *data);  /* into CSRMatrix::pos / ::data storage */
+int  osp_result_device(const osp_result *r, const uint64_t **d_pos, const void **d_data);
+int  osp_result_stats(const osp_result *r, osp_stats *stats);
+void osp_result_free(osp_result *r);
+
+/* Task-size lists the reference's timing models read from TaskProvider
+ * (getMultiplyTasks/getMergeTasks, SimOuterSPACE.cpp:59-64; MultiplyTask/MergeTask :34-42):
+ * per non-empty k-slice (nnzc, nnzr), and per output row (#ways, output nnz).
+ * Two-call pattern: pass NULL arrays to obtain the counts. */
+int  osp_task_sizes(osp_ctx *ctx, const osp_spgemm_args *args, const osp_result *r,
+                    uint64_t *n_multiply, uint32_t *multiply_nnzc_nnzr,
+                    uint64_t *n_merge, uint32_t *merge_ways_out);
+
+/* ---- device CSR->CSC of one operand: coo2csr<true> (SimSpGEMM.cpp:111-117,878) -------- */
+/* Stable: inside an output slice the source slice ids ascend.  pos_out[n_minor+1], data_out[nnz].
+ * flags: OSP_DEVICE_POINTERS or 0. */
+int  osp_csr2csc(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint64_t *pos, const void *data,
+                 uint32_t flags, uint64_t *pos_out, void *data_out);
+
+/* ---- host loaders (the reference's .mtx surface) -------------------------------------- */
+typedef struct osp_coo osp_coo;
+int  osp_readcoo(const char *path, int symmetric, osp_coo **out);          /* readcoo, SimSpGEMM.cpp:55-100 */
+int  osp_coo_dims(const osp_coo *c, uint64_t *nrow, uint64_t *ncol, uint64_t *nnz);
+int  osp_coo_copy(const osp_coo *c, uint32_t *rows, uint32_t *cols, float *vals);
+void osp_coo_free(osp_coo *c);
+/* coo2csr<transpose> + dupcheck (SimSpGEMM.cpp:43-53,102-152): pos[N+1], data[nnz]. */
+int  osp_coo2csr(uint64_t nnz, const uint32_t *rows, const uint32_t *cols, const float *vals,
+                 uint64_t N, int transpose, uint64_t *pos, void *data);
+
+const char *osp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSP_B200_H */

@@ -1,0 +1,125 @@
+// osp_device.cuh -- device-side building blocks shared by every kernel of the engine.
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//   Elem   8 B  {uint32 idx; float val}   == reference CSRElement (simulator/common.h:10-16)
+//   pos    8 B  uint64                    == reference CSRMatrix::pos (common.h:41)
+//   Task  16 B  {uint32 k; float a; uint64 off}: one non-zero A(i,k) annotated with the offset of
+//               its run of partial products inside the output-row bins (one LDG.128 per task).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace osp {
+
+struct __align__(8) Elem {
+    uint32_t idx;
+    float val;
+};
+static_assert(sizeof(Elem) == 8, "Elem must match the reference's packed CSRElement");
+
+struct __align__(16) Task {
+    uint32_t k;     // inner index: which row of B this non-zero multiplies
+    float a;        // A(i,k)
+    uint64_t off;   // absolute offset (in elements) of the run inside the partial-product bins
+};
+static_assert(sizeof(Task) == 16, "Task is one 128-bit load");
+
+// Scalars the kernels report back to the host (one pinned-mirror copy per call).
+struct DevScalars {
+    unsigned long long products;     // P
+    unsigned long long block_nnz;    // unique outputs of the current row block
+    unsigned int err;                // first OSP_ERR_* raised on the device
+    unsigned int max_idx;            // reduction result of k_max_idx
+    unsigned int xl_count;           // rows queued for the long-row kernel
+    unsigned int tile_counter;       // dynamic tile ids of the look-back scan
+    unsigned long long last_nonempty;  // k_last_nonempty result
+    unsigned int tile_counter2;
+    unsigned int pad;
+};
+
+constexpr unsigned int FULL = 0xffffffffu;
+
+__device__ __forceinline__ unsigned int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ uint32_t pow2ceil(uint32_t v) {
+    return v <= 1 ? 1u : 1u << (32 - __clz(v - 1));
+}
+
+// ---- decoupled look-back (single-pass chained scan) --------------------------------------
+// One 64-bit status word per tile: flag in the top two bits, value in the low 62, so a single
+// relaxed load sees a consistent (flag, value) pair.
+constexpr uint64_t LB_FLAG_AGG = 1ull << 62;
+constexpr uint64_t LB_FLAG_PREFIX = 2ull << 62;
+constexpr uint64_t LB_VALUE_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by every lane of ONE warp.  Publishes this tile's aggregate, walks back over the
+// predecessors 32 at a time until an inclusive prefix is found, publishes the tile's own
+// inclusive prefix and returns the exclusive prefix (same value in every lane).
+__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *state, uint32_t tile, uint64_t aggregate) {
+    const unsigned int lane = lane_id();
+    if (tile == 0) {
+        if (lane == 0) st_relaxed_u64(state, LB_FLAG_PREFIX | aggregate);
+        return 0;
+    }
+    if (lane == 0) st_relaxed_u64(state + tile, LB_FLAG_AGG | aggregate);
+    uint64_t exclusive = 0;
+    int64_t base = int64_t(tile) - 1;
+    while (true) {
+        int64_t idx = base - lane;
+        uint64_t word = LB_FLAG_PREFIX;  // tiles before 0 contribute an inclusive prefix of 0
+        if (idx >= 0) {
+            word = ld_relaxed_u64(state + idx);
+            while ((word >> 62) == 0) word = ld_relaxed_u64(state + idx);
+        }
+        unsigned int has_prefix = __ballot_sync(FULL, (word >> 62) == 2);
+        unsigned int first = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+        uint64_t v = (lane <= first) ? (word & LB_VALUE_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        exclusive += v;
+        if (has_prefix) break;
+        base -= 32;
+    }
+    if (lane == 0) st_relaxed_u64(state + tile, LB_FLAG_PREFIX | (exclusive + aggregate));
+    return exclusive;
+}
+
+// ---- block-wide exclusive scan of a small per-thread count (blockDim.x <= 1024) -----------
+// `warp_sums` is a 33-entry shared array.  Contains two __syncthreads().
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t *warp_sums, uint32_t &total) {
+    const unsigned int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    uint32_t incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < nwarps ? warp_sums[lane] : 0;
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(FULL, wi, o);
+            if (lane >= o) wi += y;
+        }
+        warp_sums[lane] = wi - w;                 // exclusive offsets of the warps
+        if (lane == 31) warp_sums[32] = wi;       // block total
+    }
+    __syncthreads();
+    total = warp_sums[32];
+    uint32_t r = warp_sums[warp] + incl - x;
+    return r;
+}
+
+}  // namespace osp

@@ -1,0 +1,94 @@
+"""CPU suite: the C-ABI library loads, exports every symbol include/osp_b200.h declares, its host
+loaders agree with the oracle, and it refuses to compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+import outerspace_b200 as osp
+from outerspace_b200 import api
+from conftest import GOLDEN, ROOT, load_npz
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "osp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(osp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = api.load_library()
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/osp_b200.h but not exported"
+    assert sorted(api.ABI_SYMBOLS) == syms
+    assert b"sm_100a" in lib.osp_version()
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(api.SpgemmArgs) == 8 * 8 + 8
+    assert osp.ELEM.itemsize == 8 and osp.ELEM.fields["val"][1] == 4     # packed CSRElement, common.h:10-16
+
+
+def test_host_readcoo_matches_oracle():
+    for name, sym in (("mlp100_fc2_weight.mtx", False), ("loader_corner.mtx", False), ("loader_corner.mtx", True)):
+        path = os.path.join(GOLDEN, name)
+        coo, nrow, ncol = osp.readcoo(path, sym=sym)
+        rows, cols, vals, onrow, oncol = oracle.readcoo(path, sym=sym)
+        assert (nrow, ncol) == (onrow, oncol)
+        assert np.array_equal(coo.rows, rows) and np.array_equal(coo.cols, cols)
+        assert np.array_equal(coo.vals.view(np.uint32), vals.view(np.uint32))
+    with pytest.raises(osp.OspError):
+        osp.readcoo(os.path.join(GOLDEN, "does_not_exist.mtx"))
+
+
+def test_host_coo2csr_matches_golden_and_oracle():
+    g = load_npz("mlp100")
+    coo = osp.COO(g["rows"], g["cols"], g["vals"])
+    csc = osp.coo2csr(coo, int(g["ncol"]), transpose=True)
+    csr = osp.coo2csr(coo, int(g["nrow"]))
+    assert np.array_equal(csc.pos, g["csc_pos"]) and np.array_equal(csc.data, g["csc_data"])
+    assert np.array_equal(csr.pos, g["csr_pos"]) and np.array_equal(csr.data, g["csr_data"])
+    rng = np.random.default_rng(11)
+    for _ in range(5):
+        n = int(rng.integers(1, 400))
+        keys = rng.choice(97 * 53, size=min(n, 97 * 53), replace=False)
+        rows, cols = (keys // 53).astype(np.uint32), (keys % 53).astype(np.uint32)
+        vals = rng.standard_normal(len(keys)).astype(np.float32)
+        for tr, N in ((False, 97), (True, 53)):
+            got = osp.coo2csr(osp.COO(rows, cols, vals), N, transpose=tr)
+            rc, pos, data = oracle.coo2csr(rows, cols, vals, N, transpose=tr)
+            assert rc == 0 and np.array_equal(got.pos, pos) and np.array_equal(got.data, data)
+    # empty operand
+    e = osp.coo2csr(osp.COO(np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.float32)), 4)
+    assert list(e.pos) == [0, 0, 0, 0, 0] and e.nnz == 0
+
+
+def test_host_coo2csr_errors():
+    dup = osp.COO(np.array([0, 1, 1], np.uint32), np.array([2, 3, 3], np.uint32), np.ones(3, np.float32))
+    with pytest.raises(osp.DuplicateEntry) as ei:
+        osp.coo2csr(dup, 4)
+    assert ei.value.code == 233                      # the int the reference throws, SimSpGEMM.cpp:49
+    with pytest.raises(osp.OspError) as ei:
+        osp.coo2csr(osp.COO(np.array([5], np.uint32), np.array([0], np.uint32), np.ones(1, np.float32)), 4)
+    assert ei.value.code == api.OSP_ERR_INDEX
+    # the reference's single-slice fix-up corner is NOT reproduced (documented divergence)
+    one = osp.coo2csr(osp.COO(np.array([0, 0], np.uint32), np.array([0, 2], np.uint32), np.ones(2, np.float32)), 3)
+    assert list(one.pos) == [0, 2, 2, 2]
+
+
+def test_no_cpu_fallback():
+    lib = api.load_library()
+    if lib.osp_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(osp.OspError) as ei:
+        osp.Engine(0)
+    assert ei.value.code == api.OSP_ERR_NO_DEVICE
+    # the product package never imports the oracle
+    import sys
+    src = open(os.path.join(ROOT, "outerspace_b200", "api.py")).read()
+    assert "import oracle" not in src and "from oracle" not in src

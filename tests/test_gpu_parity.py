@@ -1,0 +1,233 @@
+"""GPU suite: the CUDA path (through the C ABI) against the oracle -- bit-exact row_ptr, col_idx AND
+values (the engine's merge is the deterministic k-ordered one).  Sizes here finish in seconds on the
+oracle; full-size configs are covered by the property tests in test_gpu_properties.py."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+import outerspace_b200 as osp
+from outerspace_b200 import api, synth
+from conftest import GOLDEN, load_npz
+from helpers import assert_bit_exact, check_csr_invariants, operands, oracle_spgemm, pack, rand_sparse
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["ex3x3", "rand_dups", "empty_slices", "long_row", "mlp_like_int"]
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("a_is_csr", [False, True])
+def test_golden(engine, name, a_is_csr):
+    g = load_npz(name)
+    b = pack(g["b_csr_pos"], g["b_csr_data"])
+    a = pack(g["a_csr_pos"], g["a_csr_data"]) if a_is_csr else pack(g["a_csc_pos"], g["a_csc_data"])
+    res = engine.spgemm(a, b, a_is_csr=a_is_csr)
+    got = res.to_host()
+    st = res.stats()
+    res.free()
+    assert_bit_exact(got, pack(g["c_pos"], g["c_data"]), name)
+    assert st["products"] == int(g["products"]) and st["nnz_c"] == len(g["c_data"])
+    assert st["kernel_launches"] > 0
+
+
+def test_mtx_pipeline_like_reference_main(engine):
+    """readcoo -> coo2csr<true>/coo2csr -> TaskProvider, the call sequence of SimSpGEMM.cpp:844-893
+    (with A*A instead of F1*F2^T)."""
+    g = load_npz("mlp100")
+    coo, nrow, ncol = osp.readcoo(os.path.join(GOLDEN, "mlp100_fc2_weight.mtx"))
+    csc = osp.coo2csr(coo, ncol, transpose=True)
+    csr = osp.coo2csr(coo, nrow)
+    provider = osp.TaskProvider(csc, csr, engine=engine)
+    assert_bit_exact(provider.mergedResult, pack(g["c_pos"], g["c_data"]), "mlp100")
+    nnzc, nnzr = np.diff(csc.pos.astype(np.int64)), np.diff(csr.pos.astype(np.int64))
+    keep = (nnzc > 0) & (nnzr > 0)
+    assert np.array_equal(provider.getMultiplyTasks(), np.stack([nnzc[keep], nnzr[keep]], 1).astype(np.uint32))
+    merge = provider.getMergeTasks()
+    assert merge.shape[0] == provider.mergedResult.NRow()
+    assert np.array_equal(merge[:, 1], np.diff(provider.mergedResult.pos.astype(np.int64)).astype(np.uint32))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_vs_oracle(engine, seed):
+    rng = np.random.default_rng(seed)
+    m, k, n = (int(x) for x in rng.integers(1, 300, size=3))
+    A, B = rand_sparse(rng, m, k, rng.uniform(0.01, 0.3)), rand_sparse(rng, k, n, rng.uniform(0.01, 0.3))
+    a_csc, a_csr, b_csr = operands(A, B)
+    want, prod = oracle_spgemm(a_csc, b_csr)
+    for a, is_csr, flags in ((a_csc, False, 0), (a_csr, True, 0), (a_csr, True, api.OSP_ROWWISE_ORDER)):
+        res = engine.spgemm(a, b_csr, a_is_csr=is_csr, flags=flags)
+        got = res.to_host()
+        assert res.stats()["products"] == prod
+        res.free()
+        assert_bit_exact(got, want, f"seed {seed} csr={is_csr} flags={flags}")
+        check_csr_invariants(got, n)
+
+
+def test_task_sizes_match_reference_structure(engine):
+    """The sizes the untouched timing models consume equal those of the reference's TaskProvider."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(5)
+    A, B = rand_sparse(rng, 60, 50, 0.1), rand_sparse(rng, 50, 70, 0.1)
+    a_csc, _, b_csr = operands(A, B)
+    tp = oracle.ref_taskprovider(a_csc.pos, a_csc.data, b_csr.pos, b_csr.data)
+    provider = osp.TaskProvider(a_csc, b_csr, engine=engine)
+    assert np.array_equal(provider.getMultiplyTasks(), tp["mult_sizes"])
+    assert np.array_equal(provider.getMergeTasks()[:, 0], tp["merge_ways"][:, 0])     # ways per output row
+
+
+def test_er_config2_scaled(engine):
+    """config 2 shape at 1/4 linear scale (ER, density 1e-3): uniform short rows."""
+    a, b, dims = synth.build_workload("er16k", scale_down=4)
+    a_csc = synth.transpose_host(a, dims["n_k"])
+    want, prod = oracle_spgemm(a_csc, b)
+    res = engine.spgemm(a, b, a_is_csr=True, cols_b=dims["cols"])
+    got = res.to_host(); res.free()
+    assert_bit_exact(got, want, "er16k/4")
+
+
+def test_rmat_small(engine):
+    """config 3 shape at scale 12: skewed rows incl. rows beyond the shared-memory sort capacity."""
+    a, b, dims = synth.build_workload("rmat20", scale_down=256)
+    a_csc = synth.transpose_host(a, dims["n_k"])
+    want, prod = oracle_spgemm(a_csc, b)
+    res = engine.spgemm(a, b, a_is_csr=True)
+    got = res.to_host(); st = res.stats(); res.free()
+    assert st["rows_long"] > 0, "test should exercise the long-row path"
+    assert_bit_exact(got, want, "rmat12")
+    res = engine.spgemm(a_csc, b, a_is_csr=False)
+    got = res.to_host(); res.free()
+    assert_bit_exact(got, want, "rmat12 from CSC")
+
+
+def test_mlp_batch_small(engine):
+    """config 5 shape with a small batch: every output row is long and compresses ~40x."""
+    rng = np.random.default_rng(9)
+    x = synth.pruned_dense(48, 1024, 0.10, seed=1, nonneg=True)
+    w = synth.pruned_dense(1024, 1024, 0.10, seed=2)
+    wt = synth.transpose_host(w, 1024)
+    x_csc = synth.transpose_host(x, 1024)
+    want, prod = oracle_spgemm(x_csc, wt)
+    res = engine.spgemm(x, wt, a_is_csr=True, cols_b=1024)
+    got = res.to_host(); res.free()
+    assert_bit_exact(got, want, "mlp batch 48")
+
+
+def test_row_chunking_gives_same_bits(engine):
+    rng = np.random.default_rng(21)
+    A, B = rand_sparse(rng, 400, 300, 0.05), rand_sparse(rng, 300, 350, 0.05)
+    a_csc, a_csr, b_csr = operands(A, B)
+    want, prod = oracle_spgemm(a_csc, b_csr)
+    eng = osp.Engine(0)
+    try:
+        eng.set_workspace_limit(64 * 1024)            # 8192 partial products per block
+        res = eng.spgemm(a_csr, b_csr, a_is_csr=True)
+        got = res.to_host(); st = res.stats(); res.free()
+        assert st["row_chunks"] > 4
+        assert_bit_exact(got, want, "chunked")
+        res = eng.spgemm(a_csc, b_csr)
+        got = res.to_host(); res.free()
+        assert_bit_exact(got, want, "chunked from CSC")
+    finally:
+        eng.close()
+
+
+def test_edge_cases(engine):
+    E = osp.ELEM
+    # empty A (reference: maxRowId = 0 -> one empty output row)
+    a = osp.CSRMatrix(np.zeros(5, np.uint64), np.zeros(0, E))
+    b = pack([0, 1, 1, 2, 2], np.array([(0, 1.0), (3, 2.0)], E))
+    for is_csr in (False, True):
+        res = engine.spgemm(a, b, a_is_csr=is_csr)
+        got = res.to_host(); res.free()
+        assert list(got.pos) == [0, 0] and got.nnz == 0
+    # empty B
+    a = pack([0, 1, 2, 2, 2], np.array([(0, 1.0), (3, 2.0)], E))
+    b = osp.CSRMatrix(np.zeros(5, np.uint64), np.zeros(0, E))
+    res = engine.spgemm(a, b)
+    got = res.to_host(); res.free()
+    assert list(got.pos) == [0, 0, 0, 0, 0] and got.nnz == 0
+    # 1x1
+    one = pack([0, 1], np.array([(0, 3.0)], E))
+    res = engine.spgemm(one, one)
+    got = res.to_host(); res.free()
+    assert list(got.pos) == [0, 1] and got.data[0]["idx"] == 0 and got.data[0]["val"] == 9.0
+    # explicit zeros and exact cancellation stay in the structure (no numerical zero dropping)
+    A = sp.csr_matrix(np.array([[1, -1], [0, 2]], np.float32)); B = sp.csr_matrix(np.array([[1, 5], [1, 0]], np.float32))
+    a_csc, _, b_csr = operands(A, B)
+    want, _ = oracle_spgemm(a_csc, b_csr)
+    res = engine.spgemm(a_csc, b_csr)
+    got = res.to_host(); res.free()
+    assert_bit_exact(got, want, "cancellation")
+    assert got.data["val"][0] == 0.0 and got.nnz == 3
+    # explicit rows_c larger than maxRowId+1 pads empty rows
+    res = engine.spgemm(a_csc, b_csr, rows_c=5)
+    got = res.to_host(); res.free()
+    assert got.NRow() == 5 and list(got.pos[2:]) == [3, 3, 3, 3]
+
+
+def test_error_codes(engine):
+    E = osp.ELEM
+    a = pack([0, 1, 2], np.array([(0, 1.0), (1, 2.0)], E))
+    b3 = pack([0, 1, 1, 2], np.array([(0, 1.0), (1, 2.0)], E))
+    with pytest.raises(osp.OspError) as ei:                     # assert(lmat.NRow()==rmat.NRow()), SimOuterSPACE.cpp:47
+        engine.spgemm(a, b3)
+    assert ei.value.code == api.OSP_ERR_INVALID
+    bad = pack([0, 1, 2], np.array([(0, 1.0), (7, 2.0)], E))    # k index 7 >= n_k = 2 in a CSR(A)
+    b2 = pack([0, 1, 2], np.array([(0, 1.0), (1, 2.0)], E))
+    with pytest.raises(osp.OspError) as ei:
+        engine.spgemm(bad, b2, a_is_csr=True)
+    assert ei.value.code == api.OSP_ERR_INDEX
+    # engine still usable afterwards
+    res = engine.spgemm(a, b2)
+    assert res.to_host().nnz == 2
+    res.free()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_csr2csc_device_stable(engine, name):
+    """Device CSR->CSC equals coo2csr<true> of the reference (fixture made by the compiled reference)."""
+    g = load_npz(name)
+    a_csr = pack(g["a_csr_pos"], g["a_csr_data"])
+    got = engine.csr2csc(a_csr, len(g["a_csc_pos"]) - 1)
+    assert np.array_equal(got.pos, g["a_csc_pos"]) and np.array_equal(got.data, g["a_csc_data"])
+    back = engine.csr2csc(got, a_csr.NRow())
+    assert np.array_equal(back.pos, a_csr.pos) and np.array_equal(back.data, a_csr.data)
+
+
+def test_csr2csc_random_and_duplicates(engine):
+    rng = np.random.default_rng(33)
+    for _ in range(4):
+        m, n = (int(x) for x in rng.integers(1, 500, size=2))
+        a = CSR = osp.CSRMatrix.from_scipy(rand_sparse(rng, m, n, 0.1))
+        pos, data = oracle.csr2csc(m, n, a.pos, a.data)
+        got = engine.csr2csc(a, n)
+        assert np.array_equal(got.pos, pos) and np.array_equal(got.data, data)
+    dup = pack([0, 2, 3], np.array([(1, 1.0), (1, 2.0), (0, 3.0)], osp.ELEM))
+    with pytest.raises(osp.DuplicateEntry):
+        engine.csr2csc(dup, 2)
+
+
+def test_device_resident_operands(engine):
+    """HBM-resident operands through OSP_DEVICE_POINTERS (torch only provides the allocations)."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(77)
+    A, B = rand_sparse(rng, 200, 150, 0.05), rand_sparse(rng, 150, 180, 0.05)
+    a_csc, a_csr, b_csr = operands(A, B)
+    want, _ = oracle_spgemm(a_csc, b_csr)
+    dev = torch.device("cuda:0")
+
+    def up(x):
+        return torch.from_numpy(x.view(np.uint8).reshape(-1).copy()).to(dev)
+    t = [up(a_csr.pos), up(a_csr.data), up(b_csr.pos), up(b_csr.data)]
+    torch.cuda.synchronize()
+    res = engine.spgemm_device(a_csr.NRow(), t[0].data_ptr(), t[1].data_ptr(), b_csr.NRow(), t[2].data_ptr(),
+                               t[3].data_ptr(), a_is_csr=True)
+    got = res.to_host()
+    dpos, ddata = res.device_pointers()
+    assert dpos and ddata
+    res.free()
+    assert_bit_exact(got, want, "device operands")

@@ -1,0 +1,56 @@
+"""Ad-hoc phase timing of named workloads with HBM-resident operands (development aid, not bench.py)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+import torch  # noqa: E402
+
+import outerspace_b200 as osp  # noqa: E402
+from outerspace_b200 import api, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="er16k")
+    ap.add_argument("--scale-down", type=int, default=1)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    t0 = time.time()
+    a, b, dims = synth.build_workload(args.workload, args.scale_down)
+    print(f"built {args.workload}/{args.scale_down}: nnzA={a.nnz} nnzB={b.nnz} dims={dims} in {time.time()-t0:.1f}s", flush=True)
+    dev = torch.device("cuda:0")
+
+    def up(x):
+        return torch.from_numpy(x.view(np.uint8).reshape(-1)).to(dev)
+    t = [up(a.pos), up(a.data), up(b.pos), up(b.data)]
+    torch.cuda.synchronize()
+    eng = osp.Engine(0)
+    for it in range(args.iters):
+        w0 = time.perf_counter()
+        res = eng.spgemm_device(a.NRow(), t[0].data_ptr(), t[1].data_ptr(), b.NRow(), t[2].data_ptr(), t[3].data_ptr(),
+                                a_is_csr=True, cols_b=dims["cols"], flags=args.flags | api.OSP_PROFILE_PHASES)
+        wall = (time.perf_counter() - w0) * 1e3
+        st = res.stats()
+        gbs = st["algorithmic_bytes"] / (st["ms_total"] * 1e-3) / 1e9
+        print(json.dumps(dict(it=it, wall_ms=round(wall, 3), gflops=round(2 * st["products"] / (st["ms_total"] * 1e6), 2),
+                              alg_gbs=round(gbs, 1), **{k: (round(v, 4) if isinstance(v, float) else v) for k, v in st.items()})), flush=True)
+        if args.check and it == 0:
+            import oracle
+            got = res.to_host()
+            pos, data, prod = oracle.spgemm_rowblocks(a.pos, a.data, b.pos, b.data, 4096)
+            ok = np.array_equal(got.pos, pos) and np.array_equal(got.data["idx"], data["idx"]) and \
+                np.array_equal(got.data["val"].view(np.uint32), data["val"].view(np.uint32))
+            print("oracle check:", "BIT-EXACT" if ok else "MISMATCH", flush=True)
+        res.free()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
