@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 outer-product SpGEMM engine (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one C = A*A of the named synthetic workload: HBM-resident CSR(A), CSR(B) -> HBM-resident
+CSR(C) (device CSR->CSC conversion + symbolic count + multiply + [exchange] + merge), through the C ABI
+(include/osp_b200.h).  N=1 runs BASELINE.json configs[1] (ER 16384^2, density 1e-3); N>1 runs configs[3]
+(ER 2^23, 8 nnz/row) k-sharded over the ranks with an NCCL all-to-allv of the partial products.
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for every field.
+
+The oracle (oracle/, oracle/_ref) is used here ONLY for the `cpu_baseline` object and the
+`--impl reference` arm; it is never on the measured GPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "spgemm_gflops"          # 2*P / t, P = sum_k nnz(A(:,k))*nnz(B(k,:))   (SimSpGEMM.cpp:884-891 counts 1*P)
+UNIT = "GFLOP/s"
+L2_FLUSH_BYTES = 256 << 20        # > 126 MB L2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: nvidia-smi sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (the ONLY users of oracle/ in this file)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(a_csr, b_csr, n_k, reps: int):
+    """Times the reference's own functional path on the host: TaskProvider's constructor
+    (multiplyPhase + mergePhase, SimOuterSPACE.cpp:46-132) compiled unmodified into oracle/_ref, or --
+    when oracle/_ref could not be built -- the oracle restatement.  Single-threaded: the reference has
+    no threading.  Returns (seconds per run list, kind, products)."""
+    import oracle
+    from outerspace_b200 import synth
+    a_csc = synth.transpose_host(a_csr, n_k)
+    secs = []
+    prod = oracle.flops(a_csc.pos, b_csr.pos)
+    if oracle.ref_available():
+        for _ in range(reps):
+            secs.append(oracle.ref_taskprovider(a_csc.pos, a_csc.data, b_csr.pos, b_csr.data)["seconds"])
+        return secs, "reference", prod
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle.spgemm(a_csc.pos, a_csc.data, b_csr.pos, b_csr.data)
+        secs.append(time.perf_counter() - t0)
+    return secs, "port", prod
+
+
+def workload_for(n_gpus: int, name: str | None):
+    if name:
+        return name
+    return "er16k" if n_gpus == 1 else "er8m"
+
+
+WORKLOAD_DESC = {
+    "mlp_fc2": "configs[0]: pruned-MLP fc2 weight 1000x1000 @1%, C=A*A",
+    "er16k": "configs[1]: Erdos-Renyi 16384x16384 density 1e-3, C=A*A",
+    "rmat20": "configs[2]: R-MAT scale 20, edge factor 16, C=A*A",
+    "er8m": "configs[3]: Erdos-Renyi 2^23 x 2^23, 8 nnz/row, C=A*A",
+    "mlp_batch": "configs[4]: activation 65536x4096 (10%) x weight^T 4096x4096 (10%)",
+}
+# bounded CPU samples: scale_down so that one reference run takes O(1 s)
+CPU_SAMPLE_SCALE = {"mlp_fc2": 1, "er16k": 1, "rmat20": 64, "er8m": 64, "mlp_batch": 2048}
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    if rank != 0:
+        return
+    from outerspace_b200 import synth
+    wl = workload_for(args.gpus, args.workload)
+    sd = CPU_SAMPLE_SCALE[wl]
+    a, b, dims = synth.build_workload(wl, sd)
+    secs, kind, prod = cpu_reference_run(a, b, dims["n_k"], args.warmup + args.steps)
+    timed = secs[args.warmup:]
+    ms = 1e3 * sum(timed) / len(timed)
+    value = 2.0 * prod / (ms * 1e-3) / 1e9
+    sample = f"{wl} at 1/{sd} linear scale (rows={dims['rows']}, P={prod}), one TaskProvider ctor per step" if sd > 1 \
+        else f"full {wl} (rows={dims['rows']}, P={prod}), one TaskProvider ctor per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC[wl], "name": wl, "sample_scale_down": sd},
+        "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def dominant_kernel(kernel_rows, stats):
+    """kernel_rows: list over steps of [(name, ms)].  -> (name, avg ms per launch, launches/step, share)."""
+    agg, cnt = {}, {}
+    for rows in kernel_rows:
+        for name, ms in rows:
+            agg[name] = agg.get(name, 0.0) + ms
+            cnt[name] = cnt.get(name, 0) + 1
+    total = sum(agg.values()) or 1.0
+    name = max(agg, key=agg.get)
+    return name, agg[name] / cnt[name], cnt[name] / len(kernel_rows), agg[name] / total, \
+        {k: round(v / len(kernel_rows), 5) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}
+
+
+def kernel_algorithmic_bytes(name: str, st: dict) -> tuple[int, str]:
+    """Algorithmic bytes of ONE launch of the named kernel when it covers the whole workload
+    (DESIGN.md "Kernels": from the reference's DRAM model analyzeMultiplyTask / analyzeMergeTask,
+    SimOuterSPACE.cpp:176-196)."""
+    P, nnz_a, nnz_b, nnz_c = st["products"], st["nnz_a"], st["nnz_b"], st["nnz_c"]
+    m, n = st["rows_c"], st["n_k"]
+    if "multiply" in name:
+        return 8 * nnz_a + 8 * nnz_b + 16 * (n + 1) + 8 * P, "multiply: 8nnzA + 8nnzB + 16(n+1) + 8P"
+    if "merge" in name:
+        return 8 * P + 8 * nnz_c + 8 * (m + 1), "merge: 8P + 8nnzC + 8(m+1)"
+    if "gather" in name:
+        return 16 * nnz_c, "gather: 16 nnzC"
+    return 16 * nnz_a + 8 * (m + n + 2), "convert/symbolic: 16nnzA + 8(m+n+2)"
+
+
+def run_ours(args, rank: int, world: int, local_rank: int) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import outerspace_b200 as osp
+    from outerspace_b200 import api, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = workload_for(args.gpus, args.workload)
+    a, b, dims = synth.build_workload(wl, args.scale_down)
+    peak, peak_src = peaks()
+
+    def up(x):
+        return torch.from_numpy(x.view(np.uint8).reshape(-1)).to(dev)
+
+    flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        flush_buf.fill_(1)
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+
+    if world == 1:
+        t = [up(a.pos), up(a.data), up(b.pos), up(b.data)]
+        eng = osp.Engine(local_rank)
+        stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+
+        def step(flags=0):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            res = eng.spgemm_device(a.NRow(), t[0].data_ptr(), t[1].data_ptr(), b.NRow(), t[2].data_ptr(),
+                                    t[3].data_ptr(), a_is_csr=True, cols_b=dims["cols"], flags=flags)
+            e1.record(stream)
+            e1.synchronize()
+            return res, e0.elapsed_time(e1)
+
+        for _ in range(args.warmup):
+            flush_l2()
+            res, _ = step()
+            res.free()
+        # ---- timed region: K steps, L2 flushed before each, device time per step from CUDA events ----
+        torch.cuda.synchronize()
+        sampler.start()
+        wall0 = time.perf_counter()
+        ms_steps, launches, st = [], 0, None
+        for _ in range(args.steps):
+            flush_l2()
+            res, ms = step()
+            st = res.stats()
+            launches += st["kernel_launches"]
+            ms_steps.append(ms)
+            res.free()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop()
+        ms_per_step = sum(ms_steps) / len(ms_steps)
+
+        # ---- per-kernel durations (event pair per launch), a separate short pass ----
+        kernel_rows = []
+        for _ in range(max(3, min(args.steps, 10))):
+            flush_l2()
+            res, _ = step(api.OSP_PROFILE_KERNELS)
+            kernel_rows.append(res.kernel_times())
+            res.free()
+        kname, k_ms, k_launches, k_share, k_table = dominant_kernel(kernel_rows, st)
+        k_bytes, k_formula = kernel_algorithmic_bytes(kname, st)
+        k_bytes_per_launch = k_bytes / max(k_launches, 1.0)
+        achieved = k_bytes_per_launch / (k_ms * 1e-3) / 1e9
+
+        # ---- e2e: host CSRMatrix operands (pinned) -> osp_spgemm -> host CSRMatrix result ----
+        def pinned_like(x):
+            buf = torch.empty(max(x.nbytes, 8), dtype=torch.uint8, pin_memory=True)
+            v = buf.numpy()[: x.nbytes].view(x.dtype)
+            v[...] = x
+            return buf, v
+        keep = [pinned_like(x) for x in (a.pos, a.data, b.pos, b.data)]
+        ha = osp.CSRMatrix(keep[0][1], keep[1][1])
+        hb = osp.CSRMatrix(keep[2][1], keep[3][1])
+        out_pos_buf = torch.empty((st["rows_c"] + 1) * 8, dtype=torch.uint8, pin_memory=True)
+        out_dat_buf = torch.empty(max(st["nnz_c"], 1) * 8, dtype=torch.uint8, pin_memory=True)
+        out_pos = out_pos_buf.numpy().view(np.uint64)
+        out_dat = out_dat_buf.numpy().view(osp.ELEM)
+        e2e_ms = []
+        for i in range(args.warmup + args.steps):
+            flush_l2()
+            t0 = time.perf_counter()
+            res = eng.spgemm(ha, hb, a_is_csr=True, cols_b=dims["cols"])
+            res.copy_into(out_pos[: res.rows + 1], out_dat[: res.nnz])
+            dt = time.perf_counter() - t0
+            res.free()
+            if i >= args.warmup:
+                e2e_ms.append(dt * 1e3)
+        e2e_ms_step = sum(e2e_ms) / len(e2e_ms)
+        h2d = int(a.pos.nbytes + a.data.nbytes + b.pos.nbytes + b.data.nbytes)
+        d2h = int((st["rows_c"] + 1) * 8 + st["nnz_c"] * 8)
+        eng.close()
+        products = st["products"]
+        alg_bytes = st["algorithmic_bytes"]
+    else:
+        from outerspace_b200 import distributed as osd
+        out = osd.bench_sharded(a, b, dims, args, rank, world, local_rank, flush_l2, sampler)
+        ms_per_step, wall, clocks, launches, st = out["ms_per_step"], out["wall"], out["clocks"], out["launches"], out["stats"]
+        kname, k_ms, k_launches, k_share, k_table = out["kernel"]
+        k_bytes_per_launch, k_formula = out["kernel_bytes"], out["kernel_formula"]
+        achieved = k_bytes_per_launch / (k_ms * 1e-3) / 1e9
+        e2e_ms_step, h2d, d2h = out["e2e_ms"], out["h2d"], out["d2h"]
+        products, alg_bytes = st["products"], st["algorithmic_bytes"]
+
+    if world > 1:
+        tmax = torch.tensor([ms_per_step, e2e_ms_step], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_per_step, e2e_ms_step = float(tmax[0]), float(tmax[1])
+        ltot = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(ltot)
+        launches = int(ltot[0])
+
+    if rank == 0:
+        value = 2.0 * products / (ms_per_step * 1e-3) / 1e9
+        e2e_value = 2.0 * products / (e2e_ms_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[wl], "name": wl, "scale_down": args.scale_down,
+                       "rows": st["rows_c"], "n_k": st["n_k"], "nnz_a": st["nnz_a"], "products": products,
+                       "nnz_c": st["nnz_c"], "parallelism": "single" if world == 1 else f"k-shard{world}+alltoallv",
+                       "timed_region": "HBM-resident CSR(A),CSR(B) -> HBM-resident CSR(C); CUDA events on the engine stream",
+                       "l2": f"L2 flushed ({L2_FLUSH_BYTES >> 20} MiB write) before every step, outside the event pair"},
+            "algorithmic_gbs": round(alg_bytes / (ms_per_step * 1e-3) / 1e9, 2),
+            "algorithmic_frac_of_hbm_peak": round(alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+            "wall_s_timed_region": round(wall, 4),
+            "clocks": clocks,
+            "gpu_launches": int(launches),
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "ms_per_step": round(e2e_ms_step, 4),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "path": "host CSRMatrix (pinned) -> osp_spgemm -> osp_result_copy to host CSRMatrix"},
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "avg_launch_ms": round(k_ms, 5), "launches_per_step": k_launches,
+                         "algorithmic_bytes_per_launch": int(k_bytes_per_launch), "formula": k_formula,
+                         "share_of_kernel_time": round(k_share, 4), "kernel_ms_per_step": k_table},
+        }
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            try:
+                with open(prof) as f:
+                    tr = json.load(f)
+                if tr.get("workload") == wl and kname in tr.get("kernels", {}):
+                    line["roofline"]["traffic"] = tr["kernels"][kname]["dram_bytes_per_launch"]
+                    line["roofline"]["traffic_source"] = tr.get("source")
+            except (OSError, ValueError, KeyError):
+                pass
+        if world == 1 and not args.no_cpu_baseline:
+            sd = CPU_SAMPLE_SCALE[wl] if args.scale_down == 1 else 1
+            ca, cb, cdims = (a, b, dims) if sd == 1 else synth.build_workload(wl, sd)
+            secs, kind, cprod = cpu_reference_run(ca, cb, cdims["n_k"], 3)
+            best = min(secs)
+            line["cpu_baseline"] = {
+                "value": round(2.0 * cprod / best / 1e9, 5), "unit": UNIT, "cores": 1, "kind": kind,
+                "sample": (f"full {wl}" if sd == 1 else f"{wl} at 1/{sd} linear scale") +
+                          f" (P={cprod}), TaskProvider ctor, best of 3, {best:.3f} s",
+                "host_cores_available": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=list(WORKLOAD_DESC))
+    ap.add_argument("--scale-down", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

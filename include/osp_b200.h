@@ -48,6 +48,8 @@ extern "C" {
                                     k-slice order (same bins, same result; see DESIGN.md "multiply order") */
 #define OSP_PROFILE_PHASES   8u  /* synchronise between phases so that stats.ms_* are per-phase times */
 
+#define OSP_PROFILE_KERNELS 16u  /* record a CUDA-event pair around every kernel launch (osp_result_kernels) */
+
 typedef struct osp_ctx osp_ctx;        /* one per GPU; single owner, one call at a time */
 typedef struct osp_result osp_result;  /* C = A*B in HBM until freed */
 
@@ -96,6 +98,9 @@ int  osp_result_dims(const osp_result *r, uint64_t *rows, uint64_t *nnz);
 int  osp_result_copy(osp_result *r, uint64_t *pos, void *data);  /* into CSRMatrix::pos / ::data storage */
 int  osp_result_device(const osp_result *r, const uint64_t **d_pos, const void **d_data);
 int  osp_result_stats(const osp_result *r, osp_stats *stats);
+/* Per-launch device times of a call made with OSP_PROFILE_KERNELS, in launch order (two-call pattern:
+ * pass names = ms = NULL to get the count in *n; then arrays of *n entries).  Names are static strings. */
+int  osp_result_kernels(const osp_result *r, uint64_t *n, const char **names, float *ms);
 void osp_result_free(osp_result *r);
 
 /* Task-size lists the reference's timing models read from TaskProvider

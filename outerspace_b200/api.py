@@ -32,11 +32,12 @@ OSP_A_IS_CSR = 1
 OSP_DEVICE_POINTERS = 2
 OSP_ROWWISE_ORDER = 4
 OSP_PROFILE_PHASES = 8
+OSP_PROFILE_KERNELS = 16
 
 # every symbol include/osp_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "osp_device_count", "osp_create", "osp_destroy", "osp_last_error", "osp_set_workspace_limit", "osp_stream",
-    "osp_spgemm", "osp_result_dims", "osp_result_copy", "osp_result_device", "osp_result_stats", "osp_result_free",
+    "osp_spgemm", "osp_result_dims", "osp_result_copy", "osp_result_device", "osp_result_stats", "osp_result_kernels", "osp_result_free",
     "osp_task_sizes", "osp_csr2csc", "osp_readcoo", "osp_coo_dims", "osp_coo_copy", "osp_coo_free", "osp_coo2csr",
     "osp_version",
 ]
@@ -105,6 +106,7 @@ def load_library() -> C.CDLL:
     lib.osp_result_copy.argtypes = [vp, vp, vp]
     lib.osp_result_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     lib.osp_result_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.osp_result_kernels.argtypes = [vp, C.POINTER(u64), vp, vp]
     lib.osp_result_free.argtypes = [vp]
     lib.osp_result_free.restype = None
     lib.osp_task_sizes.argtypes = [vp, C.POINTER(SpgemmArgs), vp, C.POINTER(u64), vp, C.POINTER(u64), vp]
@@ -175,6 +177,14 @@ class Result:
         s = Stats()
         self._engine._lib.osp_result_stats(self._h, C.byref(s))
         return s.as_dict()
+
+    def kernel_times(self) -> list:
+        """[(kernel name, ms)] in launch order for a call made with OSP_PROFILE_KERNELS."""
+        n = C.c_uint64()
+        self._engine._lib.osp_result_kernels(self._h, C.byref(n), None, None)
+        names, ms = (C.c_char_p * n.value)(), (C.c_float * n.value)()
+        self._engine._lib.osp_result_kernels(self._h, C.byref(n), names, ms)
+        return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
 
     def device_pointers(self) -> Tuple[int, int]:
         p, d = C.c_void_p(), C.c_void_p()

@@ -53,6 +53,10 @@ struct osp_ctx {
     DevBuf bins;
     std::vector<cudaEvent_t> events;
     size_t events_used = 0;
+    // OSP_PROFILE_KERNELS: one event pair per launch
+    bool profile_kernels = false;
+    struct KernelMark { const char *name; cudaEvent_t e0, e1; };
+    std::vector<KernelMark> marks;
 };
 
 struct osp_result {
@@ -62,6 +66,7 @@ struct osp_result {
     size_t data_cap = 0;   // elements
     uint64_t rows = 0, nnz = 0;
     osp_stats stats;
+    std::vector<std::pair<const char *, float>> kernel_ms;   // OSP_PROFILE_KERNELS
 };
 
 namespace {
@@ -70,6 +75,17 @@ int fail(osp_ctx *ctx, int code, const std::string &msg) {
     g_last_error = msg;
     if (ctx) ctx->err = msg;
     return code;
+}
+
+cudaEvent_t next_event(osp_ctx *ctx) {
+    if (ctx->events_used == ctx->events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->events.push_back(e);
+    }
+    cudaEvent_t e = ctx->events[ctx->events_used++];
+    cudaEventRecord(e, ctx->stream);
+    return e;
 }
 
 #define CU(ctx, expr)                                                                           \
@@ -84,9 +100,12 @@ int fail(osp_ctx *ctx, int code, const std::string &msg) {
 
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                                             \
     do {                                                                                        \
+        cudaEvent_t _m0 = nullptr;                                                              \
+        if ((ctx)->profile_kernels) _m0 = next_event(ctx);                                      \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                        \
         (ctx)->launches++;                                                                      \
         CU(ctx, cudaGetLastError());                                                            \
+        if (_m0) (ctx)->marks.push_back({#kernel, _m0, next_event(ctx)});                       \
     } while (0)
 
 constexpr uint32_t MERGE_CAP = 4096;
@@ -119,17 +138,6 @@ int run_scan(osp_ctx *ctx, In in, Out out, uint64_t n) {
     LAUNCH(ctx, (k_scan<In, Out>), unsigned(tiles), SCAN_BLOCK, 0, in, out, n, ctx->scan_state.as<uint64_t>(),
            &ctx->d_sc->tile_counter);
     return OSP_OK;
-}
-
-cudaEvent_t next_event(osp_ctx *ctx) {
-    if (ctx->events_used == ctx->events.size()) {
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        ctx->events.push_back(e);
-    }
-    cudaEvent_t e = ctx->events[ctx->events_used++];
-    cudaEventRecord(e, ctx->stream);
-    return e;
 }
 
 // Sorts every bucket [pos[i], pos[i+1]) of `data` by idx (stable w.r.t. nothing: keys are unique
@@ -322,6 +330,8 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     CU(ctx, cudaSetDevice(ctx->device));
     ctx->launches = 0;
     ctx->events_used = 0;
+    ctx->marks.clear();
+    ctx->profile_kernels = args->flags & OSP_PROFILE_KERNELS;
     int rc = reset_scalars(ctx);
     if (rc) return rc;
 
@@ -532,7 +542,20 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         cudaEventElapsedTime(&ms, ev_blocks[4 * b + 1], ev_blocks[4 * b + 2]); st.ms_multiply += ms;
         cudaEventElapsedTime(&ms, ev_blocks[4 * b + 2], ev_blocks[4 * b + 3]); st.ms_merge += ms;
     }
+    for (const auto &m : ctx->marks) {
+        cudaEventElapsedTime(&ms, m.e0, m.e1);
+        res->kernel_ms.emplace_back(m.name, ms);
+    }
+    ctx->profile_kernels = false;
     *out = res;
+    return OSP_OK;
+}
+
+int osp_result_kernels(const osp_result *r, uint64_t *n, const char **names, float *ms) {
+    if (!r || !n) return fail(nullptr, OSP_ERR_INVALID, "osp_result_kernels: NULL argument");
+    if (names && ms)
+        for (size_t i = 0; i < r->kernel_ms.size() && i < *n; i++) { names[i] = r->kernel_ms[i].first; ms[i] = r->kernel_ms[i].second; }
+    *n = r->kernel_ms.size();
     return OSP_OK;
 }
 
@@ -639,6 +662,7 @@ int osp_csr2csc(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint64_t
     CU(ctx, cudaSetDevice(ctx->device));
     ctx->launches = 0;
     ctx->events_used = 0;
+    ctx->profile_kernels = false;
     int rc = reset_scalars(ctx);
     if (rc) return rc;
     if (flags & OSP_DEVICE_POINTERS) {
