@@ -73,7 +73,9 @@ typedef struct osp_stats {
     uint64_t nnz_a, nnz_b, nnz_c;
     uint64_t products;            /* P = sum_k nnz(A(:,k))*nnz(B(k,:)) = mulflops_ref, SimSpGEMM.cpp:884-891 */
     uint64_t algorithmic_bytes;   /* 16P + 8nnzC + 24nnzA + 8nnzB + 8(2m+3n+5) */
-    uint64_t rows_short, rows_medium, rows_long; /* merge classes */
+    uint64_t merge_tiles;         /* tiles of consecutive rows the merge kernel took */
+    uint64_t rows_medium;         /* rows sorted by one CTA in shared memory (512 < partial products <= 4096) */
+    uint64_t rows_long;           /* rows folded through a dense accumulator (> 4096 partial products) */
     uint64_t kernel_launches;     /* kernels this call launched */
     uint64_t row_chunks;          /* output-row blocks the call was split into */
     float    ms_total;            /* first kernel to last kernel */

@@ -66,7 +66,7 @@ class Stats(C.Structure):
         ("rows_c", C.c_uint64), ("cols_b", C.c_uint64), ("n_k", C.c_uint64),
         ("nnz_a", C.c_uint64), ("nnz_b", C.c_uint64), ("nnz_c", C.c_uint64),
         ("products", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
-        ("rows_short", C.c_uint64), ("rows_medium", C.c_uint64), ("rows_long", C.c_uint64),
+        ("merge_tiles", C.c_uint64), ("rows_medium", C.c_uint64), ("rows_long", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("row_chunks", C.c_uint64),
         ("ms_total", C.c_float), ("ms_convert", C.c_float), ("ms_multiply", C.c_float), ("ms_merge", C.c_float),
         ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),

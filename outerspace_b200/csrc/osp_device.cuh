@@ -24,16 +24,21 @@ struct __align__(16) Task {
 };
 static_assert(sizeof(Task) == 16, "Task is one 128-bit load");
 
-// Scalars the kernels report back to the host (one pinned-mirror copy per call).
+// Scalars the kernels report back to the host (one pinned-mirror copy per sync).  Lives at the start
+// of the per-call zeroed arena, so every counter starts at 0.
 struct DevScalars {
-    unsigned long long products;     // P
-    unsigned long long block_nnz;    // unique outputs of the current row block
-    unsigned int err;                // first OSP_ERR_* raised on the device
-    unsigned int max_idx;            // reduction result of k_max_idx
-    unsigned int xl_count;           // rows queued for the long-row kernel
-    unsigned int tile_counter;       // dynamic tile ids of the look-back scan
-    unsigned long long last_nonempty;  // k_last_nonempty result
-    unsigned int tile_counter2;
+    unsigned long long products;       // P
+    unsigned long long cap_bound;      // sum_i min(len_i, cols) : upper bound of nnz(C)
+    unsigned long long nnz_c;          // written by the last merge tile
+    unsigned long long last_nonempty;  // 1 + index of the last row with partial products / non-zeros
+    unsigned int err;                  // first OSP_ERR_* raised on the device
+    unsigned int max_idx;              // reduction result of k_max_idx
+    unsigned int n_tiles;              // merge tiles planned
+    unsigned int n_long;               // rows queued for the CTA shared-memory sort
+    unsigned int n_xl;                 // rows queued for the long-row (dense accumulator) kernel
+    unsigned int tile_ticket;          // dynamic tile ids of the merge kernel
+    unsigned int scan_ticket[4];       // dynamic tile ids of the look-back scans (one per scan of a call)
+    unsigned int n_dups;               // rows that shrank while folding (duplicate check of csr2csc)
     unsigned int pad;
 };
 
@@ -64,25 +69,27 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
 // Called by every lane of ONE warp.  Publishes this tile's aggregate, walks back over the
 // predecessors 32 at a time until an inclusive prefix is found, publishes the tile's own
 // inclusive prefix and returns the exclusive prefix (same value in every lane).
-__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *state, uint32_t tile, uint64_t aggregate) {
+// `first` is the id of the first tile of the chain (its exclusive prefix is `carry`).
+__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *state, uint32_t tile, uint64_t aggregate,
+                                                       uint32_t first = 0, uint64_t carry = 0) {
     const unsigned int lane = lane_id();
-    if (tile == 0) {
-        if (lane == 0) st_relaxed_u64(state, LB_FLAG_PREFIX | aggregate);
-        return 0;
+    if (tile == first) {
+        if (lane == 0) st_relaxed_u64(state + tile, LB_FLAG_PREFIX | (carry + aggregate));
+        return carry;
     }
     if (lane == 0) st_relaxed_u64(state + tile, LB_FLAG_AGG | aggregate);
     uint64_t exclusive = 0;
     int64_t base = int64_t(tile) - 1;
     while (true) {
         int64_t idx = base - lane;
-        uint64_t word = LB_FLAG_PREFIX;  // tiles before 0 contribute an inclusive prefix of 0
-        if (idx >= 0) {
+        uint64_t word = LB_FLAG_PREFIX;  // tiles before `first` contribute an inclusive prefix of 0
+        if (idx >= int64_t(first)) {
             word = ld_relaxed_u64(state + idx);
             while ((word >> 62) == 0) word = ld_relaxed_u64(state + idx);
         }
         unsigned int has_prefix = __ballot_sync(FULL, (word >> 62) == 2);
-        unsigned int first = has_prefix ? (__ffs(has_prefix) - 1) : 31;
-        uint64_t v = (lane <= first) ? (word & LB_VALUE_MASK) : 0;
+        unsigned int firstp = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+        uint64_t v = (lane <= firstp) ? (word & LB_VALUE_MASK) : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
         exclusive += v;
@@ -93,26 +100,27 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *state, uint32_t
     return exclusive;
 }
 
-// ---- block-wide exclusive scan of a small per-thread count (blockDim.x <= 1024) -----------
+// ---- warp / block scans -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t x) {
+    const unsigned int lane = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(FULL, x, o);
+        if (lane >= o) x += y;
+    }
+    return x;
+}
+
+// Block-wide exclusive scan of a small per-thread count (blockDim.x <= 1024).
 // `warp_sums` is a 33-entry shared array.  Contains two __syncthreads().
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t *warp_sums, uint32_t &total) {
     const unsigned int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
-    uint32_t incl = x;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += y;
-    }
+    uint32_t incl = warp_inclusive_scan(x);
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
     if (warp == 0) {
         uint32_t w = lane < nwarps ? warp_sums[lane] : 0;
-        uint32_t wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(FULL, wi, o);
-            if (lane >= o) wi += y;
-        }
+        uint32_t wi = warp_inclusive_scan(w);
         warp_sums[lane] = wi - w;                 // exclusive offsets of the warps
         if (lane == 31) warp_sums[32] = wi;       // block total
     }

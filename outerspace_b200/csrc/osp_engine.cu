@@ -39,17 +39,20 @@ struct DevBuf {
 struct osp_ctx {
     int device = 0;
     int sm_count = 148;
+    int tiles_occ32 = 3, tiles_occ64 = 3;   // resident CTAs per SM of k_merge_tiles<K>
     size_t total_mem = 0;
     cudaStream_t stream = nullptr;
     uint64_t ws_limit = 0;          // bytes of partial-product bins per row block
     uint64_t launches = 0;
     std::string err;
-    DevScalars *d_sc = nullptr;
     DevScalars *h_sc = nullptr;     // pinned mirror
+    // per-call zeroed arena: DevScalars | look-back states of the scans | column counters
+    DevBuf arena;
+    DevScalars *d_sc = nullptr;
     // operand staging (host-pointer calls) and converted operands
-    DevBuf op_a_pos, op_a_data, op_b_pos, op_b_data, conv_pos, conv_data;
-    // symbolic / conversion scratch
-    DevBuf run_off, row_bin, col_cnt, col_ptr, tasks, scan_state, uniq, xl_list, xl_acc, xl_bits;
+    DevBuf op_a_pos, op_a_data, op_b_pos, op_b_data, conv_pos, conv_data, conv_tmp, conv_chk;
+    // symbolic / plan / conversion scratch
+    DevBuf run_off, row_bin, tile_row, long_list, xl_list, uniq, col_ptr, tasks, tile_state, xl_acc, xl_bits;
     DevBuf bins;
     std::vector<cudaEvent_t> events;
     size_t events_used = 0;
@@ -63,7 +66,6 @@ struct osp_result {
     osp_ctx *ctx = nullptr;
     uint64_t *d_pos = nullptr;
     Elem *d_data = nullptr;
-    size_t data_cap = 0;   // elements
     uint64_t rows = 0, nnz = 0;
     osp_stats stats;
     std::vector<std::pair<const char *, float>> kernel_ms;   // OSP_PROFILE_KERNELS
@@ -108,13 +110,38 @@ cudaEvent_t next_event(osp_ctx *ctx) {
         if (_m0) (ctx)->marks.push_back({#kernel, _m0, next_event(ctx)});                       \
     } while (0)
 
-constexpr uint32_t MERGE_CAP = 4096;
-constexpr size_t MERGE_SMEM = size_t(MERGE_CAP) * 12 + 34 * 4;
+constexpr size_t LONG_SMEM = size_t(MT_XL) * 12 + 34 * 4;
 
 unsigned int grid_for(uint64_t items, unsigned int per_block, unsigned int max_blocks) {
     uint64_t b = (items + per_block - 1) / per_block;
     if (b < 1) b = 1;
     return unsigned(std::min<uint64_t>(b, max_blocks));
+}
+
+uint64_t scan_tiles(uint64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+uint64_t plan_tiles(uint64_t n) { return (n + PLAN_TILE - 1) / PLAN_TILE; }
+uint64_t align16(uint64_t x) { return (x + 15) & ~15ull; }
+
+// Layout of the per-call zeroed arena.
+struct Arena {
+    uint64_t *state[3] = {nullptr, nullptr, nullptr};   // look-back states of up to three scans
+    uint32_t *counters = nullptr;                       // n_counters uint32 (column histogram / cursors)
+};
+
+// One memset zeroes the device scalars, the scan states and the counters of a call.
+int prepare_arena(osp_ctx *ctx, const uint64_t state_tiles[3], uint64_t n_counters, Arena &a) {
+    uint64_t off = align16(sizeof(DevScalars));
+    uint64_t st_off[3];
+    for (int i = 0; i < 3; i++) { st_off[i] = off; off += align16(state_tiles[i] * 8); }
+    uint64_t cnt_off = off;
+    off += align16(n_counters * 4);
+    CU(ctx, ctx->arena.reserve(off));
+    CU(ctx, cudaMemsetAsync(ctx->arena.p, 0, off, ctx->stream));
+    unsigned char *base = ctx->arena.as<unsigned char>();
+    ctx->d_sc = reinterpret_cast<DevScalars *>(base);
+    for (int i = 0; i < 3; i++) a.state[i] = reinterpret_cast<uint64_t *>(base + st_off[i]);
+    a.counters = reinterpret_cast<uint32_t *>(base + cnt_off);
+    return OSP_OK;
 }
 
 int sync_scalars(osp_ctx *ctx) {
@@ -123,79 +150,114 @@ int sync_scalars(osp_ctx *ctx) {
     return OSP_OK;
 }
 
-int reset_scalars(osp_ctx *ctx) {
-    CU(ctx, cudaMemsetAsync(ctx->d_sc, 0, sizeof(DevScalars), ctx->stream));
+// Buffers the plan kernel writes (sized before the plan's results are known).
+int reserve_plan(osp_ctx *ctx, uint64_t rows, uint64_t max_long) {
+    CU(ctx, ctx->row_bin.reserve((rows + 1) * 8));
+    CU(ctx, ctx->tile_row.reserve((rows + 2) * 4));
+    CU(ctx, ctx->long_list.reserve(std::max<uint64_t>(max_long, 1) * 4));
+    CU(ctx, ctx->xl_list.reserve(std::max<uint64_t>(max_long, 1) * 4));
     return OSP_OK;
 }
 
-template <class In, class Out>
-int run_scan(osp_ctx *ctx, In in, Out out, uint64_t n) {
-    // n >= 1
-    uint64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    CU(ctx, ctx->scan_state.reserve(tiles * 8));
-    CU(ctx, cudaMemsetAsync(ctx->scan_state.p, 0, tiles * 8, ctx->stream));
-    CU(ctx, cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, 4, ctx->stream));
-    LAUNCH(ctx, (k_scan<In, Out>), unsigned(tiles), SCAN_BLOCK, 0, in, out, n, ctx->scan_state.as<uint64_t>(),
-           &ctx->d_sc->tile_counter);
-    return OSP_OK;
-}
+struct MergeJob {
+    uint64_t rows = 0;          // rows of the plan (c_pos has rows + 1 entries)
+    uint64_t idx_range = 0;     // column ids are < idx_range
+    uint32_t n_tiles = 0, n_long = 0, n_xl = 0;
+    uint64_t *c_pos = nullptr;
+    Elem *c_data = nullptr;
+    uint64_t c_cap = 0;
+};
 
-// Sorts every bucket [pos[i], pos[i+1]) of `data` by idx (stable w.r.t. nothing: keys are unique
-// unless the operand held duplicates) and folds equal idx.  uniq[i] = surviving entries.
-int sort_buckets(osp_ctx *ctx, const uint64_t *d_pos, Elem *d_data, uint64_t n_buckets, uint64_t idx_range,
-                 uint64_t bin_base, uint64_t *n_long) {
-    CU(ctx, ctx->uniq.reserve(std::max<uint64_t>(n_buckets, 1) * 4));
-    CU(ctx, ctx->xl_list.reserve(std::max<uint64_t>(n_buckets, 1) * 4));
-    CU(ctx, cudaMemsetAsync(&ctx->d_sc->xl_count, 0, 4, ctx->stream));
-    unsigned int grid = grid_for(n_buckets, 1, unsigned(ctx->sm_count) * 64u);
-    LAUNCH(ctx, k_merge_cta, grid, 256, MERGE_SMEM, d_pos, bin_base, d_data, ctx->uniq.as<uint32_t>(), n_buckets,
-           MERGE_CAP, ctx->xl_list.as<uint32_t>(), ctx->d_sc);
-    int rc = sync_scalars(ctx);
-    if (rc) return rc;
-    uint32_t n_xl = ctx->h_sc->xl_count;
-    if (n_long) *n_long = n_xl;
-    if (n_xl) {
-        uint64_t words = (idx_range + 31) / 32;
-        uint64_t per_cta = idx_range * 4 + words * 4;
-        uint64_t budget = std::max<uint64_t>(ctx->total_mem / 16, 1ull << 28);
-        uint64_t max_ctas = budget / std::max<uint64_t>(per_cta, 1);
+// Scratch that depends on the plan's results: look-back states of the merge tiles, per-row survivor
+// counts of the long rows, the dense accumulators of the longest rows.
+int reserve_merge(osp_ctx *ctx, const MergeJob &job, unsigned int &xl_ctas) {
+    CU(ctx, ctx->tile_state.reserve(std::max<uint64_t>(job.n_tiles, 1) * 8));
+    CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, std::max<uint64_t>(job.n_tiles, 1) * 8, ctx->stream));
+    xl_ctas = 0;
+    if (job.n_long || job.n_xl) CU(ctx, ctx->uniq.reserve(job.rows * 4));
+    if (job.n_xl) {
+        const uint64_t words = (job.idx_range + 31) / 32;
+        const uint64_t per_cta = job.idx_range * 4 + words * 4;
+        const uint64_t budget = std::max<uint64_t>(ctx->total_mem / 16, 1ull << 28);
+        const uint64_t max_ctas = budget / std::max<uint64_t>(per_cta, 1);
         if (max_ctas < 1) return fail(ctx, OSP_ERR_UNSUPPORTED, "long-row accumulator does not fit: column range too large");
-        unsigned int ctas = unsigned(std::min<uint64_t>({max_ctas, uint64_t(ctx->sm_count) * 2, uint64_t(n_xl)}));
-        CU(ctx, ctx->xl_acc.reserve(uint64_t(ctas) * idx_range * 4));
-        size_t old_bits_cap = ctx->xl_bits.cap;
-        CU(ctx, ctx->xl_bits.reserve(uint64_t(ctas) * words * 4));
-        if (ctx->xl_bits.cap != old_bits_cap || true)   // the kernel leaves bits cleared, but layouts change with idx_range
-            CU(ctx, cudaMemsetAsync(ctx->xl_bits.p, 0, uint64_t(ctas) * words * 4, ctx->stream));
-        LAUNCH(ctx, k_merge_xl, ctas, 256, MERGE_SMEM, d_pos, bin_base, d_data, ctx->uniq.as<uint32_t>(),
-               ctx->xl_list.as<uint32_t>(), ctx->d_sc, MERGE_CAP, ctx->xl_acc.as<float>(), ctx->xl_bits.as<uint32_t>(),
-               idx_range);
+        xl_ctas = unsigned(std::min<uint64_t>({max_ctas, uint64_t(ctx->sm_count) * 2, uint64_t(job.n_xl)}));
+        CU(ctx, ctx->xl_acc.reserve(uint64_t(xl_ctas) * job.idx_range * 4));
+        CU(ctx, ctx->xl_bits.reserve(uint64_t(xl_ctas) * words * 4));
+        CU(ctx, cudaMemsetAsync(ctx->xl_bits.p, 0, uint64_t(xl_ctas) * words * 4, ctx->stream));
     }
     return OSP_OK;
 }
 
-// Stable transposition on the device (all pointers are device pointers).
+// Merges the rows of tiles [t0, t1) (rows [row_lo, row_hi)) whose partial products sit in `bins`
+// (bin of row i at bins[row_bin[i] - bin_base]) into C.
+int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *bins, uint64_t bin_base, uint32_t t0,
+                 uint32_t t1, uint64_t row_lo, uint64_t row_hi) {
+    if (t1 <= t0) return OSP_OK;
+    const uint64_t *row_bin = ctx->row_bin.as<uint64_t>();
+    if (job.n_long)
+        LAUNCH(ctx, k_merge_long, std::min<unsigned>(job.n_long, unsigned(ctx->sm_count) * 4u), 256, LONG_SMEM, row_bin,
+               bin_base, bins, ctx->uniq.as<uint32_t>(), ctx->long_list.as<uint32_t>(), ctx->d_sc, row_lo, row_hi);
+    if (job.n_xl)
+        LAUNCH(ctx, k_merge_xl, xl_ctas, 256, LONG_SMEM, row_bin, bin_base, bins, ctx->uniq.as<uint32_t>(),
+               ctx->xl_list.as<uint32_t>(), ctx->d_sc, ctx->xl_acc.as<float>(), ctx->xl_bits.as<uint32_t>(), job.idx_range,
+               row_lo, row_hi);
+    CU(ctx, cudaMemsetAsync(&ctx->d_sc->tile_ticket, 0, 4, ctx->stream));
+    const bool k32 = job.idx_range <= (1ull << 23);
+    const unsigned int occ = unsigned(k32 ? ctx->tiles_occ32 : ctx->tiles_occ64);
+    const unsigned int grid = std::min<unsigned>(t1 - t0, unsigned(ctx->sm_count) * occ);
+    if (k32)
+        LAUNCH(ctx, k_merge_tiles<uint32_t>, grid, MT_THREADS, 0, row_bin, bin_base, bins, ctx->tile_row.as<uint32_t>(), 0u,
+               t0, t1, job.n_tiles, ctx->uniq.as<uint32_t>(), ctx->tile_state.as<uint64_t>(), job.c_pos, job.c_data,
+               job.c_cap, job.rows, ctx->d_sc);
+    else
+        LAUNCH(ctx, k_merge_tiles<uint64_t>, grid, MT_THREADS, 0, row_bin, bin_base, bins, ctx->tile_row.as<uint32_t>(), 0u,
+               t0, t1, job.n_tiles, ctx->uniq.as<uint32_t>(), ctx->tile_state.as<uint64_t>(), job.c_pos, job.c_data,
+               job.c_cap, job.rows, ctx->d_sc);
+    return OSP_OK;
+}
+
+// Stable transposition on the device (all pointers are device pointers): histogram -> scan ->
+// bucket scatter -> per-bucket sort by source slice id (the merge machinery; a bucket that shrinks
+// while folding held a duplicate (row, col): the reference's dupcheck, SimSpGEMM.cpp:43-53).
 int csr2csc_device(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint64_t *d_pos, const Elem *d_data,
                    uint64_t nnz, uint64_t *d_pos_out, Elem *d_data_out) {
     if (nnz >= (1ull << 32)) return fail(ctx, OSP_ERR_UNSUPPORTED, "operands with >= 2^32 non-zeros are not supported");
-    if (n_minor == 0) {
-        CU(ctx, cudaMemsetAsync(d_pos_out, 0, 8, ctx->stream));
+    if (n_minor == 0 || nnz == 0) {
+        CU(ctx, cudaMemsetAsync(d_pos_out, 0, (n_minor + 1) * 8, ctx->stream));
         return OSP_OK;
     }
-    CU(ctx, ctx->col_cnt.reserve(n_minor * 4));
-    uint32_t *cnt = ctx->col_cnt.as<uint32_t>();
-    CU(ctx, cudaMemsetAsync(cnt, 0, n_minor * 4, ctx->stream));
-    unsigned int g = grid_for(nnz, 256, unsigned(ctx->sm_count) * 16u);
-    if (nnz) LAUNCH(ctx, k_hist_elems, g, 256, 0, d_data, nnz, n_minor, cnt, ctx->d_sc);
-    int rc = run_scan(ctx, U32In{cnt}, U64Out{d_pos_out, 0}, n_minor);
+    Arena ar;
+    const uint64_t st[3] = {scan_tiles(n_minor), plan_tiles(n_minor), 0};
+    int rc = prepare_arena(ctx, st, n_minor, ar);
     if (rc) return rc;
-    if (!nnz) return OSP_OK;
+    uint32_t *cnt = ar.counters;
+    LAUNCH(ctx, k_hist_elems, grid_for(nnz, 256, unsigned(ctx->sm_count) * 16u), 256, 0, d_data, nnz, n_minor, cnt, ctx->d_sc);
+    LAUNCH(ctx, (k_scan<U32In, U64Out>), unsigned(st[0]), SCAN_BLOCK, 0, U32In{cnt}, U64Out{d_pos_out}, n_minor, ar.state[0],
+           &ctx->d_sc->scan_ticket[0]);
     CU(ctx, cudaMemsetAsync(cnt, 0, n_minor * 4, ctx->stream));
-    unsigned int gw = grid_for(n_major, 8, unsigned(ctx->sm_count) * 16u);
-    LAUNCH(ctx, k_scatter_elems, gw, 256, 0, d_pos, d_data, n_major, n_minor, d_pos_out, cnt, d_data_out, ctx->d_sc);
-    rc = sort_buckets(ctx, d_pos_out, d_data_out, n_minor, std::max<uint64_t>(n_major, 1), 0, nullptr);
+    CU(ctx, ctx->conv_tmp.reserve(nnz * 8));
+    LAUNCH(ctx, k_scatter_elems, grid_for(n_major, 8, unsigned(ctx->sm_count) * 16u), 256, 0, d_pos, d_data, n_major, n_minor,
+           d_pos_out, cnt, ctx->conv_tmp.as<Elem>(), ctx->d_sc);
+    rc = reserve_plan(ctx, n_minor, std::min(n_minor, nnz));
     if (rc) return rc;
-    LAUNCH(ctx, k_check_full, grid_for(n_minor, 256, 1u << 30), 256, 0, d_pos_out, ctx->uniq.as<uint32_t>(), n_minor,
-           ctx->d_sc);
+    LAUNCH(ctx, k_plan<RowBinDirect>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinDirect{d_pos_out}, n_minor, n_major,
+           ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
+           ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1);
+    rc = sync_scalars(ctx);
+    if (rc) return rc;
+    if (ctx->h_sc->err) return fail(ctx, OSP_ERR_INDEX, "index out of range in operand");
+    MergeJob job;
+    job.rows = n_minor; job.idx_range = std::max<uint64_t>(n_major, 1);
+    job.n_tiles = ctx->h_sc->n_tiles; job.n_long = ctx->h_sc->n_long; job.n_xl = ctx->h_sc->n_xl;
+    CU(ctx, ctx->conv_chk.reserve((n_minor + 1) * 8));
+    job.c_pos = ctx->conv_chk.as<uint64_t>(); job.c_data = d_data_out; job.c_cap = nnz;
+    unsigned int xl_ctas = 0;
+    rc = reserve_merge(ctx, job, xl_ctas);
+    if (rc) return rc;
+    rc = launch_merge(ctx, job, xl_ctas, ctx->conv_tmp.as<Elem>(), 0, 0, job.n_tiles, 0, n_minor);
+    if (rc) return rc;
+    LAUNCH(ctx, k_check_same, grid_for(n_minor + 1, 256, 1u << 30), 256, 0, d_pos_out, job.c_pos, n_minor + 1, ctx->d_sc);
     rc = sync_scalars(ctx);
     if (rc) return rc;
     if (ctx->h_sc->err == 233) return fail(ctx, OSP_ERR_DUPLICATE, "duplicate (row,col) entry in operand");
@@ -220,27 +282,6 @@ int launch_multiply(osp_ctx *ctx, Src src, uint64_t t0, uint64_t t1, uint64_t pr
     return OSP_OK;
 }
 
-int grow_result(osp_result *r, uint64_t need_elems, uint64_t hint_elems) {
-    osp_ctx *ctx = r->ctx;
-    if (need_elems <= r->data_cap) return OSP_OK;
-    uint64_t want = std::max<uint64_t>({need_elems, hint_elems, r->data_cap + r->data_cap / 2, 1});
-    Elem *nd = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&nd), want * sizeof(Elem), ctx->stream);
-    if (e != cudaSuccess && want > need_elems) {
-        cudaGetLastError();
-        want = need_elems;
-        e = cudaMallocAsync(reinterpret_cast<void **>(&nd), want * sizeof(Elem), ctx->stream);
-    }
-    CU(ctx, e);
-    if (r->d_data) {
-        if (r->nnz) CU(ctx, cudaMemcpyAsync(nd, r->d_data, r->nnz * sizeof(Elem), cudaMemcpyDeviceToDevice, ctx->stream));
-        CU(ctx, cudaFreeAsync(r->d_data, ctx->stream));
-    }
-    r->d_data = nd;
-    r->data_cap = want;
-    return OSP_OK;
-}
-
 }  // namespace
 
 // ========================================================================================
@@ -248,7 +289,7 @@ int grow_result(osp_result *r, uint64_t need_elems, uint64_t hint_elems) {
 // ========================================================================================
 extern "C" {
 
-const char *osp_version(void) { return "outerspace_b200 0.1 (sm_100a)"; }
+const char *osp_version(void) { return "outerspace_b200 0.2 (sm_100a)"; }
 
 int osp_device_count(void) {
     int n = 0;
@@ -272,10 +313,13 @@ int osp_create(int device, osp_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->total_mem = prop.totalGlobalMem;
     CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CU(nullptr, cudaMalloc(reinterpret_cast<void **>(&ctx->d_sc), sizeof(DevScalars)));
     CU(nullptr, cudaMallocHost(reinterpret_cast<void **>(&ctx->h_sc), sizeof(DevScalars)));
-    CU(nullptr, cudaFuncSetAttribute(k_merge_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, int(MERGE_SMEM)));
-    CU(nullptr, cudaFuncSetAttribute(k_merge_xl, cudaFuncAttributeMaxDynamicSharedMemorySize, int(MERGE_SMEM)));
+    CU(nullptr, cudaFuncSetAttribute(k_merge_long, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LONG_SMEM)));
+    CU(nullptr, cudaFuncSetAttribute(k_merge_xl, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LONG_SMEM)));
+    CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->tiles_occ32, k_merge_tiles<uint32_t>, MT_THREADS, 0));
+    CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->tiles_occ64, k_merge_tiles<uint64_t>, MT_THREADS, 0));
+    ctx->tiles_occ32 = std::max(ctx->tiles_occ32, 1);
+    ctx->tiles_occ64 = std::max(ctx->tiles_occ64, 1);
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = ~0ull;
@@ -294,12 +338,12 @@ void osp_destroy(osp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->op_a_pos, &ctx->op_a_data, &ctx->op_b_pos, &ctx->op_b_data, &ctx->conv_pos, &ctx->conv_data,
-                      &ctx->run_off, &ctx->row_bin, &ctx->col_cnt, &ctx->col_ptr, &ctx->tasks, &ctx->scan_state,
-                      &ctx->uniq, &ctx->xl_list, &ctx->xl_acc, &ctx->xl_bits, &ctx->bins})
+    for (DevBuf *b : {&ctx->arena, &ctx->op_a_pos, &ctx->op_a_data, &ctx->op_b_pos, &ctx->op_b_data, &ctx->conv_pos,
+                      &ctx->conv_data, &ctx->conv_tmp, &ctx->conv_chk, &ctx->run_off, &ctx->row_bin, &ctx->tile_row,
+                      &ctx->long_list, &ctx->xl_list, &ctx->uniq, &ctx->col_ptr, &ctx->tasks, &ctx->tile_state,
+                      &ctx->xl_acc, &ctx->xl_bits, &ctx->bins})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
-    if (ctx->d_sc) cudaFree(ctx->d_sc);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -319,8 +363,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     if (!args->a_pos || !args->b_pos) return fail(ctx, OSP_ERR_INVALID, "osp_spgemm: NULL pos array");
     const bool a_is_csr = args->flags & OSP_A_IS_CSR;
     const bool on_device = args->flags & OSP_DEVICE_POINTERS;
-    const bool rowwise = args->flags & OSP_ROWWISE_ORDER;
-    const bool profile = args->flags & OSP_PROFILE_PHASES;
+    bool rowwise = args->flags & OSP_ROWWISE_ORDER;
     // k-dimension check: lmat.NRow() == rmat.NRow(), SimOuterSPACE.cpp:47
     if (!a_is_csr && args->a_slices != args->n_k)
         return fail(ctx, OSP_ERR_INVALID, "osp_spgemm: CSC(A) and CSR(B) must have the same number of slices");
@@ -332,8 +375,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     ctx->events_used = 0;
     ctx->marks.clear();
     ctx->profile_kernels = args->flags & OSP_PROFILE_KERNELS;
-    int rc = reset_scalars(ctx);
-    if (rc) return rc;
+    int rc;
 
     const uint64_t n_k = args->n_k;
     uint64_t nnz_a = 0, nnz_b = 0;
@@ -344,9 +386,11 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         dA_pos = args->a_pos; dB_pos = args->b_pos;
         dA_data = static_cast<const Elem *>(args->a_data);
         dB_data = static_cast<const Elem *>(args->b_data);
-        CU(ctx, cudaMemcpyAsync(&nnz_a, dA_pos + args->a_slices, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(&nnz_b, dB_pos + n_k, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(&ctx->h_sc->products, dA_pos + args->a_slices, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(&ctx->h_sc->cap_bound, dB_pos + n_k, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
+        nnz_a = ctx->h_sc->products;
+        nnz_b = ctx->h_sc->cap_bound;
     } else {
         nnz_a = args->a_pos[args->a_slices];
         nnz_b = args->b_pos[n_k];
@@ -376,7 +420,10 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     uint64_t m_a = args->a_slices;
     if (!a_is_csr) {
         // rows of A = max row id + 1 (SimOuterSPACE.cpp:49-53)
-        CU(ctx, cudaMemsetAsync(&ctx->d_sc->max_idx, 0, 4, ctx->stream));
+        Arena ar0;
+        const uint64_t st0[3] = {0, 0, 0};
+        rc = prepare_arena(ctx, st0, 0, ar0);
+        if (rc) return rc;
         if (nnz_a) LAUNCH(ctx, k_max_idx, grid_for(nnz_a, 1024, unsigned(ctx->sm_count) * 8u), 256, 0, dA_data, nnz_a, ctx->d_sc);
         rc = sync_scalars(ctx);
         if (rc) return rc;
@@ -388,159 +435,148 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         dA_pos = ctx->conv_pos.as<uint64_t>();
         dA_data = ctx->conv_data.as<Elem>();
     }
+    // rows the plan covers: every row of A, and every row the caller asked for
+    const uint64_t m_plan = std::max<uint64_t>({m_a, args->rows_c, 1});
+    const uint64_t limit_elems = std::max<uint64_t>(ctx->ws_limit / 8, 1);
 
-    // ---- dimensions of C -------------------------------------------------------------------------
+    // ---- symbolic pass, merge plan, CSR->CSC task list: launched back to back -------------------
+    Arena ar;
+    const uint64_t st[3] = {scan_tiles(std::max<uint64_t>(nnz_a, 1)), plan_tiles(m_plan), scan_tiles(std::max<uint64_t>(n_k, 1))};
+    rc = prepare_arena(ctx, st, rowwise ? 0 : n_k, ar);
+    if (rc) return rc;
     uint64_t cols_b = args->cols_b;
-    if (!cols_b) {
-        CU(ctx, cudaMemsetAsync(&ctx->d_sc->max_idx, 0, 4, ctx->stream));
-        if (nnz_b) LAUNCH(ctx, k_max_idx, grid_for(nnz_b, 1024, unsigned(ctx->sm_count) * 8u), 256, 0, dB_data, nnz_b, ctx->d_sc);
-    }
-    LAUNCH(ctx, k_last_nonempty, 1, 1, 0, dA_pos, m_a, ctx->d_sc);
-
-    // ---- symbolic pass: run offsets of every non-zero of A, P --------------------------------------
+    if (!cols_b && nnz_b)
+        LAUNCH(ctx, k_max_idx, grid_for(nnz_b, 1024, unsigned(ctx->sm_count) * 8u), 256, 0, dB_data, nnz_b, ctx->d_sc);
     CU(ctx, ctx->run_off.reserve((nnz_a + 1) * 8));
     uint64_t *run_off = ctx->run_off.as<uint64_t>();
+    uint32_t *col_cnt = rowwise ? nullptr : ar.counters;
     if (nnz_a) {
-        rc = run_scan(ctx, RunLenIn{dA_data, dB_pos, n_k, ctx->d_sc}, RunOffOut{run_off, ctx->d_sc, nnz_a}, nnz_a);
-        if (rc) return rc;
+        LAUNCH(ctx, (k_scan<SymIn, RunOffOut>), unsigned(st[0]), SCAN_BLOCK, 0, SymIn{dA_data, dB_pos, n_k, col_cnt, ctx->d_sc},
+               RunOffOut{run_off, ctx->d_sc, nnz_a}, nnz_a, ar.state[0], &ctx->d_sc->scan_ticket[0]);
     } else {
         CU(ctx, cudaMemsetAsync(run_off, 0, 8, ctx->stream));
     }
-    rc = sync_scalars(ctx);
+    rc = reserve_plan(ctx, m_plan, std::min(m_plan, std::max<uint64_t>(nnz_a, 1)));
+    if (rc) return rc;
+    LAUNCH(ctx, k_plan<RowBinFromRuns>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinFromRuns{dA_pos, m_a, run_off, nnz_a}, m_plan,
+           cols_b, ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
+           ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1);
+    if (!rowwise && nnz_a) {
+        CU(ctx, ctx->col_ptr.reserve((n_k + 1) * 4));
+        CU(ctx, ctx->tasks.reserve(nnz_a * sizeof(Task)));
+        LAUNCH(ctx, (k_scan<U32In, U32Out>), unsigned(st[2]), SCAN_BLOCK, 0, U32In{col_cnt}, U32Out{ctx->col_ptr.as<uint32_t>()},
+               n_k, ar.state[2], &ctx->d_sc->scan_ticket[2]);
+        LAUNCH(ctx, k_scatter_tasks, grid_for(nnz_a, 256, unsigned(ctx->sm_count) * 16u), 256, 0, dA_data, run_off, uint64_t(0),
+               nnz_a, ctx->col_ptr.as<uint32_t>(), col_cnt, ctx->tasks.as<Task>());
+    }
+    cudaEvent_t ev_sym = next_event(ctx);
+    rc = sync_scalars(ctx);                       // the one mid-pipeline sync: sizes of the bins and of C
     if (rc) return rc;
     if (ctx->h_sc->err) return fail(ctx, OSP_ERR_INDEX, "osp_spgemm: index of A out of range of the inner dimension");
     const uint64_t P = ctx->h_sc->products;
     if (!cols_b) cols_b = uint64_t(ctx->h_sc->max_idx) + 1;
     const uint64_t min_rows = std::max<uint64_t>(ctx->h_sc->last_nonempty, 1);
-    uint64_t rows_c = args->rows_c ? args->rows_c : min_rows;
+    // reference rule numRows = max row id of A + 1 (SimOuterSPACE.cpp:49-53): the last row of A holding a
+    // non-zero, whether or not it meets a non-empty row of B
+    const uint64_t rows_c = args->rows_c ? args->rows_c : min_rows;
     if (rows_c < ctx->h_sc->last_nonempty)
         return fail(ctx, OSP_ERR_INDEX, "osp_spgemm: rows_c is smaller than the largest row id of A + 1");
 
-    CU(ctx, ctx->row_bin.reserve((rows_c + 1) * 8));
-    uint64_t *row_bin = ctx->row_bin.as<uint64_t>();
-    LAUNCH(ctx, k_row_bins, grid_for(rows_c + 1, 256, 1u << 30), 256, 0, dA_pos, m_a, run_off, nnz_a, rows_c, row_bin);
+    MergeJob job;
+    job.rows = m_plan; job.idx_range = std::max<uint64_t>(cols_b, 1);
+    job.n_tiles = ctx->h_sc->n_tiles; job.n_long = ctx->h_sc->n_long; job.n_xl = ctx->h_sc->n_xl;
+    const uint64_t cap_bound = args->cols_b ? ctx->h_sc->cap_bound : std::min<uint64_t>(ctx->h_sc->cap_bound, P);
 
     // ---- result object ------------------------------------------------------------------------------
     osp_result *res = new osp_result();
     res->ctx = ctx;
-    res->rows = rows_c;
     std::memset(&res->stats, 0, sizeof(res->stats));
-    {
-        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_pos), (rows_c + 1) * 8, ctx->stream);
-        if (e != cudaSuccess) { delete res; CU(ctx, e); }
-    }
     auto bail = [&](int code) { osp_result_free(res); return code; };
-
-    // ---- row blocks ------------------------------------------------------------------------------------
-    const uint64_t limit_elems = std::max<uint64_t>(ctx->ws_limit / 8, 1);
-    std::vector<uint64_t> block_rows;   // boundaries r0 < r1 < ...
-    std::vector<uint64_t> h_row_bin, h_a_pos;
-    block_rows.push_back(0);
-    if (P <= limit_elems) {
-        block_rows.push_back(rows_c);
-    } else {
-        h_row_bin.resize(rows_c + 1);
-        CU(ctx, cudaMemcpyAsync(h_row_bin.data(), row_bin, (rows_c + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
-        uint64_t r0 = 0;
-        while (r0 < rows_c) {
-            uint64_t target = h_row_bin[r0] + limit_elems;
-            uint64_t r1 = std::upper_bound(h_row_bin.begin() + r0, h_row_bin.end(), target) - h_row_bin.begin() - 1;
-            if (r1 <= r0) r1 = r0 + 1;
-            if (r1 > rows_c) r1 = rows_c;
-            block_rows.push_back(r1);
-            r0 = r1;
+    {
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_pos), (m_plan + 1) * 8, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_data), std::max<uint64_t>(cap_bound, 1) * 8, ctx->stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            bail(0);
+            return fail(ctx, OSP_ERR_OOM, std::string("result allocation: ") + cudaGetErrorString(e));
         }
     }
-    const size_t n_blocks = block_rows.size() - 1;
-    if (n_blocks > 1) {
-        h_a_pos.resize(m_a + 1);
+    job.c_pos = res->d_pos; job.c_data = res->d_data; job.c_cap = std::max<uint64_t>(cap_bound, 1);
+    unsigned int xl_ctas = 0;
+    rc = reserve_merge(ctx, job, xl_ctas);
+    if (rc) return bail(rc);
+
+    // ---- row blocks: tiles [tb[b], tb[b+1]) ---------------------------------------------------------------
+    std::vector<uint32_t> tb;            // tile boundaries of the blocks
+    std::vector<uint64_t> blk_row, blk_bin, blk_e;   // per boundary: row, bin offset, offset into A's data
+    if (P <= limit_elems) {
+        tb = {0u, job.n_tiles};
+        blk_row = {0, m_plan}; blk_bin = {0, P}; blk_e = {0, nnz_a};
+    } else {
+        rowwise = true;                  // blocks are row ranges: their tasks are taken in row order of A
+        std::vector<uint32_t> h_tile_row(job.n_tiles + 1);
+        std::vector<uint64_t> h_row_bin(m_plan + 1), h_a_pos(m_a + 1);
+        CU(ctx, cudaMemcpyAsync(h_tile_row.data(), ctx->tile_row.p, (job.n_tiles + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(h_row_bin.data(), ctx->row_bin.p, (m_plan + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaMemcpyAsync(h_a_pos.data(), dA_pos, (m_a + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
+        auto push = [&](uint32_t t) {
+            const uint64_t r = h_tile_row[t];
+            tb.push_back(t); blk_row.push_back(r); blk_bin.push_back(h_row_bin[r]); blk_e.push_back(h_a_pos[std::min(r, m_a)]);
+        };
+        push(0);
+        uint32_t t = 0;
+        while (t < job.n_tiles) {
+            const uint64_t start = h_row_bin[h_tile_row[t]];
+            uint32_t u = t + 1;
+            while (u < job.n_tiles && h_row_bin[h_tile_row[u + 1]] - start <= limit_elems) u++;
+            push(u);
+            t = u;
+        }
     }
+    const size_t n_blocks = tb.size() - 1;
+    uint64_t max_block = 0;
+    for (size_t b = 0; b < n_blocks; b++) max_block = std::max(max_block, blk_bin[b + 1] - blk_bin[b]);
+    rc = [&]() -> int { CU(ctx, ctx->bins.reserve(std::max<uint64_t>(max_block, 1) * 8)); return OSP_OK; }();
+    if (rc) return bail(rc);
+    Elem *bins = ctx->bins.as<Elem>();
 
-    cudaEvent_t ev_sym = next_event(ctx);
-    std::vector<cudaEvent_t> ev_blocks;   // 4 per block: start, after convert, after multiply, after merge
-    uint64_t nnz_c = 0, rows_long = 0;
-
+    std::vector<cudaEvent_t> ev_blocks;   // 3 per block: start, after multiply, after merge
     for (size_t b = 0; b < n_blocks; b++) {
-        const uint64_t r0 = block_rows[b], r1 = block_rows[b + 1], rows = r1 - r0;
-        uint64_t e0, e1, bin0, bin1;
-        if (n_blocks == 1) {
-            e0 = 0; e1 = nnz_a; bin0 = 0; bin1 = P;
-        } else {
-            e0 = h_a_pos[std::min(r0, m_a)]; e1 = h_a_pos[std::min(r1, m_a)];
-            bin0 = h_row_bin[r0]; bin1 = h_row_bin[r1];
-        }
-        const uint64_t p_block = bin1 - bin0;
+        const uint64_t bin0 = blk_bin[b], p_block = blk_bin[b + 1] - bin0;
         ev_blocks.push_back(next_event(ctx));
-        CU(ctx, ctx->bins.reserve(std::max<uint64_t>(p_block, 1) * 8));
-        Elem *bins = ctx->bins.as<Elem>();
-
-        if (!rowwise && e1 > e0 && p_block) {
-            // CSR -> CSC of this block of A: histogram, scan, scatter into the k-ordered task list
-            CU(ctx, ctx->col_cnt.reserve(n_k * 4));
-            CU(ctx, ctx->col_ptr.reserve((n_k + 1) * 4));
-            CU(ctx, ctx->tasks.reserve((e1 - e0) * sizeof(Task)));
-            uint32_t *cnt = ctx->col_cnt.as<uint32_t>();
-            CU(ctx, cudaMemsetAsync(cnt, 0, n_k * 4, ctx->stream));
-            unsigned int g = grid_for(e1 - e0, 256, unsigned(ctx->sm_count) * 16u);
-            LAUNCH(ctx, k_col_hist, g, 256, 0, dA_data, e0, e1, cnt);
-            rc = run_scan(ctx, U32In{cnt}, U32OutFromU64{ctx->col_ptr.as<uint32_t>()}, n_k);
-            if (rc) return bail(rc);
-            LAUNCH(ctx, k_scatter_tasks, g, 256, 0, dA_data, run_off, e0, e1, ctx->col_ptr.as<uint32_t>(), cnt,
-                   ctx->tasks.as<Task>());
-        }
-        if (profile) CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (rowwise) rc = launch_multiply(ctx, TaskSrcSoA{dA_data, run_off}, blk_e[b], blk_e[b + 1], p_block, dB_pos, dB_data, bins, bin0);
+        else rc = launch_multiply(ctx, TaskSrcAoS{ctx->tasks.as<Task>()}, 0, nnz_a, p_block, dB_pos, dB_data, bins, bin0);
+        if (rc) return bail(rc);
         ev_blocks.push_back(next_event(ctx));
-
-        if (rowwise) rc = launch_multiply(ctx, TaskSrcSoA{dA_data, run_off}, e0, e1, p_block, dB_pos, dB_data, bins, bin0);
-        else rc = launch_multiply(ctx, TaskSrcAoS{ctx->tasks.as<Task>()}, 0, e1 - e0, p_block, dB_pos, dB_data, bins, bin0);
+        rc = launch_merge(ctx, job, xl_ctas, bins, bin0, tb[b], tb[b + 1], blk_row[b], blk_row[b + 1]);
         if (rc) return bail(rc);
-        if (profile) CU(ctx, cudaStreamSynchronize(ctx->stream));
-        ev_blocks.push_back(next_event(ctx));
-
-        uint64_t n_long = 0;
-        rc = sort_buckets(ctx, row_bin + r0, bins, rows, cols_b, bin0, &n_long);
-        if (rc) return bail(rc);
-        rows_long += n_long;
-        rc = run_scan(ctx, U32In{ctx->uniq.as<uint32_t>()},
-                      U64OutTotal{res->d_pos + r0, nnz_c, rows, ctx->d_sc}, rows);
-        if (rc) return bail(rc);
-        rc = sync_scalars(ctx);
-        if (rc) return bail(rc);
-        const uint64_t block_nnz = ctx->h_sc->block_nnz;
-        uint64_t hint = n_blocks == 1 ? block_nnz
-                                      : uint64_t(double(nnz_c + block_nnz) * double(rows_c) / double(r1) * 1.05);
-        rc = grow_result(res, nnz_c + block_nnz, hint);
-        if (rc) return bail(rc);
-        if (block_nnz)
-            LAUNCH(ctx, k_gather_rows, grid_for(rows, 8, unsigned(ctx->sm_count) * 32u), 256, 0, row_bin + r0, bin0, bins,
-                   ctx->uniq.as<uint32_t>(), res->d_pos + r0, rows, res->d_data);
-        nnz_c += block_nnz;
-        res->nnz = nnz_c;
         ev_blocks.push_back(next_event(ctx));
     }
-    // U64OutTotal wrote d_pos[r1] = carry + total for the last block, i.e. d_pos[rows_c] = nnz_c.
     cudaEvent_t ev_end = next_event(ctx);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    rc = sync_scalars(ctx);
+    if (rc) return bail(rc);
+    if (ctx->h_sc->err) return bail(fail(ctx, OSP_ERR_CUDA, "osp_spgemm: internal capacity check failed on the device"));
+    const uint64_t nnz_c = ctx->h_sc->nnz_c;
+    res->rows = rows_c;
+    res->nnz = nnz_c;
 
-    osp_stats &st = res->stats;
-    st.rows_c = rows_c; st.cols_b = cols_b; st.n_k = n_k;
-    st.nnz_a = nnz_a; st.nnz_b = nnz_b; st.nnz_c = nnz_c; st.products = P;
-    st.algorithmic_bytes = 16 * P + 8 * nnz_c + 24 * nnz_a + 8 * nnz_b + 8 * (2 * rows_c + 3 * n_k + 5);
-    st.rows_long = rows_long;
-    st.kernel_launches = ctx->launches;
-    st.row_chunks = n_blocks;
-    st.ms_h2d = ms_h2d;
-    cudaEventElapsedTime(&st.ms_total, ev_begin, ev_end);
+    osp_stats &stt = res->stats;
+    stt.rows_c = rows_c; stt.cols_b = cols_b; stt.n_k = n_k;
+    stt.nnz_a = nnz_a; stt.nnz_b = nnz_b; stt.nnz_c = nnz_c; stt.products = P;
+    stt.algorithmic_bytes = 16 * P + 8 * nnz_c + 24 * nnz_a + 8 * nnz_b + 8 * (2 * rows_c + 3 * n_k + 5);
+    stt.rows_medium = job.n_long; stt.rows_long = job.n_xl; stt.merge_tiles = job.n_tiles;
+    stt.kernel_launches = ctx->launches;
+    stt.row_chunks = n_blocks;
+    stt.ms_h2d = ms_h2d;
+    cudaEventElapsedTime(&stt.ms_total, ev_begin, ev_end);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev_begin, ev_sym);
-    st.ms_convert = ms;
+    stt.ms_convert = ms;
     for (size_t b = 0; b < n_blocks; b++) {
-        cudaEventElapsedTime(&ms, ev_blocks[4 * b], ev_blocks[4 * b + 1]); st.ms_convert += ms;
-        cudaEventElapsedTime(&ms, ev_blocks[4 * b + 1], ev_blocks[4 * b + 2]); st.ms_multiply += ms;
-        cudaEventElapsedTime(&ms, ev_blocks[4 * b + 2], ev_blocks[4 * b + 3]); st.ms_merge += ms;
+        cudaEventElapsedTime(&ms, ev_blocks[3 * b], ev_blocks[3 * b + 1]); stt.ms_multiply += ms;
+        cudaEventElapsedTime(&ms, ev_blocks[3 * b + 1], ev_blocks[3 * b + 2]); stt.ms_merge += ms;
     }
     for (const auto &m : ctx->marks) {
         cudaEventElapsedTime(&ms, m.e0, m.e1);
@@ -663,8 +699,7 @@ int osp_csr2csc(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint64_t
     ctx->launches = 0;
     ctx->events_used = 0;
     ctx->profile_kernels = false;
-    int rc = reset_scalars(ctx);
-    if (rc) return rc;
+    int rc;
     if (flags & OSP_DEVICE_POINTERS) {
         uint64_t nnz = 0;
         CU(ctx, cudaMemcpyAsync(&nnz, pos + n_major, 8, cudaMemcpyDeviceToHost, ctx->stream));

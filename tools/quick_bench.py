@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--kernels", action="store_true", help="print per-kernel event times of the last iteration")
+    ap.add_argument("--flush", action="store_true", help="flush L2 (256 MiB write) before every iteration")
     args = ap.parse_args()
     t0 = time.time()
     a, b, dims = synth.build_workload(args.workload, args.scale_down)
@@ -32,10 +34,16 @@ def main():
     t = [up(a.pos), up(a.data), up(b.pos), up(b.data)]
     torch.cuda.synchronize()
     eng = osp.Engine(0)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.flush else None
     for it in range(args.iters):
+        if args.flush:
+            flush_buf.fill_(it & 1)
+            torch.cuda.synchronize()
+        if args.kernels and it == args.iters - 1:
+            args.flags |= api.OSP_PROFILE_KERNELS
         w0 = time.perf_counter()
         res = eng.spgemm_device(a.NRow(), t[0].data_ptr(), t[1].data_ptr(), b.NRow(), t[2].data_ptr(), t[3].data_ptr(),
-                                a_is_csr=True, cols_b=dims["cols"], flags=args.flags | api.OSP_PROFILE_PHASES)
+                                a_is_csr=True, cols_b=dims["cols"], flags=args.flags)
         wall = (time.perf_counter() - w0) * 1e3
         st = res.stats()
         gbs = st["algorithmic_bytes"] / (st["ms_total"] * 1e-3) / 1e9
@@ -48,6 +56,9 @@ def main():
             ok = np.array_equal(got.pos, pos) and np.array_equal(got.data["idx"], data["idx"]) and \
                 np.array_equal(got.data["val"].view(np.uint32), data["val"].view(np.uint32))
             print("oracle check:", "BIT-EXACT" if ok else "MISMATCH", flush=True)
+        if args.kernels and it == args.iters - 1:
+            for name, ms in res.kernel_times():
+                print(f"   {ms*1e3:9.1f} us  {name}", flush=True)
         res.free()
     eng.close()
 
