@@ -83,6 +83,9 @@ typedef struct osp_stats {
     float    ms_multiply;
     float    ms_merge;
     float    ms_h2d, ms_d2h;      /* host-pointer calls only */
+    float    ms_exchange;         /* osp_dist_spgemm: the all-to-allv of partial products */
+    float    reserved_f;
+    uint64_t exchange_bytes_out;  /* osp_dist_spgemm: bytes of partial products this rank sent to other ranks */
 } osp_stats;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -112,6 +115,22 @@ void osp_result_free(osp_result *r);
 int  osp_task_sizes(osp_ctx *ctx, const osp_spgemm_args *args, const osp_result *r,
                     uint64_t *n_multiply, uint32_t *multiply_nnzc_nnzr,
                     uint64_t *n_merge, uint32_t *merge_ways_out);
+
+/* ---- k-sharded multi-GPU path: one process (and one osp_ctx) per GPU ------------------------ */
+/* The reference is single-process; BASELINE.json north_star adds: each GPU runs the outer products of
+ * its k-range (TaskProvider::multiplyPhase, SimOuterSPACE.cpp:74-97, restricted to k0 <= i < k1), partial
+ * products travel to the owner of their output row with an NCCL all-to-allv, owners merge
+ * (mergePhase, :98-132).  Owners are contiguous row blocks [rows*r/world, rows*(r+1)/world). */
+typedef struct osp_dist osp_dist;
+int  osp_dist_unique_id(void *id128);               /* ncclGetUniqueId: 128 bytes, made on one rank, given to all */
+int  osp_dist_create(osp_ctx *ctx, const void *id128, int rank, int world, osp_dist **out);
+void osp_dist_destroy(osp_dist *d);
+int  osp_dist_rows(const osp_dist *d, uint64_t rows_c, uint64_t *row_begin, uint64_t *row_end);
+/* args = this rank's shard: CSR(A[:, k0:k1]) with k ids relative to k0 (OSP_A_IS_CSR required; a_slices
+ * <= rows_c rows), CSR(B[k0:k1, :]) with n_k = k1 - k0; rows_c and cols_b = dimensions of C (required,
+ * the same on every rank).  Collective: every rank of the communicator must call it.  *out holds this
+ * rank's rows [row_begin, row_end) of C, bit-identical to the single-GPU result. */
+int  osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out);
 
 /* ---- device CSR->CSC of one operand: coo2csr<true> (SimSpGEMM.cpp:111-117,878) -------- */
 /* Stable: inside an output slice the source slice ids ascend.  pos_out[n_minor+1], data_out[nnz].

@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "osp_device_count", "osp_create", "osp_destroy", "osp_last_error", "osp_set_workspace_limit", "osp_stream",
     "osp_spgemm", "osp_result_dims", "osp_result_copy", "osp_result_device", "osp_result_stats", "osp_result_kernels", "osp_result_free",
     "osp_task_sizes", "osp_csr2csc", "osp_readcoo", "osp_coo_dims", "osp_coo_copy", "osp_coo_free", "osp_coo2csr",
-    "osp_version",
+    "osp_version", "osp_dist_unique_id", "osp_dist_create", "osp_dist_destroy", "osp_dist_rows", "osp_dist_spgemm",
 ]
 
 
@@ -69,7 +69,8 @@ class Stats(C.Structure):
         ("merge_tiles", C.c_uint64), ("rows_medium", C.c_uint64), ("rows_long", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("row_chunks", C.c_uint64),
         ("ms_total", C.c_float), ("ms_convert", C.c_float), ("ms_multiply", C.c_float), ("ms_merge", C.c_float),
-        ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
+        ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_exchange", C.c_float), ("reserved_f", C.c_float),
+        ("exchange_bytes_out", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
@@ -117,6 +118,12 @@ def load_library() -> C.CDLL:
     lib.osp_coo_free.argtypes = [vp]
     lib.osp_coo_free.restype = None
     lib.osp_coo2csr.argtypes = [u64, vp, vp, vp, u64, i32, vp, vp]
+    lib.osp_dist_unique_id.argtypes = [vp]
+    lib.osp_dist_create.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
+    lib.osp_dist_destroy.argtypes = [vp]
+    lib.osp_dist_destroy.restype = None
+    lib.osp_dist_rows.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(u64)]
+    lib.osp_dist_spgemm.argtypes = [vp, C.POINTER(SpgemmArgs), C.POINTER(vp)]
     _lib = lib
     return lib
 

@@ -1,0 +1,306 @@
+// osp_dist.inl -- k-sharded multi-GPU SpGEMM (one process per GPU) on top of the single-GPU engine.
+//
+// BASELINE.json north_star: "each GPU runs the outer products for its k-range, then partial products
+// are exchanged by output-row ownership with an NCCL all-to-allv over NVLink and merged locally".
+// NCCL is reached through dlopen("libnccl.so.2") so that the library has no link-time dependency on it
+// (the CPU-only ABI test loads the library without NCCL) and shares the copy torch already loaded.
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+
+struct NcclApi {
+    void *handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+
+NcclApi *nccl_api(std::string &err) {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (h) {
+            api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+            api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+            api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+            api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(h, "ncclGroupStart"));
+            api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+            api.Send = reinterpret_cast<decltype(api.Send)>(dlsym(h, "ncclSend"));
+            api.Recv = reinterpret_cast<decltype(api.Recv)>(dlsym(h, "ncclRecv"));
+            api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
+            api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+            if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send &&
+                api.Recv && api.AllGather && api.GetErrorString)
+                api.handle = h;
+        }
+    }
+    if (!api.handle) { err = "NCCL (libnccl.so.2) could not be loaded"; return nullptr; }
+    return &api;
+}
+
+}  // namespace
+
+struct osp_dist {
+    osp_ctx *ctx = nullptr;
+    NcclApi *nccl = nullptr;
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    DevBuf lens_send, lens_recv, recv_buf, bins2, src_off, dst_off, bounds_idx, bounds_dev, bounds_all;
+    uint64_t *h_bounds = nullptr;      // pinned [world * (world + 1)]
+};
+
+namespace {
+
+#define NC(ctx, d, expr)                                                                        \
+    do {                                                                                        \
+        ncclResult_t _r = (expr);                                                               \
+        if (_r != ncclSuccess)                                                                  \
+            return fail(ctx, OSP_ERR_CUDA, std::string(#expr) + ": " + (d)->nccl->GetErrorString(_r)); \
+    } while (0)
+
+uint64_t block_begin(uint64_t rows, int world, int r) { return rows * uint64_t(r) / uint64_t(world); }
+
+}  // namespace
+
+extern "C" {
+
+int osp_dist_unique_id(void *id128) {
+    if (!id128) return fail(nullptr, OSP_ERR_INVALID, "osp_dist_unique_id: NULL argument");
+    std::string err;
+    NcclApi *api = nccl_api(err);
+    if (!api) return fail(nullptr, OSP_ERR_UNSUPPORTED, err);
+    ncclUniqueId id;
+    ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, OSP_ERR_CUDA, std::string("ncclGetUniqueId: ") + api->GetErrorString(r));
+    std::memcpy(id128, &id, sizeof(id));
+    return OSP_OK;
+}
+
+int osp_dist_create(osp_ctx *ctx, const void *id128, int rank, int world, osp_dist **out) {
+    if (!ctx || !id128 || !out || world < 1 || rank < 0 || rank >= world)
+        return fail(ctx, OSP_ERR_INVALID, "osp_dist_create: bad argument");
+    *out = nullptr;
+    std::string err;
+    NcclApi *api = nccl_api(err);
+    if (!api) return fail(ctx, OSP_ERR_UNSUPPORTED, err);
+    CU(ctx, cudaSetDevice(ctx->device));
+    osp_dist *d = new osp_dist();
+    d->ctx = ctx; d->nccl = api; d->rank = rank; d->world = world;
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    ncclResult_t r = api->CommInitRank(&d->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        delete d;
+        return fail(ctx, OSP_ERR_CUDA, std::string("ncclCommInitRank: ") + api->GetErrorString(r));
+    }
+    cudaMallocHost(reinterpret_cast<void **>(&d->h_bounds), size_t(world) * (world + 1) * 8);
+    *out = d;
+    return OSP_OK;
+}
+
+void osp_dist_destroy(osp_dist *d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    cudaStreamSynchronize(d->ctx->stream);
+    if (d->comm) d->nccl->CommDestroy(d->comm);
+    for (DevBuf *b : {&d->lens_send, &d->lens_recv, &d->recv_buf, &d->bins2, &d->src_off, &d->dst_off, &d->bounds_idx,
+                      &d->bounds_dev, &d->bounds_all})
+        b->release();
+    if (d->h_bounds) cudaFreeHost(d->h_bounds);
+    delete d;
+}
+
+int osp_dist_rows(const osp_dist *d, uint64_t rows_c, uint64_t *row_begin, uint64_t *row_end) {
+    if (!d) return fail(nullptr, OSP_ERR_INVALID, "osp_dist_rows: NULL argument");
+    if (row_begin) *row_begin = block_begin(rows_c, d->world, d->rank);
+    if (row_end) *row_end = block_begin(rows_c, d->world, d->rank + 1);
+    return OSP_OK;
+}
+
+// This rank's shard: CSR(A[:, k0:k1]) with k ids relative to k0 (args->a_slices rows, OSP_A_IS_CSR
+// required), CSR(B[k0:k1, :]) with args->n_k = k1 - k0 rows; args->rows_c = rows of C (the same on
+// every rank, required) and args->cols_b = columns of C (required).  The result holds this rank's
+// block of rows of C = sum over ranks of A_g * B_g: rows [row_begin, row_end) of osp_dist_rows.
+int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) {
+    if (!d || !args || !out) return fail(d ? d->ctx : nullptr, OSP_ERR_INVALID, "osp_dist_spgemm: NULL argument");
+    osp_ctx *ctx = d->ctx;
+    *out = nullptr;
+    if (!(args->flags & OSP_A_IS_CSR) || !args->rows_c || !args->cols_b || !args->a_pos || !args->b_pos)
+        return fail(ctx, OSP_ERR_INVALID, "osp_dist_spgemm: needs CSR(A) shards, rows_c and cols_b");
+    if (args->a_slices > args->rows_c) return fail(ctx, OSP_ERR_INVALID, "osp_dist_spgemm: shard has more rows than C");
+    if (args->n_k >= (1ull << 32) || args->rows_c >= (1ull << 32) || args->cols_b >= (1ull << 32))
+        return fail(ctx, OSP_ERR_INVALID, "osp_dist_spgemm: dimensions must fit index_t (uint32)");
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    ctx->events_used = 0;
+    ctx->marks.clear();
+    ctx->profile_kernels = args->flags & OSP_PROFILE_KERNELS;
+    const int G = d->world, me = d->rank;
+    const uint64_t m = args->rows_c, m_a = args->a_slices, n_k = args->n_k, cols_b = args->cols_b;
+    const uint64_t R0 = block_begin(m, G, me), R1 = block_begin(m, G, me + 1), RL = R1 - R0;
+    int rc;
+    Operands op;
+    rc = stage_operands(ctx, args, op);
+    if (rc) return rc;
+    const uint64_t nnz_a = op.nnz_a;
+    cudaEvent_t ev_begin = next_event(ctx);
+
+    // ---- local symbolic pass over the shard ------------------------------------------------------
+    Arena ar;
+    const uint64_t st[4] = {scan_tiles(std::max<uint64_t>(nnz_a, 1)), plan_tiles(std::max<uint64_t>(RL, 1)),
+                            scan_tiles(std::max<uint64_t>(RL * G, 1)), scan_tiles(std::max<uint64_t>(RL * G, 1))};
+    rc = prepare_arena(ctx, st, 0, ar);
+    if (rc) return rc;
+    CU(ctx, ctx->run_off.reserve((nnz_a + 1) * 8));
+    uint64_t *run_off = ctx->run_off.as<uint64_t>();
+    if (nnz_a)
+        LAUNCH(ctx, (k_scan<SymIn, RunOffOut>), unsigned(st[0]), SCAN_BLOCK, 0, SymIn{op.a_data, op.b_pos, n_k, nullptr, ctx->d_sc},
+               RunOffOut{run_off, ctx->d_sc, nnz_a}, nnz_a, ar.state[0], &ctx->d_sc->scan_ticket[0]);
+    else
+        CU(ctx, cudaMemsetAsync(run_off, 0, 8, ctx->stream));
+    CU(ctx, ctx->row_bin.reserve((m + 1) * 8));
+    CU(ctx, d->lens_send.reserve(std::max<uint64_t>(m, 1) * 4));
+    uint64_t *row_bin = ctx->row_bin.as<uint64_t>();
+    LAUNCH(ctx, k_shard_rows, grid_for(m + 1, 256, 1u << 30), 256, 0, op.a_pos, m_a, run_off, nnz_a, m, row_bin,
+           d->lens_send.as<uint32_t>(), ctx->d_sc);
+    // send offsets at the owners' row boundaries, all-gathered: bounds_all[s][dst] = row_bin_s[R_dst]
+    CU(ctx, d->bounds_idx.reserve((G + 1) * 8));
+    CU(ctx, d->bounds_dev.reserve((G + 1) * 8));
+    CU(ctx, d->bounds_all.reserve(uint64_t(G) * (G + 1) * 8));
+    {
+        std::vector<uint64_t> idx(G + 1);
+        for (int r = 0; r <= G; r++) idx[r] = block_begin(m, G, r);
+        std::memcpy(d->h_bounds, idx.data(), (G + 1) * 8);
+        CU(ctx, cudaMemcpyAsync(d->bounds_idx.p, d->h_bounds, (G + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));           // h_bounds is reused as the landing buffer below
+    }
+    LAUNCH(ctx, k_pick_u64, 1, 256, 0, row_bin, d->bounds_idx.as<uint64_t>(), uint32_t(G + 1), d->bounds_dev.as<uint64_t>());
+    NC(ctx, d, d->nccl->AllGather(d->bounds_dev.p, d->bounds_all.p, G + 1, ncclUint64, d->comm, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d->h_bounds, d->bounds_all.p, uint64_t(G) * (G + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = sync_scalars(ctx);
+    if (rc) return rc;
+    if (ctx->h_sc->err == 6) return fail(ctx, OSP_ERR_UNSUPPORTED, "osp_dist_spgemm: a row of one shard holds >= 2^32 partial products");
+    if (ctx->h_sc->err) return fail(ctx, OSP_ERR_INDEX, "osp_dist_spgemm: index of A out of range of the shard's inner dimension");
+    const uint64_t P_local = ctx->h_sc->products;
+    auto bound = [&](int s, int r) { return d->h_bounds[uint64_t(s) * (G + 1) + r]; };
+    std::vector<uint64_t> recv_cnt(G), recv_off(G + 1, 0);
+    for (int s = 0; s < G; s++) { recv_cnt[s] = bound(s, me + 1) - bound(s, me); recv_off[s + 1] = recv_off[s] + recv_cnt[s]; }
+    const uint64_t P_owned = recv_off[G];
+
+    // ---- per-row counts to the owners; multiply; partial products to the owners --------------------
+    CU(ctx, d->lens_recv.reserve(std::max<uint64_t>(RL * G, 1) * 4));
+    NC(ctx, d, d->nccl->GroupStart());
+    for (int r = 0; r < G; r++) {
+        const uint64_t b0 = block_begin(m, G, r), b1 = block_begin(m, G, r + 1);
+        if (b1 > b0) NC(ctx, d, d->nccl->Send(d->lens_send.as<uint32_t>() + b0, b1 - b0, ncclUint32, r, d->comm, ctx->stream));
+        if (RL) NC(ctx, d, d->nccl->Recv(d->lens_recv.as<uint32_t>() + uint64_t(r) * RL, RL, ncclUint32, r, d->comm, ctx->stream));
+    }
+    NC(ctx, d, d->nccl->GroupEnd());
+    CU(ctx, ctx->bins.reserve(std::max<uint64_t>(P_local, 1) * 8));
+    CU(ctx, d->recv_buf.reserve(std::max<uint64_t>(P_owned, 1) * 8));
+    CU(ctx, d->bins2.reserve(std::max<uint64_t>(P_owned, 1) * 8));
+    cudaEvent_t ev_sym = next_event(ctx);
+    rc = launch_multiply(ctx, TaskSrcSoA{op.a_data, run_off}, 0, nnz_a, P_local, op.b_pos, op.b_data, ctx->bins.as<Elem>(), 0);
+    if (rc) return rc;
+    cudaEvent_t ev_mul = next_event(ctx);
+    NC(ctx, d, d->nccl->GroupStart());
+    for (int r = 0; r < G; r++) {
+        const uint64_t cnt = bound(me, r + 1) - bound(me, r);
+        if (cnt) NC(ctx, d, d->nccl->Send(ctx->bins.as<Elem>() + bound(me, r), cnt * 8, ncclUint8, r, d->comm, ctx->stream));
+        if (recv_cnt[r]) NC(ctx, d, d->nccl->Recv(d->recv_buf.as<Elem>() + recv_off[r], recv_cnt[r] * 8, ncclUint8, r, d->comm, ctx->stream));
+    }
+    NC(ctx, d, d->nccl->GroupEnd());
+    cudaEvent_t ev_xchg = next_event(ctx);
+
+    // ---- regroup source-major -> row-major, plan, merge ------------------------------------------------
+    osp_result *res = new osp_result();
+    res->ctx = ctx;
+    std::memset(&res->stats, 0, sizeof(res->stats));
+    auto bail = [&](int code) { osp_result_free(res); return code; };
+    MergeJob job;
+    job.rows = std::max<uint64_t>(RL, 1); job.idx_range = cols_b;
+    uint64_t nnz_c = 0;
+    if (RL) {
+        const uint64_t n = RL * G;
+        if ((rc = [&]() -> int {
+                CU(ctx, d->src_off.reserve((n + 1) * 8));
+                CU(ctx, d->dst_off.reserve((n + 1) * 8));
+                return OSP_OK;
+            }())) return bail(rc);
+        const uint32_t *lens = d->lens_recv.as<uint32_t>();
+        LAUNCH(ctx, (k_scan<U32In, U64Out>), unsigned(st[2]), SCAN_BLOCK, 0, U32In{lens}, U64Out{d->src_off.as<uint64_t>()}, n,
+               ar.state[2], &ctx->d_sc->scan_ticket[2]);
+        LAUNCH(ctx, (k_scan<TransposedIn, U64Out>), unsigned(st[3]), SCAN_BLOCK, 0, TransposedIn{lens, RL, uint64_t(G)},
+               U64Out{d->dst_off.as<uint64_t>()}, n, ar.state[3], &ctx->d_sc->scan_ticket[3]);
+        LAUNCH(ctx, k_regroup, grid_for(RL, 8, unsigned(ctx->sm_count) * 32u), 256, 0, d->recv_buf.as<Elem>(),
+               d->src_off.as<uint64_t>(), d->dst_off.as<uint64_t>(), lens, RL, uint32_t(G), d->bins2.as<Elem>());
+        rc = reserve_plan(ctx, RL, RL);
+        if (rc) return bail(rc);
+        LAUNCH(ctx, k_plan<RowBinStrided>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinStrided{d->dst_off.as<uint64_t>(), uint64_t(G)}, RL,
+               cols_b, ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
+               ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1);
+        rc = sync_scalars(ctx);
+        if (rc) return bail(rc);
+        job.n_tiles = ctx->h_sc->n_tiles; job.n_long = ctx->h_sc->n_long; job.n_xl = ctx->h_sc->n_xl;
+        const uint64_t cap = std::max<uint64_t>(ctx->h_sc->cap_bound, 1);
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_pos), (RL + 1) * 8, ctx->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_data), cap * 8, ctx->stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            bail(0);
+            return fail(ctx, OSP_ERR_OOM, std::string("result allocation: ") + cudaGetErrorString(e));
+        }
+        job.c_pos = res->d_pos; job.c_data = res->d_data; job.c_cap = cap;
+        unsigned int xl_ctas = 0;
+        rc = reserve_merge(ctx, job, xl_ctas);
+        if (rc) return bail(rc);
+        rc = launch_merge(ctx, job, xl_ctas, d->bins2.as<Elem>(), 0, 0, job.n_tiles, 0, RL);
+        if (rc) return bail(rc);
+    } else {
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_pos), 8, ctx->stream);
+        if (e != cudaSuccess) { cudaGetLastError(); bail(0); return fail(ctx, OSP_ERR_OOM, "result allocation"); }
+        cudaMemsetAsync(res->d_pos, 0, 8, ctx->stream);
+    }
+    cudaEvent_t ev_end = next_event(ctx);
+    rc = sync_scalars(ctx);
+    if (rc) return bail(rc);
+    if (ctx->h_sc->err) return bail(fail(ctx, OSP_ERR_CUDA, "osp_dist_spgemm: internal capacity check failed on the device"));
+    if (RL) nnz_c = ctx->h_sc->nnz_c;
+    res->rows = RL;
+    res->nnz = nnz_c;
+    osp_stats &stt = res->stats;
+    stt.rows_c = RL; stt.cols_b = cols_b; stt.n_k = n_k;
+    stt.nnz_a = nnz_a; stt.nnz_b = op.nnz_b; stt.nnz_c = nnz_c; stt.products = P_local;
+    // this rank's share of the algorithmic bytes: its multiplies (8P_local out) + its merge (8P_owned in, C out)
+    stt.algorithmic_bytes = 8 * P_local + 8 * P_owned + 8 * nnz_c + 24 * nnz_a + 8 * op.nnz_b + 8 * (2 * RL + 3 * n_k + 5);
+    stt.merge_tiles = job.n_tiles; stt.rows_medium = job.n_long; stt.rows_long = job.n_xl;
+    stt.kernel_launches = ctx->launches;
+    stt.row_chunks = 1;
+    stt.ms_h2d = op.ms_h2d;
+    cudaEventElapsedTime(&stt.ms_total, ev_begin, ev_end);
+    cudaEventElapsedTime(&stt.ms_convert, ev_begin, ev_sym);
+    cudaEventElapsedTime(&stt.ms_multiply, ev_sym, ev_mul);
+    cudaEventElapsedTime(&stt.ms_exchange, ev_mul, ev_xchg);
+    cudaEventElapsedTime(&stt.ms_merge, ev_xchg, ev_end);
+    stt.exchange_bytes_out = 8 * (P_local - (bound(me, me + 1) - bound(me, me)));
+    float ms = 0.f;
+    for (const auto &mk : ctx->marks) {
+        cudaEventElapsedTime(&ms, mk.e0, mk.e1);
+        res->kernel_ms.emplace_back(mk.name, ms);
+    }
+    ctx->profile_kernels = false;
+    *out = res;
+    return OSP_OK;
+}
+
+}  // extern "C"

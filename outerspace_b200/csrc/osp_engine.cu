@@ -124,22 +124,22 @@ uint64_t align16(uint64_t x) { return (x + 15) & ~15ull; }
 
 // Layout of the per-call zeroed arena.
 struct Arena {
-    uint64_t *state[3] = {nullptr, nullptr, nullptr};   // look-back states of up to three scans
+    uint64_t *state[4] = {nullptr, nullptr, nullptr, nullptr};   // look-back states of up to four scans
     uint32_t *counters = nullptr;                       // n_counters uint32 (column histogram / cursors)
 };
 
 // One memset zeroes the device scalars, the scan states and the counters of a call.
-int prepare_arena(osp_ctx *ctx, const uint64_t state_tiles[3], uint64_t n_counters, Arena &a) {
+int prepare_arena(osp_ctx *ctx, const uint64_t state_tiles[4], uint64_t n_counters, Arena &a) {
     uint64_t off = align16(sizeof(DevScalars));
-    uint64_t st_off[3];
-    for (int i = 0; i < 3; i++) { st_off[i] = off; off += align16(state_tiles[i] * 8); }
+    uint64_t st_off[4];
+    for (int i = 0; i < 4; i++) { st_off[i] = off; off += align16(state_tiles[i] * 8); }
     uint64_t cnt_off = off;
     off += align16(n_counters * 4);
     CU(ctx, ctx->arena.reserve(off));
     CU(ctx, cudaMemsetAsync(ctx->arena.p, 0, off, ctx->stream));
     unsigned char *base = ctx->arena.as<unsigned char>();
     ctx->d_sc = reinterpret_cast<DevScalars *>(base);
-    for (int i = 0; i < 3; i++) a.state[i] = reinterpret_cast<uint64_t *>(base + st_off[i]);
+    for (int i = 0; i < 4; i++) a.state[i] = reinterpret_cast<uint64_t *>(base + st_off[i]);
     a.counters = reinterpret_cast<uint32_t *>(base + cnt_off);
     return OSP_OK;
 }
@@ -228,7 +228,7 @@ int csr2csc_device(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint6
         return OSP_OK;
     }
     Arena ar;
-    const uint64_t st[3] = {scan_tiles(n_minor), plan_tiles(n_minor), 0};
+    const uint64_t st[4] = {scan_tiles(n_minor), plan_tiles(n_minor), 0, 0};
     int rc = prepare_arena(ctx, st, n_minor, ar);
     if (rc) return rc;
     uint32_t *cnt = ar.counters;
@@ -262,6 +262,52 @@ int csr2csc_device(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint6
     if (rc) return rc;
     if (ctx->h_sc->err == 233) return fail(ctx, OSP_ERR_DUPLICATE, "duplicate (row,col) entry in operand");
     if (ctx->h_sc->err) return fail(ctx, OSP_ERR_INDEX, "index out of range in operand");
+    return OSP_OK;
+}
+
+// Operands of a call as device pointers (host operands are staged into the context's buffers).
+struct Operands {
+    const uint64_t *a_pos = nullptr, *b_pos = nullptr;
+    const Elem *a_data = nullptr, *b_data = nullptr;
+    uint64_t nnz_a = 0, nnz_b = 0;
+    float ms_h2d = 0.f;
+};
+
+int stage_operands(osp_ctx *ctx, const osp_spgemm_args *args, Operands &op) {
+    const uint64_t n_k = args->n_k;
+    if (args->flags & OSP_DEVICE_POINTERS) {
+        op.a_pos = args->a_pos; op.b_pos = args->b_pos;
+        op.a_data = static_cast<const Elem *>(args->a_data);
+        op.b_data = static_cast<const Elem *>(args->b_data);
+        CU(ctx, cudaMemcpyAsync(&ctx->h_sc->products, op.a_pos + args->a_slices, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(&ctx->h_sc->cap_bound, op.b_pos + n_k, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        op.nnz_a = ctx->h_sc->products;
+        op.nnz_b = ctx->h_sc->cap_bound;
+    } else {
+        op.nnz_a = args->a_pos[args->a_slices];
+        op.nnz_b = args->b_pos[n_k];
+        CU(ctx, ctx->op_a_pos.reserve((args->a_slices + 1) * 8));
+        CU(ctx, ctx->op_b_pos.reserve((n_k + 1) * 8));
+        CU(ctx, ctx->op_a_data.reserve(std::max<uint64_t>(op.nnz_a, 1) * 8));
+        CU(ctx, ctx->op_b_data.reserve(std::max<uint64_t>(op.nnz_b, 1) * 8));
+        cudaEvent_t e0 = next_event(ctx);
+        CU(ctx, cudaMemcpyAsync(ctx->op_a_pos.p, args->a_pos, (args->a_slices + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->op_b_pos.p, args->b_pos, (n_k + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (op.nnz_a && args->a_data)
+            CU(ctx, cudaMemcpyAsync(ctx->op_a_data.p, args->a_data, op.nnz_a * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (op.nnz_b && args->b_data)
+            CU(ctx, cudaMemcpyAsync(ctx->op_b_data.p, args->b_data, op.nnz_b * 8, cudaMemcpyHostToDevice, ctx->stream));
+        cudaEvent_t e1 = next_event(ctx);
+        CU(ctx, cudaEventSynchronize(e1));
+        cudaEventElapsedTime(&op.ms_h2d, e0, e1);
+        op.a_pos = ctx->op_a_pos.as<uint64_t>(); op.b_pos = ctx->op_b_pos.as<uint64_t>();
+        op.a_data = ctx->op_a_data.as<Elem>(); op.b_data = ctx->op_b_data.as<Elem>();
+    }
+    if ((op.nnz_a && !args->a_data) || (op.nnz_b && !args->b_data))
+        return fail(ctx, OSP_ERR_INVALID, "osp_spgemm: NULL data array");
+    if (op.nnz_a >= (1ull << 32) || op.nnz_b >= (1ull << 32))
+        return fail(ctx, OSP_ERR_UNSUPPORTED, "operands with >= 2^32 non-zeros are not supported");
     return OSP_OK;
 }
 
@@ -378,41 +424,13 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     int rc;
 
     const uint64_t n_k = args->n_k;
-    uint64_t nnz_a = 0, nnz_b = 0;
-    const uint64_t *dA_pos, *dB_pos;
-    const Elem *dA_data, *dB_data;
-    float ms_h2d = 0.f;
-    if (on_device) {
-        dA_pos = args->a_pos; dB_pos = args->b_pos;
-        dA_data = static_cast<const Elem *>(args->a_data);
-        dB_data = static_cast<const Elem *>(args->b_data);
-        CU(ctx, cudaMemcpyAsync(&ctx->h_sc->products, dA_pos + args->a_slices, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(&ctx->h_sc->cap_bound, dB_pos + n_k, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
-        nnz_a = ctx->h_sc->products;
-        nnz_b = ctx->h_sc->cap_bound;
-    } else {
-        nnz_a = args->a_pos[args->a_slices];
-        nnz_b = args->b_pos[n_k];
-        CU(ctx, ctx->op_a_pos.reserve((args->a_slices + 1) * 8));
-        CU(ctx, ctx->op_b_pos.reserve((n_k + 1) * 8));
-        CU(ctx, ctx->op_a_data.reserve(std::max<uint64_t>(nnz_a, 1) * 8));
-        CU(ctx, ctx->op_b_data.reserve(std::max<uint64_t>(nnz_b, 1) * 8));
-        cudaEvent_t e0 = next_event(ctx);
-        CU(ctx, cudaMemcpyAsync(ctx->op_a_pos.p, args->a_pos, (args->a_slices + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(ctx->op_b_pos.p, args->b_pos, (n_k + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        if (nnz_a) CU(ctx, cudaMemcpyAsync(ctx->op_a_data.p, args->a_data, nnz_a * 8, cudaMemcpyHostToDevice, ctx->stream));
-        if (nnz_b) CU(ctx, cudaMemcpyAsync(ctx->op_b_data.p, args->b_data, nnz_b * 8, cudaMemcpyHostToDevice, ctx->stream));
-        cudaEvent_t e1 = next_event(ctx);
-        CU(ctx, cudaEventSynchronize(e1));
-        cudaEventElapsedTime(&ms_h2d, e0, e1);
-        dA_pos = ctx->op_a_pos.as<uint64_t>(); dB_pos = ctx->op_b_pos.as<uint64_t>();
-        dA_data = ctx->op_a_data.as<Elem>(); dB_data = ctx->op_b_data.as<Elem>();
-    }
-    if ((nnz_a && !args->a_data) || (nnz_b && !args->b_data))
-        return fail(ctx, OSP_ERR_INVALID, "osp_spgemm: NULL data array");
-    if (nnz_a >= (1ull << 32) || nnz_b >= (1ull << 32))
-        return fail(ctx, OSP_ERR_UNSUPPORTED, "operands with >= 2^32 non-zeros are not supported");
+    Operands op;
+    rc = stage_operands(ctx, args, op);
+    if (rc) return rc;
+    const uint64_t nnz_a = op.nnz_a, nnz_b = op.nnz_b;
+    const uint64_t *dA_pos = op.a_pos, *dB_pos = op.b_pos;
+    const Elem *dA_data = op.a_data, *dB_data = op.b_data;   // dA_* are re-pointed at the converted operand below
+    const float ms_h2d = op.ms_h2d;
 
     cudaEvent_t ev_begin = next_event(ctx);
 
@@ -421,7 +439,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     if (!a_is_csr) {
         // rows of A = max row id + 1 (SimOuterSPACE.cpp:49-53)
         Arena ar0;
-        const uint64_t st0[3] = {0, 0, 0};
+        const uint64_t st0[4] = {0, 0, 0, 0};
         rc = prepare_arena(ctx, st0, 0, ar0);
         if (rc) return rc;
         if (nnz_a) LAUNCH(ctx, k_max_idx, grid_for(nnz_a, 1024, unsigned(ctx->sm_count) * 8u), 256, 0, dA_data, nnz_a, ctx->d_sc);
@@ -441,7 +459,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
 
     // ---- symbolic pass, merge plan, CSR->CSC task list: launched back to back -------------------
     Arena ar;
-    const uint64_t st[3] = {scan_tiles(std::max<uint64_t>(nnz_a, 1)), plan_tiles(m_plan), scan_tiles(std::max<uint64_t>(n_k, 1))};
+    const uint64_t st[4] = {scan_tiles(std::max<uint64_t>(nnz_a, 1)), plan_tiles(m_plan), scan_tiles(std::max<uint64_t>(n_k, 1)), 0};
     rc = prepare_arena(ctx, st, rowwise ? 0 : n_k, ar);
     if (rc) return rc;
     uint64_t cols_b = args->cols_b;
@@ -725,3 +743,5 @@ int osp_csr2csc(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint64_t
 }
 
 }  // extern "C"
+
+#include "osp_dist.inl"

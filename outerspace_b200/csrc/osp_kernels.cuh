@@ -756,4 +756,55 @@ __global__ void k_check_same(const uint64_t *a, const uint64_t *b, uint64_t n, D
     if (i < n && a[i] != b[i]) atomicMax(&sc->err, 233u);
 }
 
+// =====================================================================================
+// k-sharded multi-GPU path (DESIGN.md "Multi-GPU"): each rank multiplies its k-range and the
+// partial products travel to the owner of their output row (contiguous row blocks), where the
+// segments of the G sources are regrouped row by row in ascending source (= ascending k) order.
+// =====================================================================================
+// Bin start of every row of the shard's product and the per-row partial-product counts the owners need.
+__global__ void k_shard_rows(const uint64_t *a_pos, uint64_t m_a, const uint64_t *run_off, uint64_t nnz_a, uint64_t rows,
+                             uint64_t *row_bin, uint32_t *lens, DevScalars *sc) {
+    uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (i > rows) return;
+    const uint64_t s = run_off[i <= m_a ? a_pos[i] : nnz_a];
+    row_bin[i] = s;
+    if (i < rows) {
+        const uint64_t e = run_off[i + 1 <= m_a ? a_pos[i + 1] : nnz_a];
+        if (e - s >= (1ull << 32)) atomicMax(&sc->err, 6u);      // OSP_ERR_UNSUPPORTED
+        lens[i] = uint32_t(e - s);
+    }
+}
+__global__ void k_pick_u64(const uint64_t *src, const uint64_t *index, uint32_t n, uint64_t *dst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[index[i]];
+}
+// lens[s * RL + i] read in (i, s) order
+struct TransposedIn {
+    const uint32_t *lens;
+    uint64_t RL;
+    uint64_t G;
+    __device__ uint64_t operator()(uint64_t j, bool valid) const { return valid ? lens[(j % G) * RL + j / G] : 0; }
+};
+struct RowBinStrided {         // row i of the owner starts at dst_off[i * G]
+    const uint64_t *off;
+    uint64_t G;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return off[i * G]; }
+    __device__ __forceinline__ bool nonempty(uint64_t i) const { return off[(i + 1) * G] > off[i * G]; }
+};
+// One warp per owned row: copies the row's segment of every source (received source-major) into the
+// row-major bins, sources in ascending order.
+__global__ void k_regroup(const Elem *__restrict__ recv, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ dst_off,
+                          const uint32_t *__restrict__ lens, uint64_t RL, uint32_t G, Elem *__restrict__ bins) {
+    uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
+    uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t i = warp; i < RL; i += nwarps) {
+        for (uint32_t s = 0; s < G; s++) {
+            const uint32_t n = lens[s * RL + i];
+            const Elem *src = recv + src_off[s * RL + i];
+            Elem *dst = bins + dst_off[i * G + s];
+            for (uint32_t t = lane_id(); t < n; t += 32) dst[t] = src[t];
+        }
+    }
+}
+
 }  // namespace osp
