@@ -141,6 +141,8 @@ int  osp_csr2csc(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint64_
 /* ---- host loaders (the reference's .mtx surface) -------------------------------------- */
 typedef struct osp_coo osp_coo;
 int  osp_readcoo(const char *path, int symmetric, osp_coo **out);          /* readcoo, SimSpGEMM.cpp:55-100 */
+int  osp_readcoo_buffer(const char *text, uint64_t len, int symmetric, osp_coo **out);  /* same, text in memory (the
+                                                                reference's readcoo takes a std::istream) */
 int  osp_coo_dims(const osp_coo *c, uint64_t *nrow, uint64_t *ncol, uint64_t *nnz);
 int  osp_coo_copy(const osp_coo *c, uint32_t *rows, uint32_t *cols, float *vals);
 void osp_coo_free(osp_coo *c);

@@ -38,7 +38,7 @@ OSP_PROFILE_KERNELS = 16
 ABI_SYMBOLS = [
     "osp_device_count", "osp_create", "osp_destroy", "osp_last_error", "osp_set_workspace_limit", "osp_stream",
     "osp_spgemm", "osp_result_dims", "osp_result_copy", "osp_result_device", "osp_result_stats", "osp_result_kernels", "osp_result_free",
-    "osp_task_sizes", "osp_csr2csc", "osp_readcoo", "osp_coo_dims", "osp_coo_copy", "osp_coo_free", "osp_coo2csr",
+    "osp_task_sizes", "osp_csr2csc", "osp_readcoo", "osp_readcoo_buffer", "osp_coo_dims", "osp_coo_copy", "osp_coo_free", "osp_coo2csr",
     "osp_version", "osp_dist_unique_id", "osp_dist_create", "osp_dist_destroy", "osp_dist_rows", "osp_dist_spgemm",
 ]
 
@@ -90,6 +90,15 @@ def load_library() -> C.CDLL:
             f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(make -C outerspace_b200/csrc). This engine has no CPU fallback."
         )
+    if "OSP_NCCL_LIB" not in os.environ:
+        # multi-GPU path: use the NCCL build torch ships (found without importing torch)
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["OSP_NCCL_LIB"] = cand
+                break
     lib = C.CDLL(_LIB_PATH)
     vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
     lib.osp_version.restype = C.c_char_p

@@ -27,7 +27,13 @@ NcclApi *nccl_api(std::string &err) {
     static bool tried = false;
     if (!tried) {
         tried = true;
-        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        // 1. the copy this process already holds (torch's bundled one when torch was imported first);
+        // 2. OSP_NCCL_LIB (the Python front end points it at torch's bundled copy, so that a later
+        //    `import torch` finds the version it was built against under the same soname); 3. the system copy.
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h)
+            if (const char *path = std::getenv("OSP_NCCL_LIB")) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
         if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
         if (h) {
             api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));

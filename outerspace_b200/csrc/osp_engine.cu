@@ -408,7 +408,6 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     *out = nullptr;
     if (!args->a_pos || !args->b_pos) return fail(ctx, OSP_ERR_INVALID, "osp_spgemm: NULL pos array");
     const bool a_is_csr = args->flags & OSP_A_IS_CSR;
-    const bool on_device = args->flags & OSP_DEVICE_POINTERS;
     bool rowwise = args->flags & OSP_ROWWISE_ORDER;
     // k-dimension check: lmat.NRow() == rmat.NRow(), SimOuterSPACE.cpp:47
     if (!a_is_csr && args->a_slices != args->n_k)

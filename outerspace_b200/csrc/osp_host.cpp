@@ -59,29 +59,20 @@ struct HostElem {
 
 extern "C" {
 
-int osp_readcoo(const char *path, int symmetric, osp_coo **out) {
-    if (!path || !out) return OSP_ERR_INVALID;
+// Parses Matrix-Market text held in memory (the reference reads from a std::istream, SimSpGEMM.cpp:55).
+int osp_readcoo_buffer(const char *text, uint64_t len, int symmetric, osp_coo **out) {
+    if ((!text && len) || !out) return OSP_ERR_INVALID;
     *out = nullptr;
-    FILE *f = std::fopen(path, "rb");
-    if (!f) return OSP_ERR_IO;
     osp_coo *c = new osp_coo();
     std::string line;
     bool header_seen = false;
-    char buf[1 << 16];
-    bool eof = false;
-    while (!eof) {
-        // one logical line (arbitrary length)
-        line.clear();
-        bool got_any = false;
-        while (true) {
-            if (!std::fgets(buf, sizeof(buf), f)) { eof = true; break; }
-            got_any = true;
-            size_t n = std::strlen(buf);
-            if (n && buf[n - 1] == '\n') { line.append(buf, n - 1); break; }
-            line.append(buf, n);
-        }
-        if (!got_any) break;
-        size_t first = line.find_first_not_of(" \t");
+    uint64_t at = 0;
+    while (at < len) {
+        uint64_t nl = at;
+        while (nl < len && text[nl] != '\n') nl++;
+        line.assign(text + at, nl - at);
+        at = nl + 1;
+        size_t first = line.find_first_not_of(" \t\r");
         if (first == std::string::npos || line[first] == '%') continue;
         const char *s = line.c_str();
         if (!header_seen) {
@@ -97,7 +88,6 @@ int osp_readcoo(const char *path, int symmetric, osp_coo **out) {
         double v = 1.0;
         if (!parse_u64(s, r) || !parse_u64(s, col)) {   // the reference reads garbage here; we refuse
             delete c;
-            std::fclose(f);
             return OSP_ERR_INVALID;
         }
         double parsed;
@@ -107,9 +97,21 @@ int osp_readcoo(const char *path, int symmetric, osp_coo **out) {
             c->rows.push_back(uint32_t(col - 1)); c->cols.push_back(uint32_t(r - 1)); c->vals.push_back(float(v));
         }
     }
-    std::fclose(f);
     *out = c;
     return OSP_OK;
+}
+
+int osp_readcoo(const char *path, int symmetric, osp_coo **out) {
+    if (!path || !out) return OSP_ERR_INVALID;
+    *out = nullptr;
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return OSP_ERR_IO;
+    std::string text;
+    char buf[1 << 16];
+    size_t n;
+    while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, n);
+    std::fclose(f);
+    return osp_readcoo_buffer(text.data(), text.size(), symmetric, out);
 }
 
 int osp_coo_dims(const osp_coo *c, uint64_t *nrow, uint64_t *ncol, uint64_t *nnz) {
