@@ -3,8 +3,9 @@
 // Data layout in HBM (DESIGN.md "Data layout"):
 //   Elem   8 B  {uint32 idx; float val}   == reference CSRElement (simulator/common.h:10-16)
 //   pos    8 B  uint64                    == reference CSRMatrix::pos (common.h:41)
-//   Task  16 B  {uint32 k; float a; uint64 off}: one non-zero A(i,k) annotated with the offset of
-//               its run of partial products inside the output-row bins (one LDG.128 per task).
+//   Task  16 B  {uint32 bs; float a; uint64 off<<24|len}: one non-zero A(i,k) annotated with where row k
+//               of B starts, and with the offset and length of its run of partial products inside the
+//               output-row bins (one LDG.128 per task, no further look-ups in the multiply).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,10 +18,11 @@ struct __align__(8) Elem {
 };
 static_assert(sizeof(Elem) == 8, "Elem must match the reference's packed CSRElement");
 
+constexpr int TASK_LEN_BITS = 24;     // a run (row of B) holds < 2^24 partial products; offsets < 2^40
 struct __align__(16) Task {
-    uint32_t k;     // inner index: which row of B this non-zero multiplies
-    float a;        // A(i,k)
-    uint64_t off;   // absolute offset (in elements) of the run inside the partial-product bins
+    uint32_t bs;       // offset of row k of B inside B's data array (nnz(B) < 2^32)
+    float a;           // A(i,k)
+    uint64_t offlen;   // (absolute offset of the run inside the partial-product bins << 24) | run length
 };
 static_assert(sizeof(Task) == 16, "Task is one 128-bit load");
 
@@ -29,7 +31,7 @@ static_assert(sizeof(Task) == 16, "Task is one 128-bit load");
 struct DevScalars {
     unsigned long long products;       // P
     unsigned long long cap_bound;      // sum_i min(len_i, cols) : upper bound of nnz(C)
-    unsigned long long nnz_c;          // written by the last merge tile
+    unsigned long long nnz_c[2];       // running nnz(C) over the row blocks (ping-pong carry of the C.pos scan)
     unsigned long long last_nonempty;  // 1 + index of the last row with partial products / non-zeros
     unsigned int err;                  // first OSP_ERR_* raised on the device
     unsigned int max_idx;              // reduction result of k_max_idx
@@ -85,7 +87,12 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *state, uint32_t
         uint64_t word = LB_FLAG_PREFIX;  // tiles before `first` contribute an inclusive prefix of 0
         if (idx >= int64_t(first)) {
             word = ld_relaxed_u64(state + idx);
-            while ((word >> 62) == 0) word = ld_relaxed_u64(state + idx);
+            unsigned int ns = 32;
+            while ((word >> 62) == 0) {           // predecessor still merging: back off, do not hammer L2
+                __nanosleep(ns);
+                if (ns < 1024) ns <<= 1;
+                word = ld_relaxed_u64(state + idx);
+            }
         }
         unsigned int has_prefix = __ballot_sync(FULL, (word >> 62) == 2);
         unsigned int firstp = has_prefix ? (__ffs(has_prefix) - 1) : 31;

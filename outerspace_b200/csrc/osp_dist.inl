@@ -216,7 +216,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     CU(ctx, d->recv_buf.reserve(std::max<uint64_t>(P_owned, 1) * 8));
     CU(ctx, d->bins2.reserve(std::max<uint64_t>(P_owned, 1) * 8));
     cudaEvent_t ev_sym = next_event(ctx);
-    rc = launch_multiply(ctx, TaskSrcSoA{op.a_data, run_off}, 0, nnz_a, P_local, op.b_pos, op.b_data, ctx->bins.as<Elem>(), 0);
+    rc = launch_multiply(ctx, TaskSrcSoA{op.a_data, run_off, op.b_pos}, 0, nnz_a, P_local, op.b_data, ctx->bins.as<Elem>(), 0);
     if (rc) return rc;
     cudaEvent_t ev_mul = next_event(ctx);
     NC(ctx, d, d->nccl->GroupStart());
@@ -270,7 +270,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
         unsigned int xl_ctas = 0;
         rc = reserve_merge(ctx, job, xl_ctas);
         if (rc) return bail(rc);
-        rc = launch_merge(ctx, job, xl_ctas, d->bins2.as<Elem>(), 0, 0, job.n_tiles, 0, RL);
+        rc = launch_merge(ctx, job, xl_ctas, d->bins2.as<Elem>(), 0, 0, job.n_tiles, 0, RL, 0);
         if (rc) return bail(rc);
     } else {
         cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_pos), 8, ctx->stream);
@@ -281,7 +281,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     rc = sync_scalars(ctx);
     if (rc) return bail(rc);
     if (ctx->h_sc->err) return bail(fail(ctx, OSP_ERR_CUDA, "osp_dist_spgemm: internal capacity check failed on the device"));
-    if (RL) nnz_c = ctx->h_sc->nnz_c;
+    if (RL) nnz_c = ctx->h_sc->nnz_c[1];
     res->rows = RL;
     res->nnz = nnz_c;
     osp_stats &stt = res->stats;

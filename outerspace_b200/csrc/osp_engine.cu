@@ -39,7 +39,7 @@ struct DevBuf {
 struct osp_ctx {
     int device = 0;
     int sm_count = 148;
-    int tiles_occ32 = 3, tiles_occ64 = 3;   // resident CTAs per SM of k_merge_tiles<K>
+    int tiles_occ[3] = {3, 3, 2};           // resident CTAs per SM of k_merge_tiles: u32 keys, u64 keys, bitmap mode
     size_t total_mem = 0;
     cudaStream_t stream = nullptr;
     uint64_t ws_limit = 0;          // bytes of partial-product bins per row block
@@ -111,6 +111,10 @@ cudaEvent_t next_event(osp_ctx *ctx) {
     } while (0)
 
 constexpr size_t LONG_SMEM = size_t(MT_XL) * 12 + 34 * 4;
+// dynamic shared memory of k_merge_tiles: per warp one row of scratch (+ the bitmap scratch)
+size_t tiles_smem(bool bitmap) {
+    return size_t(MW_THREADS / 32) * (size_t(MT_LONG) * 8 + (bitmap ? BM_SCRATCH : 0));
+}
 
 unsigned int grid_for(uint64_t items, unsigned int per_block, unsigned int max_blocks) {
     uint64_t b = (items + per_block - 1) / per_block;
@@ -168,13 +172,12 @@ struct MergeJob {
     uint64_t c_cap = 0;
 };
 
-// Scratch that depends on the plan's results: look-back states of the merge tiles, per-row survivor
-// counts of the long rows, the dense accumulators of the longest rows.
+// Scratch that depends on the plan's results: look-back states of the C.pos scan, per-row survivor
+// counts, the dense accumulators of the longest rows.
 int reserve_merge(osp_ctx *ctx, const MergeJob &job, unsigned int &xl_ctas) {
-    CU(ctx, ctx->tile_state.reserve(std::max<uint64_t>(job.n_tiles, 1) * 8));
-    CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, std::max<uint64_t>(job.n_tiles, 1) * 8, ctx->stream));
+    CU(ctx, ctx->tile_state.reserve(scan_tiles(std::max<uint64_t>(job.rows, 1)) * 8));
+    CU(ctx, ctx->uniq.reserve(std::max<uint64_t>(job.rows, 1) * 4));
     xl_ctas = 0;
-    if (job.n_long || job.n_xl) CU(ctx, ctx->uniq.reserve(job.rows * 4));
     if (job.n_xl) {
         const uint64_t words = (job.idx_range + 31) / 32;
         const uint64_t per_cta = job.idx_range * 4 + words * 4;
@@ -189,31 +192,40 @@ int reserve_merge(osp_ctx *ctx, const MergeJob &job, unsigned int &xl_ctas) {
     return OSP_OK;
 }
 
-// Merges the rows of tiles [t0, t1) (rows [row_lo, row_hi)) whose partial products sit in `bins`
-// (bin of row i at bins[row_bin[i] - bin_base]) into C.
+// Merges the rows [row_lo, row_hi) = tiles [t0, t1) whose partial products sit in `bins` (bin of row i at
+// bins[row_bin[i] - bin_base]) into C.  `block` counts the row blocks of a call (carry of the C.pos scan).
 int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *bins, uint64_t bin_base, uint32_t t0,
-                 uint32_t t1, uint64_t row_lo, uint64_t row_hi) {
-    if (t1 <= t0) return OSP_OK;
+                 uint32_t t1, uint64_t row_lo, uint64_t row_hi, unsigned int block) {
+    if (t1 <= t0 || row_hi <= row_lo) return OSP_OK;
     const uint64_t *row_bin = ctx->row_bin.as<uint64_t>();
+    uint32_t *uniq = ctx->uniq.as<uint32_t>();
     if (job.n_long)
         LAUNCH(ctx, k_merge_long, std::min<unsigned>(job.n_long, unsigned(ctx->sm_count) * 4u), 256, LONG_SMEM, row_bin,
-               bin_base, bins, ctx->uniq.as<uint32_t>(), ctx->long_list.as<uint32_t>(), ctx->d_sc, row_lo, row_hi);
+               bin_base, bins, uniq, ctx->long_list.as<uint32_t>(), ctx->d_sc, row_lo, row_hi);
     if (job.n_xl)
-        LAUNCH(ctx, k_merge_xl, xl_ctas, 256, LONG_SMEM, row_bin, bin_base, bins, ctx->uniq.as<uint32_t>(),
-               ctx->xl_list.as<uint32_t>(), ctx->d_sc, ctx->xl_acc.as<float>(), ctx->xl_bits.as<uint32_t>(), job.idx_range,
-               row_lo, row_hi);
-    CU(ctx, cudaMemsetAsync(&ctx->d_sc->tile_ticket, 0, 4, ctx->stream));
+        LAUNCH(ctx, k_merge_xl, xl_ctas, 256, LONG_SMEM, row_bin, bin_base, bins, uniq, ctx->xl_list.as<uint32_t>(), ctx->d_sc,
+               ctx->xl_acc.as<float>(), ctx->xl_bits.as<uint32_t>(), job.idx_range, row_lo, row_hi);
     const bool k32 = job.idx_range <= (1ull << 23);
-    const unsigned int occ = unsigned(k32 ? ctx->tiles_occ32 : ctx->tiles_occ64);
-    const unsigned int grid = std::min<unsigned>(t1 - t0, unsigned(ctx->sm_count) * occ);
-    if (k32)
-        LAUNCH(ctx, k_merge_tiles<uint32_t>, grid, MT_THREADS, 0, row_bin, bin_base, bins, ctx->tile_row.as<uint32_t>(), 0u,
-               t0, t1, job.n_tiles, ctx->uniq.as<uint32_t>(), ctx->tile_state.as<uint64_t>(), job.c_pos, job.c_data,
-               job.c_cap, job.rows, ctx->d_sc);
-    else
-        LAUNCH(ctx, k_merge_tiles<uint64_t>, grid, MT_THREADS, 0, row_bin, bin_base, bins, ctx->tile_row.as<uint32_t>(), 0u,
-               t0, t1, job.n_tiles, ctx->uniq.as<uint32_t>(), ctx->tile_state.as<uint64_t>(), job.c_pos, job.c_data,
-               job.c_cap, job.rows, ctx->d_sc);
+    const uint32_t bm_words = job.idx_range <= 32ull * BM_WORDS ? uint32_t((job.idx_range + 31) / 32) : 0u;
+    const int variant = bm_words ? 2 : k32 ? 0 : 1;
+    const unsigned int warps_per_cta = MW_THREADS / 32;
+    const unsigned int grid = std::min<unsigned>((t1 - t0 + warps_per_cta - 1) / warps_per_cta,
+                                                 unsigned(ctx->sm_count) * unsigned(ctx->tiles_occ[variant]));
+    const size_t smem = tiles_smem(bm_words != 0);
+#define MT_ARGS row_bin, bin_base, bins, ctx->tile_row.as<uint32_t>(), bm_words, t0, t1, uniq
+    if (variant == 2) LAUNCH(ctx, (k_merge_tiles<uint32_t, true>), grid, MW_THREADS, smem, MT_ARGS);
+    else if (variant == 0) LAUNCH(ctx, (k_merge_tiles<uint32_t, false>), grid, MW_THREADS, smem, MT_ARGS);
+    else LAUNCH(ctx, (k_merge_tiles<uint64_t, false>), grid, MW_THREADS, smem, MT_ARGS);
+#undef MT_ARGS
+    // survivors per row -> C.pos (running total carried across row blocks), then the rows into C.data
+    const uint64_t n = row_hi - row_lo;
+    CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, scan_tiles(n) * 8, ctx->stream));
+    CU(ctx, cudaMemsetAsync(&ctx->d_sc->scan_ticket[3], 0, 4, ctx->stream));
+    LAUNCH(ctx, (k_scan<U32In, U64OutCarry>), unsigned(scan_tiles(n)), SCAN_BLOCK, 0, U32In{uniq + row_lo},
+           U64OutCarry{job.c_pos + row_lo, &ctx->d_sc->nnz_c[block & 1], &ctx->d_sc->nnz_c[(block + 1) & 1], n}, n,
+           ctx->tile_state.as<uint64_t>(), &ctx->d_sc->scan_ticket[3]);
+    LAUNCH(ctx, k_gather_rows, std::min<unsigned>((t1 - t0 + 7) / 8, unsigned(ctx->sm_count) * 8u), 256, 0, row_bin, bin_base,
+           bins, ctx->tile_row.as<uint32_t>(), t0, t1, uniq, job.c_pos, job.c_data);
     return OSP_OK;
 }
 
@@ -255,7 +267,7 @@ int csr2csc_device(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint6
     unsigned int xl_ctas = 0;
     rc = reserve_merge(ctx, job, xl_ctas);
     if (rc) return rc;
-    rc = launch_merge(ctx, job, xl_ctas, ctx->conv_tmp.as<Elem>(), 0, 0, job.n_tiles, 0, n_minor);
+    rc = launch_merge(ctx, job, xl_ctas, ctx->conv_tmp.as<Elem>(), 0, 0, job.n_tiles, 0, n_minor, 0);
     if (rc) return rc;
     LAUNCH(ctx, k_check_same, grid_for(n_minor + 1, 256, 1u << 30), 256, 0, d_pos_out, job.c_pos, n_minor + 1, ctx->d_sc);
     rc = sync_scalars(ctx);
@@ -312,19 +324,12 @@ int stage_operands(osp_ctx *ctx, const osp_spgemm_args *args, Operands &op) {
 }
 
 template <class Src>
-int launch_multiply(osp_ctx *ctx, Src src, uint64_t t0, uint64_t t1, uint64_t products, const uint64_t *b_pos,
-                    const Elem *b_data, Elem *bins, uint64_t bin_base) {
+int launch_multiply(osp_ctx *ctx, Src src, uint64_t t0, uint64_t t1, uint64_t products, const Elem *b_data, Elem *bins,
+                    uint64_t bin_base) {
     uint64_t n = t1 - t0;
     if (!n || !products) return OSP_OK;
-    double avg = double(products) / double(n);
-    int G = avg <= 4.0 ? 4 : avg <= 8.0 ? 8 : avg <= 16.0 ? 16 : 32;
     unsigned int grid = grid_for(n, 256, unsigned(ctx->sm_count) * 32u);
-    switch (G) {
-        case 4: LAUNCH(ctx, (k_multiply<4, Src>), grid, 256, 0, src, t0, t1, b_pos, b_data, bins, bin_base); break;
-        case 8: LAUNCH(ctx, (k_multiply<8, Src>), grid, 256, 0, src, t0, t1, b_pos, b_data, bins, bin_base); break;
-        case 16: LAUNCH(ctx, (k_multiply<16, Src>), grid, 256, 0, src, t0, t1, b_pos, b_data, bins, bin_base); break;
-        default: LAUNCH(ctx, (k_multiply<32, Src>), grid, 256, 0, src, t0, t1, b_pos, b_data, bins, bin_base); break;
-    }
+    LAUNCH(ctx, k_multiply<Src>, grid, 256, 0, src, t0, t1, b_data, bins, bin_base);
     return OSP_OK;
 }
 
@@ -362,10 +367,18 @@ int osp_create(int device, osp_ctx **out) {
     CU(nullptr, cudaMallocHost(reinterpret_cast<void **>(&ctx->h_sc), sizeof(DevScalars)));
     CU(nullptr, cudaFuncSetAttribute(k_merge_long, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LONG_SMEM)));
     CU(nullptr, cudaFuncSetAttribute(k_merge_xl, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LONG_SMEM)));
-    CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->tiles_occ32, k_merge_tiles<uint32_t>, MT_THREADS, 0));
-    CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->tiles_occ64, k_merge_tiles<uint64_t>, MT_THREADS, 0));
-    ctx->tiles_occ32 = std::max(ctx->tiles_occ32, 1);
-    ctx->tiles_occ64 = std::max(ctx->tiles_occ64, 1);
+    {
+        auto k32 = k_merge_tiles<uint32_t, false>;
+        auto k64 = k_merge_tiles<uint64_t, false>;
+        auto kbm = k_merge_tiles<uint32_t, true>;
+        CU(nullptr, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tiles_smem(false))));
+        CU(nullptr, cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tiles_smem(false))));
+        CU(nullptr, cudaFuncSetAttribute(kbm, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tiles_smem(true))));
+        CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->tiles_occ[0], k32, MW_THREADS, tiles_smem(false)));
+        CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->tiles_occ[1], k64, MW_THREADS, tiles_smem(false)));
+        CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->tiles_occ[2], kbm, MW_THREADS, tiles_smem(true)));
+        for (int &o : ctx->tiles_occ) o = std::max(o, 1);
+    }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = ~0ull;
@@ -483,14 +496,16 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         CU(ctx, ctx->tasks.reserve(nnz_a * sizeof(Task)));
         LAUNCH(ctx, (k_scan<U32In, U32Out>), unsigned(st[2]), SCAN_BLOCK, 0, U32In{col_cnt}, U32Out{ctx->col_ptr.as<uint32_t>()},
                n_k, ar.state[2], &ctx->d_sc->scan_ticket[2]);
-        LAUNCH(ctx, k_scatter_tasks, grid_for(nnz_a, 256, unsigned(ctx->sm_count) * 16u), 256, 0, dA_data, run_off, uint64_t(0),
-               nnz_a, ctx->col_ptr.as<uint32_t>(), col_cnt, ctx->tasks.as<Task>());
+        LAUNCH(ctx, k_scatter_tasks, grid_for(nnz_a, 256, unsigned(ctx->sm_count) * 16u), 256, 0, dA_data, run_off, dB_pos,
+               uint64_t(0), nnz_a, ctx->col_ptr.as<uint32_t>(), col_cnt, ctx->tasks.as<Task>(), ctx->d_sc);
     }
     cudaEvent_t ev_sym = next_event(ctx);
     rc = sync_scalars(ctx);                       // the one mid-pipeline sync: sizes of the bins and of C
     if (rc) return rc;
+    if (ctx->h_sc->err == 6) return fail(ctx, OSP_ERR_UNSUPPORTED, "osp_spgemm: a row of B holds >= 2^24 non-zeros");
     if (ctx->h_sc->err) return fail(ctx, OSP_ERR_INDEX, "osp_spgemm: index of A out of range of the inner dimension");
     const uint64_t P = ctx->h_sc->products;
+    if (P >> 40) return fail(ctx, OSP_ERR_UNSUPPORTED, "osp_spgemm: more than 2^40 partial products");
     if (!cols_b) cols_b = uint64_t(ctx->h_sc->max_idx) + 1;
     const uint64_t min_rows = std::max<uint64_t>(ctx->h_sc->last_nonempty, 1);
     // reference rule numRows = max row id of A + 1 (SimOuterSPACE.cpp:49-53): the last row of A holding a
@@ -563,11 +578,11 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     for (size_t b = 0; b < n_blocks; b++) {
         const uint64_t bin0 = blk_bin[b], p_block = blk_bin[b + 1] - bin0;
         ev_blocks.push_back(next_event(ctx));
-        if (rowwise) rc = launch_multiply(ctx, TaskSrcSoA{dA_data, run_off}, blk_e[b], blk_e[b + 1], p_block, dB_pos, dB_data, bins, bin0);
-        else rc = launch_multiply(ctx, TaskSrcAoS{ctx->tasks.as<Task>()}, 0, nnz_a, p_block, dB_pos, dB_data, bins, bin0);
+        if (rowwise) rc = launch_multiply(ctx, TaskSrcSoA{dA_data, run_off, dB_pos}, blk_e[b], blk_e[b + 1], p_block, dB_data, bins, bin0);
+        else rc = launch_multiply(ctx, TaskSrcAoS{ctx->tasks.as<Task>()}, 0, nnz_a, p_block, dB_data, bins, bin0);
         if (rc) return bail(rc);
         ev_blocks.push_back(next_event(ctx));
-        rc = launch_merge(ctx, job, xl_ctas, bins, bin0, tb[b], tb[b + 1], blk_row[b], blk_row[b + 1]);
+        rc = launch_merge(ctx, job, xl_ctas, bins, bin0, tb[b], tb[b + 1], blk_row[b], blk_row[b + 1], unsigned(b));
         if (rc) return bail(rc);
         ev_blocks.push_back(next_event(ctx));
     }
@@ -575,7 +590,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     rc = sync_scalars(ctx);
     if (rc) return bail(rc);
     if (ctx->h_sc->err) return bail(fail(ctx, OSP_ERR_CUDA, "osp_spgemm: internal capacity check failed on the device"));
-    const uint64_t nnz_c = ctx->h_sc->nnz_c;
+    const uint64_t nnz_c = ctx->h_sc->nnz_c[n_blocks & 1];
     res->rows = rows_c;
     res->nnz = nnz_c;
 

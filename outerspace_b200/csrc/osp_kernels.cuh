@@ -99,7 +99,9 @@ struct SymIn {
         uint32_t k = a[p].idx;
         if (k >= n_k) { atomicMax(&sc->err, 4u); return 0; }   // OSP_ERR_INDEX
         if (col_cnt) atomicAdd(&col_cnt[k], 1u);
-        return b_pos[k + 1] - b_pos[k];
+        const uint64_t len = b_pos[k + 1] - b_pos[k];
+        if (len >> TASK_LEN_BITS) { atomicMax(&sc->err, 6u); return 0; }   // OSP_ERR_UNSUPPORTED
+        return len;
     }
 };
 struct RunOffOut {
@@ -143,10 +145,10 @@ __global__ void k_max_idx(const Elem *d, uint64_t nnz, DevScalars *sc) {
 // Also: row_bin[] (bin start of every row), the queues of long rows, the upper bound of nnz(C)
 // and the reference's row count rule numRows = maxRowId + 1 (SimOuterSPACE.cpp:49-53).
 // =====================================================================================
-constexpr uint32_t MT_CAP = 3072;      // partial products per tile (soft)
+constexpr uint32_t MT_CAP = 512;       // partial products per tile (soft): one warp merges a tile
 constexpr uint32_t MT_LONG = 512;      // longest row sorted in registers by one warp
 constexpr uint32_t MT_STAGE = MT_CAP + MT_LONG;
-constexpr uint32_t MT_RMAX = 1024;     // rows per tile
+constexpr uint32_t MT_RMAX = 32;       // rows per tile (one lane per row)
 constexpr uint32_t MT_XL = 4096;       // longest row sorted in shared memory by one CTA
 
 constexpr int PLAN_BLOCK = 256;
@@ -248,13 +250,15 @@ k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *ti
 // inside a column is immaterial (each task owns a distinct run), so slots are claimed with an
 // atomic; `col_cnt` (the histogram built by the symbolic pass) is counted down.
 // =====================================================================================
-__global__ void k_scatter_tasks(const Elem *a, const uint64_t *run_off, uint64_t e0, uint64_t e1,
-                                const uint32_t *col_ptr, uint32_t *col_cnt, Task *tasks) {
+__global__ void k_scatter_tasks(const Elem *a, const uint64_t *run_off, const uint64_t *b_pos, uint64_t e0, uint64_t e1,
+                                const uint32_t *col_ptr, uint32_t *col_cnt, Task *tasks, DevScalars *sc) {
     for (uint64_t p = e0 + blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; p < e1; p += uint64_t(gridDim.x) * blockDim.x) {
-        Elem e = a[p];
-        uint32_t c = atomicSub(&col_cnt[e.idx], 1u);
+        const Elem e = a[p];
+        const uint64_t off = run_off[p], len = run_off[p + 1] - off;
+        const uint32_t c = atomicSub(&col_cnt[e.idx], 1u);
+        if (len >> TASK_LEN_BITS) { atomicMax(&sc->err, 6u); continue; }     // OSP_ERR_UNSUPPORTED
         Task t;
-        t.k = e.idx; t.a = e.val; t.off = run_off[p];
+        t.bs = uint32_t(b_pos[e.idx]); t.a = e.val; t.offlen = (off << TASK_LEN_BITS) | len;
         tasks[col_ptr[e.idx] + c - 1] = t;
     }
 }
@@ -285,56 +289,64 @@ __global__ void k_hist_elems(const Elem *d, uint64_t nnz, uint64_t n_minor, uint
 }
 
 // =====================================================================================
-// Multiply phase: every task streams row k of B, scales it by A(i,k) and writes the run of
-// (col, a*b) partial products into row i's bin.  G lanes cooperate on one run (G | 32), so a
-// warp works on 32/G runs at once; G is picked from the mean row length of B.
-// Task sources: Task[] (k-slice order) or {Elem[], run_off[]} (row order of A).
+// Multiply phase (warp-flat).  A warp takes 32 tasks, scans their run lengths and then walks the
+// concatenation of the 32 runs 32 partial products at a time: every lane finds the task of its
+// element with a 5-step search over the scanned lengths (shuffles), reads the element of B(k,:),
+// multiplies by A(i,k) and writes (col, a*b) into row i's bin.  Every lane is busy whatever the run
+// lengths are, loads and stores are contiguous inside a run, and there is no per-run loop.
+// Task sources: packed Task[] (k-slice order: the CSC of A) or {Elem[], run_off[]} (row order of A).
 // =====================================================================================
 struct TaskSrcAoS {
     const Task *t;
-    __device__ __forceinline__ void load(uint64_t i, uint32_t &k, float &a, uint64_t &off) const {
+    __device__ __forceinline__ void load(uint64_t i, uint32_t &bs, float &a, uint64_t &off, uint32_t &len) const {
         const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(t + i));   // one 128-bit load
-        k = raw.x; a = __uint_as_float(raw.y);
-        off = (uint64_t(raw.w) << 32) | raw.z;
+        bs = raw.x; a = __uint_as_float(raw.y);
+        const uint64_t offlen = (uint64_t(raw.w) << 32) | raw.z;
+        off = offlen >> TASK_LEN_BITS;
+        len = uint32_t(offlen) & ((1u << TASK_LEN_BITS) - 1);
     }
 };
 struct TaskSrcSoA {
     const Elem *a_data;
     const uint64_t *run_off;
-    __device__ __forceinline__ void load(uint64_t i, uint32_t &k, float &a, uint64_t &off) const {
-        Elem e = a_data[i];
-        k = e.idx; a = e.val; off = run_off[i];
+    const uint64_t *b_pos;
+    __device__ __forceinline__ void load(uint64_t i, uint32_t &bs, float &a, uint64_t &off, uint32_t &len) const {
+        const Elem e = a_data[i];
+        a = e.val; off = run_off[i];
+        len = uint32_t(run_off[i + 1] - off);
+        bs = uint32_t(b_pos[e.idx]);
     }
 };
 
-template <int G, class Src>
+template <class Src>
 __global__ void __launch_bounds__(256)
-k_multiply(Src src, uint64_t t0, uint64_t t1, const uint64_t *__restrict__ b_pos, const Elem *__restrict__ b_data,
-           Elem *__restrict__ bins, uint64_t bin_base) {
+k_multiply(Src src, uint64_t t0, uint64_t t1, const Elem *__restrict__ b_data, Elem *__restrict__ bins, uint64_t bin_base) {
     const unsigned int lane = lane_id();
     const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
     const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
-    constexpr int RUNS = 32 / G;
-    const unsigned int g = lane / G, tl = lane % G;
     for (uint64_t base = t0 + warp * 32; base < t1; base += nwarps * 32) {
-        uint32_t k = 0; float a = 0.f; uint64_t off = 0, bs = 0; uint32_t bl = 0;
-        if (base + lane < t1) {
-            src.load(base + lane, k, a, off);
-            bs = b_pos[k];
-            bl = uint32_t(b_pos[k + 1] - bs);
-        }
-#pragma unroll 1
-        for (int j0 = 0; j0 < 32; j0 += RUNS) {
-            const int srcl = j0 + g;
-            const uint64_t bs_j = __shfl_sync(FULL, bs, srcl);
-            const uint32_t bl_j = __shfl_sync(FULL, bl, srcl);
-            const float a_j = __shfl_sync(FULL, a, srcl);
-            const uint64_t off_j = __shfl_sync(FULL, off, srcl) - bin_base;
-            if (__ballot_sync(FULL, bl_j != 0) == 0) continue;
-            for (uint32_t t = tl; t < bl_j; t += G) {
-                Elem b = b_data[bs_j + t];
-                Elem o; o.idx = b.idx; o.val = __fmul_rn(a_j, b.val);     // rounded on its own: no FMA
-                bins[off_j + t] = o;
+        uint32_t bs = 0, len = 0; float a = 0.f; uint64_t off = 0;
+        if (base + lane < t1) src.load(base + lane, bs, a, off, len);
+        const uint32_t incl = warp_inclusive_scan(len);
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        const uint32_t excl = incl - len;
+        const uint32_t dbs = bs - excl;                       // B index of element e of this task: dbs + e
+        const uint64_t doff = off - bin_base - excl;          // bin index of element e of this task: doff + e
+        for (uint32_t e0 = 0; e0 < total; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            uint32_t t = 0;                                    // number of tasks that end at or before e
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t v = __shfl_sync(FULL, incl, t + step - 1);
+                if (v <= e) t += step;
+            }
+            const float a_t = __shfl_sync(FULL, a, t);
+            const uint32_t dbs_t = __shfl_sync(FULL, dbs, t);
+            const uint64_t doff_t = __shfl_sync(FULL, doff, t);
+            if (e < total) {
+                const Elem b = b_data[dbs_t + e];
+                Elem o; o.idx = b.idx; o.val = __fmul_rn(a_t, b.val);     // rounded on its own: no FMA
+                bins[doff_t + e] = o;
             }
         }
     }
@@ -495,45 +507,54 @@ k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, 
 }
 
 // =====================================================================================
-// Merge, the main kernel.  A persistent grid takes merge tiles in order (dynamic ticket).
-// Per tile:
-//   1. rows of 0/1 partial products are handled one per thread; every other row is taken by a
-//      warp, which loads the row's bin (coalesced), sorts 32*E keys (col << pb | arrival position)
-//      in registers with a bitonic network over shuffles, left-folds equal columns in arrival (= k)
-//      order with separately rounded adds and leaves the compacted row in shared memory;
-//   2. a block scan of the surviving counts + one decoupled look-back across tiles give the tile's
-//      offset in C, so rows go straight from shared memory to their final place in C.data and
-//      C.pos is written on the way -- no second pass over the merged rows, no scan kernel.
-// A long row (a tile of its own) was merged in place by k_merge_long / k_merge_xl; its compacted
-// prefix is copied from the bin.
-// K = uint32_t when col << 9 fits 32 bits (cols <= 2^23), else uint64_t.
+// Merge of one short row by one warp, building blocks:
+//   bitonic_regs      sorts 32*E keys (col << pb | arrival position) held E per lane in registers
+//                     (compare-exchange over shuffles);
+//   merge_row_regs    loads a row's bin (coalesced), sorts, left-folds equal columns in arrival (= k)
+//                     order with separately rounded adds, writes the compacted row;
+//   merge_row_bitmap  the same result without a sort, for small column ranges.
 // =====================================================================================
 template <int E, class K>
 __device__ __forceinline__ void bitonic_regs(K (&x)[E], const unsigned int lane) {
     constexpr int N = 32 * E;
+    // levels k = 2 .. E: both partners in this lane (compile-time register pairs and directions)
 #pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
+    for (int k = 2; k <= E; k <<= 1) {
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= E) {                       // partner in lane ^ (j / E), same register
-                const int lj = j / E;
-                const bool lower = (lane & lj) == 0;
-                const bool up = ((lane * E) & k) == 0;      // k >= 2j >= 2E here: direction is per lane
-                const bool keep_min = lower == up;
 #pragma unroll
-                for (int e = 0; e < E; e++) {
-                    const K y = __shfl_xor_sync(FULL, x[e], lj);
-                    x[e] = keep_min ? min(x[e], y) : max(x[e], y);
+            for (int e = 0; e < E; e++) {
+                if ((e & j) == 0) {
+                    const K lo = min(x[e], x[e | j]), hi = max(x[e], x[e | j]);
+                    const bool up = k < E ? ((e & k) == 0) : ((lane & 1) == 0);   // i = lane*E + e
+                    x[e] = up ? lo : hi;
+                    x[e | j] = up ? hi : lo;
                 }
-            } else {                            // both elements in this lane
+            }
+        }
+    }
+    // levels k = 2E .. N: a runtime loop (keeps the code small enough for the instruction cache):
+    // partners in lane ^ (j / E) while j >= E, then the in-lane tail j = E/2 .. 1
+#pragma unroll 1
+    for (int k = 2 * E; k <= N; k <<= 1) {
+        const bool up = ((lane * E) & k) == 0;
+#pragma unroll 1
+        for (int lj = k / (2 * E); lj > 0; lj >>= 1) {
+            const bool keep_min = ((lane & lj) == 0) == up;
 #pragma unroll
-                for (int e = 0; e < E; e++) {
-                    if ((e & j) == 0) {
-                        const K lo = min(x[e], x[e | j]), hi = max(x[e], x[e | j]);
-                        const bool up = k < E ? ((e & k) == 0) : (((lane * E) & k) == 0);   // i = lane*E + e
-                        x[e] = up ? lo : hi;
-                        x[e | j] = up ? hi : lo;
-                    }
+            for (int e = 0; e < E; e++) {
+                const K y = __shfl_xor_sync(FULL, x[e], lj);
+                x[e] = keep_min ? min(x[e], y) : max(x[e], y);
+            }
+        }
+#pragma unroll
+        for (int j = E >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                if ((e & j) == 0) {
+                    const K lo = min(x[e], x[e | j]), hi = max(x[e], x[e | j]);
+                    x[e] = up ? lo : hi;
+                    x[e | j] = up ? hi : lo;
                 }
             }
         }
@@ -544,10 +565,11 @@ template <int V> struct ILog2 { static constexpr int value = 1 + ILog2<V / 2>::v
 template <> struct ILog2<1> { static constexpr int value = 0; };
 
 // One warp merges one row of 2 <= len <= 32*E partial products.  `src` = the row's bin in global
-// memory, `region` = the row's len-element slot of the tile's staging buffer.  Returns the number of
-// surviving entries, left at region[0 .. uniq).
+// memory, `region` = a len-element scratch in shared memory, `out` = where the compacted row goes (may
+// be `src`: every input is in registers before the first output is written).  Returns the number of
+// surviving entries.
 template <int E, class K>
-__device__ __forceinline__ uint32_t merge_row_regs(const Elem *__restrict__ src, Elem *region, const uint32_t len,
+__device__ __forceinline__ uint32_t merge_row_regs(const Elem *src, Elem *region, Elem *out, const uint32_t len,
                                                    const unsigned int lane) {
     constexpr int N = 32 * E;
     constexpr int PB = ILog2<N>::value;
@@ -612,143 +634,248 @@ __device__ __forceinline__ uint32_t merge_row_regs(const Elem *__restrict__ src,
     for (int e = 0; e < E; e++) {
         if (head[e]) {
             Elem o; o.idx = col[e]; o.val = v[e];
-            region[r++] = o;
+            out[r++] = o;
         }
     }
     return total;
 }
 
-constexpr int MT_THREADS = 256;
+// ---- bitmap-rank merge of one row (column range <= 32 * BM_WORDS) -----------------------------------
+// No sort: every partial product sets the bit of its column in a per-warp bitmap, a prefix popcount over
+// the bitmap words turns a column into its rank among the row's distinct columns (= its place in the
+// sorted, folded row), and equal columns are folded into that place in ascending arrival (= k) order.
+// Shared-memory read-modify-writes are plain loads/stores re-checked after a __syncwarp and retried by the
+// lanes that lost a race (shared atomics cost ~2 cycles per lane; races here are rare).
+constexpr uint32_t BM_WORDS = 512;                 // bitmap words per warp: columns < 16384
+constexpr uint32_t BM_SCRATCH = BM_WORDS * 4 + BM_WORDS * 2 + MT_LONG * 2;   // bitmap | word prefixes | first arrival per rank
 
-template <class K>
-__global__ void __launch_bounds__(MT_THREADS, 3)
-k_merge_tiles(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, const Elem *__restrict__ bins,
-              const uint32_t *__restrict__ tile_row, const uint32_t t_first, const uint32_t t0, const uint32_t t1,
-              const uint32_t n_tiles, const uint32_t *__restrict__ uniq_long, uint64_t *tile_state,
-              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, const uint64_t c_cap, const uint64_t rows,
-              DevScalars *sc) {
-    __shared__ __align__(16) Elem stage[MT_STAGE];
-    __shared__ uint32_t s_start[MT_RMAX + 1];
-    __shared__ uint32_t s_off[MT_RMAX + 1];
-    __shared__ uint16_t s_work[MT_RMAX];
-    __shared__ uint32_t s_warp[33];
-    __shared__ uint32_t s_tile, s_nwork, s_next;
-    __shared__ uint64_t s_base;
-    const unsigned int lane = lane_id(), warp = threadIdx.x >> 5;
-
-    while (true) {
-        __syncthreads();                        // previous tile fully retired (stage, s_* reusable)
-        if (threadIdx.x == 0) {
-            s_tile = t0 + atomicAdd(&sc->tile_ticket, 1u);
-            s_nwork = 0;
-            s_next = 0;
-        }
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= t1) break;
-        const uint64_t r0 = tile_row[tile], r1 = tile_row[tile + 1];
-        const uint32_t R = uint32_t(r1 - r0);
-        const uint64_t bin0 = row_bin[r0];
-        const uint64_t tile_len = row_bin[r1] - bin0;
-        const bool single_long = R == 1 && tile_len > MT_LONG;
-        uint32_t total = 0;
-        if (single_long) {
-            total = uniq_long[r0];
-            if (threadIdx.x == 0) { s_off[0] = 0; s_off[1] = total; }
-        } else {
-            for (uint32_t j = threadIdx.x; j <= R; j += MT_THREADS) s_start[j] = uint32_t(row_bin[r0 + j] - bin0);
-            __syncthreads();
-            // rows with 0 / 1 partial products: one thread each; the others are queued for the warps
-            uint32_t cnt[MT_RMAX / MT_THREADS];
+template <int E>
+__device__ __forceinline__ uint32_t merge_row_bitmap(const Elem *__restrict__ src, Elem *region, const uint32_t len,
+                                                     const uint32_t words, unsigned char *scratch, const unsigned int lane) {
+    uint32_t *bm = reinterpret_cast<uint32_t *>(scratch);
+    uint16_t *pre = reinterpret_cast<uint16_t *>(scratch + BM_WORDS * 4);
+    uint16_t *first = reinterpret_cast<uint16_t *>(scratch + BM_WORDS * 4 + BM_WORDS * 2);
+    const uint32_t wpl = (((words + 31) >> 5) + 3) & ~3u;        // bitmap words per lane, multiple of 4, <= 16
+    // lane owns the words {4*(lane + 32*q) .. +3}: conflict-free 128-bit accesses
+    for (uint32_t q = 0; q < wpl; q += 4) *reinterpret_cast<uint4 *>(bm + 4 * lane + 32 * q) = make_uint4(0, 0, 0, 0);
+    for (uint32_t q = lane; q < (len + 1) / 2; q += 32) reinterpret_cast<uint32_t *>(first)[q] = 0xFFFFFFFFu;
+    uint32_t col[E];
+    float val[E];
+    bool valid[E];
 #pragma unroll
-            for (int q = 0; q < int(MT_RMAX / MT_THREADS); q++) {
-                const uint32_t j = threadIdx.x * (MT_RMAX / MT_THREADS) + q;
-                cnt[q] = 0;
-                if (j < R) {
-                    const uint32_t st = s_start[j], len = s_start[j + 1] - st;
-                    if (len == 1) {
-                        stage[st] = bins[bin0 - bin_base + st];
-                        cnt[q] = 1;
-                    } else if (len > 1) {
-                        s_work[atomicAdd(&s_nwork, 1u)] = uint16_t(j);
-                    }
-                }
-            }
-            __syncthreads();
-            const uint32_t nwork = s_nwork;
-            while (true) {
-                uint32_t w = 0;
-                if (lane == 0) w = atomicAdd(&s_next, 1u);
-                w = __shfl_sync(FULL, w, 0);
-                if (w >= nwork) break;
-                const uint32_t j = s_work[w];
-                const uint32_t st = s_start[j], len = s_start[j + 1] - st;
-                const Elem *src = bins + (bin0 - bin_base + st);
-                Elem *region = stage + st;
-                uint32_t u;
-                if (len <= 32) u = merge_row_regs<1, K>(src, region, len, lane);
-                else if (len <= 64) u = merge_row_regs<2, K>(src, region, len, lane);
-                else if (len <= 128) u = merge_row_regs<4, K>(src, region, len, lane);
-                else if (len <= 256) u = merge_row_regs<8, K>(src, region, len, lane);
-                else u = merge_row_regs<16, K>(src, region, len, lane);
-                if (lane == 0) s_off[j] = u;          // surviving count, turned into an offset below
-            }
-            __syncthreads();
-            // exclusive scan of the surviving counts over the tile's rows (4 consecutive rows per thread)
-            uint32_t mine = 0;
+    for (int e = 0; e < E; e++) {
+        const uint32_t p = e * 32 + lane;
+        valid[e] = p < len;
+        col[e] = 0; val[e] = 0.f;
+        if (valid[e]) { const Elem el = src[p]; col[e] = el.idx; val[e] = el.val; }
+    }
+    __syncwarp();
+    // set the bits: all loads, then all stores (independent accesses in flight), verify, retry what got lost
+    {
+        uint32_t cur[E];
+        bool pend[E];
 #pragma unroll
-            for (int q = 0; q < int(MT_RMAX / MT_THREADS); q++) {
-                const uint32_t j = threadIdx.x * (MT_RMAX / MT_THREADS) + q;
-                if (j < R) {
-                    const uint32_t len = s_start[j + 1] - s_start[j];
-                    if (len > 1) cnt[q] = s_off[j];
-                    mine += cnt[q];
-                }
-            }
-            uint32_t ex = block_exclusive_scan(mine, s_warp, total);
+        for (int e = 0; e < E; e++) { pend[e] = valid[e]; cur[e] = pend[e] ? bm[col[e] >> 5] : 0; }
+        while (true) {
 #pragma unroll
-            for (int q = 0; q < int(MT_RMAX / MT_THREADS); q++) {
-                const uint32_t j = threadIdx.x * (MT_RMAX / MT_THREADS) + q;
-                if (j < R) { s_off[j] = ex; ex += cnt[q]; }
-            }
-            if (threadIdx.x == 0) s_off[R] = total;
-        }
-        if (warp == 0) {
-            const uint64_t base = lookback_exclusive(tile_state, tile, total, t_first, 0);
-            if (lane == 0) {
-                s_base = base;
-                if (base + total > c_cap) atomicMax(&sc->err, 3u);       // cannot happen: c_cap is an upper bound
-                if (tile == n_tiles - 1) {
-                    c_pos[rows] = base + total;
-                    sc->nnz_c = base + total;
+            for (int e = 0; e < E; e++)
+                if (pend[e]) bm[col[e] >> 5] = cur[e] | (1u << (col[e] & 31));
+            __syncwarp();
+            bool any = false;
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                if (pend[e]) {
+                    cur[e] = bm[col[e] >> 5];
+                    pend[e] = !((cur[e] >> (col[e] & 31)) & 1u);
+                    any |= pend[e];
                 }
             }
+            if (!__any_sync(FULL, any)) break;
         }
-        __syncthreads();
-        const uint64_t base = s_base;
-        if (base + total > c_cap) continue;
-        for (uint32_t j = threadIdx.x; j < R; j += MT_THREADS) c_pos[r0 + j] = base + s_off[j];
-        Elem *dst = c_data + base;
-        if (single_long) {
-            const Elem *src = bins + (bin0 - bin_base);
-            for (uint32_t i = threadIdx.x; i < total; i += MT_THREADS) dst[i] = src[i];
-        } else if (total >= 16u * R) {
-            for (uint32_t j = warp; j < R; j += MT_THREADS / 32) {
-                const uint32_t o = s_off[j], n = s_off[j + 1] - o, st = s_start[j];
-                for (uint32_t i = lane; i < n; i += 32) dst[o + i] = stage[st + i];
-            }
-        } else {
-            for (uint32_t i = threadIdx.x; i < total; i += MT_THREADS) {
-                uint32_t lo = 0, hi = R;                     // last j with s_off[j] <= i
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (s_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    // exclusive prefix popcount over the words, in word order: lane's chunk q covers words 4*(lane+32q)..+3,
+    // so word order = (q, lane): scan the per-chunk counts chunk after chunk
+    uint32_t uniq = 0;
+    for (uint32_t q = 0; q < wpl; q += 4) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(bm + 4 * lane + 32 * q);
+        const uint32_t c0 = __popc(v.x), c1 = __popc(v.y), c2 = __popc(v.z), c3 = __popc(v.w);
+        const uint32_t cnt = c0 + c1 + c2 + c3;
+        const uint32_t incl = warp_inclusive_scan(cnt);
+        const uint32_t b0 = uniq + incl - cnt;
+        uint2 pk;
+        pk.x = b0 | ((b0 + c0) << 16);
+        pk.y = (b0 + c0 + c1) | ((b0 + c0 + c1 + c2) << 16);
+        *reinterpret_cast<uint2 *>(pre + 4 * lane + 32 * q) = pk;
+        uniq += __shfl_sync(FULL, incl, 31);
+    }
+    __syncwarp();
+    // rank of every partial product among the row's distinct columns
+    uint32_t rank[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const uint32_t w = col[e] >> 5;
+        rank[e] = valid[e] ? pre[w] + __popc(bm[w] & ((1u << (col[e] & 31)) - 1)) : 0;
+    }
+    // the earliest arrival (smallest position) of every rank opens its place: racing minimum, all slots at once
+    {
+        bool want[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) want[e] = valid[e];
+        while (true) {
+#pragma unroll
+            for (int e = 0; e < E; e++)
+                if (want[e]) first[rank[e]] = uint16_t(e * 32 + lane);
+            __syncwarp();
+            bool any = false;
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                if (valid[e]) {
+                    const uint32_t cur = first[rank[e]];
+                    want[e] = cur > uint32_t(e * 32 + lane);        // someone later overwrote an earlier arrival: redo
+                    any |= want[e];
                 }
-                dst[i] = stage[s_start[lo] + (i - s_off[lo])];
+            }
+            __syncwarp();
+            if (!__any_sync(FULL, any)) break;
+        }
+    }
+    bool loser[E];
+    bool any_loser = false;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        loser[e] = valid[e] && first[rank[e]] != uint32_t(e * 32 + lane);
+        any_loser |= loser[e];
+        if (valid[e] && !loser[e]) { Elem o; o.idx = col[e]; o.val = val[e]; region[rank[e]] = o; }
+    }
+    __syncwarp();
+    // later arrivals are added in arrival order: slot after slot, inside a slot lowest lane first
+    if (__any_sync(FULL, any_loser)) {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            bool pending = loser[e];
+            while (__any_sync(FULL, pending)) {
+                if (pending) { const uint32_t cur = first[rank[e]]; if (!(cur & 0x8000u) || (cur & 0x7FFFu) > lane) first[rank[e]] = uint16_t(0x8000u | lane); }
+                __syncwarp();
+                const bool mine = pending && first[rank[e]] == (0x8000u | lane);
+                __syncwarp();
+                if (mine) {
+                    region[rank[e]].val = __fadd_rn(region[rank[e]].val, val[e]);
+                    first[rank[e]] = 0;
+                    pending = false;
+                }
+                __syncwarp();
             }
         }
     }
+    return uniq;
 }
+
+// =====================================================================================
+// Merge, the main kernel.  Every warp takes tiles of consecutive short rows (<= 32 rows, one lane
+// per row; < MT_CAP + MT_LONG partial products) and merges the rows one after the other: register
+// bitonic sort or bitmap rank, then the k-ordered left fold.  The compacted row is written back over
+// the start of its own bin and uniq[row] = surviving entries.  Tiles are independent: no ordering,
+// no look-back, no CTA barrier.  (A chained single-pass variant that wrote C directly was measured
+// and dropped: with thousands of tiles in flight the look-back wave and in-order retirement cost more
+// than the extra pass -- profiles/README.md.)  k_scan over uniq[] then gives C.pos and k_gather_rows
+// moves the rows into C.data.
+// K = uint32_t when col << 9 fits 32 bits (cols <= 2^23), else uint64_t; BM enables the bitmap method.
+// =====================================================================================
+constexpr int MW_THREADS = 256;
+
+template <class K, bool BM>
+__global__ void __launch_bounds__(MW_THREADS, BM ? 3 : 4)
+k_merge_tiles(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, Elem *bins,
+              const uint32_t *__restrict__ tile_row, const uint32_t bm_words, const uint32_t t0, const uint32_t t1,
+              uint32_t *__restrict__ uniq) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const unsigned int lane = lane_id(), warp = threadIdx.x >> 5;
+    constexpr uint32_t PER_WARP = MT_LONG * 8 + (BM ? BM_SCRATCH : 0);
+    Elem *region = reinterpret_cast<Elem *>(smem + warp * PER_WARP);
+    unsigned char *scratch = smem + warp * PER_WARP + MT_LONG * 8;
+    const uint32_t bm_min = bm_words > 64 ? 64u : 32u;     // rows longer than this take the bitmap method
+    const uint32_t gwarp = blockIdx.x * (MW_THREADS / 32) + warp, nwarps = gridDim.x * (MW_THREADS / 32);
+
+    for (uint32_t tile = t0 + gwarp; tile < t1; tile += nwarps) {
+        const uint64_t r0 = tile_row[tile], r1 = tile_row[tile + 1];
+        const uint32_t R = uint32_t(r1 - r0);                          // <= 32
+        const uint64_t st_j = row_bin[min(r0 + lane, r1)];
+        const uint64_t en_j = row_bin[min(r0 + lane + 1, r1)];
+        const uint64_t len64 = en_j - st_j;
+        if (R == 1 && __shfl_sync(FULL, len64, 0) > MT_LONG) continue;   // long row: k_merge_long / k_merge_xl
+        const uint32_t len_j = lane < R ? uint32_t(len64) : 0;
+        uint32_t uniq_j = len_j;                                        // rows of 0 / 1 partial products stay as they are
+        unsigned int todo = __ballot_sync(FULL, len_j > 1);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t len = __shfl_sync(FULL, len_j, j);
+            Elem *bin = bins + (__shfl_sync(FULL, st_j, j) - bin_base);
+            uint32_t u;
+            if (BM && bm_words && len > bm_min) {
+                if (len <= 128) u = merge_row_bitmap<4>(bin, region, len, bm_words, scratch, lane);
+                else if (len <= 256) u = merge_row_bitmap<8>(bin, region, len, bm_words, scratch, lane);
+                else u = merge_row_bitmap<16>(bin, region, len, bm_words, scratch, lane);
+                __syncwarp();
+                for (uint32_t i = lane; i < u; i += 32) bin[i] = region[i];
+            }
+            else if (len <= 32) u = merge_row_regs<1, K>(bin, region, bin, len, lane);
+            else if (len <= 64) u = merge_row_regs<2, K>(bin, region, bin, len, lane);
+            else if (len <= 128) u = merge_row_regs<4, K>(bin, region, bin, len, lane);
+            else if (len <= 256) u = merge_row_regs<8, K>(bin, region, bin, len, lane);
+            else u = merge_row_regs<16, K>(bin, region, bin, len, lane);
+            if (int(lane) == j) uniq_j = u;
+            __syncwarp();
+        }
+        if (lane < R) uniq[r0 + lane] = uniq_j;
+    }
+}
+
+// Moves the merged rows (prefix of each bin) into the CSR data array of C.  Same tiles as the merge:
+// lane j of a warp reads the bounds of row j, then the warp copies the rows one after the other
+// (consecutive rows are consecutive in C, so the stores of a tile form one contiguous stream).
+__global__ void __launch_bounds__(256)
+k_gather_rows(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, const Elem *__restrict__ bins,
+              const uint32_t *__restrict__ tile_row, const uint32_t t0, const uint32_t t1,
+              const uint32_t *__restrict__ uniq, const uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data) {
+    const unsigned int lane = lane_id();
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t tile = t0 + gwarp; tile < t1; tile += nwarps) {
+        const uint64_t r0 = tile_row[tile], r1 = tile_row[tile + 1];
+        const uint32_t R = uint32_t(r1 - r0);
+        const uint64_t st_j = lane < R ? row_bin[r0 + lane] - bin_base : 0;
+        const uint64_t dst_j = lane < R ? c_pos[r0 + lane] : 0;
+        const uint32_t n_j = lane < R ? uniq[r0 + lane] : 0;
+        const uint32_t n_max = __reduce_max_sync(FULL, n_j);
+        if (n_max <= 4) {                       // tiny rows: one lane per row
+            for (uint32_t i = 0; i < n_j; i++) c_data[dst_j + i] = bins[st_j + i];
+            continue;
+        }
+        unsigned int todo = __ballot_sync(FULL, n_j > 0);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t n = __shfl_sync(FULL, n_j, j);
+            const Elem *src = bins + __shfl_sync(FULL, st_j, j);
+            Elem *dst = c_data + __shfl_sync(FULL, dst_j, j);
+            for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+        }
+    }
+}
+
+// uniq[] -> C.pos for rows [r_lo, r_hi): exclusive scan plus the running total of the earlier row blocks
+// (carry_in), whose successor is left in carry_out; the last block also closes C.pos.
+struct U64OutCarry {
+    uint64_t *y;
+    const unsigned long long *carry_in;
+    unsigned long long *carry_out;
+    uint64_t n;
+    __device__ void operator()(uint64_t i, uint64_t v, uint64_t) const {
+        const uint64_t c = *carry_in;
+        y[i] = c + v;
+        if (i == n) *carry_out = c + v;
+    }
+};
 
 // Duplicate check of the stable conversion: a bucket that shrank while folding held a duplicate.
 __global__ void k_check_same(const uint64_t *a, const uint64_t *b, uint64_t n, DevScalars *sc) {
