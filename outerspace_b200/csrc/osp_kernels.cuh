@@ -517,44 +517,73 @@ k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, 
 template <int E, class K>
 __device__ __forceinline__ void bitonic_regs(K (&x)[E], const unsigned int lane) {
     constexpr int N = 32 * E;
-    // levels k = 2 .. E: both partners in this lane (compile-time register pairs and directions)
+    if constexpr (E <= 4) {
+        // short rows: the whole network unrolled (a loop would cost as much as its body here)
 #pragma unroll
-    for (int k = 2; k <= E; k <<= 1) {
+        for (int k = 2; k <= N; k <<= 1) {
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j >= E) {                       // partner in lane ^ (j / E), same register
+                    const int lj = j / E;
+                    const bool keep_min = ((lane & lj) == 0) == (((lane * E) & k) == 0);
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                if ((e & j) == 0) {
-                    const K lo = min(x[e], x[e | j]), hi = max(x[e], x[e | j]);
-                    const bool up = k < E ? ((e & k) == 0) : ((lane & 1) == 0);   // i = lane*E + e
-                    x[e] = up ? lo : hi;
-                    x[e | j] = up ? hi : lo;
+                    for (int e = 0; e < E; e++) {
+                        const K y = __shfl_xor_sync(FULL, x[e], lj);
+                        x[e] = keep_min ? min(x[e], y) : max(x[e], y);
+                    }
+                } else {                            // both elements in this lane
+#pragma unroll
+                    for (int e = 0; e < E; e++) {
+                        if ((e & j) == 0) {
+                            const K lo = min(x[e], x[e | j]), hi = max(x[e], x[e | j]);
+                            const bool up = k < E ? ((e & k) == 0) : (((lane * E) & k) == 0);   // i = lane*E + e
+                            x[e] = up ? lo : hi;
+                            x[e | j] = up ? hi : lo;
+                        }
+                    }
                 }
             }
         }
-    }
-    // levels k = 2E .. N: a runtime loop (keeps the code small enough for the instruction cache):
-    // partners in lane ^ (j / E) while j >= E, then the in-lane tail j = E/2 .. 1
-#pragma unroll 1
-    for (int k = 2 * E; k <= N; k <<= 1) {
-        const bool up = ((lane * E) & k) == 0;
-#pragma unroll 1
-        for (int lj = k / (2 * E); lj > 0; lj >>= 1) {
-            const bool keep_min = ((lane & lj) == 0) == up;
+    } else {
+        // levels k = 2 .. E: both partners in this lane (compile-time register pairs and directions)
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                const K y = __shfl_xor_sync(FULL, x[e], lj);
-                x[e] = keep_min ? min(x[e], y) : max(x[e], y);
+        for (int k = 2; k <= E; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    if ((e & j) == 0) {
+                        const K lo = min(x[e], x[e | j]), hi = max(x[e], x[e | j]);
+                        const bool up = k < E ? ((e & k) == 0) : ((lane & 1) == 0);   // i = lane*E + e
+                        x[e] = up ? lo : hi;
+                        x[e | j] = up ? hi : lo;
+                    }
+                }
             }
         }
+        // levels k = 2E .. N: a runtime loop (keeps the code small enough for the instruction cache):
+        // partners in lane ^ (j / E) while j >= E, then the in-lane tail j = E/2 .. 1
+#pragma unroll 1
+        for (int k = 2 * E; k <= N; k <<= 1) {
+            const bool up = ((lane * E) & k) == 0;
+#pragma unroll 1
+            for (int lj = k / (2 * E); lj > 0; lj >>= 1) {
+                const bool keep_min = ((lane & lj) == 0) == up;
 #pragma unroll
-        for (int j = E >> 1; j > 0; j >>= 1) {
+                for (int e = 0; e < E; e++) {
+                    const K y = __shfl_xor_sync(FULL, x[e], lj);
+                    x[e] = keep_min ? min(x[e], y) : max(x[e], y);
+                }
+            }
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                if ((e & j) == 0) {
-                    const K lo = min(x[e], x[e | j]), hi = max(x[e], x[e | j]);
-                    x[e] = up ? lo : hi;
-                    x[e | j] = up ? hi : lo;
+            for (int j = E >> 1; j > 0; j >>= 1) {
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    if ((e & j) == 0) {
+                        const K lo = min(x[e], x[e | j]), hi = max(x[e], x[e | j]);
+                        x[e] = up ? lo : hi;
+                        x[e | j] = up ? hi : lo;
+                    }
                 }
             }
         }
@@ -596,6 +625,29 @@ __device__ __forceinline__ uint32_t merge_row_regs(const Elem *src, Elem *region
         col[e] = uint32_t(key[e] >> PB);
         v[e] = s < len ? fstage[uint32_t(key[e]) & (N - 1)] : 0.f;
     }
+    // heads (first arrival of a column); most rows hold no duplicate column at all: then the sorted
+    // row IS the result
+    uint32_t prev = __shfl_up_sync(FULL, col[E - 1], 1);
+    const uint32_t next_first = __shfl_down_sync(FULL, col[0], 1);   // padding (all ones >> PB) past the end
+    {
+        bool dup = false;
+        uint32_t pc = prev;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const uint32_t s = lane * E + e;
+            dup |= s < len && s > 0 && pc == col[e];
+            pc = col[e];
+        }
+        if (!__any_sync(FULL, dup)) {
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                const uint32_t s = lane * E + e;
+                if (s < len) { Elem o; o.idx = col[e]; o.val = v[e]; out[s] = o; }
+            }
+            return len;
+        }
+    }
     __syncwarp();
     uint32_t *scol = reinterpret_cast<uint32_t *>(region);
     float *sval = fstage + len;
@@ -605,9 +657,7 @@ __device__ __forceinline__ uint32_t merge_row_regs(const Elem *src, Elem *region
         if (s < len) { scol[s] = col[e]; sval[s] = v[e]; }
     }
     __syncwarp();
-    // heads and their left folds
-    uint32_t prev = __shfl_up_sync(FULL, col[E - 1], 1);
-    const uint32_t next_first = __shfl_down_sync(FULL, col[0], 1);   // padding (all ones >> PB) past the end
+    // left folds of the heads
     bool head[E];
     uint32_t nheads = 0;
 #pragma unroll
@@ -643,58 +693,41 @@ __device__ __forceinline__ uint32_t merge_row_regs(const Elem *src, Elem *region
 // ---- bitmap-rank merge of one row (column range <= 32 * BM_WORDS) -----------------------------------
 // No sort: every partial product sets the bit of its column in a per-warp bitmap, a prefix popcount over
 // the bitmap words turns a column into its rank among the row's distinct columns (= its place in the
-// sorted, folded row), and equal columns are folded into that place in ascending arrival (= k) order.
-// Shared-memory read-modify-writes are plain loads/stores re-checked after a __syncwarp and retried by the
-// lanes that lost a race (shared atomics cost ~2 cycles per lane; races here are rare).
+// sorted, folded row), the earliest arrival of a column opens that place and later arrivals are added in
+// arrival (= k) order.  Shared-memory read-modify-writes are plain loads/stores re-checked after a
+// __syncwarp and retried by the lanes that lost a race (shared atomics cost ~2 cycles per lane; races
+// here are rare).  Runtime loops over the 32-element slots of the row keep the code small: the unrolled
+// per-E variants of an earlier version thrashed the instruction cache (profiles/README.md).
 constexpr uint32_t BM_WORDS = 512;                 // bitmap words per warp: columns < 16384
-constexpr uint32_t BM_SCRATCH = BM_WORDS * 4 + BM_WORDS * 2 + MT_LONG * 2;   // bitmap | word prefixes | first arrival per rank
+// per-warp scratch: bitmap | word prefixes (u16) | first arrival per rank (u16) | rank per element (u16)
+constexpr uint32_t BM_SCRATCH = BM_WORDS * 4 + BM_WORDS * 2 + MT_LONG * 2 + MT_LONG * 2;
 
-template <int E>
-__device__ __forceinline__ uint32_t merge_row_bitmap(const Elem *__restrict__ src, Elem *region, const uint32_t len,
-                                                     const uint32_t words, unsigned char *scratch, const unsigned int lane) {
+__device__ __noinline__ uint32_t merge_row_bitmap(Elem *bin, Elem *region, const uint32_t len, const uint32_t words,
+                                                  unsigned char *scratch, const unsigned int lane) {
     uint32_t *bm = reinterpret_cast<uint32_t *>(scratch);
     uint16_t *pre = reinterpret_cast<uint16_t *>(scratch + BM_WORDS * 4);
     uint16_t *first = reinterpret_cast<uint16_t *>(scratch + BM_WORDS * 4 + BM_WORDS * 2);
+    uint16_t *rnk = first + MT_LONG;
     const uint32_t wpl = (((words + 31) >> 5) + 3) & ~3u;        // bitmap words per lane, multiple of 4, <= 16
-    // lane owns the words {4*(lane + 32*q) .. +3}: conflict-free 128-bit accesses
+    // lane owns the words {4*lane + 32*q .. +3}: conflict-free 128-bit accesses
     for (uint32_t q = 0; q < wpl; q += 4) *reinterpret_cast<uint4 *>(bm + 4 * lane + 32 * q) = make_uint4(0, 0, 0, 0);
     for (uint32_t q = lane; q < (len + 1) / 2; q += 32) reinterpret_cast<uint32_t *>(first)[q] = 0xFFFFFFFFu;
-    uint32_t col[E];
-    float val[E];
-    bool valid[E];
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-        const uint32_t p = e * 32 + lane;
-        valid[e] = p < len;
-        col[e] = 0; val[e] = 0.f;
-        if (valid[e]) { const Elem el = src[p]; col[e] = el.idx; val[e] = el.val; }
+    for (uint32_t p = lane; p < len; p += 32) region[p] = bin[p];          // stage the row (the bin is overwritten below)
+    __syncwarp();
+    // set the bits
+    for (uint32_t p0 = 0; p0 < len; p0 += 32) {
+        const uint32_t p = p0 + lane;
+        bool pend = p < len;
+        const uint32_t col = pend ? region[p].idx : 0;
+        const uint32_t w = col >> 5, bit = 1u << (col & 31);
+        do {
+            if (pend) { const uint32_t cur = bm[w]; if (!(cur & bit)) bm[w] = cur | bit; }
+            __syncwarp();
+            if (pend) pend = !(bm[w] & bit);
+        } while (__any_sync(FULL, pend));
     }
     __syncwarp();
-    // set the bits: all loads, then all stores (independent accesses in flight), verify, retry what got lost
-    {
-        uint32_t cur[E];
-        bool pend[E];
-#pragma unroll
-        for (int e = 0; e < E; e++) { pend[e] = valid[e]; cur[e] = pend[e] ? bm[col[e] >> 5] : 0; }
-        while (true) {
-#pragma unroll
-            for (int e = 0; e < E; e++)
-                if (pend[e]) bm[col[e] >> 5] = cur[e] | (1u << (col[e] & 31));
-            __syncwarp();
-            bool any = false;
-#pragma unroll
-            for (int e = 0; e < E; e++) {
-                if (pend[e]) {
-                    cur[e] = bm[col[e] >> 5];
-                    pend[e] = !((cur[e] >> (col[e] & 31)) & 1u);
-                    any |= pend[e];
-                }
-            }
-            if (!__any_sync(FULL, any)) break;
-        }
-    }
-    // exclusive prefix popcount over the words, in word order: lane's chunk q covers words 4*(lane+32q)..+3,
-    // so word order = (q, lane): scan the per-chunk counts chunk after chunk
+    // exclusive prefix popcount over the words, in word order (chunk q of every lane, then chunk q+4, ...)
     uint32_t uniq = 0;
     for (uint32_t q = 0; q < wpl; q += 4) {
         const uint4 v = *reinterpret_cast<const uint4 *>(bm + 4 * lane + 32 * q);
@@ -709,58 +742,48 @@ __device__ __forceinline__ uint32_t merge_row_bitmap(const Elem *__restrict__ sr
         uniq += __shfl_sync(FULL, incl, 31);
     }
     __syncwarp();
-    // rank of every partial product among the row's distinct columns
-    uint32_t rank[E];
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-        const uint32_t w = col[e] >> 5;
-        rank[e] = valid[e] ? pre[w] + __popc(bm[w] & ((1u << (col[e] & 31)) - 1)) : 0;
-    }
-    // the earliest arrival (smallest position) of every rank opens its place: racing minimum, all slots at once
-    {
-        bool want[E];
-#pragma unroll
-        for (int e = 0; e < E; e++) want[e] = valid[e];
-        while (true) {
-#pragma unroll
-            for (int e = 0; e < E; e++)
-                if (want[e]) first[rank[e]] = uint16_t(e * 32 + lane);
+    // rank of every partial product; the smallest position of a rank opens its place (slots ascend in position)
+    for (uint32_t p0 = 0; p0 < len; p0 += 32) {
+        const uint32_t p = p0 + lane;
+        const bool valid = p < len;
+        const uint32_t col = valid ? region[p].idx : 0;
+        const uint32_t w = col >> 5;
+        const uint32_t r = valid ? pre[w] + __popc(bm[w] & ((1u << (col & 31)) - 1)) : 0;
+        if (valid) rnk[p] = uint16_t(r);
+        bool want = valid;
+        do {
+            if (want && first[r] > p) first[r] = uint16_t(p);
             __syncwarp();
-            bool any = false;
-#pragma unroll
-            for (int e = 0; e < E; e++) {
-                if (valid[e]) {
-                    const uint32_t cur = first[rank[e]];
-                    want[e] = cur > uint32_t(e * 32 + lane);        // someone later overwrote an earlier arrival: redo
-                    any |= want[e];
-                }
-            }
-            __syncwarp();
-            if (!__any_sync(FULL, any)) break;
-        }
+            want = valid && first[r] > p;
+        } while (__any_sync(FULL, want));
     }
-    bool loser[E];
+    __syncwarp();
+    // first arrivals write their entry; later arrivals are flagged (top bit of rnk)
     bool any_loser = false;
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-        loser[e] = valid[e] && first[rank[e]] != uint32_t(e * 32 + lane);
-        any_loser |= loser[e];
-        if (valid[e] && !loser[e]) { Elem o; o.idx = col[e]; o.val = val[e]; region[rank[e]] = o; }
+    for (uint32_t p0 = 0; p0 < len; p0 += 32) {
+        const uint32_t p = p0 + lane;
+        if (p < len) {
+            const uint32_t r = rnk[p];
+            if (first[r] == p) bin[r] = region[p];
+            else { rnk[p] = uint16_t(r | 0x8000u); any_loser = true; }
+        }
     }
     __syncwarp();
     // later arrivals are added in arrival order: slot after slot, inside a slot lowest lane first
     if (__any_sync(FULL, any_loser)) {
-#pragma unroll
-        for (int e = 0; e < E; e++) {
-            bool pending = loser[e];
+        for (uint32_t p0 = 0; p0 < len; p0 += 32) {
+            const uint32_t p = p0 + lane;
+            const uint32_t rr = p < len ? rnk[p] : 0;
+            bool pending = (rr & 0x8000u) != 0;
+            const uint32_t r = rr & 0x7FFFu;
             while (__any_sync(FULL, pending)) {
-                if (pending) { const uint32_t cur = first[rank[e]]; if (!(cur & 0x8000u) || (cur & 0x7FFFu) > lane) first[rank[e]] = uint16_t(0x8000u | lane); }
+                if (pending) { const uint32_t cur = first[r]; if (!(cur & 0x8000u) || (cur & 0x7FFFu) > lane) first[r] = uint16_t(0x8000u | lane); }
                 __syncwarp();
-                const bool mine = pending && first[rank[e]] == (0x8000u | lane);
+                const bool mine = pending && first[r] == (0x8000u | lane);
                 __syncwarp();
                 if (mine) {
-                    region[rank[e]].val = __fadd_rn(region[rank[e]].val, val[e]);
-                    first[rank[e]] = 0;
+                    bin[r].val = __fadd_rn(__ldcg(&bin[r].val), region[p].val);
+                    first[r] = 0;
                     pending = false;
                 }
                 __syncwarp();
@@ -793,7 +816,6 @@ k_merge_tiles(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, Ele
     constexpr uint32_t PER_WARP = MT_LONG * 8 + (BM ? BM_SCRATCH : 0);
     Elem *region = reinterpret_cast<Elem *>(smem + warp * PER_WARP);
     unsigned char *scratch = smem + warp * PER_WARP + MT_LONG * 8;
-    const uint32_t bm_min = bm_words > 64 ? 64u : 32u;     // rows longer than this take the bitmap method
     const uint32_t gwarp = blockIdx.x * (MW_THREADS / 32) + warp, nwarps = gridDim.x * (MW_THREADS / 32);
 
     for (uint32_t tile = t0 + gwarp; tile < t1; tile += nwarps) {
@@ -812,18 +834,16 @@ k_merge_tiles(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, Ele
             const uint32_t len = __shfl_sync(FULL, len_j, j);
             Elem *bin = bins + (__shfl_sync(FULL, st_j, j) - bin_base);
             uint32_t u;
-            if (BM && bm_words && len > bm_min) {
-                if (len <= 128) u = merge_row_bitmap<4>(bin, region, len, bm_words, scratch, lane);
-                else if (len <= 256) u = merge_row_bitmap<8>(bin, region, len, bm_words, scratch, lane);
-                else u = merge_row_bitmap<16>(bin, region, len, bm_words, scratch, lane);
-                __syncwarp();
-                for (uint32_t i = lane; i < u; i += 32) bin[i] = region[i];
+            if constexpr (BM) {
+                if (len > 32) u = merge_row_bitmap(bin, region, len, bm_words, scratch, lane);
+                else u = merge_row_regs<1, uint32_t>(bin, region, bin, len, lane);
+            } else {
+                if (len <= 32) u = merge_row_regs<1, K>(bin, region, bin, len, lane);
+                else if (len <= 64) u = merge_row_regs<2, K>(bin, region, bin, len, lane);
+                else if (len <= 128) u = merge_row_regs<4, K>(bin, region, bin, len, lane);
+                else if (len <= 256) u = merge_row_regs<8, K>(bin, region, bin, len, lane);
+                else u = merge_row_regs<16, K>(bin, region, bin, len, lane);
             }
-            else if (len <= 32) u = merge_row_regs<1, K>(bin, region, bin, len, lane);
-            else if (len <= 64) u = merge_row_regs<2, K>(bin, region, bin, len, lane);
-            else if (len <= 128) u = merge_row_regs<4, K>(bin, region, bin, len, lane);
-            else if (len <= 256) u = merge_row_regs<8, K>(bin, region, bin, len, lane);
-            else u = merge_row_regs<16, K>(bin, region, bin, len, lane);
             if (int(lane) == j) uniq_j = u;
             __syncwarp();
         }
