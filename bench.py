@@ -228,7 +228,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             res = eng.spgemm_device(a.NRow(), t[0].data_ptr(), t[1].data_ptr(), b.NRow(), t[2].data_ptr(),
-                                    t[3].data_ptr(), a_is_csr=True, cols_b=dims["cols"], flags=flags)
+                                    t[3].data_ptr(), a_is_csr=True, cols_b=dims["cols"], flags=flags, a_nnz=a.nnz, b_nnz=b.nnz)
             e1.record(stream)
             e1.synchronize()
             return res, e0.elapsed_time(e1)

@@ -65,6 +65,8 @@ typedef struct osp_spgemm_args {
     uint64_t        cols_b;    /* 0 = derive as max col id of B + 1; otherwise every col id must be < cols_b */
     uint32_t        flags;
     uint32_t        reserved;
+    uint64_t        a_nnz;     /* OSP_DEVICE_POINTERS only: a_pos[a_slices] and b_pos[n_k] when the caller knows them */
+    uint64_t        b_nnz;     /* (saves a device->host read at the start of the call); 0 = read them from the device */
 } osp_spgemm_args;
 
 /* Counters of one call (all sizes in elements, times in milliseconds of device time). */

@@ -58,6 +58,7 @@ class SpgemmArgs(C.Structure):
         ("a_slices", C.c_uint64), ("a_pos", C.c_void_p), ("a_data", C.c_void_p),
         ("n_k", C.c_uint64), ("b_pos", C.c_void_p), ("b_data", C.c_void_p),
         ("rows_c", C.c_uint64), ("cols_b", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("a_nnz", C.c_uint64), ("b_nnz", C.c_uint64),
     ]
 
 
@@ -264,7 +265,7 @@ class Engine:
         return self._lib.osp_stream(self._h) or 0
 
     def _args(self, a_slices, a_pos, a_data, n_k, b_pos, b_data, rows_c, cols_b, flags) -> SpgemmArgs:
-        return SpgemmArgs(a_slices, a_pos, a_data, n_k, b_pos, b_data, rows_c, cols_b, flags, 0)
+        return SpgemmArgs(a_slices, a_pos, a_data, n_k, b_pos, b_data, rows_c, cols_b, flags, 0, 0, 0)
 
     def spgemm(self, a: CSRMatrix, b: CSRMatrix, a_is_csr: bool = False, rows_c: int = 0, cols_b: int = 0,
                flags: int = 0) -> Result:
@@ -278,10 +279,12 @@ class Engine:
         return Result(self, h)
 
     def spgemm_device(self, a_slices: int, a_pos_ptr: int, a_data_ptr: int, n_k: int, b_pos_ptr: int, b_data_ptr: int,
-                      a_is_csr: bool = False, rows_c: int = 0, cols_b: int = 0, flags: int = 0) -> Result:
+                      a_is_csr: bool = False, rows_c: int = 0, cols_b: int = 0, flags: int = 0, a_nnz: int = 0,
+                      b_nnz: int = 0) -> Result:
         """Same, with operands already resident in HBM (raw device pointers)."""
         f = flags | OSP_DEVICE_POINTERS | (OSP_A_IS_CSR if a_is_csr else 0)
         self._last_args = self._args(a_slices, a_pos_ptr, a_data_ptr, n_k, b_pos_ptr, b_data_ptr, rows_c, cols_b, f)
+        self._last_args.a_nnz, self._last_args.b_nnz = a_nnz, b_nnz
         h = C.c_void_p()
         self._check(self._lib.osp_spgemm(self._h, C.byref(self._last_args), C.byref(h)))
         return Result(self, h)

@@ -42,6 +42,8 @@ struct osp_ctx {
     int tiles_occ[3] = {3, 3, 2};           // resident CTAs per SM of k_merge_tiles: u32 keys, u64 keys, bitmap mode
     size_t total_mem = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;      // long-row merge kernels run beside the tile merge
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint64_t ws_limit = 0;          // bytes of partial-product bins per row block
     uint64_t launches = 0;
     std::string err;
@@ -178,7 +180,7 @@ int reserve_merge(osp_ctx *ctx, const MergeJob &job, unsigned int &xl_ctas) {
     CU(ctx, ctx->tile_state.reserve(scan_tiles(std::max<uint64_t>(job.rows, 1)) * 8));
     CU(ctx, ctx->uniq.reserve(std::max<uint64_t>(job.rows, 1) * 4));
     xl_ctas = 0;
-    if (job.n_xl) {
+    if (job.n_xl && job.idx_range > DENSE_MAX_COLS) {
         const uint64_t words = (job.idx_range + 31) / 32;
         const uint64_t per_cta = job.idx_range * 4 + words * 4;
         const uint64_t budget = std::max<uint64_t>(ctx->total_mem / 16, 1ull << 28);
@@ -199,12 +201,38 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
     if (t1 <= t0 || row_hi <= row_lo) return OSP_OK;
     const uint64_t *row_bin = ctx->row_bin.as<uint64_t>();
     uint32_t *uniq = ctx->uniq.as<uint32_t>();
-    if (job.n_long)
-        LAUNCH(ctx, k_merge_long, std::min<unsigned>(job.n_long, unsigned(ctx->sm_count) * 4u), 256, LONG_SMEM, row_bin,
-               bin_base, bins, uniq, ctx->long_list.as<uint32_t>(), ctx->d_sc, row_lo, row_hi);
-    if (job.n_xl)
-        LAUNCH(ctx, k_merge_xl, xl_ctas, 256, LONG_SMEM, row_bin, bin_base, bins, uniq, ctx->xl_list.as<uint32_t>(), ctx->d_sc,
-               ctx->xl_acc.as<float>(), ctx->xl_bits.as<uint32_t>(), job.idx_range, row_lo, row_hi);
+    // long rows on a second stream, beside the tile merge (disjoint rows, disjoint bins)
+    const bool fork = (job.n_long || job.n_xl) && !ctx->profile_kernels;
+    if (fork) {
+        CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    }
+    {
+        cudaStream_t main_stream = ctx->stream;
+        if (fork) ctx->stream = ctx->stream2;          // LAUNCH uses ctx->stream
+        int rc2 = [&]() -> int {
+            if (!job.n_long && !job.n_xl) return OSP_OK;
+            if (job.idx_range <= DENSE_MAX_COLS) {
+                // small column range: every long row goes through the dense shared-memory accumulator
+                const size_t sm = dense_smem(job.idx_range);
+                const unsigned per_sm = unsigned(std::max<size_t>(1, std::min<size_t>(4, (200u << 10) / sm)));
+                LAUNCH(ctx, k_merge_dense, std::min<unsigned>(job.n_long + job.n_xl, unsigned(ctx->sm_count) * per_sm), DENSE_THREADS,
+                       sm, row_bin, bin_base, bins, uniq, ctx->long_list.as<uint32_t>(), ctx->xl_list.as<uint32_t>(), ctx->d_sc,
+                       uint32_t(job.idx_range), row_lo, row_hi);
+                return OSP_OK;
+            }
+            if (job.n_long)
+                LAUNCH(ctx, k_merge_long, std::min<unsigned>(job.n_long, unsigned(ctx->sm_count) * 4u), 256, LONG_SMEM, row_bin,
+                       bin_base, bins, uniq, ctx->long_list.as<uint32_t>(), ctx->d_sc, row_lo, row_hi);
+            if (job.n_xl)
+                LAUNCH(ctx, k_merge_xl, xl_ctas, 256, LONG_SMEM, row_bin, bin_base, bins, uniq, ctx->xl_list.as<uint32_t>(),
+                       ctx->d_sc, ctx->xl_acc.as<float>(), ctx->xl_bits.as<uint32_t>(), job.idx_range, row_lo, row_hi);
+            return OSP_OK;
+        }();
+        ctx->stream = main_stream;
+        if (rc2) return rc2;
+        if (fork) CU(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+    }
     const bool k32 = job.idx_range <= (1ull << 23);
     const uint32_t bm_words = job.idx_range <= 32ull * BM_WORDS ? uint32_t((job.idx_range + 31) / 32) : 0u;
     const int variant = bm_words ? 2 : k32 ? 0 : 1;
@@ -217,6 +245,7 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
     else if (variant == 0) LAUNCH(ctx, (k_merge_tiles<uint32_t, false>), grid, MW_THREADS, smem, MT_ARGS);
     else LAUNCH(ctx, (k_merge_tiles<uint64_t, false>), grid, MW_THREADS, smem, MT_ARGS);
 #undef MT_ARGS
+    if (fork) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     // survivors per row -> C.pos (running total carried across row blocks), then the rows into C.data
     const uint64_t n = row_hi - row_lo;
     CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, scan_tiles(n) * 8, ctx->stream));
@@ -291,11 +320,16 @@ int stage_operands(osp_ctx *ctx, const osp_spgemm_args *args, Operands &op) {
         op.a_pos = args->a_pos; op.b_pos = args->b_pos;
         op.a_data = static_cast<const Elem *>(args->a_data);
         op.b_data = static_cast<const Elem *>(args->b_data);
-        CU(ctx, cudaMemcpyAsync(&ctx->h_sc->products, op.a_pos + args->a_slices, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(&ctx->h_sc->cap_bound, op.b_pos + n_k, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
-        op.nnz_a = ctx->h_sc->products;
-        op.nnz_b = ctx->h_sc->cap_bound;
+        if (args->a_nnz && args->b_nnz) {
+            op.nnz_a = args->a_nnz;
+            op.nnz_b = args->b_nnz;
+        } else {
+            CU(ctx, cudaMemcpyAsync(&ctx->h_sc->products, op.a_pos + args->a_slices, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaMemcpyAsync(&ctx->h_sc->cap_bound, op.b_pos + n_k, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            op.nnz_a = ctx->h_sc->products;
+            op.nnz_b = ctx->h_sc->cap_bound;
+        }
     } else {
         op.nnz_a = args->a_pos[args->a_slices];
         op.nnz_b = args->b_pos[n_k];
@@ -364,9 +398,13 @@ int osp_create(int device, osp_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->total_mem = prop.totalGlobalMem;
     CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    CU(nullptr, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CU(nullptr, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CU(nullptr, cudaMallocHost(reinterpret_cast<void **>(&ctx->h_sc), sizeof(DevScalars)));
     CU(nullptr, cudaFuncSetAttribute(k_merge_long, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LONG_SMEM)));
     CU(nullptr, cudaFuncSetAttribute(k_merge_xl, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LONG_SMEM)));
+    CU(nullptr, cudaFuncSetAttribute(k_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dense_smem(DENSE_MAX_COLS))));
     {
         auto k32 = k_merge_tiles<uint32_t, false>;
         auto k64 = k_merge_tiles<uint64_t, false>;
@@ -404,6 +442,9 @@ void osp_destroy(osp_ctx *ctx) {
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

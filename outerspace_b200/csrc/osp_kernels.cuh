@@ -145,7 +145,7 @@ __global__ void k_max_idx(const Elem *d, uint64_t nnz, DevScalars *sc) {
 // Also: row_bin[] (bin start of every row), the queues of long rows, the upper bound of nnz(C)
 // and the reference's row count rule numRows = maxRowId + 1 (SimOuterSPACE.cpp:49-53).
 // =====================================================================================
-constexpr uint32_t MT_CAP = 512;       // partial products per tile (soft): one warp merges a tile
+constexpr uint32_t MT_CAP = 512;       // partial products per tile (soft, = 2^9): one warp merges a tile
 constexpr uint32_t MT_LONG = 512;      // longest row sorted in registers by one warp
 constexpr uint32_t MT_STAGE = MT_CAP + MT_LONG;
 constexpr uint32_t MT_RMAX = 32;       // rows per tile (one lane per row)
@@ -184,6 +184,10 @@ k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *ti
     const uint32_t tile = s_tile;
     const unsigned int lane = lane_id(), warp = threadIdx.x >> 5;
     const uint64_t i0 = uint64_t(tile) * PLAN_TILE + uint64_t(threadIdx.x) * PLAN_ITEMS;
+    // partial products per tile: MT_CAP, less when the whole product is small, so that there are enough
+    // tiles (one warp each) to fill the machine: 2^cap_shift ~ P / 4096 within [32, MT_CAP]
+    int cap_shift = 5;
+    while (cap_shift < 9 && (sc->products >> (cap_shift + 1)) >= 4096) cap_shift++;
 
     uint64_t s[PLAN_ITEMS + 1];
 #pragma unroll
@@ -199,7 +203,7 @@ k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *ti
         if (i < rows) {
             const uint64_t len = s[it + 1] - s[it];
             const uint64_t plen = s[it] - sp;
-            flag[it] = i == 0 || (i % MT_RMAX) == 0 || len > MT_LONG || plen > MT_LONG || (sp / MT_CAP) != (s[it] / MT_CAP);
+            flag[it] = i == 0 || (i % MT_RMAX) == 0 || len > MT_LONG || plen > MT_LONG || (sp >> cap_shift) != (s[it] >> cap_shift);
             row_bin[i] = s[it];
             if (len > MT_XL) xl_list[atomicAdd(&sc->n_xl, 1u)] = uint32_t(i);
             else if (len > MT_LONG) long_list[atomicAdd(&sc->n_long, 1u)] = uint32_t(i);
@@ -502,6 +506,79 @@ k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, 
             produced += total;
         }
         if (threadIdx.x == 0) uniq[row] = uint32_t(produced);
+        __syncthreads();
+    }
+}
+
+// =====================================================================================
+// Merge, long rows over a small column range (cols <= DENSE_MAX_COLS): one CTA per row folds the
+// partial products into a dense accumulator in shared memory -- acc[col], seen[col] -- and then
+// emits the seen columns in ascending order.  The row is consumed T partial products at a time in
+// arrival order; products of one chunk that hit the same column are serialised by an arbitration
+// on owner[col] (the lowest position goes first), so every column is still summed in ascending
+// arrival (= k) order with separately rounded adds.  No sort, no global scratch.
+// Shared: float acc[cols] | uint16 owner[cols] | uint8 seen[cols] | uint32 warp_sums[33]
+// =====================================================================================
+constexpr uint32_t DENSE_MAX_COLS = 16384;
+constexpr int DENSE_THREADS = 512;
+__host__ __device__ inline size_t dense_smem(uint64_t cols) { return size_t((cols + 15) & ~15ull) * 7 + 34 * 4; }
+
+__global__ void __launch_bounds__(DENSE_THREADS)
+k_merge_dense(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, uint32_t *uniq,
+              const uint32_t *long_list, const uint32_t *xl_list, const DevScalars *sc, uint32_t cols,
+              uint64_t row_lo, uint64_t row_hi) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t cpad = (cols + 15) & ~15u;
+    float *acc = reinterpret_cast<float *>(smem);
+    uint16_t *owner = reinterpret_cast<uint16_t *>(smem + size_t(cpad) * 4);
+    unsigned char *seen = smem + size_t(cpad) * 6;
+    uint32_t *warp_sums = reinterpret_cast<uint32_t *>(smem + size_t(cpad) * 7);
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t c = tid; c < cpad; c += DENSE_THREADS) { owner[c] = 0xFFFF; seen[c] = 0; }
+    __syncthreads();
+    const uint32_t n_long = sc->n_long, n_all = n_long + sc->n_xl;
+    for (uint32_t x = blockIdx.x; x < n_all; x += gridDim.x) {
+        const uint64_t row = x < n_long ? long_list[x] : xl_list[x - n_long];
+        if (row < row_lo || row >= row_hi) continue;
+        const uint64_t len = row_bin[row + 1] - row_bin[row];
+        Elem *bin = bins + (row_bin[row] - bin_base);
+        for (uint64_t c0 = 0; c0 < len; c0 += DENSE_THREADS) {
+            const uint64_t p = c0 + tid;
+            bool pending = p < len;
+            Elem e; e.idx = 0; e.val = 0.f;
+            if (pending) e = bin[p];
+            while (__syncthreads_or(pending)) {
+                // the lowest pending position of every column wins this round (racing minimum, re-checked)
+                bool want = pending;
+                do {
+                    if (want && owner[e.idx] > tid) owner[e.idx] = uint16_t(tid);
+                    __syncthreads();
+                    want = pending && owner[e.idx] > tid;
+                } while (__syncthreads_or(want));
+                if (pending && owner[e.idx] == tid) {
+                    acc[e.idx] = seen[e.idx] ? __fadd_rn(acc[e.idx], e.val) : e.val;
+                    seen[e.idx] = 1;
+                    owner[e.idx] = 0xFFFF;
+                    pending = false;
+                }
+            }
+        }
+        __syncthreads();
+        // emit the seen columns in ascending order over the (fully consumed) bin
+        const uint32_t per = (cols + DENSE_THREADS - 1) / DENSE_THREADS;
+        const uint32_t cb = min(tid * per, cols), ce = min(cb + per, cols);
+        uint32_t cnt = 0;
+        for (uint32_t c = cb; c < ce; c++) cnt += seen[c];
+        uint32_t total;
+        uint32_t o = block_exclusive_scan(cnt, warp_sums, total);
+        for (uint32_t c = cb; c < ce; c++) {
+            if (seen[c]) {
+                Elem r; r.idx = c; r.val = acc[c];
+                bin[o++] = r;
+                seen[c] = 0;
+            }
+        }
+        if (tid == 0) uniq[row] = total;
         __syncthreads();
     }
 }

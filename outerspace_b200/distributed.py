@@ -111,16 +111,16 @@ class DistEngine:
     def spgemm(self, a_g: CSRMatrix, b_g: CSRMatrix, rows_c: int, cols_b: int, flags: int = 0) -> api.Result:
         """Host shard operands -> this rank's row block of C (collective call)."""
         args = api.SpgemmArgs(a_g.NRow(), a_g.pos.ctypes.data, api._ptr(a_g.data), b_g.NRow(), b_g.pos.ctypes.data,
-                              api._ptr(b_g.data), rows_c, cols_b, flags | api.OSP_A_IS_CSR, 0)
+                              api._ptr(b_g.data), rows_c, cols_b, flags | api.OSP_A_IS_CSR, 0, 0, 0)
         self._keep = (a_g, b_g, args)
         h = C.c_void_p()
         self._engine._check(self._lib.osp_dist_spgemm(self._h, C.byref(args), C.byref(h)))
         return api.Result(self._engine, h)
 
     def spgemm_device(self, a_slices: int, a_pos_ptr: int, a_data_ptr: int, n_k: int, b_pos_ptr: int, b_data_ptr: int,
-                      rows_c: int, cols_b: int, flags: int = 0) -> api.Result:
+                      rows_c: int, cols_b: int, flags: int = 0, a_nnz: int = 0, b_nnz: int = 0) -> api.Result:
         args = api.SpgemmArgs(a_slices, a_pos_ptr, a_data_ptr, n_k, b_pos_ptr, b_data_ptr, rows_c, cols_b,
-                              flags | api.OSP_A_IS_CSR | api.OSP_DEVICE_POINTERS, 0)
+                              flags | api.OSP_A_IS_CSR | api.OSP_DEVICE_POINTERS, 0, a_nnz, b_nnz)
         h = C.c_void_p()
         self._engine._check(self._lib.osp_dist_spgemm(self._h, C.byref(args), C.byref(h)))
         return api.Result(self._engine, h)
@@ -154,7 +154,7 @@ def bench_sharded(a: CSRMatrix, b: CSRMatrix, dims: dict, args, rank: int, world
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         res = deng.spgemm_device(a_g.NRow(), t[0].data_ptr(), t[1].data_ptr(), b_g.NRow(), t[2].data_ptr(), t[3].data_ptr(),
-                                 dims["rows"], dims["cols"], flags=flags)
+                                 dims["rows"], dims["cols"], flags=flags, a_nnz=a_g.nnz, b_nnz=b_g.nnz)
         e1.record(stream)
         e1.synchronize()
         return res, e0.elapsed_time(e1)

@@ -29,8 +29,20 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.osp_version()
 
 
-def test_struct_layouts_match_header():
-    assert ctypes.sizeof(api.SpgemmArgs) == 8 * 8 + 8
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof/offsetof of the C structs, as gcc sees include/osp_b200.h, equal the ctypes mirrors."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "osp_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(osp_spgemm_args), offsetof(osp_spgemm_args, flags),'
+                   ' offsetof(osp_spgemm_args, b_nnz), sizeof(osp_stats), offsetof(osp_stats, ms_total),'
+                   ' offsetof(osp_stats, exchange_bytes_out));return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    A, S = api.SpgemmArgs, api.Stats
+    assert got == [ctypes.sizeof(A), A.flags.offset, A.b_nnz.offset, ctypes.sizeof(S), S.ms_total.offset,
+                   S.exchange_bytes_out.offset]
     assert osp.ELEM.itemsize == 8 and osp.ELEM.fields["val"][1] == 4     # packed CSRElement, common.h:10-16
 
 

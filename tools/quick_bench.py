@@ -43,7 +43,7 @@ def main():
             args.flags |= api.OSP_PROFILE_KERNELS
         w0 = time.perf_counter()
         res = eng.spgemm_device(a.NRow(), t[0].data_ptr(), t[1].data_ptr(), b.NRow(), t[2].data_ptr(), t[3].data_ptr(),
-                                a_is_csr=True, cols_b=dims["cols"], flags=args.flags)
+                                a_is_csr=True, cols_b=dims["cols"], flags=args.flags, a_nnz=a.nnz, b_nnz=b.nnz)
         wall = (time.perf_counter() - w0) * 1e3
         st = res.stats()
         gbs = st["algorithmic_bytes"] / (st["ms_total"] * 1e-3) / 1e9
