@@ -18,8 +18,8 @@ namespace osp {
 
 // =====================================================================================
 // Generic single-pass exclusive scan (decoupled look-back).
-//   In : (idx, valid) -> uint64 contribution; called by ALL lanes of every warp (valid = idx < n),
-//        so functors may use warp collectives.
+//   In : load(idx, valid) -> key, then value(key, valid) -> uint64 contribution (two stages so that the
+//        first-level loads of all the items of a thread are in flight together).
 //   Out: (idx, exclusive prefix, own contribution) for idx < n, and once (n, total, 0).
 // =====================================================================================
 constexpr int SCAN_BLOCK = 256;
@@ -40,17 +40,27 @@ k_scan(In in, Out out, uint64_t n, uint64_t *tile_state, unsigned int *ticket) {
 
     uint64_t excl[SCAN_ITEMS], own[SCAN_ITEMS];
     uint64_t running = 0;
+    // two-stage input: all the first-level loads of a thread are issued before anything depends on them
+    uint64_t key[SCAN_ITEMS];
 #pragma unroll
     for (int it = 0; it < SCAN_ITEMS; it++) {
-        uint64_t idx = wbase + it * 32 + lane;
-        uint64_t x = in(idx, idx < n);
+        const uint64_t idx = wbase + it * 32 + lane;
+        key[it] = in.load(idx, idx < n);
+    }
+#pragma unroll
+    for (int it = 0; it < SCAN_ITEMS; it++) {
+        const uint64_t idx = wbase + it * 32 + lane;
+        own[it] = in.value(key[it], idx < n);
+    }
+#pragma unroll
+    for (int it = 0; it < SCAN_ITEMS; it++) {
+        uint64_t x = own[it];
         uint64_t incl = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint64_t y = __shfl_up_sync(FULL, incl, o);
             if (lane >= o) incl += y;
         }
-        own[it] = x;
         excl[it] = running + incl - x;
         running += __shfl_sync(FULL, incl, 31);
     }
@@ -94,12 +104,12 @@ struct SymIn {
     uint64_t n_k;
     uint32_t *col_cnt;
     DevScalars *sc;
-    __device__ uint64_t operator()(uint64_t p, bool valid) const {
+    __device__ uint64_t load(uint64_t p, bool valid) const { return valid ? a[p].idx : ~0ull; }
+    __device__ uint64_t value(uint64_t k, bool valid) const {
         if (!valid) return 0;
-        uint32_t k = a[p].idx;
         if (k >= n_k) { atomicMax(&sc->err, 4u); return 0; }   // OSP_ERR_INDEX
-        if (col_cnt) atomicAdd(&col_cnt[k], 1u);
         const uint64_t len = b_pos[k + 1] - b_pos[k];
+        if (col_cnt) atomicAdd(&col_cnt[k], 1u);
         if (len >> TASK_LEN_BITS) { atomicMax(&sc->err, 6u); return 0; }   // OSP_ERR_UNSUPPORTED
         return len;
     }
@@ -115,7 +125,8 @@ struct RunOffOut {
 };
 struct U32In {
     const uint32_t *x;
-    __device__ uint64_t operator()(uint64_t i, bool valid) const { return valid ? x[i] : 0; }
+    __device__ uint64_t load(uint64_t i, bool valid) const { return valid ? x[i] : 0; }
+    __device__ uint64_t value(uint64_t v, bool) const { return v; }
 };
 struct U64Out {
     uint64_t *y;
@@ -336,21 +347,33 @@ k_multiply(Src src, uint64_t t0, uint64_t t1, const Elem *__restrict__ b_data, E
         const uint32_t excl = incl - len;
         const uint32_t dbs = bs - excl;                       // B index of element e of this task: dbs + e
         const uint64_t doff = off - bin_base - excl;          // bin index of element e of this task: doff + e
-        for (uint32_t e0 = 0; e0 < total; e0 += 32) {
-            const uint32_t e = e0 + lane;
-            uint32_t t = 0;                                    // number of tasks that end at or before e
+        for (uint32_t e0 = 0; e0 < total; e0 += 64) {          // two independent 32-element chunks per turn
+            const uint32_t e[2] = {e0 + lane, e0 + 32 + lane};
+            uint32_t t[2] = {0, 0};                            // number of tasks that end at or before e
 #pragma unroll
             for (int step = 16; step > 0; step >>= 1) {
-                const uint32_t v = __shfl_sync(FULL, incl, t + step - 1);
-                if (v <= e) t += step;
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const uint32_t v = __shfl_sync(FULL, incl, t[u] + step - 1);
+                    if (v <= e[u]) t[u] += step;
+                }
             }
-            const float a_t = __shfl_sync(FULL, a, t);
-            const uint32_t dbs_t = __shfl_sync(FULL, dbs, t);
-            const uint64_t doff_t = __shfl_sync(FULL, doff, t);
-            if (e < total) {
-                const Elem b = b_data[dbs_t + e];
-                Elem o; o.idx = b.idx; o.val = __fmul_rn(a_t, b.val);     // rounded on its own: no FMA
-                bins[doff_t + e] = o;
+            float a_t[2]; uint32_t dbs_t[2]; uint64_t doff_t[2]; Elem b[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                a_t[u] = __shfl_sync(FULL, a, t[u] & 31);
+                dbs_t[u] = __shfl_sync(FULL, dbs, t[u] & 31);
+                doff_t[u] = __shfl_sync(FULL, doff, t[u] & 31);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (e[u] < total) b[u] = b_data[dbs_t[u] + e[u]];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (e[u] < total) {
+                    Elem o; o.idx = b[u].idx; o.val = __fmul_rn(a_t[u], b[u].val);     // rounded on its own: no FMA
+                    bins[doff_t[u] + e[u]] = o;
+                }
             }
         }
     }
@@ -1007,7 +1030,8 @@ struct TransposedIn {
     const uint32_t *lens;
     uint64_t RL;
     uint64_t G;
-    __device__ uint64_t operator()(uint64_t j, bool valid) const { return valid ? lens[(j % G) * RL + j / G] : 0; }
+    __device__ uint64_t load(uint64_t j, bool valid) const { return valid ? lens[(j % G) * RL + j / G] : 0; }
+    __device__ uint64_t value(uint64_t v, bool) const { return v; }
 };
 struct RowBinStrided {         // row i of the owner starts at dst_off[i * G]
     const uint64_t *off;
