@@ -214,7 +214,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     NC(ctx, d, d->nccl->GroupEnd());
     CU(ctx, ctx->bins.reserve(std::max<uint64_t>(P_local, 1) * 8));
     CU(ctx, d->recv_buf.reserve(std::max<uint64_t>(P_owned, 1) * 8));
-    CU(ctx, d->bins2.reserve(std::max<uint64_t>(P_owned, 1) * 8));
+    CU(ctx, d->bins2.reserve(std::max<uint64_t>(P_owned, 1) * 8 + 16));
     cudaEvent_t ev_sym = next_event(ctx);
     rc = launch_multiply(ctx, TaskSrcSoA{op.a_data, run_off, op.b_pos}, 0, nnz_a, P_local, op.b_data, ctx->bins.as<Elem>(), 0);
     if (rc) return rc;

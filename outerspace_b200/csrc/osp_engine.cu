@@ -39,7 +39,8 @@ struct DevBuf {
 struct osp_ctx {
     int device = 0;
     int sm_count = 148;
-    int tiles_occ[3] = {3, 3, 2};           // resident CTAs per SM of k_merge_tiles: u32 keys, u64 keys, bitmap mode
+    size_t l2_bytes = 126u << 20;
+    int chain_occ = 1;                      // resident CTAs per SM of k_merge_chain
     size_t total_mem = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;      // long-row merge kernels run beside the tile merge
@@ -113,10 +114,6 @@ cudaEvent_t next_event(osp_ctx *ctx) {
     } while (0)
 
 constexpr size_t LONG_SMEM = size_t(MT_XL) * 12 + 34 * 4;
-// dynamic shared memory of k_merge_tiles: per warp one row of scratch (+ the bitmap scratch)
-size_t tiles_smem(bool bitmap) {
-    return size_t(MW_THREADS / 32) * (size_t(MT_LONG) * 8 + (bitmap ? BM_SCRATCH : 0));
-}
 
 unsigned int grid_for(uint64_t items, unsigned int per_block, unsigned int max_blocks) {
     uint64_t b = (items + per_block - 1) / per_block;
@@ -174,10 +171,10 @@ struct MergeJob {
     uint64_t c_cap = 0;
 };
 
-// Scratch that depends on the plan's results: look-back states of the C.pos scan, per-row survivor
-// counts, the dense accumulators of the longest rows.
+// Scratch that depends on the plan's results: look-back states of the tile chain, survivor counts of the
+// long rows, the dense accumulators of the longest rows.
 int reserve_merge(osp_ctx *ctx, const MergeJob &job, unsigned int &xl_ctas) {
-    CU(ctx, ctx->tile_state.reserve(scan_tiles(std::max<uint64_t>(job.rows, 1)) * 8));
+    CU(ctx, ctx->tile_state.reserve((uint64_t(job.n_tiles) + 1) * 8));
     CU(ctx, ctx->uniq.reserve(std::max<uint64_t>(job.rows, 1) * 4));
     xl_ctas = 0;
     if (job.n_xl && job.idx_range > DENSE_MAX_COLS) {
@@ -201,60 +198,35 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
     if (t1 <= t0 || row_hi <= row_lo) return OSP_OK;
     const uint64_t *row_bin = ctx->row_bin.as<uint64_t>();
     uint32_t *uniq = ctx->uniq.as<uint32_t>();
-    // long rows on a second stream, beside the tile merge (disjoint rows, disjoint bins)
-    const bool fork = (job.n_long || job.n_xl) && !ctx->profile_kernels;
-    if (fork) {
-        CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-        CU(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-    }
-    {
-        cudaStream_t main_stream = ctx->stream;
-        if (fork) ctx->stream = ctx->stream2;          // LAUNCH uses ctx->stream
-        int rc2 = [&]() -> int {
-            if (!job.n_long && !job.n_xl) return OSP_OK;
-            if (job.idx_range <= DENSE_MAX_COLS) {
-                // small column range: every long row goes through the dense shared-memory accumulator
-                const size_t sm = dense_smem(job.idx_range);
-                const unsigned per_sm = unsigned(std::max<size_t>(1, std::min<size_t>(4, (200u << 10) / sm)));
-                LAUNCH(ctx, k_merge_dense, std::min<unsigned>(job.n_long + job.n_xl, unsigned(ctx->sm_count) * per_sm), DENSE_THREADS,
-                       sm, row_bin, bin_base, bins, uniq, ctx->long_list.as<uint32_t>(), ctx->xl_list.as<uint32_t>(), ctx->d_sc,
-                       uint32_t(job.idx_range), row_lo, row_hi);
-                return OSP_OK;
-            }
+    // long rows first (in place, survivors counted): the chain copies them when it reaches their tile
+    if (job.n_long || job.n_xl) {
+        if (job.idx_range <= DENSE_MAX_COLS) {
+            // small column range: every long row goes through the dense shared-memory accumulator
+            const size_t sm = dense_smem(job.idx_range);
+            const unsigned per_sm = unsigned(std::max<size_t>(1, std::min<size_t>(4, (200u << 10) / sm)));
+            LAUNCH(ctx, k_merge_dense, std::min<unsigned>(job.n_long + job.n_xl, unsigned(ctx->sm_count) * per_sm), DENSE_THREADS,
+                   sm, row_bin, bin_base, bins, uniq, ctx->long_list.as<uint32_t>(), ctx->xl_list.as<uint32_t>(), ctx->d_sc,
+                   uint32_t(job.idx_range), row_lo, row_hi);
+        } else {
             if (job.n_long)
                 LAUNCH(ctx, k_merge_long, std::min<unsigned>(job.n_long, unsigned(ctx->sm_count) * 4u), 256, LONG_SMEM, row_bin,
                        bin_base, bins, uniq, ctx->long_list.as<uint32_t>(), ctx->d_sc, row_lo, row_hi);
             if (job.n_xl)
                 LAUNCH(ctx, k_merge_xl, xl_ctas, 256, LONG_SMEM, row_bin, bin_base, bins, uniq, ctx->xl_list.as<uint32_t>(),
                        ctx->d_sc, ctx->xl_acc.as<float>(), ctx->xl_bits.as<uint32_t>(), job.idx_range, row_lo, row_hi);
-            return OSP_OK;
-        }();
-        ctx->stream = main_stream;
-        if (rc2) return rc2;
-        if (fork) CU(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+        }
     }
-    const bool k32 = job.idx_range <= (1ull << 23);
-    const uint32_t bm_words = job.idx_range <= 32ull * BM_WORDS ? uint32_t((job.idx_range + 31) / 32) : 0u;
-    const int variant = bm_words ? 2 : k32 ? 0 : 1;
-    const unsigned int warps_per_cta = MW_THREADS / 32;
-    const unsigned int grid = std::min<unsigned>((t1 - t0 + warps_per_cta - 1) / warps_per_cta,
-                                                 unsigned(ctx->sm_count) * unsigned(ctx->tiles_occ[variant]));
-    const size_t smem = tiles_smem(bm_words != 0);
-#define MT_ARGS row_bin, bin_base, bins, ctx->tile_row.as<uint32_t>(), bm_words, t0, t1, uniq
-    if (variant == 2) LAUNCH(ctx, (k_merge_tiles<uint32_t, true>), grid, MW_THREADS, smem, MT_ARGS);
-    else if (variant == 0) LAUNCH(ctx, (k_merge_tiles<uint32_t, false>), grid, MW_THREADS, smem, MT_ARGS);
-    else LAUNCH(ctx, (k_merge_tiles<uint64_t, false>), grid, MW_THREADS, smem, MT_ARGS);
-#undef MT_ARGS
-    if (fork) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    // survivors per row -> C.pos (running total carried across row blocks), then the rows into C.data
-    const uint64_t n = row_hi - row_lo;
-    CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, scan_tiles(n) * 8, ctx->stream));
-    CU(ctx, cudaMemsetAsync(&ctx->d_sc->scan_ticket[3], 0, 4, ctx->stream));
-    LAUNCH(ctx, (k_scan<U32In, U64OutCarry>), unsigned(scan_tiles(n)), SCAN_BLOCK, 0, U32In{uniq + row_lo},
-           U64OutCarry{job.c_pos + row_lo, &ctx->d_sc->nnz_c[block & 1], &ctx->d_sc->nnz_c[(block + 1) & 1], n}, n,
-           ctx->tile_state.as<uint64_t>(), &ctx->d_sc->scan_ticket[3]);
-    LAUNCH(ctx, k_gather_rows, std::min<unsigned>((t1 - t0 + 7) / 8, unsigned(ctx->sm_count) * 8u), 256, 0, row_bin, bin_base,
-           bins, ctx->tile_row.as<uint32_t>(), t0, t1, uniq, job.c_pos, job.c_data);
+    // one pass from the bins to C: tiles in row order, chained by a decoupled look-back (C.pos on the way)
+    const uint32_t n_chain = t1 - t0;
+    CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, uint64_t(n_chain) * 8, ctx->stream));
+    CU(ctx, cudaMemsetAsync(&ctx->d_sc->tile_ticket, 0, 4, ctx->stream));
+    const int carry_slot = int(block & 1);
+#define MC_ARGS row_bin, bin_base, bins, ctx->tile_row.as<uint32_t>(), t0, n_chain, uniq, ctx->tile_state.as<uint64_t>(), ctx->d_sc, \
+                carry_slot, job.c_pos, job.c_data
+    const unsigned int grid = std::min<unsigned>(n_chain, unsigned(ctx->sm_count) * unsigned(ctx->chain_occ));   // persistent CTAs
+    if (job.idx_range <= (1ull << 23)) LAUNCH(ctx, k_merge_chain<uint32_t>, grid, MC_THREADS, sizeof(MergeChainSmem), MC_ARGS);
+    else LAUNCH(ctx, k_merge_chain<uint64_t>, grid, MC_THREADS, sizeof(MergeChainSmem), MC_ARGS);
+#undef MC_ARGS
     return OSP_OK;
 }
 
@@ -277,7 +249,7 @@ int csr2csc_device(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint6
     LAUNCH(ctx, (k_scan<U32In, U64Out>), unsigned(st[0]), SCAN_BLOCK, 0, U32In{cnt}, U64Out{d_pos_out}, n_minor, ar.state[0],
            &ctx->d_sc->scan_ticket[0]);
     CU(ctx, cudaMemsetAsync(cnt, 0, n_minor * 4, ctx->stream));
-    CU(ctx, ctx->conv_tmp.reserve(nnz * 8));
+    CU(ctx, ctx->conv_tmp.reserve(nnz * 8 + 16));
     LAUNCH(ctx, k_scatter_elems, grid_for(n_major, 8, unsigned(ctx->sm_count) * 16u), 256, 0, d_pos, d_data, n_major, n_minor,
            d_pos_out, cnt, ctx->conv_tmp.as<Elem>(), ctx->d_sc);
     rc = reserve_plan(ctx, n_minor, std::min(n_minor, nnz));
@@ -397,6 +369,7 @@ int osp_create(int device, osp_ctx **out) {
     CU(nullptr, cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     ctx->total_mem = prop.totalGlobalMem;
+    if (prop.l2CacheSize > 0) ctx->l2_bytes = size_t(prop.l2CacheSize);
     CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     CU(nullptr, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -406,16 +379,15 @@ int osp_create(int device, osp_ctx **out) {
     CU(nullptr, cudaFuncSetAttribute(k_merge_xl, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LONG_SMEM)));
     CU(nullptr, cudaFuncSetAttribute(k_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dense_smem(DENSE_MAX_COLS))));
     {
-        auto k32 = k_merge_tiles<uint32_t, false>;
-        auto k64 = k_merge_tiles<uint64_t, false>;
-        auto kbm = k_merge_tiles<uint32_t, true>;
-        CU(nullptr, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tiles_smem(false))));
-        CU(nullptr, cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tiles_smem(false))));
-        CU(nullptr, cudaFuncSetAttribute(kbm, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tiles_smem(true))));
-        CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->tiles_occ[0], k32, MW_THREADS, tiles_smem(false)));
-        CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->tiles_occ[1], k64, MW_THREADS, tiles_smem(false)));
-        CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->tiles_occ[2], kbm, MW_THREADS, tiles_smem(true)));
-        for (int &o : ctx->tiles_occ) o = std::max(o, 1);
+        auto k32 = k_merge_chain<uint32_t>;
+        auto k64 = k_merge_chain<uint64_t>;
+        CU(nullptr, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MergeChainSmem))));
+        CU(nullptr, cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MergeChainSmem))));
+        // persistent grid: never more CTAs than can be resident (a waiting CTA must not keep a ticket holder off the machine)
+        int o32 = 1, o64 = 1;
+        CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o32, k32, MC_THREADS, sizeof(MergeChainSmem)));
+        CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o64, k64, MC_THREADS, sizeof(MergeChainSmem)));
+        ctx->chain_occ = std::max(1, std::min(o32, o64));
     }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -462,7 +434,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     *out = nullptr;
     if (!args->a_pos || !args->b_pos) return fail(ctx, OSP_ERR_INVALID, "osp_spgemm: NULL pos array");
     const bool a_is_csr = args->flags & OSP_A_IS_CSR;
-    bool rowwise = args->flags & OSP_ROWWISE_ORDER;
+    bool rowwise = args->flags & OSP_ROWWISE_ORDER;   // settled below once nnz(A), nnz(B) are known
     // k-dimension check: lmat.NRow() == rmat.NRow(), SimOuterSPACE.cpp:47
     if (!a_is_csr && args->a_slices != args->n_k)
         return fail(ctx, OSP_ERR_INVALID, "osp_spgemm: CSC(A) and CSR(B) must have the same number of slices");
@@ -510,6 +482,14 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     const uint64_t m_plan = std::max<uint64_t>({m_a, args->rows_c, 1});
     const uint64_t limit_elems = std::max<uint64_t>(ctx->ws_limit / 8, 1);
 
+    // ---- multiply order: outer-product (k-slice) order while the bins are expected to stay in L2 -- B is
+    // streamed once and the scattered 8-byte bin writes are absorbed by L2 -- and row order beyond, where the
+    // bins are written as ONE stream and the rows of B are gathered instead (measured: profiles/README.md).
+    // Expected P = nnz(A) nnz(B) / n_k (exact in expectation for uniform operands).
+    if (!(args->flags & (OSP_ROWWISE_ORDER | OSP_KSLICE_ORDER))) {
+        const double p_est = n_k ? double(nnz_a) * double(nnz_b) / double(n_k) : 0.0;
+        rowwise = p_est * 8.0 > double(ctx->l2_bytes) * 0.5;
+    }
     // ---- symbolic pass, merge plan, CSR->CSC task list: launched back to back -------------------
     Arena ar;
     const uint64_t st[4] = {scan_tiles(std::max<uint64_t>(nnz_a, 1)), plan_tiles(m_plan), scan_tiles(std::max<uint64_t>(n_k, 1)), 0};
@@ -611,7 +591,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     const size_t n_blocks = tb.size() - 1;
     uint64_t max_block = 0;
     for (size_t b = 0; b < n_blocks; b++) max_block = std::max(max_block, blk_bin[b + 1] - blk_bin[b]);
-    rc = [&]() -> int { CU(ctx, ctx->bins.reserve(std::max<uint64_t>(max_block, 1) * 8)); return OSP_OK; }();
+    rc = [&]() -> int { CU(ctx, ctx->bins.reserve(std::max<uint64_t>(max_block, 1) * 8 + 16)); return OSP_OK; }();
     if (rc) return bail(rc);
     Elem *bins = ctx->bins.as<Elem>();
 

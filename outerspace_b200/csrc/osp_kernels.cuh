@@ -13,6 +13,7 @@
 //                           writing CSRMatrix mergedResult (SimOuterSPACE.cpp:140) directly
 #pragma once
 #include "osp_device.cuh"
+#include <cstddef>
 
 namespace osp {
 
@@ -156,10 +157,11 @@ __global__ void k_max_idx(const Elem *d, uint64_t nnz, DevScalars *sc) {
 // Also: row_bin[] (bin start of every row), the queues of long rows, the upper bound of nnz(C)
 // and the reference's row count rule numRows = maxRowId + 1 (SimOuterSPACE.cpp:49-53).
 // =====================================================================================
-constexpr uint32_t MT_CAP = 512;       // partial products per tile (soft, = 2^9): one warp merges a tile
+constexpr int MT_CAP_SHIFT_MIN = 8, MT_CAP_SHIFT_MAX = 11;
+constexpr uint32_t MT_CAP = 1u << MT_CAP_SHIFT_MAX;   // partial products per tile (soft): one CTA merges a tile
 constexpr uint32_t MT_LONG = 512;      // longest row sorted in registers by one warp
-constexpr uint32_t MT_STAGE = MT_CAP + MT_LONG;
-constexpr uint32_t MT_RMAX = 32;       // rows per tile (one lane per row)
+constexpr uint32_t MT_STAGE = MT_CAP + MT_LONG;       // hard bound of a tile of short rows (shared-memory stage)
+constexpr uint32_t MT_RMAX = 256;      // rows per tile (one thread per row in the tile's scans)
 constexpr uint32_t MT_XL = 4096;       // longest row sorted in shared memory by one CTA
 
 constexpr int PLAN_BLOCK = 256;
@@ -196,9 +198,10 @@ k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *ti
     const unsigned int lane = lane_id(), warp = threadIdx.x >> 5;
     const uint64_t i0 = uint64_t(tile) * PLAN_TILE + uint64_t(threadIdx.x) * PLAN_ITEMS;
     // partial products per tile: MT_CAP, less when the whole product is small, so that there are enough
-    // tiles (one warp each) to fill the machine: 2^cap_shift ~ P / 4096 within [32, MT_CAP]
-    int cap_shift = 5;
-    while (cap_shift < 9 && (sc->products >> (cap_shift + 1)) >= 4096) cap_shift++;
+    // tiles for every persistent CTA of the merge (444 on a B200): 2^cap_shift ~ P / 1024 within [256, MT_CAP]
+    const uint64_t p_all = rb(rows);
+    int cap_shift = MT_CAP_SHIFT_MIN;
+    while (cap_shift < MT_CAP_SHIFT_MAX && (p_all >> (cap_shift + 1)) >= 1024) cap_shift++;
 
     uint64_t s[PLAN_ITEMS + 1];
 #pragma unroll
@@ -607,379 +610,445 @@ k_merge_dense(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bin
 }
 
 // =====================================================================================
-// Merge of one short row by one warp, building blocks:
-//   bitonic_regs      sorts 32*E keys (col << pb | arrival position) held E per lane in registers
-//                     (compare-exchange over shuffles);
-//   merge_row_regs    loads a row's bin (coalesced), sorts, left-folds equal columns in arrival (= k)
-//                     order with separately rounded adds, writes the compacted row;
-//   merge_row_bitmap  the same result without a sort, for small column ranges.
+// Merge of short rows, building blocks:
+//   sort_grouped        sorts (col << pb | arrival position) keys held E per lane in registers, one row per
+//                       group of 2^T lanes (flip-bitonic network over VIMNMX and shuffles);
+//   merge_rows_grouped  reads the rows' partial products from the shared-memory stage of their tile, sorts,
+//                       left-folds equal columns in arrival (= k) order with separately rounded adds and
+//                       writes the compacted rows into the tile's output stage.
 // =====================================================================================
+template <int V> struct ILog2 { static constexpr int value = 1 + ILog2<V / 2>::value; };
+template <> struct ILog2<1> { static constexpr int value = 0; };
+
+
+// Output stage of a tile: element s lives at ostage[swz(s)].  The XOR swizzle spreads the blocked writes
+// of the sorted rows (lane l holds sorted positions l*E .. l*E+E-1) over all banks and keeps linear reads
+// conflict-free (it permutes inside aligned groups of 16 elements = 128 B).
+__device__ __forceinline__ uint32_t swz(uint32_t s) { return s ^ ((s >> 4) & 15u); }
+
+// ---- grouped sort: several short rows per warp ------------------------------------------------------
+// A row of len <= N = E << T partial products is sorted by a group of G = 1 << T lanes, E keys per lane,
+// so a warp sorts 32 / G rows at once.  Bitonic network in its "flip" form: the first stage of every merge
+// level compares i with i ^ (k - 1), the others i with i ^ j, and EVERY compare-exchange is ascending --
+// the in-lane stages have compile-time partners and directions (two VIMNMX per pair), the cross-lane stages
+// one shuffle and a min-or-max per key.  Levels up to E run inside a lane; T more levels cross lanes.
+// T is a template parameter: the whole network is straight-line code, no register moves at loop edges.
+extern __shared__ __align__(16) unsigned char osp_smem[];     // the dynamic shared memory of every kernel here
+__device__ __forceinline__ uint32_t &smem_u32_at(uint32_t off) { return *reinterpret_cast<uint32_t *>(osp_smem + off); }
+__device__ __forceinline__ float &smem_f32_at(uint32_t off) { return *reinterpret_cast<float *>(osp_smem + off); }
+__device__ __forceinline__ uint2 &smem_u2_at(uint32_t off) { return *reinterpret_cast<uint2 *>(osp_smem + off); }
+
 template <int E, class K>
-__device__ __forceinline__ void bitonic_regs(K (&x)[E], const unsigned int lane) {
-    constexpr int N = 32 * E;
-    if constexpr (E <= 4) {
-        // short rows: the whole network unrolled (a loop would cost as much as its body here)
+__device__ __forceinline__ void ce_inlane(K (&x)[E], const int a, const int b) {
+    const K lo = min(x[a], x[b]), hi = max(x[a], x[b]);
+    x[a] = lo; x[b] = hi;
+}
+template <int E, int T, class K>
+__device__ __forceinline__ void sort_grouped(K (&x)[E], const unsigned int lig) {
 #pragma unroll
-        for (int k = 2; k <= N; k <<= 1) {
+    for (int k = 2; k <= E; k <<= 1) {
 #pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                if (j >= E) {                       // partner in lane ^ (j / E), same register
-                    const int lj = j / E;
-                    const bool keep_min = ((lane & lj) == 0) == (((lane * E) & k) == 0);
+        for (int e = 0; e < E; e++)
+            if (e < (e ^ (k - 1))) ce_inlane<E, K>(x, e, e ^ (k - 1));
 #pragma unroll
-                    for (int e = 0; e < E; e++) {
-                        const K y = __shfl_xor_sync(FULL, x[e], lj);
-                        x[e] = keep_min ? min(x[e], y) : max(x[e], y);
-                    }
-                } else {                            // both elements in this lane
+        for (int j = k >> 2; j > 0; j >>= 1) {
 #pragma unroll
-                    for (int e = 0; e < E; e++) {
-                        if ((e & j) == 0) {
-                            const K lo = min(x[e], x[e | j]), hi = max(x[e], x[e | j]);
-                            const bool up = k < E ? ((e & k) == 0) : (((lane * E) & k) == 0);   // i = lane*E + e
-                            x[e] = up ? lo : hi;
-                            x[e | j] = up ? hi : lo;
-                        }
-                    }
-                }
+            for (int e = 0; e < E; e++)
+                if ((e & j) == 0) ce_inlane<E, K>(x, e, e | j);
+        }
+    }
+#pragma unroll
+    for (int t = 1; t <= T; t++) {
+        {   // flip stage: (lane, e) <-> (lane ^ (2^t - 1), E - 1 - e); the lane whose bit t-1 is clear keeps the minima
+            const bool keep_min = ((lig >> (t - 1)) & 1u) == 0;
+            K y[E];
+#pragma unroll
+            for (int e = 0; e < E; e++) y[e] = __shfl_xor_sync(FULL, x[E - 1 - e], (1 << t) - 1);
+#pragma unroll
+            for (int e = 0; e < E; e++) x[e] = keep_min ? min(x[e], y[e]) : max(x[e], y[e]);
+        }
+#pragma unroll
+        for (int lj = (1 << t) >> 2; lj > 0; lj >>= 1) {
+            const bool keep_min = (lig & lj) == 0;
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                const K y = __shfl_xor_sync(FULL, x[e], lj);
+                x[e] = keep_min ? min(x[e], y) : max(x[e], y);
             }
         }
-    } else {
-        // levels k = 2 .. E: both partners in this lane (compile-time register pairs and directions)
 #pragma unroll
-        for (int k = 2; k <= E; k <<= 1) {
+        for (int j = E >> 1; j > 0; j >>= 1) {
 #pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-                for (int e = 0; e < E; e++) {
-                    if ((e & j) == 0) {
-                        const K lo = min(x[e], x[e | j]), hi = max(x[e], x[e | j]);
-                        const bool up = k < E ? ((e & k) == 0) : ((lane & 1) == 0);   // i = lane*E + e
-                        x[e] = up ? lo : hi;
-                        x[e | j] = up ? hi : lo;
-                    }
-                }
-            }
-        }
-        // levels k = 2E .. N: a runtime loop (keeps the code small enough for the instruction cache):
-        // partners in lane ^ (j / E) while j >= E, then the in-lane tail j = E/2 .. 1
-#pragma unroll 1
-        for (int k = 2 * E; k <= N; k <<= 1) {
-            const bool up = ((lane * E) & k) == 0;
-#pragma unroll 1
-            for (int lj = k / (2 * E); lj > 0; lj >>= 1) {
-                const bool keep_min = ((lane & lj) == 0) == up;
-#pragma unroll
-                for (int e = 0; e < E; e++) {
-                    const K y = __shfl_xor_sync(FULL, x[e], lj);
-                    x[e] = keep_min ? min(x[e], y) : max(x[e], y);
-                }
-            }
-#pragma unroll
-            for (int j = E >> 1; j > 0; j >>= 1) {
-#pragma unroll
-                for (int e = 0; e < E; e++) {
-                    if ((e & j) == 0) {
-                        const K lo = min(x[e], x[e | j]), hi = max(x[e], x[e | j]);
-                        x[e] = up ? lo : hi;
-                        x[e | j] = up ? hi : lo;
-                    }
-                }
-            }
+            for (int e = 0; e < E; e++)
+                if ((e & j) == 0) ce_inlane<E, K>(x, e, e | j);
         }
     }
 }
 
-template <int V> struct ILog2 { static constexpr int value = 1 + ILog2<V / 2>::value; };
-template <> struct ILog2<1> { static constexpr int value = 0; };
-
-// One warp merges one row of 2 <= len <= 32*E partial products.  `src` = the row's bin in global
-// memory, `region` = a len-element scratch in shared memory, `out` = where the compacted row goes (may
-// be `src`: every input is in registers before the first output is written).  Returns the number of
-// surviving entries.
-template <int E, class K>
-__device__ __forceinline__ uint32_t merge_row_regs(const Elem *src, Elem *region, Elem *out, const uint32_t len,
-                                                   const unsigned int lane) {
-    constexpr int N = 32 * E;
-    constexpr int PB = ILog2<N>::value;
+// Groups of G = 1 << T lanes merge one row each (2 <= len <= E << T; len = 0: the group idles).  `row_off`,
+// `o0`, `len` are the group's own (uniform inside a group): the byte offset in shared memory of the row's
+// partial products in the tile's input stage (reused as fold scratch once every input is in registers) and
+// the index of the row's first element in the output stage at byte offset `ost_off`.  Returns the row's
+// number of surviving entries.
+template <int E, int T, class K>
+__device__ __forceinline__ uint32_t merge_rows_grouped(const uint32_t row_off, const uint32_t ost_off, const uint32_t o0,
+                                                       const uint32_t len, const unsigned int lane) {
+    constexpr int LE = ILog2<E>::value;
+    constexpr uint32_t G = 1u << T, PB = LE + T, N = uint32_t(E) << T;
+    const uint32_t lig = lane & (G - 1);
     K key[E];
-    float *fstage = reinterpret_cast<float *>(region);
+    {
+        const uint32_t a0 = row_off + lig * 8;
 #pragma unroll
-    for (int e = 0; e < E; e++) {
-        const uint32_t p = e * 32 + lane;
-        key[e] = ~K(0);
-        if (p < len) {
-            const Elem el = src[p];
-            key[e] = (K(el.idx) << PB) | K(p);
-            fstage[p] = el.val;
+        for (int e = 0; e < E; e++) {
+            const uint32_t p = uint32_t(e) * G + lig;
+            const K k = (K(smem_u32_at(a0 + uint32_t(e) * G * 8)) << PB) | K(p);    // past the row: harmless bytes of the stage
+            key[e] = p < len ? k : ~K(0);
         }
     }
-    __syncwarp();
-    bitonic_regs<E, K>(key, lane);
-    // lane now holds sorted positions lane*E .. lane*E+E-1
+    sort_grouped<E, T, K>(key, lig);
+    // lane now holds the sorted positions lig*E .. lig*E+E-1 of its group's row
     uint32_t col[E];
     float v[E];
 #pragma unroll
     for (int e = 0; e < E; e++) {
-        const uint32_t s = lane * E + e;
         col[e] = uint32_t(key[e] >> PB);
-        v[e] = s < len ? fstage[uint32_t(key[e]) & (N - 1)] : 0.f;
+        v[e] = smem_f32_at(row_off + 4 + (uint32_t(key[e]) & (N - 1)) * 8);       // padding keys read harmless bytes
     }
-    // heads (first arrival of a column); most rows hold no duplicate column at all: then the sorted
-    // row IS the result
+    const uint32_t s0 = lig * E;
     uint32_t prev = __shfl_up_sync(FULL, col[E - 1], 1);
-    const uint32_t next_first = __shfl_down_sync(FULL, col[0], 1);   // padding (all ones >> PB) past the end
+    const uint32_t next_first = __shfl_down_sync(FULL, col[0], 1);
     {
         bool dup = false;
         uint32_t pc = prev;
 #pragma unroll
         for (int e = 0; e < E; e++) {
-            const uint32_t s = lane * E + e;
-            dup |= s < len && s > 0 && pc == col[e];
+            dup |= s0 + e < len && s0 + e > 0 && pc == col[e];
             pc = col[e];
         }
-        if (!__any_sync(FULL, dup)) {
-            __syncwarp();
+        if (!__any_sync(FULL, dup)) {               // no duplicate column in any of the rows: sorted = merged
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                const uint32_t s = lane * E + e;
-                if (s < len) { Elem o; o.idx = col[e]; o.val = v[e]; out[s] = o; }
-            }
+            for (int e = 0; e < E; e++)
+                if (s0 + e < len) smem_u2_at(ost_off + swz(o0 + s0 + e) * 8) = make_uint2(col[e], __float_as_uint(v[e]));
             return len;
         }
     }
-    __syncwarp();
-    uint32_t *scol = reinterpret_cast<uint32_t *>(region);
-    float *sval = fstage + len;
+    __syncwarp();                                   // every lane has read its inputs: the rows become scratch
+    uint32_t *scol = reinterpret_cast<uint32_t *>(osp_smem + row_off);
+    float *sval = reinterpret_cast<float *>(osp_smem + row_off) + len;
+    Elem *ostage = reinterpret_cast<Elem *>(osp_smem + ost_off);
 #pragma unroll
-    for (int e = 0; e < E; e++) {
-        const uint32_t s = lane * E + e;
-        if (s < len) { scol[s] = col[e]; sval[s] = v[e]; }
-    }
+    for (int e = 0; e < E; e++)
+        if (s0 + e < len) { scol[s0 + e] = col[e]; sval[s0 + e] = v[e]; }
     __syncwarp();
-    // left folds of the heads
+    // left folds of the heads (first arrival of a column), in arrival (= k) order
     bool head[E];
     uint32_t nheads = 0;
 #pragma unroll
     for (int e = 0; e < E; e++) {
-        const uint32_t s = lane * E + e;
+        const uint32_t s = s0 + e;
         head[e] = s < len && (s == 0 || prev != col[e]);
         prev = col[e];
         if (head[e]) {
             nheads++;
             const uint32_t nxt = e + 1 < E ? col[e + 1 < E ? e + 1 : 0] : next_first;
-            const bool more = s + 1 < len && nxt == col[e];
-            if (more) {
+            if (s + 1 < len && nxt == col[e]) {
                 float sum = v[e];
                 for (uint32_t u = s + 1; u < len && scol[u] == col[e]; u++) sum = __fadd_rn(sum, sval[u]);
                 v[e] = sum;
             }
         }
     }
-    const uint32_t incl = warp_inclusive_scan(nheads);
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    uint32_t r = incl - nheads;
-    __syncwarp();
+    uint32_t incl = nheads;                          // inclusive scan inside the group
+#pragma unroll
+    for (uint32_t o = 1; o < G; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, incl, o);
+        if (lig >= o) incl += y;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, lane | (G - 1));
+    uint32_t r = o0 + incl - nheads;
 #pragma unroll
     for (int e = 0; e < E; e++) {
         if (head[e]) {
             Elem o; o.idx = col[e]; o.val = v[e];
-            out[r++] = o;
+            ostage[swz(r++)] = o;
         }
     }
     return total;
 }
 
-// ---- bitmap-rank merge of one row (column range <= 32 * BM_WORDS) -----------------------------------
-// No sort: every partial product sets the bit of its column in a per-warp bitmap, a prefix popcount over
-// the bitmap words turns a column into its rank among the row's distinct columns (= its place in the
-// sorted, folded row), the earliest arrival of a column opens that place and later arrivals are added in
-// arrival (= k) order.  Shared-memory read-modify-writes are plain loads/stores re-checked after a
-// __syncwarp and retried by the lanes that lost a race (shared atomics cost ~2 cycles per lane; races
-// here are rare).  Runtime loops over the 32-element slots of the row keep the code small: the unrolled
-// per-E variants of an earlier version thrashed the instruction cache (profiles/README.md).
-constexpr uint32_t BM_WORDS = 512;                 // bitmap words per warp: columns < 16384
-// per-warp scratch: bitmap | word prefixes (u16) | first arrival per rank (u16) | rank per element (u16)
-constexpr uint32_t BM_SCRATCH = BM_WORDS * 4 + BM_WORDS * 2 + MT_LONG * 2 + MT_LONG * 2;
-
-__device__ __noinline__ uint32_t merge_row_bitmap(Elem *bin, Elem *region, const uint32_t len, const uint32_t words,
-                                                  unsigned char *scratch, const unsigned int lane) {
-    uint32_t *bm = reinterpret_cast<uint32_t *>(scratch);
-    uint16_t *pre = reinterpret_cast<uint16_t *>(scratch + BM_WORDS * 4);
-    uint16_t *first = reinterpret_cast<uint16_t *>(scratch + BM_WORDS * 4 + BM_WORDS * 2);
-    uint16_t *rnk = first + MT_LONG;
-    const uint32_t wpl = (((words + 31) >> 5) + 3) & ~3u;        // bitmap words per lane, multiple of 4, <= 16
-    // lane owns the words {4*lane + 32*q .. +3}: conflict-free 128-bit accesses
-    for (uint32_t q = 0; q < wpl; q += 4) *reinterpret_cast<uint4 *>(bm + 4 * lane + 32 * q) = make_uint4(0, 0, 0, 0);
-    for (uint32_t q = lane; q < (len + 1) / 2; q += 32) reinterpret_cast<uint32_t *>(first)[q] = 0xFFFFFFFFu;
-    for (uint32_t p = lane; p < len; p += 32) region[p] = bin[p];          // stage the row (the bin is overwritten below)
-    __syncwarp();
-    // set the bits
-    for (uint32_t p0 = 0; p0 < len; p0 += 32) {
-        const uint32_t p = p0 + lane;
-        bool pend = p < len;
-        const uint32_t col = pend ? region[p].idx : 0;
-        const uint32_t w = col >> 5, bit = 1u << (col & 31);
-        do {
-            if (pend) { const uint32_t cur = bm[w]; if (!(cur & bit)) bm[w] = cur | bit; }
-            __syncwarp();
-            if (pend) pend = !(bm[w] & bit);
-        } while (__any_sync(FULL, pend));
-    }
-    __syncwarp();
-    // exclusive prefix popcount over the words, in word order (chunk q of every lane, then chunk q+4, ...)
-    uint32_t uniq = 0;
-    for (uint32_t q = 0; q < wpl; q += 4) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(bm + 4 * lane + 32 * q);
-        const uint32_t c0 = __popc(v.x), c1 = __popc(v.y), c2 = __popc(v.z), c3 = __popc(v.w);
-        const uint32_t cnt = c0 + c1 + c2 + c3;
-        const uint32_t incl = warp_inclusive_scan(cnt);
-        const uint32_t b0 = uniq + incl - cnt;
-        uint2 pk;
-        pk.x = b0 | ((b0 + c0) << 16);
-        pk.y = (b0 + c0 + c1) | ((b0 + c0 + c1 + c2) << 16);
-        *reinterpret_cast<uint2 *>(pre + 4 * lane + 32 * q) = pk;
-        uniq += __shfl_sync(FULL, incl, 31);
-    }
-    __syncwarp();
-    // rank of every partial product; the smallest position of a rank opens its place (slots ascend in position)
-    for (uint32_t p0 = 0; p0 < len; p0 += 32) {
-        const uint32_t p = p0 + lane;
-        const bool valid = p < len;
-        const uint32_t col = valid ? region[p].idx : 0;
-        const uint32_t w = col >> 5;
-        const uint32_t r = valid ? pre[w] + __popc(bm[w] & ((1u << (col & 31)) - 1)) : 0;
-        if (valid) rnk[p] = uint16_t(r);
-        bool want = valid;
-        do {
-            if (want && first[r] > p) first[r] = uint16_t(p);
-            __syncwarp();
-            want = valid && first[r] > p;
-        } while (__any_sync(FULL, want));
-    }
-    __syncwarp();
-    // first arrivals write their entry; later arrivals are flagged (top bit of rnk)
-    bool any_loser = false;
-    for (uint32_t p0 = 0; p0 < len; p0 += 32) {
-        const uint32_t p = p0 + lane;
-        if (p < len) {
-            const uint32_t r = rnk[p];
-            if (first[r] == p) bin[r] = region[p];
-            else { rnk[p] = uint16_t(r | 0x8000u); any_loser = true; }
-        }
-    }
-    __syncwarp();
-    // later arrivals are added in arrival order: slot after slot, inside a slot lowest lane first
-    if (__any_sync(FULL, any_loser)) {
-        for (uint32_t p0 = 0; p0 < len; p0 += 32) {
-            const uint32_t p = p0 + lane;
-            const uint32_t rr = p < len ? rnk[p] : 0;
-            bool pending = (rr & 0x8000u) != 0;
-            const uint32_t r = rr & 0x7FFFu;
-            while (__any_sync(FULL, pending)) {
-                if (pending) { const uint32_t cur = first[r]; if (!(cur & 0x8000u) || (cur & 0x7FFFu) > lane) first[r] = uint16_t(0x8000u | lane); }
-                __syncwarp();
-                const bool mine = pending && first[r] == (0x8000u | lane);
-                __syncwarp();
-                if (mine) {
-                    bin[r].val = __fadd_rn(__ldcg(&bin[r].val), region[p].val);
-                    first[r] = 0;
-                    pending = false;
-                }
-                __syncwarp();
-            }
-        }
-    }
-    return uniq;
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) and its mbarrier ---------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
 }
 
 // =====================================================================================
-// Merge, the main kernel.  Every warp takes tiles of consecutive short rows (<= 32 rows, one lane
-// per row; < MT_CAP + MT_LONG partial products) and merges the rows one after the other: register
-// bitonic sort or bitmap rank, then the k-ordered left fold.  The compacted row is written back over
-// the start of its own bin and uniq[row] = surviving entries.  Tiles are independent: no ordering,
-// no look-back, no CTA barrier.  (A chained single-pass variant that wrote C directly was measured
-// and dropped: with thousands of tiles in flight the look-back wave and in-order retirement cost more
-// than the extra pass -- profiles/README.md.)  k_scan over uniq[] then gives C.pos and k_gather_rows
-// moves the rows into C.data.
-// K = uint32_t when col << 9 fits 32 bits (cols <= 2^23), else uint64_t; BM enables the bitmap method.
+// Merge, the main kernel: one pass from the partial-product bins to CSR C.
+// Persistent CTAs take tiles in ticket (= row) order.  A tile is a run of consecutive short rows --
+// <= MT_RMAX rows, < MT_STAGE partial products, contiguous in the bins.  Per tile:
+//   1. ONE TMA bulk copy (cp.async.bulk + mbarrier) pulls the tile into shared memory;
+//   2. the warps take the rows one after the other: register bitonic sort by (col, arrival position),
+//      k-ordered left fold of equal columns, compacted row into the tile's output stage;
+//   3. a block scan of the surviving counts gives the row offsets inside the tile and the tile's aggregate,
+//      published at once for the decoupled look-back across tiles;
+//   4. the tile's offset in C is resolved and its output stage streams to C.data / C.pos ONE TILE LATER:
+//      the chain retires tiles in order, so a tile that waited for its predecessors right after its own
+//      sort would idle its CTA; deferred by one tile, the wait falls on predecessors that have had a whole
+//      sort of slack, and the next tile's bulk copy is in flight underneath.
+// C is written exactly once, in its final place.  Long rows are tiles of their own: merged in place
+// beforehand (k_merge_long / k_merge_xl / k_merge_dense, uniq[row] survivors at the start of their bin) and
+// copied here so that the chain stays in row order.
+// HBM traffic = the algorithmic minimum of the merge: 8 P read + 8 nnz(C) + 8 (m+1) written.
+// K = uint32_t when col << 9 fits 32 bits (cols <= 2^23), else uint64_t.
 // =====================================================================================
-constexpr int MW_THREADS = 256;
+constexpr int MC_THREADS = 256;
+constexpr int MC_OCC = 3;                              // resident CTAs per SM (shared memory: 3 stages each)
+static_assert(MT_RMAX == MC_THREADS, "one thread per row of a tile");
+constexpr uint32_t MC_STAGE_ELEMS = MT_STAGE + 16;     // + alignment shift, rounded for the swizzle groups
+struct __align__(16) MergeChainSmem {
+    Elem stage[MC_STAGE_ELEMS];        // input of the tile being sorted (TMA destination)
+    Elem ostage[2][MC_STAGE_ELEMS];    // output of the tile being sorted / of the tile awaiting its offset
+    uint32_t rstart[3][MT_RMAX + 1];   // bin start of every row relative to the tile (next, current, previous tile)
+    uint32_t rout[3][MT_RMAX];         // survivors per row, then their exclusive scan
+    uint32_t warp_sums[33];
+    uint32_t ticket, next_batch;
+    uint16_t order[MT_RMAX];           // the tile's rows grouped by size class, longest class first
+    uint32_t cls_cnt[8], cls_off[8], cls_b0[8];   // per class: rows, start in order[], first batch; cls_b0[7] = batches
+    uint64_t base;
+    uint64_t mbar;
+};
+struct TileDesc {                      // uniform across the CTA
+    uint32_t idx;                      // position in the chain
+    uint32_t R, n_in, n_out;
+    uint64_t r0, g0;                   // first row, first partial product (relative to the bins pointer)
+    bool is_long, last;
+};
 
-template <class K, bool BM>
-__global__ void __launch_bounds__(MW_THREADS, BM ? 3 : 4)
-k_merge_tiles(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, Elem *bins,
-              const uint32_t *__restrict__ tile_row, const uint32_t bm_words, const uint32_t t0, const uint32_t t1,
-              uint32_t *__restrict__ uniq) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const unsigned int lane = lane_id(), warp = threadIdx.x >> 5;
-    constexpr uint32_t PER_WARP = MT_LONG * 8 + (BM ? BM_SCRATCH : 0);
-    Elem *region = reinterpret_cast<Elem *>(smem + warp * PER_WARP);
-    unsigned char *scratch = smem + warp * PER_WARP + MT_LONG * 8;
-    const uint32_t gwarp = blockIdx.x * (MW_THREADS / 32) + warp, nwarps = gridDim.x * (MW_THREADS / 32);
-
-    for (uint32_t tile = t0 + gwarp; tile < t1; tile += nwarps) {
-        const uint64_t r0 = tile_row[tile], r1 = tile_row[tile + 1];
-        const uint32_t R = uint32_t(r1 - r0);                          // <= 32
-        const uint64_t st_j = row_bin[min(r0 + lane, r1)];
-        const uint64_t en_j = row_bin[min(r0 + lane + 1, r1)];
-        const uint64_t len64 = en_j - st_j;
-        if (R == 1 && __shfl_sync(FULL, len64, 0) > MT_LONG) continue;   // long row: k_merge_long / k_merge_xl
-        const uint32_t len_j = lane < R ? uint32_t(len64) : 0;
-        uint32_t uniq_j = len_j;                                        // rows of 0 / 1 partial products stay as they are
-        unsigned int todo = __ballot_sync(FULL, len_j > 1);
-        while (todo) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t len = __shfl_sync(FULL, len_j, j);
-            Elem *bin = bins + (__shfl_sync(FULL, st_j, j) - bin_base);
-            uint32_t u;
-            if constexpr (BM) {
-                if (len > 32) u = merge_row_bitmap(bin, region, len, bm_words, scratch, lane);
-                else u = merge_row_regs<1, uint32_t>(bin, region, bin, len, lane);
-            } else {
-                if (len <= 32) u = merge_row_regs<1, K>(bin, region, bin, len, lane);
-                else if (len <= 64) u = merge_row_regs<2, K>(bin, region, bin, len, lane);
-                else if (len <= 128) u = merge_row_regs<4, K>(bin, region, bin, len, lane);
-                else if (len <= 256) u = merge_row_regs<8, K>(bin, region, bin, len, lane);
-                else u = merge_row_regs<16, K>(bin, region, bin, len, lane);
-            }
-            if (int(lane) == j) uniq_j = u;
-            __syncwarp();
-        }
-        if (lane < R) uniq[r0 + lane] = uniq_j;
-    }
+// look-back, split: publish the aggregate now, resolve the exclusive prefix later (one warp, all lanes)
+__device__ __forceinline__ void lb_publish(uint64_t *state, uint32_t idx, uint64_t aggregate, uint64_t carry) {
+    if (lane_id() == 0) st_relaxed_u64(state + idx, idx == 0 ? (LB_FLAG_PREFIX | (carry + aggregate)) : (LB_FLAG_AGG | aggregate));
 }
-
-// Moves the merged rows (prefix of each bin) into the CSR data array of C.  Same tiles as the merge:
-// lane j of a warp reads the bounds of row j, then the warp copies the rows one after the other
-// (consecutive rows are consecutive in C, so the stores of a tile form one contiguous stream).
-__global__ void __launch_bounds__(256)
-k_gather_rows(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, const Elem *__restrict__ bins,
-              const uint32_t *__restrict__ tile_row, const uint32_t t0, const uint32_t t1,
-              const uint32_t *__restrict__ uniq, const uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data) {
+__device__ __forceinline__ uint64_t lb_resolve(uint64_t *state, uint32_t idx, uint64_t aggregate, uint64_t carry) {
+    if (idx == 0) return carry;
     const unsigned int lane = lane_id();
-    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t tile = t0 + gwarp; tile < t1; tile += nwarps) {
-        const uint64_t r0 = tile_row[tile], r1 = tile_row[tile + 1];
-        const uint32_t R = uint32_t(r1 - r0);
-        const uint64_t st_j = lane < R ? row_bin[r0 + lane] - bin_base : 0;
-        const uint64_t dst_j = lane < R ? c_pos[r0 + lane] : 0;
-        const uint32_t n_j = lane < R ? uniq[r0 + lane] : 0;
-        const uint32_t n_max = __reduce_max_sync(FULL, n_j);
-        if (n_max <= 4) {                       // tiny rows: one lane per row
-            for (uint32_t i = 0; i < n_j; i++) c_data[dst_j + i] = bins[st_j + i];
-            continue;
+    uint64_t exclusive = 0;
+    int64_t base = int64_t(idx) - 1;
+    while (true) {
+        const int64_t i = base - lane;
+        uint64_t word = LB_FLAG_PREFIX;                  // before the chain: prefix 0 (never reached: tile 0 holds a prefix)
+        if (i >= 0) {
+            word = ld_relaxed_u64(state + i);
+            unsigned int ns = 32;
+            while ((word >> 62) == 0) {                  // predecessor still sorting: back off
+                __nanosleep(ns);
+                if (ns < 512) ns <<= 1;
+                word = ld_relaxed_u64(state + i);
+            }
         }
-        unsigned int todo = __ballot_sync(FULL, n_j > 0);
-        while (todo) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t n = __shfl_sync(FULL, n_j, j);
-            const Elem *src = bins + __shfl_sync(FULL, st_j, j);
-            Elem *dst = c_data + __shfl_sync(FULL, dst_j, j);
-            for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+        const unsigned int has_prefix = __ballot_sync(FULL, (word >> 62) == 2);
+        const unsigned int firstp = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+        uint64_t v = (lane <= firstp) ? (word & LB_VALUE_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        exclusive += v;
+        if (has_prefix) break;
+        base -= 32;
+    }
+    if (lane == 0) st_relaxed_u64(state + idx, LB_FLAG_PREFIX | (exclusive + aggregate));
+    return exclusive;
+}
+
+template <class K>
+__global__ void __launch_bounds__(MC_THREADS, MC_OCC)
+k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, const Elem *__restrict__ bins,
+              const uint32_t *__restrict__ tile_row, const uint32_t t0, const uint32_t n_chain,
+              const uint32_t *__restrict__ uniq, uint64_t *tile_state, DevScalars *sc, const int carry_slot,
+              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data) {
+    MergeChainSmem &sm = *reinterpret_cast<MergeChainSmem *>(osp_smem);
+    const unsigned int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const uint64_t carry = sc->nnz_c[carry_slot];
+    if (tid == 0) {
+        mbar_init(&sm.mbar, 1);
+        sm.ticket = atomicAdd(&sc->tile_ticket, 1u);
+        sm.next_batch = 0;
+    }
+    if (tid < 8) sm.cls_cnt[tid] = 0;
+    __syncthreads();
+
+    // Opens tile `idx`: descriptor, the bulk copy of its partial products into the stage (the stage must be
+    // free), the row starts into rstart[slot].
+    auto open_tile = [&](uint32_t idx, uint32_t slot) -> TileDesc {
+        TileDesc d;
+        d.idx = idx;
+        const uint32_t tile = t0 + idx;
+        d.r0 = tile_row[tile];
+        const uint64_t r1 = tile_row[tile + 1];
+        d.R = uint32_t(r1 - d.r0);
+        const uint64_t b0 = row_bin[d.r0], b1 = row_bin[r1];
+        d.g0 = b0 - bin_base;
+        d.last = idx + 1 == n_chain;
+        d.is_long = d.R == 1 && b1 - b0 > MT_LONG;
+        d.n_in = d.is_long ? 0u : uint32_t(b1 - b0);
+        d.n_out = 0;
+        if (!d.is_long) {
+            if (tid == 0 && d.n_in) {
+                const uint32_t shift = uint32_t(d.g0 & 1);          // the window starts one element early when g0 is odd
+                const uint32_t bytes = ((d.n_in + shift) * 8 + 15) & ~15u;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the stage
+                mbar_expect_tx(&sm.mbar, bytes);
+                tma_load_1d(sm.stage, bins + (d.g0 - shift), bytes, &sm.mbar);
+            }
+            for (uint32_t j = tid; j <= d.R; j += MC_THREADS) sm.rstart[slot][j] = uint32_t(row_bin[d.r0 + j] - b0);
         }
+        return d;
+    };
+    // Resolves the offset of tile `d` in C and streams its output stage out.
+    auto retire_tile = [&](const TileDesc &d, uint32_t slot, uint32_t obuf) {
+        if (warp == 0) {
+            const uint64_t excl = lb_resolve(tile_state, d.idx, d.n_out, carry);
+            if (lane == 0) sm.base = excl;
+        }
+        __syncthreads();
+        const uint64_t base = sm.base;
+        if (tid == 0 && d.last) { c_pos[d.r0 + d.R] = base + d.n_out; sc->nnz_c[carry_slot ^ 1] = base + d.n_out; }
+        if (d.is_long) {
+            const Elem *src = bins + d.g0;
+            for (uint32_t i = tid; i < d.n_out; i += MC_THREADS) c_data[base + i] = src[i];
+            if (tid == 0) c_pos[d.r0] = base;
+            return;
+        }
+        const uint32_t *rout = sm.rout[slot];
+        if (tid < d.R) c_pos[d.r0 + tid] = base + rout[tid];
+        const Elem *ostage = sm.ostage[obuf];
+        if (d.n_out == d.n_in) {                             // no duplicate column in the tile: rows are back to back
+            for (uint32_t p = tid; p < d.n_out; p += MC_THREADS) c_data[base + p] = ostage[swz(p)];
+        } else {
+            const uint32_t *rstart = sm.rstart[slot];
+            for (uint32_t j = warp; j < d.R; j += MC_THREADS / 32) {
+                const uint32_t s = rstart[j], o = rout[j];
+                const uint32_t u = (j + 1 < d.R ? rout[j + 1] : d.n_out) - o;
+                for (uint32_t i = lane; i < u; i += 32) c_data[base + o + i] = ostage[swz(s + i)];
+            }
+        }
+    };
+
+    uint32_t it = 0, n_tma = 0;
+    TileDesc cur, prev;
+    cur.idx = sm.ticket;
+    prev.idx = 0xFFFFFFFFu;
+    if (cur.idx < n_chain) cur = open_tile(cur.idx, 0);
+    while (cur.idx < n_chain) {
+        const uint32_t slot = it % 3, ob = it & 1;
+        __syncthreads();                                     // rstart[slot] is visible
+        // ---- sort: stage -> ostage[ob], survivors per row ----
+        if (cur.is_long) {
+            cur.n_out = uniq[cur.r0];
+        } else {
+            uint32_t *rstart = sm.rstart[slot], *rout = sm.rout[slot];
+            Elem *ostage = sm.ostage[ob];
+            const uint32_t R = cur.R;
+            // size classes (while the bulk copy is in flight): class c sorts rows of <= 8 << c partial products,
+            // 32 >> c rows per warp at a time (class 6: 257..512, one row per warp, 16 keys per lane)
+            uint32_t my_len = 0, my_cls = 7, my_pos = 0;
+            if (tid < R) {
+                my_len = rstart[tid + 1] - rstart[tid];
+                if (my_len <= 1) rout[tid] = my_len;            // rows of 0 / 1 partial products need no merge
+                else {
+                    my_cls = my_len <= 8 ? 0u : 29u - uint32_t(__clz(my_len - 1));
+                    my_pos = atomicAdd(&sm.cls_cnt[my_cls], 1u);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t off = 0, b = 0;
+#pragma unroll
+                for (int c = 6; c >= 0; c--) {
+                    const uint32_t n = sm.cls_cnt[c];
+                    sm.cls_off[c] = off; sm.cls_b0[c] = b;
+                    off += n;
+                    b += c == 6 ? n : (n + (32u >> c) - 1) >> (5 - c);
+                }
+                sm.cls_b0[7] = b;
+            }
+            __syncthreads();
+            if (my_cls < 7) sm.order[sm.cls_off[my_cls] + my_pos] = uint16_t(tid);
+            Elem *stage = sm.stage + uint32_t(cur.g0 & 1);
+            const uint32_t stage_off = uint32_t(offsetof(MergeChainSmem, stage)) + uint32_t(cur.g0 & 1) * 8;
+            const uint32_t ost_off = uint32_t(offsetof(MergeChainSmem, ostage)) + ob * uint32_t(sizeof(Elem) * MC_STAGE_ELEMS);
+            if (cur.n_in) { mbar_wait(&sm.mbar, n_tma & 1); n_tma++; }
+            if (my_len == 1) ostage[swz(rstart[tid])] = stage[rstart[tid]];
+            __syncthreads();                                  // order[] is complete
+            const uint32_t n_batches = sm.cls_b0[7];
+            while (true) {
+                uint32_t b = 0;
+                if (lane == 0) b = atomicAdd(&sm.next_batch, 1u);
+                b = __shfl_sync(FULL, b, 0);
+                if (b >= n_batches) break;
+                int c = 6;
+                while (c > 0 && b >= sm.cls_b0[c - 1]) c--;     // cls_b0 ascends from class 6 down to class 0
+                const uint32_t T = c == 6 ? 5u : uint32_t(c);
+                const uint32_t idx = c == 6 ? b - sm.cls_b0[6] : ((b - sm.cls_b0[c]) << (5 - c)) + (lane >> T);
+                const bool valid = idx < sm.cls_cnt[c];
+                uint32_t j = 0, s = 0, len = 0;
+                if (valid) {
+                    j = sm.order[sm.cls_off[c] + idx];
+                    s = rstart[j];
+                    len = rstart[j + 1] - s;
+                }
+                const uint32_t row_off = stage_off + s * 8;
+                uint32_t u;
+                switch (c) {
+                    case 0: u = merge_rows_grouped<8, 0, K>(row_off, ost_off, s, len, lane); break;
+                    case 1: u = merge_rows_grouped<8, 1, K>(row_off, ost_off, s, len, lane); break;
+                    case 2: u = merge_rows_grouped<8, 2, K>(row_off, ost_off, s, len, lane); break;
+                    case 3: u = merge_rows_grouped<8, 3, K>(row_off, ost_off, s, len, lane); break;
+                    case 4: u = merge_rows_grouped<8, 4, K>(row_off, ost_off, s, len, lane); break;
+                    case 5: u = merge_rows_grouped<8, 5, K>(row_off, ost_off, s, len, lane); break;
+                    default: u = merge_rows_grouped<16, 5, K>(row_off, ost_off, s, len, lane); break;
+                }
+                if (valid && (lane & ((1u << T) - 1)) == 0) rout[j] = u;
+            }
+            __syncthreads();
+            // ---- offsets of the rows inside the tile, the tile's aggregate ----
+            const uint32_t my_u = tid < R ? rout[tid] : 0u;       // MT_RMAX == MC_THREADS: one row per thread
+            uint32_t n_out;
+            const uint32_t my_off = block_exclusive_scan(my_u, sm.warp_sums, n_out);
+            if (tid < R) rout[tid] = my_off;
+            cur.n_out = n_out;
+        }
+        if (warp == 0) lb_publish(tile_state, cur.idx, cur.n_out, carry);
+        // ---- next tile: ticket, bulk copy into the (now free) stage ----
+        if (tid == 0) { sm.ticket = atomicAdd(&sc->tile_ticket, 1u); sm.next_batch = 0; }
+        if (tid < 8) sm.cls_cnt[tid] = 0;
+        __syncthreads();                                     // also: every warp is done with the stage
+        TileDesc nxt;
+        nxt.idx = sm.ticket;
+        if (nxt.idx < n_chain) nxt = open_tile(nxt.idx, (it + 1) % 3);
+        // ---- the previous tile leaves (its predecessors have had this tile's sort to publish) ----
+        if (prev.idx != 0xFFFFFFFFu) retire_tile(prev, (it + 2) % 3, ob ^ 1);
+        prev = cur;
+        cur = nxt;
+        it++;
+    }
+    if (prev.idx != 0xFFFFFFFFu) {
+        __syncthreads();
+        retire_tile(prev, (it + 2) % 3, (it & 1) ^ 1);
     }
 }
 

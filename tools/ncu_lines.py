@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Per-CUDA-source-line instruction and stall-sample shares of one kernel in an .ncu-rep
-(ncu --page source --print-source cuda,sass), read here without a GPU."""
+(ncu --page source --print-source cuda,sass), read here without a GPU.
+usage: ncu_lines.py REP KERNEL [TOP] [inst|stall]"""
 import csv, io, re, subprocess, sys, collections
 
-def main(path, kernel, top=40):
+def main(path, kernel, top=40, key="inst"):
     out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass",
                           "--kernel-name", f"regex:{kernel}"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -34,8 +35,9 @@ def main(path, kernel, top=40):
     tot = sum(v[0] for v in per_line.values()) or 1
     tots = sum(v[1] for v in per_line.values()) or 1
     print(f"kernel {kernel}: {tot} warp instructions, {tots} stall samples")
-    for (line, text), (inst, st, _) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
+    idx = 0 if key == "inst" else 1
+    for (line, text), (inst, st, _) in sorted(per_line.items(), key=lambda kv: -kv[1][idx])[:top]:
         print(f"{100*inst/tot:5.1f}% inst {100*st/tots:5.1f}% stall  L{line:>4} {text}")
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40)
+    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40, sys.argv[4] if len(sys.argv) > 4 else "inst")
