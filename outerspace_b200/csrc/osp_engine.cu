@@ -40,10 +40,10 @@ struct osp_ctx {
     int device = 0;
     int sm_count = 148;
     size_t l2_bytes = 126u << 20;
-    int chain_occ = 1;                      // resident CTAs per SM of k_merge_chain
+    int chain_occ[3] = {1, 1, 1};           // resident CTAs per SM of k_merge_chain: u32 keys, u64 keys, bitmap variant
     size_t total_mem = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;      // long-row merge kernels run beside the tile merge
+    cudaStream_t stream2 = nullptr;      // the CSR->CSC task list is built beside the merge plan
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint64_t ws_limit = 0;          // bytes of partial-product bins per row block
     uint64_t launches = 0;
@@ -221,11 +221,16 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
     CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, uint64_t(n_chain) * 8, ctx->stream));
     CU(ctx, cudaMemsetAsync(&ctx->d_sc->tile_ticket, 0, 4, ctx->stream));
     const int carry_slot = int(block & 1);
+    // small column range: rows of more than 128 partial products are merged by bitmap rank instead of a sort
+    const uint32_t bm_words = job.idx_range <= 32ull * BM_WORDS ? uint32_t((job.idx_range + 31) / 32) : 0u;
+    const uint32_t bm_wpl = (((bm_words + 31) / 32) + 3) & ~3u;           // bitmap words per lane, a multiple of 4
 #define MC_ARGS row_bin, bin_base, bins, ctx->tile_row.as<uint32_t>(), t0, n_chain, uniq, ctx->tile_state.as<uint64_t>(), ctx->d_sc, \
-                carry_slot, job.c_pos, job.c_data
-    const unsigned int grid = std::min<unsigned>(n_chain, unsigned(ctx->sm_count) * unsigned(ctx->chain_occ));   // persistent CTAs
-    if (job.idx_range <= (1ull << 23)) LAUNCH(ctx, k_merge_chain<uint32_t>, grid, MC_THREADS, sizeof(MergeChainSmem), MC_ARGS);
-    else LAUNCH(ctx, k_merge_chain<uint64_t>, grid, MC_THREADS, sizeof(MergeChainSmem), MC_ARGS);
+                carry_slot, job.c_pos, job.c_data, bm_wpl
+    const int variant = bm_words ? 2 : job.idx_range <= (1ull << 23) ? 0 : 1;
+    const unsigned int grid = std::min<unsigned>(n_chain, unsigned(ctx->sm_count) * unsigned(ctx->chain_occ[variant]));   // persistent CTAs
+    if (variant == 2) LAUNCH(ctx, (k_merge_chain<uint32_t, true>), grid, MC_THREADS, sizeof(MergeChainSmem<true>), MC_ARGS);
+    else if (variant == 0) LAUNCH(ctx, (k_merge_chain<uint32_t, false>), grid, MC_THREADS, sizeof(MergeChainSmem<false>), MC_ARGS);
+    else LAUNCH(ctx, (k_merge_chain<uint64_t, false>), grid, MC_THREADS, sizeof(MergeChainSmem<false>), MC_ARGS);
 #undef MC_ARGS
     return OSP_OK;
 }
@@ -379,15 +384,17 @@ int osp_create(int device, osp_ctx **out) {
     CU(nullptr, cudaFuncSetAttribute(k_merge_xl, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LONG_SMEM)));
     CU(nullptr, cudaFuncSetAttribute(k_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dense_smem(DENSE_MAX_COLS))));
     {
-        auto k32 = k_merge_chain<uint32_t>;
-        auto k64 = k_merge_chain<uint64_t>;
-        CU(nullptr, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MergeChainSmem))));
-        CU(nullptr, cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MergeChainSmem))));
-        // persistent grid: never more CTAs than can be resident (a waiting CTA must not keep a ticket holder off the machine)
-        int o32 = 1, o64 = 1;
-        CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o32, k32, MC_THREADS, sizeof(MergeChainSmem)));
-        CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o64, k64, MC_THREADS, sizeof(MergeChainSmem)));
-        ctx->chain_occ = std::max(1, std::min(o32, o64));
+        auto k32 = k_merge_chain<uint32_t, false>;
+        auto k64 = k_merge_chain<uint64_t, false>;
+        auto kbm = k_merge_chain<uint32_t, true>;
+        CU(nullptr, cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MergeChainSmem<false>))));
+        CU(nullptr, cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MergeChainSmem<false>))));
+        CU(nullptr, cudaFuncSetAttribute(kbm, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MergeChainSmem<true>))));
+        // persistent grids: as many CTAs as can be resident
+        CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->chain_occ[0], k32, MC_THREADS, sizeof(MergeChainSmem<false>)));
+        CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->chain_occ[1], k64, MC_THREADS, sizeof(MergeChainSmem<false>)));
+        CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->chain_occ[2], kbm, MC_THREADS, sizeof(MergeChainSmem<true>)));
+        for (int &o : ctx->chain_occ) o = std::max(o, 1);
     }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -446,6 +453,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     ctx->events_used = 0;
     ctx->marks.clear();
     ctx->profile_kernels = args->flags & OSP_PROFILE_KERNELS;
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));   // side-stream work of a call that bailed out early
     int rc;
 
     const uint64_t n_k = args->n_k;
@@ -507,19 +515,35 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     } else {
         CU(ctx, cudaMemsetAsync(run_off, 0, 8, ctx->stream));
     }
+    // CSR->CSC task list on a second stream: it needs only the symbolic pass, not the plan, and the host
+    // round trip below waits for the plan alone; the multiply joins it
+    bool forked = false;
+    if (!rowwise && nnz_a) {
+        CU(ctx, ctx->col_ptr.reserve((n_k + 1) * 4));
+        CU(ctx, ctx->tasks.reserve(nnz_a * sizeof(Task)));
+        cudaStream_t main_stream = ctx->stream;
+        forked = !ctx->profile_kernels;
+        if (forked) {
+            CU(ctx, cudaEventRecord(ctx->ev_fork, main_stream));
+            CU(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+            ctx->stream = ctx->stream2;                 // LAUNCH uses ctx->stream
+        }
+        rc = [&]() -> int {
+            LAUNCH(ctx, (k_scan<U32In, U32Out>), unsigned(st[2]), SCAN_BLOCK, 0, U32In{col_cnt}, U32Out{ctx->col_ptr.as<uint32_t>()},
+                   n_k, ar.state[2], &ctx->d_sc->scan_ticket[2]);
+            LAUNCH(ctx, k_scatter_tasks, grid_for(nnz_a, 256, unsigned(ctx->sm_count) * 16u), 256, 0, dA_data, run_off, dB_pos,
+                   uint64_t(0), nnz_a, ctx->col_ptr.as<uint32_t>(), col_cnt, ctx->tasks.as<Task>(), ctx->d_sc);
+            return OSP_OK;
+        }();
+        ctx->stream = main_stream;
+        if (rc) return rc;
+        if (forked) CU(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+    }
     rc = reserve_plan(ctx, m_plan, std::min(m_plan, std::max<uint64_t>(nnz_a, 1)));
     if (rc) return rc;
     LAUNCH(ctx, k_plan<RowBinFromRuns>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinFromRuns{dA_pos, m_a, run_off, nnz_a}, m_plan,
            cols_b, ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
            ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1);
-    if (!rowwise && nnz_a) {
-        CU(ctx, ctx->col_ptr.reserve((n_k + 1) * 4));
-        CU(ctx, ctx->tasks.reserve(nnz_a * sizeof(Task)));
-        LAUNCH(ctx, (k_scan<U32In, U32Out>), unsigned(st[2]), SCAN_BLOCK, 0, U32In{col_cnt}, U32Out{ctx->col_ptr.as<uint32_t>()},
-               n_k, ar.state[2], &ctx->d_sc->scan_ticket[2]);
-        LAUNCH(ctx, k_scatter_tasks, grid_for(nnz_a, 256, unsigned(ctx->sm_count) * 16u), 256, 0, dA_data, run_off, dB_pos,
-               uint64_t(0), nnz_a, ctx->col_ptr.as<uint32_t>(), col_cnt, ctx->tasks.as<Task>(), ctx->d_sc);
-    }
     cudaEvent_t ev_sym = next_event(ctx);
     rc = sync_scalars(ctx);                       // the one mid-pipeline sync: sizes of the bins and of C
     if (rc) return rc;
@@ -599,6 +623,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     for (size_t b = 0; b < n_blocks; b++) {
         const uint64_t bin0 = blk_bin[b], p_block = blk_bin[b + 1] - bin0;
         ev_blocks.push_back(next_event(ctx));
+        if (forked && b == 0) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
         if (rowwise) rc = launch_multiply(ctx, TaskSrcSoA{dA_data, run_off, dB_pos}, blk_e[b], blk_e[b + 1], p_block, dB_data, bins, bin0);
         else rc = launch_multiply(ctx, TaskSrcAoS{ctx->tasks.as<Task>()}, 0, nnz_a, p_block, dB_data, bins, bin0);
         if (rc) return bail(rc);

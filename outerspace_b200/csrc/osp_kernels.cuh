@@ -777,6 +777,94 @@ __device__ __forceinline__ uint32_t merge_rows_grouped(const uint32_t row_off, c
     return total;
 }
 
+// ---- bitmap-rank merge of one longer row over a small column range (cols <= 32 * BM_WORDS) -------------
+// No sort: every partial product sets the bit of its column in a per-warp bitmap; a prefix popcount over the
+// bitmap words turns a column into its rank among the row's distinct columns (= its place in the sorted,
+// folded row); the earliest arrival of a column (atomicMin over arrival positions) opens that place and the
+// later arrivals are added one by one in arrival (= k) order with separately rounded adds.  S 32-element
+// slots of the row live in registers, every pass works on all of them at once (independent shared-memory
+// operations, five warp-level syncs per row).
+constexpr uint32_t BM_WORDS = 512;                         // bitmap words per warp: columns < 16384
+constexpr uint32_t BM_SCRATCH = BM_WORDS * 4 + BM_WORDS * 2;   // per warp: bitmap | exclusive popcount prefix per word (u16)
+__device__ __forceinline__ uint4 &smem_u4_at(uint32_t off) { return *reinterpret_cast<uint4 *>(osp_smem + off); }
+__device__ __forceinline__ uint16_t &smem_u16_at(uint32_t off) { return *reinterpret_cast<uint16_t *>(osp_smem + off); }
+
+template <int S>
+__device__ __forceinline__ uint32_t merge_row_bitmap(const uint32_t row_off, const uint32_t ost_off, const uint32_t o0,
+                                                     const uint32_t len, const uint32_t wpl, const uint32_t scr_off,
+                                                     const unsigned int lane) {
+    const uint32_t bm_off = scr_off, pre_off = scr_off + BM_WORDS * 4;
+    // lane owns the bitmap words {4*lane + 128*q .. +3}: conflict-free 128-bit accesses
+    for (uint32_t q = 0; q < wpl; q += 4) smem_u4_at(bm_off + (4 * lane + 32 * q) * 4) = make_uint4(0, 0, 0, 0);
+    uint32_t col[S];
+    float val[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const uint32_t p = s * 32 + lane;
+        col[s] = 0xFFFFFFFFu; val[s] = 0.f;
+        if (p < len) { const uint2 e = smem_u2_at(row_off + p * 8); col[s] = e.x; val[s] = __uint_as_float(e.y); }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < S; s++)
+        if (col[s] != 0xFFFFFFFFu) atomicOr(&smem_u32_at(bm_off + (col[s] >> 5) * 4), 1u << (col[s] & 31));
+    __syncwarp();
+    // exclusive prefix popcount over the words, in word order (chunk q of every lane, then chunk q+4, ...)
+    uint32_t uniq = 0;
+    for (uint32_t q = 0; q < wpl; q += 4) {
+        const uint4 w = smem_u4_at(bm_off + (4 * lane + 32 * q) * 4);
+        const uint32_t c0 = __popc(w.x), c1 = __popc(w.y), c2 = __popc(w.z), c3 = __popc(w.w);
+        const uint32_t cnt = c0 + c1 + c2 + c3;
+        const uint32_t incl = warp_inclusive_scan(cnt);
+        const uint32_t b0 = uniq + incl - cnt;
+        uint2 pk;
+        pk.x = b0 | ((b0 + c0) << 16);
+        pk.y = (b0 + c0 + c1) | ((b0 + c0 + c1 + c2) << 16);
+        smem_u2_at(pre_off + (4 * lane + 32 * q) * 2) = pk;
+        uniq += __shfl_sync(FULL, incl, 31);
+    }
+    // first[rank] = earliest arrival position, kept in the row's own input span (its elements are in registers)
+    for (uint32_t i = lane; i < uniq; i += 32) smem_u32_at(row_off + i * 4) = 0xFFFFFFFFu;
+    __syncwarp();
+    uint32_t r[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        r[s] = 0;
+        if (col[s] != 0xFFFFFFFFu) {
+            const uint32_t w = col[s] >> 5;
+            r[s] = smem_u16_at(pre_off + w * 2) + __popc(smem_u32_at(bm_off + w * 4) & ((1u << (col[s] & 31)) - 1));
+            atomicMin(&smem_u32_at(row_off + r[s] * 4), uint32_t(s * 32 + lane));
+        }
+    }
+    __syncwarp();
+    uint32_t losers = 0;                              // slots of this lane that are later arrivals of their column
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        if (col[s] != 0xFFFFFFFFu) {
+            if (smem_u32_at(row_off + r[s] * 4) == uint32_t(s * 32 + lane))
+                smem_u2_at(ost_off + swz(o0 + r[s]) * 8) = make_uint2(col[s], __float_as_uint(val[s]));
+            else losers |= 1u << s;
+        }
+    }
+    __syncwarp();
+    if (__any_sync(FULL, losers != 0)) {              // later arrivals: slot after slot, inside a slot lowest lane first
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            unsigned int b = __ballot_sync(FULL, (losers >> s) & 1u);
+            while (b) {
+                const unsigned int l = __ffs(b) - 1;
+                b &= b - 1;
+                if (lane == l) {
+                    const uint32_t a = ost_off + swz(o0 + r[s]) * 8 + 4;
+                    smem_f32_at(a) = __fadd_rn(smem_f32_at(a), val[s]);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    return uniq;
+}
+
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) and its mbarrier ---------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -810,7 +898,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 //   4. the tile's offset in C is resolved and its output stage streams to C.data / C.pos ONE TILE LATER:
 //      the chain retires tiles in order, so a tile that waited for its predecessors right after its own
 //      sort would idle its CTA; deferred by one tile, the wait falls on predecessors that have had a whole
-//      sort of slack, and the next tile's bulk copy is in flight underneath.
+//      sort of slack, and the next tile's bulk copy is in flight underneath.  (Prefetching one tile further
+//      into a second input stage was measured and dropped: it costs a resident CTA per SM and gains nothing.)
 // C is written exactly once, in its final place.  Long rows are tiles of their own: merged in place
 // beforehand (k_merge_long / k_merge_xl / k_merge_dense, uniq[row] survivors at the start of their bin) and
 // copied here so that the chain stays in row order.
@@ -821,17 +910,21 @@ constexpr int MC_THREADS = 256;
 constexpr int MC_OCC = 3;                              // resident CTAs per SM (shared memory: 3 stages each)
 static_assert(MT_RMAX == MC_THREADS, "one thread per row of a tile");
 constexpr uint32_t MC_STAGE_ELEMS = MT_STAGE + 16;     // + alignment shift, rounded for the swizzle groups
+template <bool BM>
 struct __align__(16) MergeChainSmem {
     Elem stage[MC_STAGE_ELEMS];        // input of the tile being sorted (TMA destination)
     Elem ostage[2][MC_STAGE_ELEMS];    // output of the tile being sorted / of the tile awaiting its offset
     uint32_t rstart[3][MT_RMAX + 1];   // bin start of every row relative to the tile (next, current, previous tile)
     uint32_t rout[3][MT_RMAX];         // survivors per row, then their exclusive scan
     uint32_t warp_sums[33];
-    uint32_t ticket, next_batch;
+    uint32_t next_batch;
     uint16_t order[MT_RMAX];           // the tile's rows grouped by size class, longest class first
     uint32_t cls_cnt[8], cls_off[8], cls_b0[8];   // per class: rows, start in order[], first batch; cls_b0[7] = batches
     uint64_t base;
     uint64_t mbar;
+    uint64_t d_r0[2], d_g0[2];         // descriptors of the tiles opened ahead (written by the opening warp)
+    uint32_t d_idx[2], d_R[2], d_nin[2], d_long[2];
+    __align__(16) unsigned char bm_scratch[BM ? (MC_THREADS / 32) * BM_SCRATCH : 16];   // per-warp bitmaps of the bitmap-rank merge
 };
 struct TileDesc {                      // uniform across the CTA
     uint32_t idx;                      // position in the chain
@@ -874,49 +967,61 @@ __device__ __forceinline__ uint64_t lb_resolve(uint64_t *state, uint32_t idx, ui
     return exclusive;
 }
 
-template <class K>
-__global__ void __launch_bounds__(MC_THREADS, MC_OCC)
+template <class K, bool BM>
+__global__ void __launch_bounds__(MC_THREADS, BM ? 2 : MC_OCC)
 k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, const Elem *__restrict__ bins,
               const uint32_t *__restrict__ tile_row, const uint32_t t0, const uint32_t n_chain,
               const uint32_t *__restrict__ uniq, uint64_t *tile_state, DevScalars *sc, const int carry_slot,
-              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data) {
-    MergeChainSmem &sm = *reinterpret_cast<MergeChainSmem *>(osp_smem);
+              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, const uint32_t bm_wpl) {
+    using Smem = MergeChainSmem<BM>;
+    Smem &sm = *reinterpret_cast<Smem *>(osp_smem);
     const unsigned int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const uint64_t carry = sc->nnz_c[carry_slot];
-    if (tid == 0) {
-        mbar_init(&sm.mbar, 1);
-        sm.ticket = atomicAdd(&sc->tile_ticket, 1u);
-        sm.next_batch = 0;
-    }
-    if (tid < 8) sm.cls_cnt[tid] = 0;
-    __syncthreads();
+    if (tid == 0) mbar_init(&sm.mbar, 1);
 
-    // Opens tile `idx`: descriptor, the bulk copy of its partial products into the stage (the stage must be
-    // free), the row starts into rstart[slot].
-    auto open_tile = [&](uint32_t idx, uint32_t slot) -> TileDesc {
-        TileDesc d;
-        d.idx = idx;
-        const uint32_t tile = t0 + idx;
-        d.r0 = tile_row[tile];
-        const uint64_t r1 = tile_row[tile + 1];
-        d.R = uint32_t(r1 - d.r0);
-        const uint64_t b0 = row_bin[d.r0], b1 = row_bin[r1];
-        d.g0 = b0 - bin_base;
-        d.last = idx + 1 == n_chain;
-        d.is_long = d.R == 1 && b1 - b0 > MT_LONG;
-        d.n_in = d.is_long ? 0u : uint32_t(b1 - b0);
-        d.n_out = 0;
-        if (!d.is_long) {
-            if (tid == 0 && d.n_in) {
-                const uint32_t shift = uint32_t(d.g0 & 1);          // the window starts one element early when g0 is odd
-                const uint32_t bytes = ((d.n_in + shift) * 8 + 15) & ~15u;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the stage
-                mbar_expect_tx(&sm.mbar, bytes);
-                tma_load_1d(sm.stage, bins + (d.g0 - shift), bytes, &sm.mbar);
-            }
-            for (uint32_t j = tid; j <= d.R; j += MC_THREADS) sm.rstart[slot][j] = uint32_t(row_bin[d.r0 + j] - b0);
+    // Opening a tile, in three steps.  (1) ONE warp takes the ticket, reads the tile's bounds and row starts
+    // (a chain of dependent global loads, ~2-3 us) and leaves the descriptor in slot `ds` -- during the sort of
+    // the current tile, whose batches the other warps keep pulling.  (2) After a barrier every thread reads the
+    // descriptor.  (3) One thread starts the bulk copy of the tile's partial products once the stage is free.
+    auto prefetch_tile = [&](uint32_t slot, uint32_t ds) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(&sc->tile_ticket, 1u);
+        idx = __shfl_sync(FULL, idx, 0);
+        uint64_t r0 = 0, g0 = 0;
+        uint32_t R = 0, n_in = 0, is_long = 0;
+        if (idx < n_chain) {
+            const uint32_t tile = t0 + idx;
+            r0 = tile_row[tile];
+            const uint64_t r1 = tile_row[tile + 1];
+            R = uint32_t(r1 - r0);
+            const uint64_t b0 = row_bin[r0], b1 = row_bin[r1];
+            g0 = b0 - bin_base;
+            is_long = R == 1 && b1 - b0 > MT_LONG;
+            n_in = is_long ? 0u : uint32_t(b1 - b0);
+            if (!is_long)
+                for (uint32_t j = lane; j <= R; j += 32) sm.rstart[slot][j] = uint32_t(row_bin[r0 + j] - b0);
         }
+        if (lane == 0) {
+            sm.d_idx[ds] = idx; sm.d_R[ds] = R; sm.d_nin[ds] = n_in; sm.d_long[ds] = is_long;
+            sm.d_r0[ds] = r0; sm.d_g0[ds] = g0;
+        }
+    };
+    auto load_desc = [&](uint32_t ds) -> TileDesc {
+        TileDesc d;
+        d.idx = sm.d_idx[ds]; d.R = sm.d_R[ds]; d.n_in = sm.d_nin[ds]; d.is_long = sm.d_long[ds] != 0;
+        d.r0 = sm.d_r0[ds]; d.g0 = sm.d_g0[ds];
+        d.last = d.idx + 1 == n_chain;
+        d.n_out = 0;
         return d;
+    };
+    auto start_copy = [&](const TileDesc &d) {
+        if (tid == 0 && d.idx < n_chain && !d.is_long && d.n_in) {
+            const uint32_t shift = uint32_t(d.g0 & 1);              // the window starts one element early when g0 is odd
+            const uint32_t bytes = ((d.n_in + shift) * 8 + 15) & ~15u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the stage
+            mbar_expect_tx(&sm.mbar, bytes);
+            tma_load_1d(sm.stage, bins + (d.g0 - shift), bytes, &sm.mbar);
+        }
     };
     // Resolves the offset of tile `d` in C and streams its output stage out.
     auto retire_tile = [&](const TileDesc &d, uint32_t slot, uint32_t obuf) {
@@ -948,17 +1053,21 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
         }
     };
 
-    uint32_t it = 0, n_tma = 0;
-    TileDesc cur, prev;
-    cur.idx = sm.ticket;
+    uint32_t it = 0, n_tma = 0;                            // bulk copies awaited so far (mbarrier phase parity)
+    if (warp == MC_THREADS / 32 - 1) prefetch_tile(0, 0);
+    __syncthreads();
+    TileDesc cur = load_desc(0), prev;
     prev.idx = 0xFFFFFFFFu;
-    if (cur.idx < n_chain) cur = open_tile(cur.idx, 0);
+    start_copy(cur);
     while (cur.idx < n_chain) {
         const uint32_t slot = it % 3, ob = it & 1;
-        __syncthreads();                                     // rstart[slot] is visible
+        if (tid == 0) sm.next_batch = 0;
+        if (tid < 8) sm.cls_cnt[tid] = 0;
+        __syncthreads();                                     // also: rstart[slot] is visible
         // ---- sort: stage -> ostage[ob], survivors per row ----
         if (cur.is_long) {
             cur.n_out = uniq[cur.r0];
+            if (warp == MC_THREADS / 32 - 1) prefetch_tile((it + 1) % 3, (it + 1) & 1);
         } else {
             uint32_t *rstart = sm.rstart[slot], *rout = sm.rout[slot];
             Elem *ostage = sm.ostage[ob];
@@ -982,19 +1091,20 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
                     const uint32_t n = sm.cls_cnt[c];
                     sm.cls_off[c] = off; sm.cls_b0[c] = b;
                     off += n;
-                    b += c == 6 ? n : (n + (32u >> c) - 1) >> (5 - c);
+                    b += c == 6 || (BM && c == 5) ? n : (n + (32u >> c) - 1) >> (5 - c);
                 }
                 sm.cls_b0[7] = b;
             }
             __syncthreads();
             if (my_cls < 7) sm.order[sm.cls_off[my_cls] + my_pos] = uint16_t(tid);
             Elem *stage = sm.stage + uint32_t(cur.g0 & 1);
-            const uint32_t stage_off = uint32_t(offsetof(MergeChainSmem, stage)) + uint32_t(cur.g0 & 1) * 8;
-            const uint32_t ost_off = uint32_t(offsetof(MergeChainSmem, ostage)) + ob * uint32_t(sizeof(Elem) * MC_STAGE_ELEMS);
+            const uint32_t stage_off = uint32_t(offsetof(Smem, stage)) + uint32_t(cur.g0 & 1) * 8;
+            const uint32_t ost_off = uint32_t(offsetof(Smem, ostage)) + ob * uint32_t(sizeof(Elem) * MC_STAGE_ELEMS);
             if (cur.n_in) { mbar_wait(&sm.mbar, n_tma & 1); n_tma++; }
             if (my_len == 1) ostage[swz(rstart[tid])] = stage[rstart[tid]];
             __syncthreads();                                  // order[] is complete
             const uint32_t n_batches = sm.cls_b0[7];
+            if (warp == MC_THREADS / 32 - 1) prefetch_tile((it + 1) % 3, (it + 1) & 1);   // the others start on the batches
             while (true) {
                 uint32_t b = 0;
                 if (lane == 0) b = atomicAdd(&sm.next_batch, 1u);
@@ -1003,7 +1113,7 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
                 int c = 6;
                 while (c > 0 && b >= sm.cls_b0[c - 1]) c--;     // cls_b0 ascends from class 6 down to class 0
                 const uint32_t T = c == 6 ? 5u : uint32_t(c);
-                const uint32_t idx = c == 6 ? b - sm.cls_b0[6] : ((b - sm.cls_b0[c]) << (5 - c)) + (lane >> T);
+                const uint32_t idx = c == 6 || (BM && c == 5) ? b - sm.cls_b0[c] : ((b - sm.cls_b0[c]) << (5 - c)) + (lane >> T);
                 const bool valid = idx < sm.cls_cnt[c];
                 uint32_t j = 0, s = 0, len = 0;
                 if (valid) {
@@ -1013,6 +1123,11 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
                 }
                 const uint32_t row_off = stage_off + s * 8;
                 uint32_t u;
+                if (BM && c >= 5) {       // small column range: rows of > 128 partial products skip the sort
+                    const uint32_t scr_off = uint32_t(offsetof(Smem, bm_scratch)) + warp * BM_SCRATCH;
+                    if (c == 5) u = merge_row_bitmap<8>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);
+                    else u = merge_row_bitmap<16>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);
+                } else
                 switch (c) {
                     case 0: u = merge_rows_grouped<8, 0, K>(row_off, ost_off, s, len, lane); break;
                     case 1: u = merge_rows_grouped<8, 1, K>(row_off, ost_off, s, len, lane); break;
@@ -1033,13 +1148,10 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
             cur.n_out = n_out;
         }
         if (warp == 0) lb_publish(tile_state, cur.idx, cur.n_out, carry);
-        // ---- next tile: ticket, bulk copy into the (now free) stage ----
-        if (tid == 0) { sm.ticket = atomicAdd(&sc->tile_ticket, 1u); sm.next_batch = 0; }
-        if (tid < 8) sm.cls_cnt[tid] = 0;
+        // ---- next tile: its descriptor is ready, bulk copy into the (now free) stage ----
         __syncthreads();                                     // also: every warp is done with the stage
-        TileDesc nxt;
-        nxt.idx = sm.ticket;
-        if (nxt.idx < n_chain) nxt = open_tile(nxt.idx, (it + 1) % 3);
+        const TileDesc nxt = load_desc((it + 1) & 1);
+        start_copy(nxt);
         // ---- the previous tile leaves (its predecessors have had this tile's sort to publish) ----
         if (prev.idx != 0xFFFFFFFFu) retire_tile(prev, (it + 2) % 3, ob ^ 1);
         prev = cur;
