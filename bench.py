@@ -328,6 +328,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             "algorithmic_gbs": round(alg_bytes / (ms_per_step * 1e-3) / 1e9, 2),
             "algorithmic_frac_of_hbm_peak": round(alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
             "wall_s_timed_region": round(wall, 4),
+            "phases_ms_rank0": {k: round(float(st.get("ms_" + k, 0.0)), 4) for k in ("convert", "multiply", "exchange", "merge", "total")},
             "clocks": clocks,
             "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "ms_per_step": round(e2e_ms_step, 4),

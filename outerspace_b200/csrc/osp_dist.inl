@@ -63,6 +63,17 @@ struct osp_dist {
     int rank = 0, world = 1;
     DevBuf lens_send, lens_recv, recv_buf, bins2, src_off, dst_off, bounds_idx, bounds_dev, bounds_all;
     uint64_t *h_bounds = nullptr;      // pinned [world * (world + 1)]
+    // peer-memory exchange (the default): every rank maps the owners' bins (CUDA IPC) and its multiply
+    // writes the partial products straight into them over NVLink
+    bool p2p = true;
+    DevBuf seg_send, seg_off, run_dst, handles_dev, flags_dev;
+    cudaIpcMemHandle_t *h_handles = nullptr;          // pinned [world]: the bins' IPC handles, all-gathered every call
+    uint32_t *h_flags = nullptr;                      // pinned [world]
+    cudaIpcMemHandle_t peer_handle[MAX_PEERS];        // what is currently mapped
+    void *peer_ptr[MAX_PEERS] = {};
+    bool peer_open[MAX_PEERS] = {};
+    void *own_exported = nullptr;                     // allocation h_handles[rank] describes
+    void *retired = nullptr;                          // previous bins allocation, freed once the peers have remapped
 };
 
 namespace {
@@ -75,6 +86,59 @@ namespace {
     } while (0)
 
 uint64_t block_begin(uint64_t rows, int world, int r) { return rows * uint64_t(r) / uint64_t(world); }
+
+// Makes this rank's bins hold `bytes` and maps every owner's bins into this process.  The previous
+// allocation of a grown buffer is kept until the next growth: peers may still have it mapped until they
+// see the new handle in this call's all-gather.  Returns OSP_OK with d->p2p cleared when some rank could
+// not map a peer (every rank then takes the NCCL path, consistently).
+int map_peer_bins(osp_dist *d, uint64_t bytes) {
+    osp_ctx *ctx = d->ctx;
+    const int G = d->world, me = d->rank;
+    if (bytes > d->bins2.cap) {
+        if (d->retired) { cudaFree(d->retired); d->retired = nullptr; }
+        d->retired = d->bins2.p;
+        d->bins2.p = nullptr; d->bins2.cap = 0;
+        CU(ctx, d->bins2.reserve(bytes));
+    }
+    d->peer_ptr[me] = d->bins2.p;
+    if (G == 1) return OSP_OK;
+    if (d->own_exported != d->bins2.p) {
+        CU(ctx, cudaIpcGetMemHandle(&d->h_handles[me], d->bins2.p));
+        d->own_exported = d->bins2.p;
+    }
+    CU(ctx, d->handles_dev.reserve(size_t(G) * sizeof(cudaIpcMemHandle_t)));
+    CU(ctx, d->flags_dev.reserve(size_t(G) * 4 + 4));
+    unsigned char *hd = d->handles_dev.as<unsigned char>();
+    CU(ctx, cudaMemcpyAsync(hd + size_t(me) * sizeof(cudaIpcMemHandle_t), &d->h_handles[me], sizeof(cudaIpcMemHandle_t),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    NC(ctx, d, d->nccl->AllGather(hd + size_t(me) * sizeof(cudaIpcMemHandle_t), hd, sizeof(cudaIpcMemHandle_t), ncclUint8, d->comm,
+                                  ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d->h_handles, hd, size_t(G) * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    uint32_t ok = 1;
+    for (int r = 0; r < G; r++) {
+        if (r == me) continue;
+        if (d->peer_open[r] && std::memcmp(&d->peer_handle[r], &d->h_handles[r], sizeof(cudaIpcMemHandle_t)) == 0) continue;
+        if (d->peer_open[r]) { cudaIpcCloseMemHandle(d->peer_ptr[r]); d->peer_open[r] = false; }
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, d->h_handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+            continue;
+        }
+        d->peer_ptr[r] = p; d->peer_handle[r] = d->h_handles[r]; d->peer_open[r] = true;
+    }
+    // every rank learns whether every mapping exists (a rank that changed nothing still takes part)
+    d->h_flags[me] = ok;
+    uint32_t *fd = d->flags_dev.as<uint32_t>();
+    CU(ctx, cudaMemcpyAsync(fd + me, &d->h_flags[me], 4, cudaMemcpyHostToDevice, ctx->stream));
+    NC(ctx, d, d->nccl->AllGather(fd + me, fd, 1, ncclUint32, d->comm, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d->h_flags, fd, size_t(G) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < G; r++)
+        if (!d->h_flags[r]) d->p2p = false;
+    return OSP_OK;
+}
 
 }  // namespace
 
@@ -110,6 +174,11 @@ int osp_dist_create(osp_ctx *ctx, const void *id128, int rank, int world, osp_di
         return fail(ctx, OSP_ERR_CUDA, std::string("ncclCommInitRank: ") + api->GetErrorString(r));
     }
     cudaMallocHost(reinterpret_cast<void **>(&d->h_bounds), size_t(world) * (world + 1) * 8);
+    cudaMallocHost(reinterpret_cast<void **>(&d->h_handles), size_t(world) * sizeof(cudaIpcMemHandle_t));
+    cudaMallocHost(reinterpret_cast<void **>(&d->h_flags), size_t(world) * 4);
+    std::memset(d->peer_handle, 0, sizeof(d->peer_handle));
+    const char *mode = std::getenv("OSP_DIST_EXCHANGE");     // "nccl": staged all-to-allv + regroup instead of peer stores
+    d->p2p = world <= MAX_PEERS && !(mode && std::string(mode) == "nccl");
     *out = d;
     return OSP_OK;
 }
@@ -119,10 +188,15 @@ void osp_dist_destroy(osp_dist *d) {
     cudaSetDevice(d->ctx->device);
     cudaStreamSynchronize(d->ctx->stream);
     if (d->comm) d->nccl->CommDestroy(d->comm);
+    for (int r = 0; r < d->world && r < MAX_PEERS; r++)
+        if (d->peer_open[r]) cudaIpcCloseMemHandle(d->peer_ptr[r]);
     for (DevBuf *b : {&d->lens_send, &d->lens_recv, &d->recv_buf, &d->bins2, &d->src_off, &d->dst_off, &d->bounds_idx,
-                      &d->bounds_dev, &d->bounds_all})
+                      &d->bounds_dev, &d->bounds_all, &d->seg_send, &d->seg_off, &d->run_dst, &d->handles_dev, &d->flags_dev})
         b->release();
+    if (d->retired) cudaFree(d->retired);
     if (d->h_bounds) cudaFreeHost(d->h_bounds);
+    if (d->h_handles) cudaFreeHost(d->h_handles);
+    if (d->h_flags) cudaFreeHost(d->h_flags);
     delete d;
 }
 
@@ -212,13 +286,69 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
         if (RL) NC(ctx, d, d->nccl->Recv(d->lens_recv.as<uint32_t>() + uint64_t(r) * RL, RL, ncclUint32, r, d->comm, ctx->stream));
     }
     NC(ctx, d, d->nccl->GroupEnd());
+    cudaEvent_t ev_sym = nullptr, ev_mul = nullptr, ev_xchg = nullptr;
+    // the same decision on every rank: segment offsets travel as uint32, so every owner's bins must stay below 2^32
+    uint64_t p_owned_max = 0;
+    for (int r = 0; r < G; r++) {
+        uint64_t p = 0;
+        for (int s2 = 0; s2 < G; s2++) p += bound(s2, r + 1) - bound(s2, r);
+        p_owned_max = std::max(p_owned_max, p);
+    }
+    bool direct = d->p2p && p_owned_max < (1ull << 32) && (m / G + 1) * uint64_t(G) < (1ull << 32);
+    if (direct) {
+        // ---- peer-memory exchange: owners lay out their bins, sources write into them ----------------
+        // owner: offsets of every (row, source) segment inside its row-major bins; back to the sources
+        const uint64_t n = RL * G;
+        if ((rc = [&]() -> int {
+                CU(ctx, d->dst_off.reserve((n + 1) * 8));
+                CU(ctx, d->seg_send.reserve(std::max<uint64_t>(n, 1) * 4));
+                CU(ctx, d->seg_off.reserve(std::max<uint64_t>(m, 1) * 4));
+                CU(ctx, d->run_dst.reserve(std::max<uint64_t>(nnz_a, 1) * 8));
+                return OSP_OK;
+            }())) return rc;
+        if (RL) {
+            LAUNCH(ctx, (k_scan<TransposedIn, U64Out>), unsigned(st[3]), SCAN_BLOCK, 0,
+                   TransposedIn{d->lens_recv.as<uint32_t>(), RL, uint64_t(G)}, U64Out{d->dst_off.as<uint64_t>()}, n, ar.state[3],
+                   &ctx->d_sc->scan_ticket[3]);
+            LAUNCH(ctx, k_seg_offsets, grid_for(n, 256, 1u << 30), 256, 0, d->dst_off.as<uint64_t>(), RL, uint32_t(G),
+                   d->seg_send.as<uint32_t>());
+        }
+        NC(ctx, d, d->nccl->GroupStart());
+        for (int r = 0; r < G; r++) {
+            const uint64_t b0 = block_begin(m, G, r), b1 = block_begin(m, G, r + 1);
+            if (RL) NC(ctx, d, d->nccl->Send(d->seg_send.as<uint32_t>() + uint64_t(r) * RL, RL, ncclUint32, r, d->comm, ctx->stream));
+            if (b1 > b0) NC(ctx, d, d->nccl->Recv(d->seg_off.as<uint32_t>() + b0, b1 - b0, ncclUint32, r, d->comm, ctx->stream));
+        }
+        NC(ctx, d, d->nccl->GroupEnd());
+        rc = map_peer_bins(d, std::max<uint64_t>(P_owned, 1) * 8 + 16);      // (host sync: the handles of all owners)
+        if (rc) return rc;
+        direct = d->p2p;
+    }
+    if (direct) {
+        ev_sym = next_event(ctx);
+        if (nnz_a && P_local) {
+            LAUNCH(ctx, k_run_dst, grid_for(m_a, 64, unsigned(ctx->sm_count) * 32u), 256, 0, op.a_pos, m_a, run_off,
+                   d->seg_off.as<uint32_t>(), m, uint32_t(G), d->run_dst.as<uint64_t>());
+            PeerBins peers;
+            for (int r = 0; r < MAX_PEERS; r++) peers.p[r] = static_cast<Elem *>(r < G ? d->peer_ptr[r] : nullptr);
+            LAUNCH(ctx, k_multiply_peer, grid_for(nnz_a, 256, unsigned(ctx->sm_count) * 32u), 256, 0, op.a_data, run_off,
+                   d->run_dst.as<uint64_t>(), op.b_pos, nnz_a, op.b_data, peers);
+        }
+        ev_mul = next_event(ctx);
+        // every rank's stores have landed once every rank's multiply has retired: one tiny collective on the stream
+        if (G > 1) {
+            uint32_t *fd = d->flags_dev.as<uint32_t>();
+            NC(ctx, d, d->nccl->AllGather(fd + me, fd, 1, ncclUint32, d->comm, ctx->stream));
+        }
+        ev_xchg = next_event(ctx);
+    } else {
     CU(ctx, ctx->bins.reserve(std::max<uint64_t>(P_local, 1) * 8));
     CU(ctx, d->recv_buf.reserve(std::max<uint64_t>(P_owned, 1) * 8));
     CU(ctx, d->bins2.reserve(std::max<uint64_t>(P_owned, 1) * 8 + 16));
-    cudaEvent_t ev_sym = next_event(ctx);
+    ev_sym = next_event(ctx);
     rc = launch_multiply(ctx, TaskSrcSoA{op.a_data, run_off, op.b_pos}, 0, nnz_a, P_local, op.b_data, ctx->bins.as<Elem>(), 0);
     if (rc) return rc;
-    cudaEvent_t ev_mul = next_event(ctx);
+    ev_mul = next_event(ctx);
     NC(ctx, d, d->nccl->GroupStart());
     for (int r = 0; r < G; r++) {
         const uint64_t cnt = bound(me, r + 1) - bound(me, r);
@@ -226,7 +356,9 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
         if (recv_cnt[r]) NC(ctx, d, d->nccl->Recv(d->recv_buf.as<Elem>() + recv_off[r], recv_cnt[r] * 8, ncclUint8, r, d->comm, ctx->stream));
     }
     NC(ctx, d, d->nccl->GroupEnd());
-    cudaEvent_t ev_xchg = next_event(ctx);
+    ev_xchg = next_event(ctx);
+
+    }
 
     // ---- regroup source-major -> row-major, plan, merge ------------------------------------------------
     osp_result *res = new osp_result();
@@ -244,12 +376,14 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
                 return OSP_OK;
             }())) return bail(rc);
         const uint32_t *lens = d->lens_recv.as<uint32_t>();
-        LAUNCH(ctx, (k_scan<U32In, U64Out>), unsigned(st[2]), SCAN_BLOCK, 0, U32In{lens}, U64Out{d->src_off.as<uint64_t>()}, n,
-               ar.state[2], &ctx->d_sc->scan_ticket[2]);
-        LAUNCH(ctx, (k_scan<TransposedIn, U64Out>), unsigned(st[3]), SCAN_BLOCK, 0, TransposedIn{lens, RL, uint64_t(G)},
-               U64Out{d->dst_off.as<uint64_t>()}, n, ar.state[3], &ctx->d_sc->scan_ticket[3]);
-        LAUNCH(ctx, k_regroup, grid_for(RL, 8, unsigned(ctx->sm_count) * 32u), 256, 0, d->recv_buf.as<Elem>(),
-               d->src_off.as<uint64_t>(), d->dst_off.as<uint64_t>(), lens, RL, uint32_t(G), d->bins2.as<Elem>());
+        if (!direct) {
+            LAUNCH(ctx, (k_scan<U32In, U64Out>), unsigned(st[2]), SCAN_BLOCK, 0, U32In{lens}, U64Out{d->src_off.as<uint64_t>()}, n,
+                   ar.state[2], &ctx->d_sc->scan_ticket[2]);
+            LAUNCH(ctx, (k_scan<TransposedIn, U64Out>), unsigned(st[3]), SCAN_BLOCK, 0, TransposedIn{lens, RL, uint64_t(G)},
+                   U64Out{d->dst_off.as<uint64_t>()}, n, ar.state[3], &ctx->d_sc->scan_ticket[3]);
+            LAUNCH(ctx, k_regroup, grid_for(RL, 8, unsigned(ctx->sm_count) * 32u), 256, 0, d->recv_buf.as<Elem>(),
+                   d->src_off.as<uint64_t>(), d->dst_off.as<uint64_t>(), lens, RL, uint32_t(G), d->bins2.as<Elem>());
+        }
         rc = reserve_plan(ctx, RL, RL);
         if (rc) return bail(rc);
         LAUNCH(ctx, k_plan<RowBinStrided>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinStrided{d->dst_off.as<uint64_t>(), uint64_t(G)}, RL,

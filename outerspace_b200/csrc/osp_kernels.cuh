@@ -1236,4 +1236,95 @@ __global__ void k_regroup(const Elem *__restrict__ recv, const uint64_t *__restr
     }
 }
 
+
+// ---- peer-memory exchange: the multiply writes straight into the owners' bins over NVLink -----------------
+// Owner side: the offset, inside the owner's row-major bins, of the segment that source s contributes to
+// owned row i (dst_off is in (i, s) order) laid out per source, ready to be sent back to the sources.
+__global__ void k_seg_offsets(const uint64_t *__restrict__ dst_off, uint64_t RL, uint32_t G, uint32_t *__restrict__ seg_send) {
+    const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;      // j = s * RL + i
+    if (j >= RL * G) return;
+    const uint64_t s = j / RL, i = j % RL;
+    seg_send[j] = uint32_t(dst_off[i * G + s]);
+}
+// Source side: destination of every run of the shard = (owner of its row << 56) | element offset inside
+// that owner's bins.  Rows are owned in blocks [m g / G, m (g + 1) / G).
+constexpr int PEER_SHIFT = 56;
+constexpr int MAX_PEERS = 16;
+__global__ void k_run_dst(const uint64_t *__restrict__ a_pos, uint64_t m_a, const uint64_t *__restrict__ run_off,
+                          const uint32_t *__restrict__ seg_off, uint64_t m, uint32_t G, uint64_t *__restrict__ run_dst) {
+    // four lanes per row: shard rows hold few non-zeros (nnz(A) / (m G) each on average)
+    const uint64_t grp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 2;
+    const uint64_t ngrp = (uint64_t(gridDim.x) * blockDim.x) >> 2;
+    const unsigned int sub = threadIdx.x & 3;
+    for (uint64_t r = grp; r < m_a; r += ngrp) {
+        const uint64_t p0 = a_pos[r], p1 = a_pos[r + 1];
+        if (p1 == p0) continue;
+        const uint64_t owner = ((r + 1) * G - 1) / m;
+        const uint64_t base = (owner << PEER_SHIFT) | uint64_t(seg_off[r]);
+        const uint64_t first = run_off[p0];
+        for (uint64_t p = p0 + sub; p < p1; p += 4) run_dst[p] = base + (run_off[p] - first);
+    }
+}
+struct PeerBins { Elem *p[MAX_PEERS]; };
+// The warp-flat multiply of k_multiply with every run going to the bins of the GPU that owns its output row:
+// peer memory mapped through CUDA IPC, 8-byte stores over NVLink that are contiguous inside a run.  The
+// exchange of the k-sharded path IS this kernel's store stream: nothing is staged, sent or regrouped.
+__global__ void __launch_bounds__(256)
+k_multiply_peer(const Elem *__restrict__ a_data, const uint64_t *__restrict__ run_off, const uint64_t *__restrict__ run_dst,
+                const uint64_t *__restrict__ b_pos, uint64_t t1, const Elem *__restrict__ b_data, const PeerBins peers) {
+    __shared__ Elem *s_peer[MAX_PEERS];
+    if (threadIdx.x < MAX_PEERS) s_peer[threadIdx.x] = peers.p[threadIdx.x];
+    __syncthreads();
+    const unsigned int lane = lane_id();
+    const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
+    const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t base = warp * 32; base < t1; base += nwarps * 32) {
+        uint32_t bs = 0, len = 0, owner = 0; float a = 0.f; uint64_t off = 0;
+        if (base + lane < t1) {
+            const uint64_t i = base + lane;
+            const Elem e = a_data[i];
+            a = e.val;
+            const uint64_t d = run_dst[i];
+            owner = uint32_t(d >> PEER_SHIFT); off = d & ((1ull << PEER_SHIFT) - 1);
+            len = uint32_t(run_off[i + 1] - run_off[i]);
+            bs = uint32_t(b_pos[e.idx]);
+        }
+        const uint32_t incl = warp_inclusive_scan(len);
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        const uint32_t excl = incl - len;
+        const uint32_t dbs = bs - excl;                       // B index of element e of this task: dbs + e
+        const uint64_t doff = off - excl;                     // bin index of element e of this task: doff + e (mod 2^64)
+        for (uint32_t e0 = 0; e0 < total; e0 += 64) {          // two independent 32-element chunks per turn
+            const uint32_t e[2] = {e0 + lane, e0 + 32 + lane};
+            uint32_t t[2] = {0, 0};                            // number of tasks that end at or before e
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const uint32_t v = __shfl_sync(FULL, incl, t[u] + step - 1);
+                    if (v <= e[u]) t[u] += step;
+                }
+            }
+            float a_t[2]; uint32_t dbs_t[2], own_t[2]; uint64_t doff_t[2]; Elem b[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                a_t[u] = __shfl_sync(FULL, a, t[u] & 31);
+                dbs_t[u] = __shfl_sync(FULL, dbs, t[u] & 31);
+                doff_t[u] = __shfl_sync(FULL, doff, t[u] & 31);
+                own_t[u] = __shfl_sync(FULL, owner, t[u] & 31);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (e[u] < total) b[u] = b_data[dbs_t[u] + e[u]];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (e[u] < total) {
+                    Elem o; o.idx = b[u].idx; o.val = __fmul_rn(a_t[u], b[u].val);     // rounded on its own: no FMA
+                    s_peer[own_t[u]][doff_t[u] + e[u]] = o;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace osp
