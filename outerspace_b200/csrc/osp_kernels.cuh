@@ -475,63 +475,78 @@ k_merge_long(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins
     }
 }
 
-// Rows longer than MT_XL: the row is consumed in chunks of MT_XL partial products.  Each chunk is
-// sorted by (col, arrival position) and folded INTO a dense per-CTA accumulator acc[cols_b]
-// (presence in bits[]), which keeps the left fold in arrival order across chunks.  The accumulator
-// is then compacted in ascending column order over the start of the row's bin; bits[] is cleared.
-__global__ void __launch_bounds__(256)
+// Rows longer than MT_XL over a large column range: a dense per-CTA accumulator acc[cols_b] in global
+// memory (L2-resident: one row at a time per CTA) with a presence bitmap.  The row is consumed XL_THREADS
+// partial products at a time in arrival order; products of one chunk that hit the same column are
+// serialised by an arbitration on a hashed owner table in shared memory (the lowest position goes first;
+// a hash collision between different columns only delays the later one), so every column is still summed
+// in ascending arrival (= k) order with separately rounded adds.  No sort.  The accumulator is then
+// compacted in ascending column order over the start of the row's bin and the bitmap is cleared.
+constexpr int XL_THREADS = 512;
+constexpr uint32_t XL_HASH_BITS = 12;
+__global__ void __launch_bounds__(XL_THREADS)
 k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, uint32_t *uniq,
            const uint32_t *xl_list, const DevScalars *sc, float *acc_all, uint32_t *bits_all, uint64_t cols_b,
            uint64_t row_lo, uint64_t row_hi) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    uint64_t *keys = reinterpret_cast<uint64_t *>(smem);
-    float *vals = reinterpret_cast<float *>(keys + MT_XL);
-    uint32_t *warp_sums = reinterpret_cast<uint32_t *>(vals + MT_XL);
+    __shared__ uint32_t owner[1u << XL_HASH_BITS];
+    __shared__ uint32_t warp_sums[33];
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < (1u << XL_HASH_BITS); i += XL_THREADS) owner[i] = 0xFFFFFFFFu;
     const uint64_t words = (cols_b + 31) >> 5;
     float *acc = acc_all + uint64_t(blockIdx.x) * cols_b;
     uint32_t *bits = bits_all + uint64_t(blockIdx.x) * words;
     const uint32_t n_xl = sc->n_xl;
+    __syncthreads();
     for (uint32_t x = blockIdx.x; x < n_xl; x += gridDim.x) {
         const uint64_t row = xl_list[x];
         if (row < row_lo || row >= row_hi) continue;
-        const uint64_t start = row_bin[row] - bin_base;
         const uint64_t len = row_bin[row + 1] - row_bin[row];
-        Elem *bin = bins + start;
-        for (uint64_t c0 = 0; c0 < len; c0 += MT_XL) {
-            const uint32_t n = uint32_t(min(uint64_t(MT_XL), len - c0)), N = pow2ceil(n);
-            for (uint32_t p = threadIdx.x; p < N; p += blockDim.x) {
-                if (p < n) {
-                    Elem e = bin[c0 + p];
-                    keys[p] = (uint64_t(e.idx) << 32) | p;
-                    vals[p] = e.val;
-                } else {
-                    keys[p] = ~0ull;
+        Elem *bin = bins + (row_bin[row] - bin_base);
+        for (uint64_t c0 = 0; c0 < len; c0 += XL_THREADS) {
+            const uint64_t p = c0 + tid;
+            bool pending = p < len;
+            Elem e; e.idx = 0; e.val = 0.f;
+            if (pending) e = bin[p];
+            const uint32_t h = (e.idx * 2654435761u) >> (32 - XL_HASH_BITS);
+            while (__syncthreads_or(pending)) {
+                if (pending) atomicMin(&owner[h], tid);
+                __syncthreads();
+                const bool win = pending && owner[h] == tid;
+                if (win) {
+                    uint32_t *w = bits + (e.idx >> 5);
+                    const uint32_t bit = 1u << (e.idx & 31);
+                    if (__ldcg(w) & bit) {
+                        acc[e.idx] = __fadd_rn(acc[e.idx], e.val);
+                    } else {
+                        acc[e.idx] = e.val;
+                        atomicOr(w, bit);
+                    }
+                    pending = false;
                 }
+                __syncthreads();
+                if (win) owner[h] = 0xFFFFFFFFu;
             }
-            __syncthreads();
-            bitonic_sort_shared(keys, N);
-            fold_sorted(keys, vals, n, N, nullptr, warp_sums, acc, bits);
-            __syncthreads();
         }
+        __syncthreads();
         // ordered compaction of the accumulator over the (fully consumed) bin
         uint64_t produced = 0;
-        for (uint64_t w0 = 0; w0 < words; w0 += blockDim.x) {
-            uint64_t w = w0 + threadIdx.x;
-            uint32_t b = w < words ? bits[w] : 0u;
+        for (uint64_t w0 = 0; w0 < words; w0 += XL_THREADS) {
+            const uint64_t w = w0 + tid;
+            uint32_t b = w < words ? __ldcg(bits + w) : 0u;
             uint32_t total;
-            uint32_t rank = block_exclusive_scan(__popc(b), warp_sums, total);
+            const uint32_t rank = block_exclusive_scan(__popc(b), warp_sums, total);
             uint64_t o = produced + rank;
             if (b) bits[w] = 0u;
             while (b) {
-                uint32_t bit = __ffs(b) - 1;
+                const uint32_t bit = __ffs(b) - 1;
                 b &= b - 1;
-                uint32_t col = uint32_t(w * 32 + bit);
-                Elem e; e.idx = col; e.val = acc[col];
-                bin[o++] = e;
+                const uint32_t col = uint32_t(w * 32 + bit);
+                Elem r; r.idx = col; r.val = acc[col];
+                bin[o++] = r;
             }
             produced += total;
         }
-        if (threadIdx.x == 0) uniq[row] = uint32_t(produced);
+        if (tid == 0) uniq[row] = uint32_t(produced);
         __syncthreads();
     }
 }
