@@ -303,6 +303,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         k_bytes_per_launch, k_formula = out["kernel_bytes"], out["kernel_formula"]
         achieved = k_bytes_per_launch / (k_ms * 1e-3) / 1e9
         e2e_ms_step, h2d, d2h = out["e2e_ms"], out["h2d"], out["d2h"]
+        n1_same = out.get("n1_same_workload")
         products, alg_bytes = st["products"], st["algorithmic_bytes"]
 
     if world > 1:
@@ -340,13 +341,16 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                          "algorithmic_bytes_per_launch": int(k_bytes_per_launch), "formula": k_formula,
                          "share_of_kernel_time": round(k_share, 4), "kernel_ms_per_step": k_table},
         }
+        if world > 1 and n1_same:
+            line["n1_same_workload"] = n1_same
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:
                 with open(prof) as f:
                     tr = json.load(f)
-                if tr.get("workload") == wl and kname in tr.get("kernels", {}):
-                    line["roofline"]["traffic"] = tr["kernels"][kname]["dram_bytes_per_launch"]
+                kbase = kname.strip("() ").split("<")[0]
+                if tr.get("workload") == wl and kbase in tr.get("kernels", {}):
+                    line["roofline"]["traffic"] = tr["kernels"][kbase]["dram_bytes_per_launch"]
                     line["roofline"]["traffic_source"] = tr.get("source")
             except (OSError, ValueError, KeyError):
                 pass

@@ -223,6 +223,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     CU(ctx, cudaSetDevice(ctx->device));
     ctx->launches = 0;
     ctx->events_used = 0;
+    ctx->call_id++;
     ctx->marks.clear();
     ctx->profile_kernels = args->flags & OSP_PROFILE_KERNELS;
     const int G = d->world, me = d->rank;
@@ -427,17 +428,14 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     stt.kernel_launches = ctx->launches;
     stt.row_chunks = 1;
     stt.ms_h2d = op.ms_h2d;
-    cudaEventElapsedTime(&stt.ms_total, ev_begin, ev_end);
-    cudaEventElapsedTime(&stt.ms_convert, ev_begin, ev_sym);
-    cudaEventElapsedTime(&stt.ms_multiply, ev_sym, ev_mul);
-    cudaEventElapsedTime(&stt.ms_exchange, ev_mul, ev_xchg);
-    cudaEventElapsedTime(&stt.ms_merge, ev_xchg, ev_end);
+    res->call_id = ctx->call_id;
+    res->spans.push_back({&stt.ms_total, nullptr, ev_begin, ev_end});
+    res->spans.push_back({&stt.ms_convert, nullptr, ev_begin, ev_sym});
+    res->spans.push_back({&stt.ms_multiply, nullptr, ev_sym, ev_mul});
+    res->spans.push_back({&stt.ms_exchange, nullptr, ev_mul, ev_xchg});
+    res->spans.push_back({&stt.ms_merge, nullptr, ev_xchg, ev_end});
     stt.exchange_bytes_out = 8 * (P_local - (bound(me, me + 1) - bound(me, me)));
-    float ms = 0.f;
-    for (const auto &mk : ctx->marks) {
-        cudaEventElapsedTime(&ms, mk.e0, mk.e1);
-        res->kernel_ms.emplace_back(mk.name, ms);
-    }
+    for (const auto &mk : ctx->marks) res->spans.push_back({nullptr, mk.name, mk.e0, mk.e1});
     ctx->profile_kernels = false;
     *out = res;
     return OSP_OK;

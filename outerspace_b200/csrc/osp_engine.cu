@@ -47,6 +47,7 @@ struct osp_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint64_t ws_limit = 0;          // bytes of partial-product bins per row block
     uint64_t launches = 0;
+    uint64_t call_id = 0;
     std::string err;
     DevScalars *h_sc = nullptr;     // pinned mirror
     // per-call zeroed arena: DevScalars | look-back states of the scans | column counters
@@ -72,9 +73,28 @@ struct osp_result {
     uint64_t rows = 0, nnz = 0;
     osp_stats stats;
     std::vector<std::pair<const char *, float>> kernel_ms;   // OSP_PROFILE_KERNELS
+    // Event pairs behind stats.ms_* and kernel_ms, read on the first osp_result_stats / osp_result_kernels --
+    // not inside the call, whose host time is part of what a caller measures.  The events belong to the
+    // context and are re-recorded by its next call: after that the times stay zero.
+    struct Span { float *dst; const char *name; cudaEvent_t e0, e1; };
+    std::vector<Span> spans;
+    uint64_t call_id = 0;
+    bool timed = false;
 };
 
 namespace {
+
+void resolve_times(osp_result *r) {
+    if (r->timed) return;
+    r->timed = true;
+    if (r->call_id != r->ctx->call_id) return;          // the events have been reused
+    for (const auto &sp : r->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (sp.dst) *sp.dst += ms;
+        else r->kernel_ms.emplace_back(sp.name, ms);
+    }
+}
 
 int fail(osp_ctx *ctx, int code, const std::string &msg) {
     g_last_error = msg;
@@ -450,6 +470,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     CU(ctx, cudaSetDevice(ctx->device));
     ctx->launches = 0;
     ctx->events_used = 0;
+    ctx->call_id++;
     ctx->marks.clear();
     ctx->profile_kernels = args->flags & OSP_PROFILE_KERNELS;
     CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));   // side-stream work of a call that bailed out early
@@ -647,18 +668,14 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     stt.kernel_launches = ctx->launches;
     stt.row_chunks = n_blocks;
     stt.ms_h2d = ms_h2d;
-    cudaEventElapsedTime(&stt.ms_total, ev_begin, ev_end);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ev_begin, ev_sym);
-    stt.ms_convert = ms;
+    res->call_id = ctx->call_id;
+    res->spans.push_back({&stt.ms_total, nullptr, ev_begin, ev_end});
+    res->spans.push_back({&stt.ms_convert, nullptr, ev_begin, ev_sym});
     for (size_t b = 0; b < n_blocks; b++) {
-        cudaEventElapsedTime(&ms, ev_blocks[3 * b], ev_blocks[3 * b + 1]); stt.ms_multiply += ms;
-        cudaEventElapsedTime(&ms, ev_blocks[3 * b + 1], ev_blocks[3 * b + 2]); stt.ms_merge += ms;
+        res->spans.push_back({&stt.ms_multiply, nullptr, ev_blocks[3 * b], ev_blocks[3 * b + 1]});
+        res->spans.push_back({&stt.ms_merge, nullptr, ev_blocks[3 * b + 1], ev_blocks[3 * b + 2]});
     }
-    for (const auto &m : ctx->marks) {
-        cudaEventElapsedTime(&ms, m.e0, m.e1);
-        res->kernel_ms.emplace_back(m.name, ms);
-    }
+    for (const auto &m : ctx->marks) res->spans.push_back({nullptr, m.name, m.e0, m.e1});
     ctx->profile_kernels = false;
     *out = res;
     return OSP_OK;
@@ -666,6 +683,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
 
 int osp_result_kernels(const osp_result *r, uint64_t *n, const char **names, float *ms) {
     if (!r || !n) return fail(nullptr, OSP_ERR_INVALID, "osp_result_kernels: NULL argument");
+    resolve_times(const_cast<osp_result *>(r));
     if (names && ms)
         for (size_t i = 0; i < r->kernel_ms.size() && i < *n; i++) { names[i] = r->kernel_ms[i].first; ms[i] = r->kernel_ms[i].second; }
     *n = r->kernel_ms.size();
@@ -702,6 +720,7 @@ int osp_result_device(const osp_result *r, const uint64_t **d_pos, const void **
 
 int osp_result_stats(const osp_result *r, osp_stats *stats) {
     if (!r || !stats) return fail(nullptr, OSP_ERR_INVALID, "osp_result_stats: NULL argument");
+    resolve_times(const_cast<osp_result *>(r));
     *stats = r->stats;
     return OSP_OK;
 }
@@ -775,6 +794,7 @@ int osp_csr2csc(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint64_t
     CU(ctx, cudaSetDevice(ctx->device));
     ctx->launches = 0;
     ctx->events_used = 0;
+    ctx->call_id++;
     ctx->profile_kernels = false;
     int rc;
     if (flags & OSP_DEVICE_POINTERS) {

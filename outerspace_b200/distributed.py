@@ -219,6 +219,29 @@ def bench_sharded(a: CSRMatrix, b: CSRMatrix, dims: dict, args, rank: int, world
         if i >= 2:
             e2e.append(float(tm[0]))
 
+    # the same workload on ONE GPU (rank 0, its full operands), so that the scaling of this line can be read
+    # against the same problem: bench.py's N=1 line is BASELINE.json configs[1], a different workload
+    n1 = None
+    if rank == 0:
+        tf = [up(a.pos), up(a.data), up(b.pos), up(b.data)]
+        ms1 = []
+        for i in range(3 + min(args.steps, 5)):
+            flush_l2()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            r1 = eng.spgemm_device(a.NRow(), tf[0].data_ptr(), tf[1].data_ptr(), b.NRow(), tf[2].data_ptr(), tf[3].data_ptr(),
+                                   a_is_csr=True, cols_b=dims["cols"], a_nnz=a.nnz, b_nnz=b.nnz)
+            e1.record(stream)
+            e1.synchronize()
+            if i >= 3:
+                ms1.append(e0.elapsed_time(e1))
+            p1 = r1.stats()["products"]
+            r1.free()
+        n1 = {"ms_per_step": round(sum(ms1) / len(ms1), 5), "value": round(2.0 * p1 / (sum(ms1) / len(ms1) * 1e-3) / 1e9, 3),
+              "unit": "GFLOP/s", "note": "same workload, single-GPU engine on rank 0, same timing rules"}
+        del tf
+    barrier()
+
     # whole-job sums
     tot = torch.tensor([st["products"], st["nnz_c"], st["algorithmic_bytes"], st["nnz_a"], st["exchange_bytes_out"],
                         a_g.pos.nbytes + a_g.data.nbytes + b_g.pos.nbytes + b_g.data.nbytes,
@@ -253,4 +276,4 @@ def bench_sharded(a: CSRMatrix, b: CSRMatrix, dims: dict, args, rank: int, world
     return dict(ms_per_step=sum(ms_steps) / len(ms_steps), wall=wall, clocks=clocks, launches=launches, stats=stats,
                 kernel=(kname, agg[kname] / cnt[kname], launches_per_step, agg[kname] / total_ms, table),
                 kernel_bytes=kbytes / max(launches_per_step, 1.0), kernel_formula=formula,
-                e2e_ms=sum(e2e) / len(e2e), h2d=tot[5], d2h=tot[6])
+                e2e_ms=sum(e2e) / len(e2e), h2d=tot[5], d2h=tot[6], n1_same_workload=n1)

@@ -57,7 +57,8 @@ def test_random_vs_oracle(engine, seed):
     A, B = rand_sparse(rng, m, k, rng.uniform(0.01, 0.3)), rand_sparse(rng, k, n, rng.uniform(0.01, 0.3))
     a_csc, a_csr, b_csr = operands(A, B)
     want, prod = oracle_spgemm(a_csc, b_csr)
-    for a, is_csr, flags in ((a_csc, False, 0), (a_csr, True, 0), (a_csr, True, api.OSP_ROWWISE_ORDER)):
+    for a, is_csr, flags in ((a_csc, False, 0), (a_csr, True, 0), (a_csr, True, api.OSP_ROWWISE_ORDER),
+                             (a_csr, True, api.OSP_KSLICE_ORDER)):
         res = engine.spgemm(a, b_csr, a_is_csr=is_csr, flags=flags)
         got = res.to_host()
         assert res.stats()["products"] == prod
@@ -231,3 +232,57 @@ def test_device_resident_operands(engine):
     assert dpos and ddata
     res.free()
     assert_bit_exact(got, want, "device operands")
+
+
+def _row_lengths_case(rng, lens, cols, dup_rate):
+    """A (rows x k) with one non-zero per (row, way) and B rows of chosen lengths: output row i merges
+    lens[i] partial products drawn from `cols` columns, a fraction of them on repeated columns."""
+    import scipy.sparse as sp
+    rows = len(lens)
+    ways = 6
+    k = rows * ways
+    a_r, a_c, b_r, b_c = [], [], [], []
+    for i, L in enumerate(lens):
+        cut = np.sort(rng.integers(0, L + 1, size=ways - 1))
+        parts = np.diff(np.concatenate(([0], cut, [L])))
+        pool = rng.choice(cols, size=max(1, int(L * (1 - dup_rate))), replace=False) if L else np.zeros(0, np.int64)
+        for w, n in enumerate(parts):
+            kk = i * ways + w
+            a_r.append(i); a_c.append(kk)
+            if n:
+                c = np.unique(rng.choice(pool, size=min(int(n), pool.size), replace=False))
+                b_r += [kk] * c.size; b_c += c.tolist()
+    A = sp.csr_matrix((rng.standard_normal(len(a_r)).astype(np.float32) + 3, (a_r, a_c)), shape=(rows, k))
+    B = sp.csr_matrix((rng.standard_normal(len(b_r)).astype(np.float32), (b_r, b_c)), shape=(k, cols))
+    return A, B
+
+
+@pytest.mark.parametrize("cols,dup_rate", [(1 << 14, 0.0), (1 << 14, 0.3), (1 << 20, 0.0), (1 << 20, 0.3), ((1 << 24) + 5, 0.2)])
+def test_every_row_length_class(engine, cols, dup_rate):
+    """Rows of every size class of the merge chain (0, 1, 2..8, ..., 257..512, long rows) side by side in the same
+    tiles; small column range = bitmap-rank variant, 2^20 = 32-bit sort keys, > 2^23 = 64-bit sort keys."""
+    rng = np.random.default_rng(cols % 1000 + int(dup_rate * 10))
+    lens = [0, 1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 127, 128, 129, 200, 255, 256, 257, 300, 400,
+            511, 512, 513, 700, 1500, 5000] * 3
+    rng.shuffle(lens)
+    A, B = _row_lengths_case(rng, lens, cols, dup_rate)
+    a_csc, a_csr, b_csr = operands(A, B)
+    want, prod = oracle_spgemm(a_csc, b_csr)
+    for flags in (0, api.OSP_ROWWISE_ORDER):
+        res = engine.spgemm(a_csr, b_csr, a_is_csr=True, cols_b=cols, flags=flags)
+        got = res.to_host(); res.free()
+        assert_bit_exact(got, want, f"length classes cols={cols} dup={dup_rate} flags={flags}")
+        check_csr_invariants(got, cols)
+
+
+def test_many_tiles_chain_order(engine):
+    """Enough tiles for several per persistent CTA: the look-back chain, the deferred retire and the tile
+    prefetch all cycle; C.pos must be the exact prefix of the survivor counts."""
+    a, b, dims = synth.build_workload("er8m", scale_down=64)
+    a_csc = synth.transpose_host(a, dims["n_k"])
+    want, prod = oracle_spgemm(a_csc, b)
+    for flags in (api.OSP_KSLICE_ORDER, api.OSP_ROWWISE_ORDER):
+        res = engine.spgemm(a, b, a_is_csr=True, cols_b=dims["cols"], flags=flags)
+        got = res.to_host(); st = res.stats(); res.free()
+        assert st["merge_tiles"] > 2000
+        assert_bit_exact(got, want, f"er8m/64 flags={flags}")
