@@ -62,11 +62,11 @@ struct osp_dist {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     DevBuf lens_send, lens_recv, recv_buf, bins2, src_off, dst_off, bounds_idx, bounds_dev, bounds_all;
-    uint64_t *h_bounds = nullptr;      // pinned [world * (world + 1)]
+    uint64_t *h_bounds = nullptr;      // pinned [world * (world + 2)]: per rank its G+1 bounds and its landing capacity
     // peer-memory exchange (the default): every rank maps the owners' bins (CUDA IPC) and its multiply
     // writes the partial products straight into them over NVLink
-    bool p2p = true;
-    DevBuf seg_send, seg_off, run_dst, handles_dev, flags_dev;
+    bool p2p = true, mapped_once = false;
+    DevBuf handles_dev, flags_dev;
     cudaIpcMemHandle_t *h_handles = nullptr;          // pinned [world]: the bins' IPC handles, all-gathered every call
     uint32_t *h_flags = nullptr;                      // pinned [world]
     cudaIpcMemHandle_t peer_handle[MAX_PEERS];        // what is currently mapped
@@ -87,24 +87,24 @@ namespace {
 
 uint64_t block_begin(uint64_t rows, int world, int r) { return rows * uint64_t(r) / uint64_t(world); }
 
-// Makes this rank's bins hold `bytes` and maps every owner's bins into this process.  The previous
+// Makes this rank's landing buffer hold `bytes` and maps every owner's landing buffer into this process.  The previous
 // allocation of a grown buffer is kept until the next growth: peers may still have it mapped until they
 // see the new handle in this call's all-gather.  Returns OSP_OK with d->p2p cleared when some rank could
 // not map a peer (every rank then takes the NCCL path, consistently).
 int map_peer_bins(osp_dist *d, uint64_t bytes) {
     osp_ctx *ctx = d->ctx;
     const int G = d->world, me = d->rank;
-    if (bytes > d->bins2.cap) {
+    if (bytes > d->recv_buf.cap) {
         if (d->retired) { cudaFree(d->retired); d->retired = nullptr; }
-        d->retired = d->bins2.p;
-        d->bins2.p = nullptr; d->bins2.cap = 0;
-        CU(ctx, d->bins2.reserve(bytes));
+        d->retired = d->recv_buf.p;
+        d->recv_buf.p = nullptr; d->recv_buf.cap = 0;
+        CU(ctx, d->recv_buf.reserve(bytes));
     }
-    d->peer_ptr[me] = d->bins2.p;
+    d->peer_ptr[me] = d->recv_buf.p;
     if (G == 1) return OSP_OK;
-    if (d->own_exported != d->bins2.p) {
-        CU(ctx, cudaIpcGetMemHandle(&d->h_handles[me], d->bins2.p));
-        d->own_exported = d->bins2.p;
+    if (d->own_exported != d->recv_buf.p) {
+        CU(ctx, cudaIpcGetMemHandle(&d->h_handles[me], d->recv_buf.p));
+        d->own_exported = d->recv_buf.p;
     }
     CU(ctx, d->handles_dev.reserve(size_t(G) * sizeof(cudaIpcMemHandle_t)));
     CU(ctx, d->flags_dev.reserve(size_t(G) * 4 + 4));
@@ -137,6 +137,9 @@ int map_peer_bins(osp_dist *d, uint64_t bytes) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     for (int r = 0; r < G; r++)
         if (!d->h_flags[r]) d->p2p = false;
+    if (!d->p2p)                                   // staged exchange from now on: nobody writes through a mapping again
+        for (int r = 0; r < G; r++)
+            if (d->peer_open[r]) { cudaIpcCloseMemHandle(d->peer_ptr[r]); d->peer_open[r] = false; }
     return OSP_OK;
 }
 
@@ -173,7 +176,7 @@ int osp_dist_create(osp_ctx *ctx, const void *id128, int rank, int world, osp_di
         delete d;
         return fail(ctx, OSP_ERR_CUDA, std::string("ncclCommInitRank: ") + api->GetErrorString(r));
     }
-    cudaMallocHost(reinterpret_cast<void **>(&d->h_bounds), size_t(world) * (world + 1) * 8);
+    cudaMallocHost(reinterpret_cast<void **>(&d->h_bounds), size_t(world) * (world + 2) * 8);
     cudaMallocHost(reinterpret_cast<void **>(&d->h_handles), size_t(world) * sizeof(cudaIpcMemHandle_t));
     cudaMallocHost(reinterpret_cast<void **>(&d->h_flags), size_t(world) * 4);
     std::memset(d->peer_handle, 0, sizeof(d->peer_handle));
@@ -191,7 +194,7 @@ void osp_dist_destroy(osp_dist *d) {
     for (int r = 0; r < d->world && r < MAX_PEERS; r++)
         if (d->peer_open[r]) cudaIpcCloseMemHandle(d->peer_ptr[r]);
     for (DevBuf *b : {&d->lens_send, &d->lens_recv, &d->recv_buf, &d->bins2, &d->src_off, &d->dst_off, &d->bounds_idx,
-                      &d->bounds_dev, &d->bounds_all, &d->seg_send, &d->seg_off, &d->run_dst, &d->handles_dev, &d->flags_dev})
+                      &d->bounds_dev, &d->bounds_all, &d->handles_dev, &d->flags_dev})
         b->release();
     if (d->retired) cudaFree(d->retired);
     if (d->h_bounds) cudaFreeHost(d->h_bounds);
@@ -255,25 +258,29 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     LAUNCH(ctx, k_shard_rows, grid_for(m + 1, 256, 1u << 30), 256, 0, op.a_pos, m_a, run_off, nnz_a, m, row_bin,
            d->lens_send.as<uint32_t>(), ctx->d_sc);
     // send offsets at the owners' row boundaries, all-gathered: bounds_all[s][dst] = row_bin_s[R_dst]
-    CU(ctx, d->bounds_idx.reserve((G + 1) * 8));
-    CU(ctx, d->bounds_dev.reserve((G + 1) * 8));
-    CU(ctx, d->bounds_all.reserve(uint64_t(G) * (G + 1) * 8));
+    // (the last word of a rank's record is the capacity of its landing buffer: every rank can tell who must grow)
+    CU(ctx, d->bounds_idx.reserve((G + 2) * 8));
+    CU(ctx, d->bounds_dev.reserve((G + 2) * 8));
+    CU(ctx, d->bounds_all.reserve(uint64_t(G) * (G + 2) * 8));
     {
-        std::vector<uint64_t> idx(G + 1);
+        std::vector<uint64_t> idx(G + 2);
         for (int r = 0; r <= G; r++) idx[r] = block_begin(m, G, r);
-        std::memcpy(d->h_bounds, idx.data(), (G + 1) * 8);
-        CU(ctx, cudaMemcpyAsync(d->bounds_idx.p, d->h_bounds, (G + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        idx[G + 1] = uint64_t(d->recv_buf.cap);
+        std::memcpy(d->h_bounds, idx.data(), (G + 2) * 8);
+        CU(ctx, cudaMemcpyAsync(d->bounds_idx.p, d->h_bounds, (G + 2) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(d->bounds_dev.as<uint64_t>() + (G + 1), d->bounds_idx.as<uint64_t>() + (G + 1), 8,
+                                cudaMemcpyDeviceToDevice, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));           // h_bounds is reused as the landing buffer below
     }
     LAUNCH(ctx, k_pick_u64, 1, 256, 0, row_bin, d->bounds_idx.as<uint64_t>(), uint32_t(G + 1), d->bounds_dev.as<uint64_t>());
-    NC(ctx, d, d->nccl->AllGather(d->bounds_dev.p, d->bounds_all.p, G + 1, ncclUint64, d->comm, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(d->h_bounds, d->bounds_all.p, uint64_t(G) * (G + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    NC(ctx, d, d->nccl->AllGather(d->bounds_dev.p, d->bounds_all.p, G + 2, ncclUint64, d->comm, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d->h_bounds, d->bounds_all.p, uint64_t(G) * (G + 2) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     rc = sync_scalars(ctx);
     if (rc) return rc;
     if (ctx->h_sc->err == 6) return fail(ctx, OSP_ERR_UNSUPPORTED, "osp_dist_spgemm: a row of one shard holds >= 2^32 partial products");
     if (ctx->h_sc->err) return fail(ctx, OSP_ERR_INDEX, "osp_dist_spgemm: index of A out of range of the shard's inner dimension");
     const uint64_t P_local = ctx->h_sc->products;
-    auto bound = [&](int s, int r) { return d->h_bounds[uint64_t(s) * (G + 1) + r]; };
+    auto bound = [&](int s, int r) { return d->h_bounds[uint64_t(s) * (G + 2) + r]; };
     std::vector<uint64_t> recv_cnt(G), recv_off(G + 1, 0);
     for (int s = 0; s < G; s++) { recv_cnt[s] = bound(s, me + 1) - bound(s, me); recv_off[s + 1] = recv_off[s] + recv_cnt[s]; }
     const uint64_t P_owned = recv_off[G];
@@ -288,56 +295,47 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     }
     NC(ctx, d, d->nccl->GroupEnd());
     cudaEvent_t ev_sym = nullptr, ev_mul = nullptr, ev_xchg = nullptr;
-    // the same decision on every rank: segment offsets travel as uint32, so every owner's bins must stay below 2^32
-    uint64_t p_owned_max = 0;
-    for (int r = 0; r < G; r++) {
-        uint64_t p = 0;
-        for (int s2 = 0; s2 < G; s2++) p += bound(s2, r + 1) - bound(s2, r);
-        p_owned_max = std::max(p_owned_max, p);
-    }
-    bool direct = d->p2p && p_owned_max < (1ull << 32) && (m / G + 1) * uint64_t(G) < (1ull << 32);
+    // ---- peer-memory exchange: every owner's landing buffer is mapped, the multiply stores into it --------
+    // Every rank knows every owner's partial-product count and landing capacity (the all-gather above), so all
+    // ranks agree, without talking, on whether a buffer grows and the IPC handles must go round again.
+    bool direct = d->p2p;
     if (direct) {
-        // ---- peer-memory exchange: owners lay out their bins, sources write into them ----------------
-        // owner: offsets of every (row, source) segment inside its row-major bins; back to the sources
-        const uint64_t n = RL * G;
-        if ((rc = [&]() -> int {
-                CU(ctx, d->dst_off.reserve((n + 1) * 8));
-                CU(ctx, d->seg_send.reserve(std::max<uint64_t>(n, 1) * 4));
-                CU(ctx, d->seg_off.reserve(std::max<uint64_t>(m, 1) * 4));
-                CU(ctx, d->run_dst.reserve(std::max<uint64_t>(nnz_a, 1) * 8));
-                return OSP_OK;
-            }())) return rc;
-        if (RL) {
-            LAUNCH(ctx, (k_scan<TransposedIn, U64Out>), unsigned(st[3]), SCAN_BLOCK, 0,
-                   TransposedIn{d->lens_recv.as<uint32_t>(), RL, uint64_t(G)}, U64Out{d->dst_off.as<uint64_t>()}, n, ar.state[3],
-                   &ctx->d_sc->scan_ticket[3]);
-            LAUNCH(ctx, k_seg_offsets, grid_for(n, 256, 1u << 30), 256, 0, d->dst_off.as<uint64_t>(), RL, uint32_t(G),
-                   d->seg_send.as<uint32_t>());
-        }
-        NC(ctx, d, d->nccl->GroupStart());
+        bool remap = !d->mapped_once;
+        std::vector<uint64_t> p_owned(G, 0);
         for (int r = 0; r < G; r++) {
-            const uint64_t b0 = block_begin(m, G, r), b1 = block_begin(m, G, r + 1);
-            if (RL) NC(ctx, d, d->nccl->Send(d->seg_send.as<uint32_t>() + uint64_t(r) * RL, RL, ncclUint32, r, d->comm, ctx->stream));
-            if (b1 > b0) NC(ctx, d, d->nccl->Recv(d->seg_off.as<uint32_t>() + b0, b1 - b0, ncclUint32, r, d->comm, ctx->stream));
+            for (int s2 = 0; s2 < G; s2++) p_owned[r] += bound(s2, r + 1) - bound(s2, r);
+            if (std::max<uint64_t>(p_owned[r], 1) * 8 + 16 > d->h_bounds[uint64_t(r) * (G + 2) + G + 1]) remap = true;
         }
-        NC(ctx, d, d->nccl->GroupEnd());
-        rc = map_peer_bins(d, std::max<uint64_t>(P_owned, 1) * 8 + 16);      // (host sync: the handles of all owners)
-        if (rc) return rc;
-        direct = d->p2p;
+        if (remap) {
+            rc = map_peer_bins(d, std::max<uint64_t>(P_owned, 1) * 8 + 16);      // (host syncs: handles, success flags)
+            if (rc) return rc;
+            direct = d->p2p;
+            d->mapped_once = true;
+        }
     }
     if (direct) {
+        CU(ctx, d->bins2.reserve(std::max<uint64_t>(P_owned, 1) * 8 + 16));
         ev_sym = next_event(ctx);
         if (nnz_a && P_local) {
-            LAUNCH(ctx, k_run_dst, grid_for(m_a, 64, unsigned(ctx->sm_count) * 32u), 256, 0, op.a_pos, m_a, run_off,
-                   d->seg_off.as<uint32_t>(), m, uint32_t(G), d->run_dst.as<uint64_t>());
-            PeerBins peers;
-            for (int r = 0; r < MAX_PEERS; r++) peers.p[r] = static_cast<Elem *>(r < G ? d->peer_ptr[r] : nullptr);
-            LAUNCH(ctx, k_multiply_peer, grid_for(nnz_a, 256, unsigned(ctx->sm_count) * 32u), 256, 0, op.a_data, run_off,
-                   d->run_dst.as<uint64_t>(), op.b_pos, nnz_a, op.b_data, peers);
+            PeerDst dst;
+            std::memset(&dst, 0, sizeof(dst));
+            dst.world = G;
+            for (int r = 0; r < G; r++) {
+                dst.base[r] = static_cast<Elem *>(d->peer_ptr[r]);
+                dst.bound[r] = bound(me, r);
+                uint64_t region = 0;                                   // where source `me` lands inside owner r's buffer
+                for (int s2 = 0; s2 < me; s2++) region += bound(s2, r + 1) - bound(s2, r);
+                dst.delta[r] = int64_t(region) - int64_t(bound(me, r));
+            }
+            dst.bound[G] = bound(me, G);
+            const uint64_t first_row = std::min<uint64_t>(block_begin(m, G, (me + 1) % G), m_a);
+            LAUNCH(ctx, k_multiply_peer, grid_for(nnz_a, 256, unsigned(ctx->sm_count) * 32u), 256, 0, op.a_data, run_off, op.b_pos,
+                   nnz_a, op.b_data, dst, op.a_pos, first_row);
         }
         ev_mul = next_event(ctx);
         // every rank's stores have landed once every rank's multiply has retired: one tiny collective on the stream
         if (G > 1) {
+            CU(ctx, d->flags_dev.reserve(size_t(G) * 4 + 4));
             uint32_t *fd = d->flags_dev.as<uint32_t>();
             NC(ctx, d, d->nccl->AllGather(fd + me, fd, 1, ncclUint32, d->comm, ctx->stream));
         }
@@ -377,14 +375,12 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
                 return OSP_OK;
             }())) return bail(rc);
         const uint32_t *lens = d->lens_recv.as<uint32_t>();
-        if (!direct) {
-            LAUNCH(ctx, (k_scan<U32In, U64Out>), unsigned(st[2]), SCAN_BLOCK, 0, U32In{lens}, U64Out{d->src_off.as<uint64_t>()}, n,
-                   ar.state[2], &ctx->d_sc->scan_ticket[2]);
-            LAUNCH(ctx, (k_scan<TransposedIn, U64Out>), unsigned(st[3]), SCAN_BLOCK, 0, TransposedIn{lens, RL, uint64_t(G)},
-                   U64Out{d->dst_off.as<uint64_t>()}, n, ar.state[3], &ctx->d_sc->scan_ticket[3]);
-            LAUNCH(ctx, k_regroup, grid_for(RL, 8, unsigned(ctx->sm_count) * 32u), 256, 0, d->recv_buf.as<Elem>(),
-                   d->src_off.as<uint64_t>(), d->dst_off.as<uint64_t>(), lens, RL, uint32_t(G), d->bins2.as<Elem>());
-        }
+        LAUNCH(ctx, (k_scan<U32In, U64Out>), unsigned(st[2]), SCAN_BLOCK, 0, U32In{lens}, U64Out{d->src_off.as<uint64_t>()}, n,
+               ar.state[2], &ctx->d_sc->scan_ticket[2]);
+        LAUNCH(ctx, (k_scan<TransposedIn, U64Out>), unsigned(st[3]), SCAN_BLOCK, 0, TransposedIn{lens, RL, uint64_t(G)},
+               U64Out{d->dst_off.as<uint64_t>()}, n, ar.state[3], &ctx->d_sc->scan_ticket[3]);
+        LAUNCH(ctx, k_regroup, grid_for(RL, 8, unsigned(ctx->sm_count) * 32u), 256, 0, d->recv_buf.as<Elem>(),
+               d->src_off.as<uint64_t>(), d->dst_off.as<uint64_t>(), lens, RL, uint32_t(G), d->bins2.as<Elem>());
         rc = reserve_plan(ctx, RL, RL);
         if (rc) return bail(rc);
         LAUNCH(ctx, k_plan<RowBinStrided>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinStrided{d->dst_off.as<uint64_t>(), uint64_t(G)}, RL,

@@ -49,7 +49,9 @@ struct osp_ctx {
     uint64_t launches = 0;
     uint64_t call_id = 0;
     std::string err;
-    DevScalars *h_sc = nullptr;     // pinned mirror
+    DevScalars *h_sc = nullptr;     // pinned mirror (mapped: k_publish writes it)
+    unsigned long long *h_seq = nullptr, seq = 0;   // sequence number of the last hand-over, polled by the host
+    DevScalars *h_sc_dev = nullptr; unsigned long long *h_seq_dev = nullptr;   // device views of the two
     // per-call zeroed arena: DevScalars | look-back states of the scans | column counters
     DevBuf arena;
     DevScalars *d_sc = nullptr;
@@ -168,6 +170,23 @@ int prepare_arena(osp_ctx *ctx, const uint64_t state_tiles[4], uint64_t n_counte
 }
 
 int sync_scalars(osp_ctx *ctx) {
+    if (ctx->h_seq_dev) {
+        // the scalars arrive by a store from the device; the host polls the sequence number (a few
+        // microseconds less GPU idle time than a copy + stream synchronisation at every hand-over)
+        const unsigned long long seq = ++ctx->seq;
+        k_publish<<<1, 32, 0, ctx->stream>>>(ctx->d_sc, ctx->h_sc_dev, ctx->h_seq_dev, seq);
+        CU(ctx, cudaGetLastError());
+        volatile unsigned long long *flag = ctx->h_seq;
+        for (unsigned long long spins = 0; *flag != seq; spins++) {
+            if ((spins & 0xFFF) == 0xFFF) {
+                cudaError_t q = cudaStreamQuery(ctx->stream);
+                if (q == cudaSuccess) { if (*flag == seq) break; }
+                else if (q != cudaErrorNotReady) { cudaGetLastError(); return fail(ctx, OSP_ERR_CUDA, std::string("device fault: ") + cudaGetErrorString(q)); }
+            }
+        }
+        __sync_synchronize();
+        return OSP_OK;
+    }
     CU(ctx, cudaMemcpyAsync(ctx->h_sc, ctx->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return OSP_OK;
@@ -399,7 +418,18 @@ int osp_create(int device, osp_ctx **out) {
     CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     CU(nullptr, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CU(nullptr, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    CU(nullptr, cudaMallocHost(reinterpret_cast<void **>(&ctx->h_sc), sizeof(DevScalars)));
+    CU(nullptr, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_sc), sizeof(DevScalars) + 64, cudaHostAllocMapped));
+    ctx->h_seq = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(ctx->h_sc) + ((sizeof(DevScalars) + 15) & ~size_t(15)));
+    *ctx->h_seq = 0;
+    if (!std::getenv("OSP_NO_MAPPED_SYNC")) {
+        void *dv = nullptr;
+        if (cudaHostGetDevicePointer(&dv, ctx->h_sc, 0) == cudaSuccess) {
+            ctx->h_sc_dev = static_cast<DevScalars *>(dv);
+            ctx->h_seq_dev = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(dv) + ((sizeof(DevScalars) + 15) & ~size_t(15)));
+        } else {
+            cudaGetLastError();
+        }
+    }
     CU(nullptr, cudaFuncSetAttribute(k_merge_long, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LONG_SMEM)));
     CU(nullptr, cudaFuncSetAttribute(k_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dense_smem(DENSE_MAX_COLS))));
     {

@@ -141,6 +141,19 @@ struct U32Out {           // column pointers of the task list (nnzA < 2^32 is ch
 // =====================================================================================
 // Small utility kernels
 // =====================================================================================
+// Hands the device scalars to the host without a copy-engine round trip: one warp writes them into mapped
+// pinned memory, fences at system scope and raises the sequence number the host is polling.
+__global__ void k_publish(const DevScalars *d, DevScalars *h, unsigned long long *h_seq, unsigned long long seq) {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(d);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(h);
+    for (unsigned int i = threadIdx.x; i < sizeof(DevScalars) / 4; i += 32) dst[i] = __ldcg(src + i);
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(h_seq) = seq;
+    }
+}
 __global__ void k_max_idx(const Elem *d, uint64_t nnz, DevScalars *sc) {
     uint32_t m = 0;
     for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < nnz; i += uint64_t(gridDim.x) * blockDim.x)
@@ -1235,80 +1248,80 @@ struct RowBinStrided {         // row i of the owner starts at dst_off[i * G]
     __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return off[i * G]; }
     __device__ __forceinline__ bool nonempty(uint64_t i) const { return off[(i + 1) * G] > off[i * G]; }
 };
-// One warp per owned row: copies the row's segment of every source (received source-major) into the
-// row-major bins, sources in ascending order.
+// One warp per owned row: the row's G segments (one per source, received source-major) become one contiguous
+// row in the row-major bins, sources in ascending order.  The lanes stride over the ROW's elements -- every
+// lane copies whatever the segment lengths are (at G = 8 a segment is a single run of ~8 partial products) --
+// and find the segment of an element by comparing its position with the scanned segment lengths.
 __global__ void k_regroup(const Elem *__restrict__ recv, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ dst_off,
                           const uint32_t *__restrict__ lens, uint64_t RL, uint32_t G, Elem *__restrict__ bins) {
+    const unsigned int lane = lane_id();
     uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
     uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
     for (uint64_t i = warp; i < RL; i += nwarps) {
-        for (uint32_t s = 0; s < G; s++) {
-            const uint32_t n = lens[s * RL + i];
-            const Elem *src = recv + src_off[s * RL + i];
-            Elem *dst = bins + dst_off[i * G + s];
-            for (uint32_t t = lane_id(); t < n; t += 32) dst[t] = src[t];
+        uint32_t l = 0;
+        uint64_t so = 0;
+        if (lane < G) { l = lens[uint64_t(lane) * RL + i]; so = src_off[uint64_t(lane) * RL + i]; }
+        const uint32_t cum = warp_inclusive_scan(l);
+        const uint32_t total = __shfl_sync(FULL, cum, 31);
+        const uint64_t rel = so - (cum - l);                  // source index of element p of segment s: rel_s + p
+        Elem *dst = bins + dst_off[i * G];
+        for (uint32_t p0 = 0; p0 < total; p0 += 32) {
+            const uint32_t p = p0 + lane;
+            uint32_t s = 0;
+            for (uint32_t k = 0; k + 1 < G; k++) s += __shfl_sync(FULL, cum, k) <= p;
+            const uint64_t src = __shfl_sync(FULL, rel, s) + p;
+            if (p < total) dst[p] = recv[src];
         }
     }
 }
 
-
-// ---- peer-memory exchange: the multiply writes straight into the owners' bins over NVLink -----------------
-// Owner side: the offset, inside the owner's row-major bins, of the segment that source s contributes to
-// owned row i (dst_off is in (i, s) order) laid out per source, ready to be sent back to the sources.
-__global__ void k_seg_offsets(const uint64_t *__restrict__ dst_off, uint64_t RL, uint32_t G, uint32_t *__restrict__ seg_send) {
-    const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;      // j = s * RL + i
-    if (j >= RL * G) return;
-    const uint64_t s = j / RL, i = j % RL;
-    seg_send[j] = uint32_t(dst_off[i * G + s]);
-}
-// Source side: destination of every run of the shard = (owner of its row << 56) | element offset inside
-// that owner's bins.  Rows are owned in blocks [m g / G, m (g + 1) / G).
-constexpr int PEER_SHIFT = 56;
+// ---- peer-memory exchange: the multiply writes straight into the owners' memory over NVLink ------------
+// Every owner holds a landing buffer made of G regions, one per source, each row-major over the owner's rows.
+// A source's partial products for one owner are therefore ONE contiguous stream, at the offsets its own
+// symbolic pass computed: destination = owner's region for this source + (run offset - offset of the owner's
+// first row in the source's local row-major order).  The owner of a run follows from its offset alone (rows
+// are owned in contiguous blocks), so the kernel needs no per-row table.
 constexpr int MAX_PEERS = 16;
-__global__ void k_run_dst(const uint64_t *__restrict__ a_pos, uint64_t m_a, const uint64_t *__restrict__ run_off,
-                          const uint32_t *__restrict__ seg_off, uint64_t m, uint32_t G, uint64_t *__restrict__ run_dst) {
-    // four lanes per row: shard rows hold few non-zeros (nnz(A) / (m G) each on average)
-    const uint64_t grp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 2;
-    const uint64_t ngrp = (uint64_t(gridDim.x) * blockDim.x) >> 2;
-    const unsigned int sub = threadIdx.x & 3;
-    for (uint64_t r = grp; r < m_a; r += ngrp) {
-        const uint64_t p0 = a_pos[r], p1 = a_pos[r + 1];
-        if (p1 == p0) continue;
-        const uint64_t owner = ((r + 1) * G - 1) / m;
-        const uint64_t base = (owner << PEER_SHIFT) | uint64_t(seg_off[r]);
-        const uint64_t first = run_off[p0];
-        for (uint64_t p = p0 + sub; p < p1; p += 4) run_dst[p] = base + (run_off[p] - first);
-    }
-}
-struct PeerBins { Elem *p[MAX_PEERS]; };
-// The warp-flat multiply of k_multiply with every run going to the bins of the GPU that owns its output row:
-// peer memory mapped through CUDA IPC, 8-byte stores over NVLink that are contiguous inside a run.  The
-// exchange of the k-sharded path IS this kernel's store stream: nothing is staged, sent or regrouped.
+struct PeerDst {
+    Elem *base[MAX_PEERS];           // owner's landing buffer (mapped through CUDA IPC; the own one directly)
+    uint64_t bound[MAX_PEERS + 1];   // local run offset at which owner r's rows begin (bound[G] = P_local)
+    int64_t delta[MAX_PEERS];        // region start inside owner r's buffer - bound[r]
+    int world;
+};
+// The warp-flat multiply of k_multiply with every run going to the GPU that owns its output row: 8-byte stores
+// over NVLink that are contiguous from run to run.  The exchange of the k-sharded path IS this kernel's store
+// stream: nothing is staged or sent.
 __global__ void __launch_bounds__(256)
-k_multiply_peer(const Elem *__restrict__ a_data, const uint64_t *__restrict__ run_off, const uint64_t *__restrict__ run_dst,
-                const uint64_t *__restrict__ b_pos, uint64_t t1, const Elem *__restrict__ b_data, const PeerBins peers) {
-    __shared__ Elem *s_peer[MAX_PEERS];
-    if (threadIdx.x < MAX_PEERS) s_peer[threadIdx.x] = peers.p[threadIdx.x];
+k_multiply_peer(const Elem *__restrict__ a_data, const uint64_t *__restrict__ run_off, const uint64_t *__restrict__ b_pos,
+                uint64_t t1, const Elem *__restrict__ b_data, const PeerDst dst, const uint64_t *__restrict__ a_pos,
+                uint64_t first_row) {
+    __shared__ Elem *s_base[MAX_PEERS];
+    if (threadIdx.x < MAX_PEERS) s_base[threadIdx.x] = dst.base[threadIdx.x];
     __syncthreads();
     const unsigned int lane = lane_id();
     const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
     const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    // The sweep over the tasks starts at `first_row` (the first row of the NEXT rank's block) and wraps round:
+    // at any moment the G sources are writing to G different owners instead of all to the same one.
+    const uint64_t rot = a_pos[first_row];
     for (uint64_t base = warp * 32; base < t1; base += nwarps * 32) {
         uint32_t bs = 0, len = 0, owner = 0; float a = 0.f; uint64_t off = 0;
         if (base + lane < t1) {
-            const uint64_t i = base + lane;
+            uint64_t i = base + lane + rot;
+            if (i >= t1) i -= t1;
             const Elem e = a_data[i];
             a = e.val;
-            const uint64_t d = run_dst[i];
-            owner = uint32_t(d >> PEER_SHIFT); off = d & ((1ull << PEER_SHIFT) - 1);
-            len = uint32_t(run_off[i + 1] - run_off[i]);
+            const uint64_t o = run_off[i];
+            len = uint32_t(run_off[i + 1] - o);
             bs = uint32_t(b_pos[e.idx]);
+            for (int r = 1; r < dst.world; r++) owner += o >= dst.bound[r];      // rows are owned in ascending blocks
+            off = o + uint64_t(dst.delta[owner]);
         }
         const uint32_t incl = warp_inclusive_scan(len);
         const uint32_t total = __shfl_sync(FULL, incl, 31);
         const uint32_t excl = incl - len;
         const uint32_t dbs = bs - excl;                       // B index of element e of this task: dbs + e
-        const uint64_t doff = off - excl;                     // bin index of element e of this task: doff + e (mod 2^64)
+        const uint64_t doff = off - excl;                     // landing index of element e of this task: doff + e (mod 2^64)
         for (uint32_t e0 = 0; e0 < total; e0 += 64) {          // two independent 32-element chunks per turn
             const uint32_t e[2] = {e0 + lane, e0 + 32 + lane};
             uint32_t t[2] = {0, 0};                            // number of tasks that end at or before e
@@ -1335,7 +1348,7 @@ k_multiply_peer(const Elem *__restrict__ a_data, const uint64_t *__restrict__ ru
             for (int u = 0; u < 2; u++) {
                 if (e[u] < total) {
                     Elem o; o.idx = b[u].idx; o.val = __fmul_rn(a_t[u], b[u].val);     // rounded on its own: no FMA
-                    s_peer[own_t[u]][doff_t[u] + e[u]] = o;
+                    s_base[own_t[u]][doff_t[u] + e[u]] = o;
                 }
             }
         }
