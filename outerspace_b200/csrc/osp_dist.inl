@@ -365,7 +365,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     std::memset(&res->stats, 0, sizeof(res->stats));
     auto bail = [&](int code) { osp_result_free(res); return code; };
     MergeJob job;
-    job.rows = std::max<uint64_t>(RL, 1); job.idx_range = cols_b;
+    job.rows = std::max<uint64_t>(RL, 1); job.idx_range = cols_b; job.long_thresh = plan_long_thresh(cols_b);
     uint64_t nnz_c = 0;
     if (RL) {
         const uint64_t n = RL * G;
@@ -385,7 +385,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
         if (rc) return bail(rc);
         LAUNCH(ctx, k_plan<RowBinStrided>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinStrided{d->dst_off.as<uint64_t>(), uint64_t(G)}, RL,
                cols_b, ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
-               ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1);
+               ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(cols_b));
         rc = sync_scalars(ctx);
         if (rc) return bail(rc);
         job.n_tiles = ctx->h_sc->n_tiles; job.n_long = ctx->h_sc->n_long; job.n_xl = ctx->h_sc->n_xl;

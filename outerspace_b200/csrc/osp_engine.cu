@@ -201,9 +201,14 @@ int reserve_plan(osp_ctx *ctx, uint64_t rows, uint64_t max_long) {
     return OSP_OK;
 }
 
+// Longest row a warp of the merge chain takes: up to MT_LONG_BM by bitmap rank when the column range is known to be
+// small at plan time, MT_LONG otherwise.  The plan and the chain must be given the same value.
+uint32_t plan_long_thresh(uint64_t idx_range) { return idx_range && idx_range <= 32ull * BM_WORDS ? MT_LONG_BM : MT_LONG; }
+
 struct MergeJob {
     uint64_t rows = 0;          // rows of the plan (c_pos has rows + 1 entries)
     uint64_t idx_range = 0;     // column ids are < idx_range
+    uint32_t long_thresh = MT_LONG;   // what the plan was cut with
     uint32_t n_tiles = 0, n_long = 0, n_xl = 0;
     uint64_t *c_pos = nullptr;
     Elem *c_data = nullptr;
@@ -264,7 +269,7 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
     const uint32_t bm_words = job.idx_range <= 32ull * BM_WORDS ? uint32_t((job.idx_range + 31) / 32) : 0u;
     const uint32_t bm_wpl = (((bm_words + 31) / 32) + 3) & ~3u;           // bitmap words per lane, a multiple of 4
 #define MC_ARGS row_bin, bin_base, bins, ctx->tile_row.as<uint32_t>(), t0, n_chain, uniq, ctx->tile_state.as<uint64_t>(), ctx->d_sc, \
-                carry_slot, job.c_pos, job.c_data, bm_wpl
+                carry_slot, job.c_pos, job.c_data, bm_wpl, job.long_thresh
     const int variant = bm_words ? 2 : job.idx_range <= (1ull << 23) ? 0 : 1;
     const unsigned int grid = std::min<unsigned>(n_chain, unsigned(ctx->sm_count) * unsigned(ctx->chain_occ[variant]));   // persistent CTAs
     if (variant == 2) LAUNCH(ctx, (k_merge_chain<uint32_t, true>), grid, MC_THREADS, sizeof(MergeChainSmem<true>), MC_ARGS);
@@ -300,12 +305,12 @@ int csr2csc_device(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint6
     if (rc) return rc;
     LAUNCH(ctx, k_plan<RowBinDirect>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinDirect{d_pos_out}, n_minor, n_major,
            ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
-           ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1);
+           ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(std::max<uint64_t>(n_major, 1)));
     rc = sync_scalars(ctx);
     if (rc) return rc;
     if (ctx->h_sc->err) return fail(ctx, OSP_ERR_INDEX, "index out of range in operand");
     MergeJob job;
-    job.rows = n_minor; job.idx_range = std::max<uint64_t>(n_major, 1);
+    job.rows = n_minor; job.idx_range = std::max<uint64_t>(n_major, 1); job.long_thresh = plan_long_thresh(job.idx_range);
     job.n_tiles = ctx->h_sc->n_tiles; job.n_long = ctx->h_sc->n_long; job.n_xl = ctx->h_sc->n_xl;
     CU(ctx, ctx->conv_chk.reserve((n_minor + 1) * 8));
     job.c_pos = ctx->conv_chk.as<uint64_t>(); job.c_data = d_data_out; job.c_cap = nnz;
@@ -593,7 +598,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     if (rc) return rc;
     LAUNCH(ctx, k_plan<RowBinFromRuns>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinFromRuns{dA_pos, m_a, run_off, nnz_a}, m_plan,
            cols_b, ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
-           ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1);
+           ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(cols_b));
     cudaEvent_t ev_sym = next_event(ctx);
     rc = sync_scalars(ctx);                       // the one mid-pipeline sync: sizes of the bins and of C
     if (rc) return rc;
@@ -610,7 +615,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         return fail(ctx, OSP_ERR_INDEX, "osp_spgemm: rows_c is smaller than the largest row id of A + 1");
 
     MergeJob job;
-    job.rows = m_plan; job.idx_range = std::max<uint64_t>(cols_b, 1);
+    job.rows = m_plan; job.idx_range = std::max<uint64_t>(cols_b, 1); job.long_thresh = plan_long_thresh(args->cols_b);
     job.n_tiles = ctx->h_sc->n_tiles; job.n_long = ctx->h_sc->n_long; job.n_xl = ctx->h_sc->n_xl;
     const uint64_t cap_bound = args->cols_b ? ctx->h_sc->cap_bound : std::min<uint64_t>(ctx->h_sc->cap_bound, P);
 

@@ -173,7 +173,8 @@ __global__ void k_max_idx(const Elem *d, uint64_t nnz, DevScalars *sc) {
 constexpr int MT_CAP_SHIFT_MIN = 8, MT_CAP_SHIFT_MAX = 11;
 constexpr uint32_t MT_CAP = 1u << MT_CAP_SHIFT_MAX;   // partial products per tile (soft): one CTA merges a tile
 constexpr uint32_t MT_LONG = 512;      // longest row sorted in registers by one warp
-constexpr uint32_t MT_STAGE = MT_CAP + MT_LONG;       // hard bound of a tile of short rows (shared-memory stage)
+constexpr uint32_t MT_LONG_BM = 640;   // longest row merged by bitmap rank by one warp (small column ranges)
+constexpr uint32_t MT_STAGE = MT_CAP + MT_LONG_BM;    // hard bound of a tile of short rows (shared-memory stage)
 constexpr uint32_t MT_RMAX = 256;      // rows per tile (one thread per row in the tile's scans)
 constexpr uint32_t MT_XL = 4096;       // longest row sorted in shared memory by one CTA
 
@@ -199,7 +200,7 @@ struct RowBinDirect {
 template <class RB>
 __global__ void __launch_bounds__(PLAN_BLOCK)
 k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *tile_row, uint32_t *long_list,
-       uint32_t *xl_list, uint64_t *tile_state, DevScalars *sc, int ticket_slot) {
+       uint32_t *xl_list, uint64_t *tile_state, DevScalars *sc, int ticket_slot, uint32_t long_thresh) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[33];
     __shared__ uint64_t s_bound[PLAN_BLOCK / 32];
@@ -230,10 +231,10 @@ k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *ti
         if (i < rows) {
             const uint64_t len = s[it + 1] - s[it];
             const uint64_t plen = s[it] - sp;
-            flag[it] = i == 0 || (i % MT_RMAX) == 0 || len > MT_LONG || plen > MT_LONG || (sp >> cap_shift) != (s[it] >> cap_shift);
+            flag[it] = i == 0 || (i % MT_RMAX) == 0 || len > long_thresh || plen > long_thresh || (sp >> cap_shift) != (s[it] >> cap_shift);
             row_bin[i] = s[it];
             if (len > MT_XL) xl_list[atomicAdd(&sc->n_xl, 1u)] = uint32_t(i);
-            else if (len > MT_LONG) long_list[atomicAdd(&sc->n_long, 1u)] = uint32_t(i);
+            else if (len > long_thresh) long_list[atomicAdd(&sc->n_long, 1u)] = uint32_t(i);
             if (rb.nonempty(i)) last = uint32_t(i + 1);
             bound += cols_hint ? min(len, cols_hint) : len;
             nflags += flag[it];
@@ -947,7 +948,7 @@ struct __align__(16) MergeChainSmem {
     uint32_t warp_sums[33];
     uint32_t next_batch;
     uint16_t order[MT_RMAX];           // the tile's rows grouped by size class, longest class first
-    uint32_t cls_cnt[8], cls_off[8], cls_b0[8];   // per class: rows, start in order[], first batch; cls_b0[7] = batches
+    uint32_t cls_cnt[8], cls_off[8], cls_b0[9];   // per class: rows, start in order[], first batch; cls_b0[8] = batches
     uint64_t base;
     uint64_t mbar;
     uint64_t d_r0[2], d_g0[2];         // descriptors of the tiles opened ahead (written by the opening warp)
@@ -1000,7 +1001,7 @@ __global__ void __launch_bounds__(MC_THREADS, BM ? 2 : MC_OCC)
 k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, const Elem *__restrict__ bins,
               const uint32_t *__restrict__ tile_row, const uint32_t t0, const uint32_t n_chain,
               const uint32_t *__restrict__ uniq, uint64_t *tile_state, DevScalars *sc, const int carry_slot,
-              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, const uint32_t bm_wpl) {
+              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, const uint32_t bm_wpl, const uint32_t long_thresh) {
     using Smem = MergeChainSmem<BM>;
     Smem &sm = *reinterpret_cast<Smem *>(osp_smem);
     const unsigned int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
@@ -1024,7 +1025,7 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
             R = uint32_t(r1 - r0);
             const uint64_t b0 = row_bin[r0], b1 = row_bin[r1];
             g0 = b0 - bin_base;
-            is_long = R == 1 && b1 - b0 > MT_LONG;
+            is_long = R == 1 && b1 - b0 > long_thresh;
             n_in = is_long ? 0u : uint32_t(b1 - b0);
             if (!is_long)
                 for (uint32_t j = lane; j <= R; j += 32) sm.rstart[slot][j] = uint32_t(row_bin[r0 + j] - b0);
@@ -1101,8 +1102,9 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
             Elem *ostage = sm.ostage[ob];
             const uint32_t R = cur.R;
             // size classes (while the bulk copy is in flight): class c sorts rows of <= 8 << c partial products,
-            // 32 >> c rows per warp at a time (class 6: 257..512, one row per warp, 16 keys per lane)
-            uint32_t my_len = 0, my_cls = 7, my_pos = 0;
+            // 32 >> c rows per warp at a time (class 6: 257..512, one row per warp, 16 keys per lane; class 7: 513..640,
+            // bitmap variant only)
+            uint32_t my_len = 0, my_cls = 8, my_pos = 0;
             if (tid < R) {
                 my_len = rstart[tid + 1] - rstart[tid];
                 if (my_len <= 1) rout[tid] = my_len;            // rows of 0 / 1 partial products need no merge
@@ -1115,33 +1117,33 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
             if (tid == 0) {
                 uint32_t off = 0, b = 0;
 #pragma unroll
-                for (int c = 6; c >= 0; c--) {
+                for (int c = 7; c >= 0; c--) {
                     const uint32_t n = sm.cls_cnt[c];
                     sm.cls_off[c] = off; sm.cls_b0[c] = b;
                     off += n;
-                    b += c == 6 || (BM && c == 5) ? n : (n + (32u >> c) - 1) >> (5 - c);
+                    b += c >= 6 || (BM && c == 5) ? n : (n + (32u >> c) - 1) >> (5 - c);
                 }
-                sm.cls_b0[7] = b;
+                sm.cls_b0[8] = b;
             }
             __syncthreads();
-            if (my_cls < 7) sm.order[sm.cls_off[my_cls] + my_pos] = uint16_t(tid);
+            if (my_cls < 8) sm.order[sm.cls_off[my_cls] + my_pos] = uint16_t(tid);
             Elem *stage = sm.stage + uint32_t(cur.g0 & 1);
             const uint32_t stage_off = uint32_t(offsetof(Smem, stage)) + uint32_t(cur.g0 & 1) * 8;
             const uint32_t ost_off = uint32_t(offsetof(Smem, ostage)) + ob * uint32_t(sizeof(Elem) * MC_STAGE_ELEMS);
             if (cur.n_in) { mbar_wait(&sm.mbar, n_tma & 1); n_tma++; }
             if (my_len == 1) ostage[swz(rstart[tid])] = stage[rstart[tid]];
             __syncthreads();                                  // order[] is complete
-            const uint32_t n_batches = sm.cls_b0[7];
+            const uint32_t n_batches = sm.cls_b0[8];
             if (warp == MC_THREADS / 32 - 1) prefetch_tile((it + 1) % 3, (it + 1) & 1);   // the others start on the batches
             while (true) {
                 uint32_t b = 0;
                 if (lane == 0) b = atomicAdd(&sm.next_batch, 1u);
                 b = __shfl_sync(FULL, b, 0);
                 if (b >= n_batches) break;
-                int c = 6;
+                int c = 7;
                 while (c > 0 && b >= sm.cls_b0[c - 1]) c--;     // cls_b0 ascends from class 6 down to class 0
-                const uint32_t T = c == 6 ? 5u : uint32_t(c);
-                const uint32_t idx = c == 6 || (BM && c == 5) ? b - sm.cls_b0[c] : ((b - sm.cls_b0[c]) << (5 - c)) + (lane >> T);
+                const uint32_t T = c >= 6 ? 5u : uint32_t(c);
+                const uint32_t idx = c >= 6 || (BM && c == 5) ? b - sm.cls_b0[c] : ((b - sm.cls_b0[c]) << (5 - c)) + (lane >> T);
                 const bool valid = idx < sm.cls_cnt[c];
                 uint32_t j = 0, s = 0, len = 0;
                 if (valid) {
@@ -1153,8 +1155,16 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
                 uint32_t u;
                 if (BM && c >= 5) {       // small column range: rows of > 128 partial products skip the sort
                     const uint32_t scr_off = uint32_t(offsetof(Smem, bm_scratch)) + warp * BM_SCRATCH;
-                    if (c == 5) u = merge_row_bitmap<8>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);
-                    else u = merge_row_bitmap<16>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);
+                    if (c == 5) {
+                        if (len <= 192) u = merge_row_bitmap<6>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);
+                        else u = merge_row_bitmap<8>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);
+                    }
+                    else if (c == 6) {                        // 257..512: as many 32-element slots as the row needs
+                        if (len <= 320) u = merge_row_bitmap<10>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);
+                        else if (len <= 384) u = merge_row_bitmap<12>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);
+                        else u = merge_row_bitmap<16>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);
+                    }
+                    else u = merge_row_bitmap<MT_LONG_BM / 32>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);   // 513..640
                 } else
                 switch (c) {
                     case 0: u = merge_rows_grouped<8, 0, K>(row_off, ost_off, s, len, lane); break;
