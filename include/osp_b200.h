@@ -50,6 +50,8 @@ extern "C" {
                                     against row k of B (B streamed once, bins scattered).  With neither flag the
                                     engine picks k-slice order while the bins are expected to stay in L2 and row
                                     order beyond (DESIGN.md "multiply order") */
+#define OSP_NO_FUSED_DENSE  64u  /* keep the bins even when every row is long over a small column range (see
+                                    DESIGN.md "fused dense rows"): multiply -> bins -> k_merge_dense */
 #define OSP_PROFILE_PHASES   8u  /* synchronise between phases so that stats.ms_* are per-phase times */
 
 #define OSP_PROFILE_KERNELS 16u  /* record a CUDA-event pair around every kernel launch (osp_result_kernels) */

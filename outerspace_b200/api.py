@@ -32,6 +32,7 @@ OSP_A_IS_CSR = 1
 OSP_DEVICE_POINTERS = 2
 OSP_ROWWISE_ORDER = 4
 OSP_KSLICE_ORDER = 32
+OSP_NO_FUSED_DENSE = 64
 OSP_PROFILE_PHASES = 8
 OSP_PROFILE_KERNELS = 16
 

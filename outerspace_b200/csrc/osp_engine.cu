@@ -437,6 +437,7 @@ int osp_create(int device, osp_ctx **out) {
     }
     CU(nullptr, cudaFuncSetAttribute(k_merge_long, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LONG_SMEM)));
     CU(nullptr, cudaFuncSetAttribute(k_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dense_smem(DENSE_MAX_COLS))));
+    CU(nullptr, cudaFuncSetAttribute(k_fused_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_dense_smem(DENSE_MAX_COLS))));
     {
         auto k32 = k_merge_chain<uint32_t, false>;
         auto k64 = k_merge_chain<uint64_t, false>;
@@ -553,6 +554,14 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         const double p_est = n_k ? double(nnz_a) * double(nnz_b) / double(n_k) : 0.0;
         rowwise = p_est * 8.0 > double(ctx->l2_bytes) * 0.5;
     }
+    // ---- fused dense rows: when the column range is small and the rows are expected to be long (config 5), the
+    // per-row bin is a dense accumulator in shared memory and no partial product ever reaches HBM.
+    bool fused = false;
+    if (args->cols_b && args->cols_b <= DENSE_MAX_COLS && !(args->flags & OSP_NO_FUSED_DENSE) && nnz_a && nnz_b && n_k) {
+        const double p_est = double(nnz_a) * double(nnz_b) / double(n_k);
+        fused = p_est / double(std::max<uint64_t>(m_a, 1)) >= 1024.0;
+        if (fused) rowwise = true;
+    }
     // ---- symbolic pass, merge plan, CSR->CSC task list: launched back to back -------------------
     Arena ar;
     const uint64_t st[4] = {scan_tiles(std::max<uint64_t>(nnz_a, 1)), plan_tiles(m_plan), scan_tiles(std::max<uint64_t>(n_k, 1)), 0};
@@ -642,7 +651,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     // ---- row blocks: tiles [tb[b], tb[b+1]) ---------------------------------------------------------------
     std::vector<uint32_t> tb;            // tile boundaries of the blocks
     std::vector<uint64_t> blk_row, blk_bin, blk_e;   // per boundary: row, bin offset, offset into A's data
-    if (P <= limit_elems) {
+    if (fused || P <= limit_elems) {
         tb = {0u, job.n_tiles};
         blk_row = {0, m_plan}; blk_bin = {0, P}; blk_e = {0, nnz_a};
     } else {
@@ -667,6 +676,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
             t = u;
         }
     }
+    if (fused) { tb = {0u, job.n_tiles}; blk_row = {0, m_plan}; blk_bin = {0, 0}; blk_e = {0, nnz_a}; }
     const size_t n_blocks = tb.size() - 1;
     uint64_t max_block = 0;
     for (size_t b = 0; b < n_blocks; b++) max_block = std::max(max_block, blk_bin[b + 1] - blk_bin[b]);
@@ -675,6 +685,28 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     Elem *bins = ctx->bins.as<Elem>();
 
     std::vector<cudaEvent_t> ev_blocks;   // 3 per block: start, after multiply, after merge
+    if (fused) {
+        rc = [&]() -> int {
+            ev_blocks.push_back(next_event(ctx));
+            const uint32_t band = uint32_t((cols_b + FD_WARPS - 1) / FD_WARPS);
+            CU(ctx, ctx->tasks.reserve(n_k * (FD_WARPS + 1) * 4));                  // the band index of B
+            CU(ctx, ctx->tile_state.reserve((m_plan + 1) * 8));
+            uint32_t *bandptr = ctx->tasks.as<uint32_t>();
+            LAUNCH(ctx, k_band_ptr, grid_for(n_k * (FD_WARPS + 1), 256, 1u << 30), 256, 0, dB_pos, dB_data, n_k, band, bandptr);
+            CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, (m_plan + 1) * 8, ctx->stream));
+            CU(ctx, cudaMemsetAsync(&ctx->d_sc->tile_ticket, 0, 4, ctx->stream));
+            ev_blocks.push_back(next_event(ctx));
+            const size_t sm = fused_dense_smem(cols_b);
+            int occ = 1;
+            CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_dense, FD_THREADS, sm));
+            const unsigned grid = unsigned(std::min<uint64_t>(m_plan, uint64_t(ctx->sm_count) * std::max(occ, 1)));
+            LAUNCH(ctx, k_fused_dense, grid, FD_THREADS, sm, dA_pos, dA_data, m_a, dB_data, bandptr, uint32_t(cols_b), m_plan,
+                   ctx->tile_state.as<uint64_t>(), ctx->d_sc, job.c_pos, job.c_data);
+            ev_blocks.push_back(next_event(ctx));
+            return OSP_OK;
+        }();
+        if (rc) return bail(rc);
+    } else
     for (size_t b = 0; b < n_blocks; b++) {
         const uint64_t bin0 = blk_bin[b], p_block = blk_bin[b + 1] - bin0;
         ev_blocks.push_back(next_event(ctx));

@@ -1196,6 +1196,128 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
     }
 }
 
+// =====================================================================================
+// Fused multiply + merge for products whose every row is long over a small column range (config 5: sparse
+// activations x sparse weights, 4096 columns, ~1.7e5 partial products per output row).  The per-output-row
+// bin IS a dense accumulator in shared memory: nothing goes through HBM between the multiply and the merge.
+//   * Persistent CTAs take output rows in ticket (= row) order.  acc[col] starts at -0.0f: x + (-0) = x for
+//     every x, so the first product of a column is stored exactly and no "seen" test sits on the add path.
+//   * The column range is cut into one band per warp.  A warp walks the row's runs (non-zeros of A(i,:) in
+//     ascending k) IN ORDER and applies, of every run, only the elements of B(k,:) inside its band -- found
+//     through a per-row band index of B built once per call -- so every column is summed in ascending k with
+//     separately rounded products and adds, and no two warps ever touch the same column: no barrier, no
+//     arbitration while a row accumulates.
+//   * Runs are taken eight at a time: (k, a) of eight runs in one coalesced load, their band bounds in one, their
+//     elements in one (eight independent loads per lane), then the eight are applied one after the other.
+//   * The row's surviving columns are counted, the count goes through the same decoupled look-back as the merge
+//     chain, and the row streams to its final place in C.
+// =====================================================================================
+constexpr int FD_THREADS = 512;
+constexpr int FD_WARPS = FD_THREADS / 32;
+constexpr int FD_RUNS = 8;
+__host__ __device__ inline size_t fused_dense_smem(uint64_t cols) { return size_t((cols + 15) & ~15ull) * 5 + 64 * 4; }
+
+// bandptr[k * (FD_WARPS + 1) + w] = index in b_data of the first element of row k with column >= w * band
+__global__ void k_band_ptr(const uint64_t *__restrict__ b_pos, const Elem *__restrict__ b_data, uint64_t n_k, uint32_t band,
+                           uint32_t *__restrict__ bandptr) {
+    const uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (t >= n_k * (FD_WARPS + 1)) return;
+    const uint64_t k = t / (FD_WARPS + 1);
+    const uint32_t w = uint32_t(t % (FD_WARPS + 1));
+    uint64_t lo = b_pos[k], hi = b_pos[k + 1];
+    const uint64_t target = uint64_t(w) * band;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (b_data[mid].idx < target) lo = mid + 1; else hi = mid;
+    }
+    bandptr[t] = uint32_t(lo);
+}
+
+__global__ void __launch_bounds__(FD_THREADS)
+k_fused_dense(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data, const uint64_t m_a,
+              const Elem *__restrict__ b_data, const uint32_t *__restrict__ bandptr, const uint32_t cols,
+              const uint64_t rows, uint64_t *tile_state, DevScalars *sc, uint64_t *__restrict__ c_pos,
+              Elem *__restrict__ c_data) {
+    const uint32_t cpad = (cols + 15) & ~15u;
+    float *acc = reinterpret_cast<float *>(osp_smem);
+    unsigned char *seen = osp_smem + size_t(cpad) * 4;
+    uint32_t *warp_sums = reinterpret_cast<uint32_t *>(osp_smem + size_t(cpad) * 5);
+    uint32_t *s_ticket = warp_sums + 34;
+    uint64_t *s_base = reinterpret_cast<uint64_t *>(warp_sums + 36);
+    const unsigned int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    for (uint32_t c = tid; c < cpad; c += FD_THREADS) { acc[c] = -0.0f; seen[c] = 0; }
+    const uint32_t per = (cols + FD_THREADS - 1) / FD_THREADS;       // columns per thread when the row is emitted
+    const uint32_t cb = min(tid * per, cols), ce = min(cb + per, cols);
+    while (true) {
+        __syncthreads();
+        if (tid == 0) *s_ticket = atomicAdd(&sc->tile_ticket, 1u);
+        __syncthreads();
+        const uint64_t row = *s_ticket;
+        if (row >= rows) break;
+        const uint64_t p0 = row < m_a ? a_pos[row] : 0, p1 = row < m_a ? a_pos[row + 1] : 0;
+        // ---- accumulate: this warp's column band of every run, runs in ascending k ----
+        for (uint64_t p = p0; p < p1; p += FD_RUNS) {
+            const uint32_t n_runs = uint32_t(min(uint64_t(FD_RUNS), p1 - p));
+            Elem ak; ak.idx = 0; ak.val = 0.f;
+            if (lane < n_runs) ak = a_data[p + lane];
+            uint32_t lo = 0, hi = 0;
+            if (lane < n_runs) {
+                lo = bandptr[uint64_t(ak.idx) * (FD_WARPS + 1) + warp];
+                hi = bandptr[uint64_t(ak.idx) * (FD_WARPS + 1) + warp + 1];
+            }
+            Elem be[FD_RUNS];
+            uint32_t lo_u[FD_RUNS], hi_u[FD_RUNS];
+            float a_u[FD_RUNS];
+#pragma unroll
+            for (int u = 0; u < FD_RUNS; u++) {
+                lo_u[u] = __shfl_sync(FULL, lo, u);
+                hi_u[u] = __shfl_sync(FULL, hi, u);
+                a_u[u] = __shfl_sync(FULL, ak.val, u);
+                be[u].idx = 0xFFFFFFFFu; be[u].val = 0.f;
+                if (lo_u[u] + lane < hi_u[u]) be[u] = b_data[lo_u[u] + lane];
+            }
+#pragma unroll
+            for (int u = 0; u < FD_RUNS; u++) {
+                if (be[u].idx != 0xFFFFFFFFu) {
+                    acc[be[u].idx] = __fadd_rn(acc[be[u].idx], __fmul_rn(a_u[u], be[u].val));
+                    seen[be[u].idx] = 1;
+                }
+                for (uint32_t q = lo_u[u] + 32 + lane; q < hi_u[u]; q += 32) {      // bands denser than one warp width
+                    const Elem b = b_data[q];
+                    acc[b.idx] = __fadd_rn(acc[b.idx], __fmul_rn(a_u[u], b.val));
+                    seen[b.idx] = 1;
+                }
+                __syncwarp();                                  // the next run may hit the same columns from other lanes
+            }
+        }
+        __syncthreads();
+        // ---- count, chain, emit ----
+        uint32_t cnt = 0;
+        for (uint32_t c = cb; c < ce; c++) cnt += seen[c];
+        uint32_t total;
+        uint32_t o = block_exclusive_scan(cnt, warp_sums, total);
+        if (warp == 0) {
+            lb_publish(tile_state, uint32_t(row), total, 0);
+            const uint64_t excl = lb_resolve(tile_state, uint32_t(row), total, 0);
+            if (lane == 0) *s_base = excl;
+        }
+        __syncthreads();
+        const uint64_t base = *s_base;
+        if (tid == 0) {
+            c_pos[row] = base;
+            if (row + 1 == rows) { c_pos[rows] = base + total; sc->nnz_c[1] = base + total; }
+        }
+        for (uint32_t c = cb; c < ce; c++) {
+            if (seen[c]) {
+                Elem r; r.idx = c; r.val = acc[c];
+                c_data[base + o++] = r;
+                seen[c] = 0;
+                acc[c] = -0.0f;
+            }
+        }
+    }
+}
+
 // uniq[] -> C.pos for rows [r_lo, r_hi): exclusive scan plus the running total of the earlier row blocks
 // (carry_in), whose successor is left in carry_out; the last block also closes C.pos.
 struct U64OutCarry {

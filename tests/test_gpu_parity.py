@@ -112,9 +112,20 @@ def test_mlp_batch_small(engine):
     wt = synth.transpose_host(w, 1024)
     x_csc = synth.transpose_host(x, 1024)
     want, prod = oracle_spgemm(x_csc, wt)
-    res = engine.spgemm(x, wt, a_is_csr=True, cols_b=1024)
-    got = res.to_host(); res.free()
-    assert_bit_exact(got, want, "mlp batch 48")
+    for flags in (0, api.OSP_NO_FUSED_DENSE):          # fused dense rows (no bins) and multiply -> bins -> k_merge_dense
+        res = engine.spgemm(x, wt, a_is_csr=True, cols_b=1024, flags=flags)
+        got = res.to_host(); res.free()
+        assert_bit_exact(got, want, f"mlp batch 48 flags={flags}")
+    # rows with no non-zero, a column range that is not a multiple of the band width, negative zeros
+    x2 = synth.pruned_dense(70, 1000, 0.15, seed=3)
+    x2.data["val"][::7] *= -1.0
+    w2 = synth.pruned_dense(1000, 999, 0.12, seed=4)
+    b2 = w2                                     # B = w2: 1000 x 999
+    want2, _ = oracle_spgemm(synth.transpose_host(x2, 1000), b2)
+    for flags in (0, api.OSP_NO_FUSED_DENSE):
+        res = engine.spgemm(x2, b2, a_is_csr=True, cols_b=999, flags=flags)
+        got = res.to_host(); st = res.stats(); res.free()
+        assert_bit_exact(got, want2, f"fused dense 70x1000x999 flags={flags}")
 
 
 def test_row_chunking_gives_same_bits(engine):
