@@ -246,9 +246,11 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     rc = prepare_arena(ctx, st, 0, ar);
     if (rc) return rc;
     CU(ctx, ctx->run_off.reserve((nnz_a + 1) * 8));
+    CU(ctx, ctx->task_bs.reserve(std::max<uint64_t>(nnz_a, 1) * 4));
     uint64_t *run_off = ctx->run_off.as<uint64_t>();
+    uint32_t *task_bs = ctx->task_bs.as<uint32_t>();
     if (nnz_a)
-        LAUNCH(ctx, (k_scan<SymIn, RunOffOut>), unsigned(st[0]), SCAN_BLOCK, 0, SymIn{op.a_data, op.b_pos, n_k, nullptr, ctx->d_sc},
+        LAUNCH(ctx, (k_scan<SymIn, RunOffOut>), unsigned(st[0]), SCAN_BLOCK, 0, SymIn{op.a_data, op.b_pos, n_k, nullptr, ctx->d_sc, task_bs},
                RunOffOut{run_off, ctx->d_sc, nnz_a}, nnz_a, ar.state[0], &ctx->d_sc->scan_ticket[0]);
     else
         CU(ctx, cudaMemsetAsync(run_off, 0, 8, ctx->stream));
@@ -329,7 +331,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
             }
             dst.bound[G] = bound(me, G);
             const uint64_t first_row = std::min<uint64_t>(block_begin(m, G, (me + 1) % G), m_a);
-            LAUNCH(ctx, k_multiply_peer, grid_for(nnz_a, 256, unsigned(ctx->sm_count) * 32u), 256, 0, op.a_data, run_off, op.b_pos,
+            LAUNCH(ctx, k_multiply_peer, grid_for(nnz_a, 256, unsigned(ctx->sm_count) * 32u), 256, 0, op.a_data, run_off, task_bs,
                    nnz_a, op.b_data, dst, op.a_pos, first_row);
         }
         ev_mul = next_event(ctx);
@@ -345,7 +347,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     CU(ctx, d->recv_buf.reserve(std::max<uint64_t>(P_owned, 1) * 8));
     CU(ctx, d->bins2.reserve(std::max<uint64_t>(P_owned, 1) * 8 + 16));
     ev_sym = next_event(ctx);
-    rc = launch_multiply(ctx, TaskSrcSoA{op.a_data, run_off, op.b_pos}, 0, nnz_a, P_local, op.b_data, ctx->bins.as<Elem>(), 0);
+    rc = launch_multiply(ctx, TaskSrcSoA{op.a_data, run_off, task_bs}, 0, nnz_a, P_local, op.b_data, ctx->bins.as<Elem>(), 0);
     if (rc) return rc;
     ev_mul = next_event(ctx);
     NC(ctx, d, d->nccl->GroupStart());

@@ -58,7 +58,7 @@ struct osp_ctx {
     // operand staging (host-pointer calls) and converted operands
     DevBuf op_a_pos, op_a_data, op_b_pos, op_b_data, conv_pos, conv_data, conv_tmp, conv_chk;
     // symbolic / plan / conversion scratch
-    DevBuf run_off, row_bin, tile_row, long_list, xl_list, uniq, col_ptr, tasks, tile_state, xl_acc, xl_bits;
+    DevBuf task_bs, run_off, row_bin, tile_row, long_list, xl_list, uniq, col_ptr, tasks, tile_state, xl_acc, xl_bits;
     DevBuf bins;
     std::vector<cudaEvent_t> events;
     size_t events_used = 0;
@@ -470,7 +470,7 @@ void osp_destroy(osp_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->arena, &ctx->op_a_pos, &ctx->op_a_data, &ctx->op_b_pos, &ctx->op_b_data, &ctx->conv_pos,
-                      &ctx->conv_data, &ctx->conv_tmp, &ctx->conv_chk, &ctx->run_off, &ctx->row_bin, &ctx->tile_row,
+                      &ctx->conv_data, &ctx->conv_tmp, &ctx->conv_chk, &ctx->task_bs, &ctx->run_off, &ctx->row_bin, &ctx->tile_row,
                       &ctx->long_list, &ctx->xl_list, &ctx->uniq, &ctx->col_ptr, &ctx->tasks, &ctx->tile_state,
                       &ctx->xl_acc, &ctx->xl_bits, &ctx->bins})
         b->release();
@@ -571,10 +571,12 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     if (!cols_b && nnz_b)
         LAUNCH(ctx, k_max_idx, grid_for(nnz_b, 1024, unsigned(ctx->sm_count) * 8u), 256, 0, dB_data, nnz_b, ctx->d_sc);
     CU(ctx, ctx->run_off.reserve((nnz_a + 1) * 8));
+    CU(ctx, ctx->task_bs.reserve(std::max<uint64_t>(nnz_a, 1) * 4));
     uint64_t *run_off = ctx->run_off.as<uint64_t>();
+    uint32_t *task_bs = ctx->task_bs.as<uint32_t>();
     uint32_t *col_cnt = rowwise ? nullptr : ar.counters;
     if (nnz_a) {
-        LAUNCH(ctx, (k_scan<SymIn, RunOffOut>), unsigned(st[0]), SCAN_BLOCK, 0, SymIn{dA_data, dB_pos, n_k, col_cnt, ctx->d_sc},
+        LAUNCH(ctx, (k_scan<SymIn, RunOffOut>), unsigned(st[0]), SCAN_BLOCK, 0, SymIn{dA_data, dB_pos, n_k, col_cnt, ctx->d_sc, task_bs},
                RunOffOut{run_off, ctx->d_sc, nnz_a}, nnz_a, ar.state[0], &ctx->d_sc->scan_ticket[0]);
     } else {
         CU(ctx, cudaMemsetAsync(run_off, 0, 8, ctx->stream));
@@ -711,7 +713,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         const uint64_t bin0 = blk_bin[b], p_block = blk_bin[b + 1] - bin0;
         ev_blocks.push_back(next_event(ctx));
         if (forked && b == 0) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-        if (rowwise) rc = launch_multiply(ctx, TaskSrcSoA{dA_data, run_off, dB_pos}, blk_e[b], blk_e[b + 1], p_block, dB_data, bins, bin0);
+        if (rowwise) rc = launch_multiply(ctx, TaskSrcSoA{dA_data, run_off, task_bs}, blk_e[b], blk_e[b + 1], p_block, dB_data, bins, bin0);
         else rc = launch_multiply(ctx, TaskSrcAoS{ctx->tasks.as<Task>()}, 0, nnz_a, p_block, dB_data, bins, bin0);
         if (rc) return bail(rc);
         ev_blocks.push_back(next_event(ctx));

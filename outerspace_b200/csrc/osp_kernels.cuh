@@ -51,7 +51,7 @@ k_scan(In in, Out out, uint64_t n, uint64_t *tile_state, unsigned int *ticket) {
 #pragma unroll
     for (int it = 0; it < SCAN_ITEMS; it++) {
         const uint64_t idx = wbase + it * 32 + lane;
-        own[it] = in.value(key[it], idx < n);
+        own[it] = in.value(key[it], idx, idx < n);
     }
 #pragma unroll
     for (int it = 0; it < SCAN_ITEMS; it++) {
@@ -105,11 +105,14 @@ struct SymIn {
     uint64_t n_k;
     uint32_t *col_cnt;
     DevScalars *sc;
+    uint32_t *task_bs;     // [nnzA] offset of row k_p of B inside B's data array, or null
     __device__ uint64_t load(uint64_t p, bool valid) const { return valid ? a[p].idx : ~0ull; }
-    __device__ uint64_t value(uint64_t k, bool valid) const {
+    __device__ uint64_t value(uint64_t k, uint64_t p, bool valid) const {
         if (!valid) return 0;
         if (k >= n_k) { atomicMax(&sc->err, 4u); return 0; }   // OSP_ERR_INDEX
-        const uint64_t len = b_pos[k + 1] - b_pos[k];
+        const uint64_t bs = b_pos[k];
+        const uint64_t len = b_pos[k + 1] - bs;
+        if (task_bs) task_bs[p] = uint32_t(bs);                // the row-order multiply reads it back as a stream
         if (col_cnt) atomicAdd(&col_cnt[k], 1u);
         if (len >> TASK_LEN_BITS) { atomicMax(&sc->err, 6u); return 0; }   // OSP_ERR_UNSUPPORTED
         return len;
@@ -127,7 +130,7 @@ struct RunOffOut {
 struct U32In {
     const uint32_t *x;
     __device__ uint64_t load(uint64_t i, bool valid) const { return valid ? x[i] : 0; }
-    __device__ uint64_t value(uint64_t v, bool) const { return v; }
+    __device__ uint64_t value(uint64_t v, uint64_t, bool) const { return v; }
 };
 struct U64Out {
     uint64_t *y;
@@ -341,12 +344,11 @@ struct TaskSrcAoS {
 struct TaskSrcSoA {
     const Elem *a_data;
     const uint64_t *run_off;
-    const uint64_t *b_pos;
+    const uint32_t *task_bs;     // b_pos[k] of every task, left by the symbolic pass: a stream instead of a random lookup
     __device__ __forceinline__ void load(uint64_t i, uint32_t &bs, float &a, uint64_t &off, uint32_t &len) const {
-        const Elem e = a_data[i];
-        a = e.val; off = run_off[i];
+        a = a_data[i].val; off = run_off[i];
         len = uint32_t(run_off[i + 1] - off);
-        bs = uint32_t(b_pos[e.idx]);
+        bs = task_bs[i];
     }
 };
 
@@ -1366,7 +1368,7 @@ struct TransposedIn {
     uint64_t RL;
     uint64_t G;
     __device__ uint64_t load(uint64_t j, bool valid) const { return valid ? lens[(j % G) * RL + j / G] : 0; }
-    __device__ uint64_t value(uint64_t v, bool) const { return v; }
+    __device__ uint64_t value(uint64_t v, uint64_t, bool) const { return v; }
 };
 struct RowBinStrided {         // row i of the owner starts at dst_off[i * G]
     const uint64_t *off;
@@ -1418,7 +1420,7 @@ struct PeerDst {
 // over NVLink that are contiguous from run to run.  The exchange of the k-sharded path IS this kernel's store
 // stream: nothing is staged or sent.
 __global__ void __launch_bounds__(256)
-k_multiply_peer(const Elem *__restrict__ a_data, const uint64_t *__restrict__ run_off, const uint64_t *__restrict__ b_pos,
+k_multiply_peer(const Elem *__restrict__ a_data, const uint64_t *__restrict__ run_off, const uint32_t *__restrict__ task_bs,
                 uint64_t t1, const Elem *__restrict__ b_data, const PeerDst dst, const uint64_t *__restrict__ a_pos,
                 uint64_t first_row) {
     __shared__ Elem *s_base[MAX_PEERS];
@@ -1435,11 +1437,10 @@ k_multiply_peer(const Elem *__restrict__ a_data, const uint64_t *__restrict__ ru
         if (base + lane < t1) {
             uint64_t i = base + lane + rot;
             if (i >= t1) i -= t1;
-            const Elem e = a_data[i];
-            a = e.val;
+            a = a_data[i].val;
             const uint64_t o = run_off[i];
             len = uint32_t(run_off[i + 1] - o);
-            bs = uint32_t(b_pos[e.idx]);
+            bs = task_bs[i];
             for (int r = 1; r < dst.world; r++) owner += o >= dst.bound[r];      // rows are owned in ascending blocks
             off = o + uint64_t(dst.delta[owner]);
         }
