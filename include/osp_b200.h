@@ -158,6 +158,13 @@ void osp_coo_free(osp_coo *c);
 int  osp_coo2csr(uint64_t nnz, const uint32_t *rows, const uint32_t *cols, const float *vals,
                  uint64_t N, int transpose, uint64_t *pos, void *data);
 
+/* The same conversion on the GPU (histogram -> scan -> bucket scatter -> per-slice sort with the merge machinery;
+ * a slice that shrinks while folding held a duplicate -> OSP_ERR_DUPLICATE = the reference's throw(233)).
+ * N = number of slices (rows for CSR, columns when transpose); n_other = range of the other index (0 = derive it;
+ * required with device pointers).  flags: OSP_DEVICE_POINTERS (triplet arrays and outputs in HBM) or 0. */
+int  osp_coo2csr_device(osp_ctx *ctx, uint64_t nnz, const uint32_t *rows, const uint32_t *cols, const float *vals,
+                        uint64_t N, uint64_t n_other, int transpose, uint32_t flags, uint64_t *pos, void *data);
+
 const char *osp_version(void);
 
 #ifdef __cplusplus

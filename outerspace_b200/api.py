@@ -41,6 +41,7 @@ ABI_SYMBOLS = [
     "osp_device_count", "osp_create", "osp_destroy", "osp_last_error", "osp_set_workspace_limit", "osp_stream",
     "osp_spgemm", "osp_result_dims", "osp_result_copy", "osp_result_device", "osp_result_stats", "osp_result_kernels", "osp_result_free",
     "osp_task_sizes", "osp_csr2csc", "osp_readcoo", "osp_readcoo_buffer", "osp_coo_dims", "osp_coo_copy", "osp_coo_free", "osp_coo2csr",
+    "osp_coo2csr_device",
     "osp_version", "osp_dist_unique_id", "osp_dist_create", "osp_dist_destroy", "osp_dist_rows", "osp_dist_spgemm",
 ]
 
@@ -130,6 +131,7 @@ def load_library() -> C.CDLL:
     lib.osp_coo_free.argtypes = [vp]
     lib.osp_coo_free.restype = None
     lib.osp_coo2csr.argtypes = [u64, vp, vp, vp, u64, i32, vp, vp]
+    lib.osp_coo2csr_device.argtypes = [vp, u64, vp, vp, vp, u64, u64, i32, u32, vp, vp]
     lib.osp_dist_unique_id.argtypes = [vp]
     lib.osp_dist_create.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
     lib.osp_dist_destroy.argtypes = [vp]
@@ -307,6 +309,17 @@ class Engine:
         out = CSRMatrix(np.empty(n_minor + 1, np.uint64), np.empty(m.nnz, ELEM))
         self._check(self._lib.osp_csr2csc(self._h, m.NRow(), n_minor, m.pos.ctypes.data, _ptr(m.data), 0,
                                           out.pos.ctypes.data, _ptr(out.data)))
+        return out
+
+    def coo2csr(self, coo: "COO", N: int, transpose: bool = False, n_other: int = 0) -> CSRMatrix:
+        """coo2csr<transpose> + dupcheck on the GPU (SimSpGEMM.cpp:43-53,102-152); raises DuplicateEntry (233)."""
+        n = len(coo)
+        out = CSRMatrix(np.zeros(N + 1, np.uint64), np.empty(n, ELEM))
+        rows = np.ascontiguousarray(coo.rows, np.uint32)
+        cols = np.ascontiguousarray(coo.cols, np.uint32)
+        vals = np.ascontiguousarray(coo.vals, np.float32)
+        self._check(self._lib.osp_coo2csr_device(self._h, n, _ptr(rows), _ptr(cols), _ptr(vals), N, n_other, int(transpose), 0,
+                                                 out.pos.ctypes.data, _ptr(out.data)))
         return out
 
     def csr2csc_device(self, n_major: int, n_minor: int, pos_ptr: int, data_ptr: int, pos_out_ptr: int,

@@ -282,8 +282,11 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
 // Stable transposition on the device (all pointers are device pointers): histogram -> scan ->
 // bucket scatter -> per-bucket sort by source slice id (the merge machinery; a bucket that shrinks
 // while folding held a duplicate (row, col): the reference's dupcheck, SimSpGEMM.cpp:43-53).
+// With `coo` set the source is a triplet list instead of a compressed matrix (COO ingest): n_minor buckets keyed
+// by coo->major, elements {coo->minor < n_major, val} -- the same machinery, the same duplicate check.
+struct CooSrc { const uint32_t *major, *minor; const float *val; };
 int csr2csc_device(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint64_t *d_pos, const Elem *d_data,
-                   uint64_t nnz, uint64_t *d_pos_out, Elem *d_data_out) {
+                   uint64_t nnz, uint64_t *d_pos_out, Elem *d_data_out, const CooSrc *coo = nullptr) {
     if (nnz >= (1ull << 32)) return fail(ctx, OSP_ERR_UNSUPPORTED, "operands with >= 2^32 non-zeros are not supported");
     if (n_minor == 0 || nnz == 0) {
         CU(ctx, cudaMemsetAsync(d_pos_out, 0, (n_minor + 1) * 8, ctx->stream));
@@ -294,13 +297,18 @@ int csr2csc_device(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint6
     int rc = prepare_arena(ctx, st, n_minor, ar);
     if (rc) return rc;
     uint32_t *cnt = ar.counters;
-    LAUNCH(ctx, k_hist_elems, grid_for(nnz, 256, unsigned(ctx->sm_count) * 16u), 256, 0, d_data, nnz, n_minor, cnt, ctx->d_sc);
+    if (coo) LAUNCH(ctx, k_hist_u32, grid_for(nnz, 256, unsigned(ctx->sm_count) * 16u), 256, 0, coo->major, nnz, n_minor, cnt, ctx->d_sc);
+    else LAUNCH(ctx, k_hist_elems, grid_for(nnz, 256, unsigned(ctx->sm_count) * 16u), 256, 0, d_data, nnz, n_minor, cnt, ctx->d_sc);
     LAUNCH(ctx, (k_scan<U32In, U64Out>), unsigned(st[0]), SCAN_BLOCK, 0, U32In{cnt}, U64Out{d_pos_out}, n_minor, ar.state[0],
            &ctx->d_sc->scan_ticket[0]);
     CU(ctx, cudaMemsetAsync(cnt, 0, n_minor * 4, ctx->stream));
     CU(ctx, ctx->conv_tmp.reserve(nnz * 8 + 16));
-    LAUNCH(ctx, k_scatter_elems, grid_for(n_major, 8, unsigned(ctx->sm_count) * 16u), 256, 0, d_pos, d_data, n_major, n_minor,
-           d_pos_out, cnt, ctx->conv_tmp.as<Elem>(), ctx->d_sc);
+    if (coo)
+        LAUNCH(ctx, k_scatter_coo, grid_for(nnz, 256, unsigned(ctx->sm_count) * 16u), 256, 0, coo->major, coo->minor, coo->val, nnz,
+               n_minor, n_major, d_pos_out, cnt, ctx->conv_tmp.as<Elem>(), ctx->d_sc);
+    else
+        LAUNCH(ctx, k_scatter_elems, grid_for(n_major, 8, unsigned(ctx->sm_count) * 16u), 256, 0, d_pos, d_data, n_major, n_minor,
+               d_pos_out, cnt, ctx->conv_tmp.as<Elem>(), ctx->d_sc);
     rc = reserve_plan(ctx, n_minor, std::min(n_minor, nnz));
     if (rc) return rc;
     LAUNCH(ctx, k_plan<RowBinDirect>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinDirect{d_pos_out}, n_minor, n_major,
@@ -886,6 +894,46 @@ int osp_csr2csc(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint64_t
     if (rc) return rc;
     CU(ctx, cudaMemcpyAsync(pos_out, ctx->conv_pos.p, (n_minor + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (nnz) CU(ctx, cudaMemcpyAsync(data_out, ctx->conv_data.p, nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return OSP_OK;
+}
+
+// COO -> CSR / CSC on the device: coo2csr<transpose> + dupcheck, SimSpGEMM.cpp:43-53,102-152.
+int osp_coo2csr_device(osp_ctx *ctx, uint64_t nnz, const uint32_t *rows, const uint32_t *cols, const float *vals, uint64_t N,
+                       uint64_t n_other, int transpose, uint32_t flags, uint64_t *pos, void *data) {
+    if (!ctx || !pos || (nnz && (!rows || !cols || !vals || !data)))
+        return fail(ctx, OSP_ERR_INVALID, "osp_coo2csr_device: NULL argument");
+    if (N >= (1ull << 32) || n_other >= (1ull << 32) || nnz >= (1ull << 32))
+        return fail(ctx, OSP_ERR_INVALID, "osp_coo2csr_device: dimensions must fit index_t (uint32)");
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    ctx->events_used = 0;
+    ctx->call_id++;
+    ctx->profile_kernels = false;
+    const uint32_t *major = transpose ? cols : rows, *minor = transpose ? rows : cols;
+    if (flags & OSP_DEVICE_POINTERS) {
+        if (!n_other) return fail(ctx, OSP_ERR_INVALID, "osp_coo2csr_device: the range of the other index is required with device pointers");
+        CooSrc src{major, minor, vals};
+        return csr2csc_device(ctx, n_other, N, nullptr, nullptr, nnz, pos, static_cast<Elem *>(data), &src);
+    }
+    if (!n_other)
+        for (uint64_t i = 0; i < nnz; i++) n_other = std::max<uint64_t>(n_other, uint64_t(minor[i]) + 1);
+    n_other = std::max<uint64_t>(n_other, 1);
+    CU(ctx, ctx->op_a_pos.reserve(std::max<uint64_t>(nnz, 1) * 4));
+    CU(ctx, ctx->op_b_pos.reserve(std::max<uint64_t>(nnz, 1) * 4));
+    CU(ctx, ctx->op_a_data.reserve(std::max<uint64_t>(nnz, 1) * 4));
+    CU(ctx, ctx->conv_pos.reserve((N + 1) * 8));
+    CU(ctx, ctx->conv_data.reserve(std::max<uint64_t>(nnz, 1) * 8));
+    if (nnz) {
+        CU(ctx, cudaMemcpyAsync(ctx->op_a_pos.p, major, nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->op_b_pos.p, minor, nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->op_a_data.p, vals, nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CooSrc src{ctx->op_a_pos.as<uint32_t>(), ctx->op_b_pos.as<uint32_t>(), ctx->op_a_data.as<float>()};
+    int rc = csr2csc_device(ctx, n_other, N, nullptr, nullptr, nnz, ctx->conv_pos.as<uint64_t>(), ctx->conv_data.as<Elem>(), &src);
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(pos, ctx->conv_pos.p, (N + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nnz) CU(ctx, cudaMemcpyAsync(data, ctx->conv_data.p, nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return OSP_OK;
 }

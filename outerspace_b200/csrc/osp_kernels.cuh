@@ -315,6 +315,26 @@ __global__ void k_scatter_elems(const uint64_t *pos, const Elem *d, uint64_t n_m
         }
     }
 }
+// COO ingest (coo2csr<transpose>, SimSpGEMM.cpp:102-152): the same bucket scatter from triplet arrays.
+// `major` = the index that becomes the slice (row for CSR, column for CSC), `minor` the one kept in the element.
+__global__ void k_hist_u32(const uint32_t *key, uint64_t nnz, uint64_t n_buckets, uint32_t *cnt, DevScalars *sc) {
+    for (uint64_t p = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; p < nnz; p += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t c = key[p];
+        if (c >= n_buckets) { atomicMax(&sc->err, 4u); continue; }
+        atomicAdd(&cnt[c], 1u);
+    }
+}
+__global__ void k_scatter_coo(const uint32_t *__restrict__ major, const uint32_t *__restrict__ minor, const float *__restrict__ val,
+                              uint64_t nnz, uint64_t n_buckets, uint64_t n_minor, const uint64_t *__restrict__ pos_out,
+                              uint32_t *cursor, Elem *__restrict__ out, DevScalars *sc) {
+    for (uint64_t p = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; p < nnz; p += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t b = major[p], m = minor[p];
+        if (b >= n_buckets || m >= n_minor) { atomicMax(&sc->err, 4u); continue; }
+        const uint32_t slot = atomicAdd(&cursor[b], 1u);
+        Elem y; y.idx = m; y.val = val[p];
+        out[pos_out[b] + slot] = y;
+    }
+}
 __global__ void k_hist_elems(const Elem *d, uint64_t nnz, uint64_t n_minor, uint32_t *cnt, DevScalars *sc) {
     for (uint64_t p = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; p < nnz; p += uint64_t(gridDim.x) * blockDim.x) {
         uint32_t c = d[p].idx;

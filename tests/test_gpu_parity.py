@@ -297,3 +297,27 @@ def test_many_tiles_chain_order(engine):
         got = res.to_host(); st = res.stats(); res.free()
         assert st["merge_tiles"] > 2000
         assert_bit_exact(got, want, f"er8m/64 flags={flags}")
+
+
+def test_coo_ingest_on_device(engine):
+    """coo2csr<false/true> + dupcheck on the GPU against the host loader path (itself pinned to the reference)."""
+    rng = np.random.default_rng(33)
+    for m, n, nnz in ((1, 1, 1), (50, 70, 400), (3000, 2500, 200000), (20, 100000, 5000)):
+        keys = rng.choice(m * n, size=min(nnz, m * n), replace=False)
+        rng.shuffle(keys)
+        coo = api.COO((keys // n).astype(np.uint32), (keys % n).astype(np.uint32),
+                      rng.standard_normal(keys.size).astype(np.float32))
+        for transpose, N in ((False, m), (True, n)):
+            want = api.coo2csr(coo, N, transpose)
+            got = engine.coo2csr(coo, N, transpose)
+            assert_bit_exact(got, want, f"coo2csr {m}x{n} transpose={transpose}")
+    # duplicates -> 233, like the reference's throw(233); out-of-range index -> OSP_ERR_INDEX
+    dup = api.COO(np.array([0, 1, 1, 2], np.uint32), np.array([3, 2, 2, 0], np.uint32), np.ones(4, np.float32))
+    with pytest.raises(api.DuplicateEntry):
+        engine.coo2csr(dup, 3)
+    bad = api.COO(np.array([0, 5], np.uint32), np.array([0, 0], np.uint32), np.ones(2, np.float32))
+    with pytest.raises(api.OspError):
+        engine.coo2csr(bad, 3)
+    empty = api.COO(np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.float32))
+    got = engine.coo2csr(empty, 4)
+    assert got.nnz == 0 and np.array_equal(got.pos, np.zeros(5, np.uint64))
