@@ -1086,7 +1086,15 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
         if (tid == 0 && d.last) { c_pos[d.r0 + d.R] = base + d.n_out; sc->nnz_c[carry_slot ^ 1] = base + d.n_out; }
         if (d.is_long) {
             const Elem *src = bins + d.g0;
-            for (uint32_t i = tid; i < d.n_out; i += MC_THREADS) c_data[base + i] = src[i];
+            uint32_t i = tid;
+            for (; i + 7 * MC_THREADS < d.n_out; i += 8 * MC_THREADS) {      // eight loads in flight per thread
+                Elem e[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) e[u] = src[i + u * MC_THREADS];
+#pragma unroll
+                for (int u = 0; u < 8; u++) c_data[base + i + u * MC_THREADS] = e[u];
+            }
+            for (; i < d.n_out; i += MC_THREADS) c_data[base + i] = src[i];
             if (tid == 0) c_pos[d.r0] = base;
             return;
         }
