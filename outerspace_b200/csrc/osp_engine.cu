@@ -49,9 +49,9 @@ struct osp_ctx {
     uint64_t launches = 0;
     uint64_t call_id = 0;
     std::string err;
-    DevScalars *h_sc = nullptr;     // pinned mirror (mapped: k_publish writes it)
-    unsigned long long *h_seq = nullptr, seq = 0;   // sequence number of the last hand-over, polled by the host
-    DevScalars *h_sc_dev = nullptr; unsigned long long *h_seq_dev = nullptr;   // device views of the two
+    DevScalars *h_sc = nullptr;     // pinned mirror
+    ulonglong2 *h_slots = nullptr, *h_slots_dev = nullptr;   // mapped hand-over slots {word, sequence number} (k_publish)
+    unsigned long long seq = 0;     // sequence number of the last hand-over
     // per-call zeroed arena: DevScalars | look-back states of the scans | column counters
     DevBuf arena;
     DevScalars *d_sc = nullptr;
@@ -170,21 +170,29 @@ int prepare_arena(osp_ctx *ctx, const uint64_t state_tiles[4], uint64_t n_counte
 }
 
 int sync_scalars(osp_ctx *ctx) {
-    if (ctx->h_seq_dev) {
-        // the scalars arrive by a store from the device; the host polls the sequence number (a few
+    if (ctx->h_slots_dev) {
+        // the scalars arrive by stores from the device; the host polls the slots' sequence numbers (a few
         // microseconds less GPU idle time than a copy + stream synchronisation at every hand-over)
         const unsigned long long seq = ++ctx->seq;
-        k_publish<<<1, 32, 0, ctx->stream>>>(ctx->d_sc, ctx->h_sc_dev, ctx->h_seq_dev, seq);
+        k_publish<<<1, 32, 0, ctx->stream>>>(ctx->d_sc, ctx->h_slots_dev, seq);
         CU(ctx, cudaGetLastError());
-        volatile unsigned long long *flag = ctx->h_seq;
-        for (unsigned long long spins = 0; *flag != seq; spins++) {
-            if ((spins & 0xFFF) == 0xFFF) {
-                cudaError_t q = cudaStreamQuery(ctx->stream);
-                if (q == cudaSuccess) { if (*flag == seq) break; }
-                else if (q != cudaErrorNotReady) { cudaGetLastError(); return fail(ctx, OSP_ERR_CUDA, std::string("device fault: ") + cudaGetErrorString(q)); }
+        volatile unsigned long long *slots = reinterpret_cast<volatile unsigned long long *>(ctx->h_slots);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(ctx->h_sc);
+        static_assert(sizeof(DevScalars) % 8 == 0, "DevScalars is handed over in 8-byte words");
+        unsigned long long spins = 0;
+        for (int i = 0; i < PUBLISH_SLOTS; i++) {
+            while (slots[2 * i + 1] != seq) {
+                if ((++spins & 0xFFF) == 0) {
+                    cudaError_t q = cudaStreamQuery(ctx->stream);
+                    if (q != cudaSuccess && q != cudaErrorNotReady) {
+                        cudaGetLastError();
+                        return fail(ctx, OSP_ERR_CUDA, std::string("device fault: ") + cudaGetErrorString(q));
+                    }
+                }
             }
+            __sync_synchronize();
+            dst[i] = slots[2 * i];
         }
-        __sync_synchronize();
         return OSP_OK;
     }
     CU(ctx, cudaMemcpyAsync(ctx->h_sc, ctx->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->stream));
@@ -431,17 +439,13 @@ int osp_create(int device, osp_ctx **out) {
     CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     CU(nullptr, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CU(nullptr, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    CU(nullptr, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_sc), sizeof(DevScalars) + 64, cudaHostAllocMapped));
-    ctx->h_seq = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(ctx->h_sc) + ((sizeof(DevScalars) + 15) & ~size_t(15)));
-    *ctx->h_seq = 0;
+    CU(nullptr, cudaMallocHost(reinterpret_cast<void **>(&ctx->h_sc), sizeof(DevScalars)));
     if (!std::getenv("OSP_NO_MAPPED_SYNC")) {
+        CU(nullptr, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_slots), sizeof(ulonglong2) * PUBLISH_SLOTS, cudaHostAllocMapped));
+        std::memset(ctx->h_slots, 0, sizeof(ulonglong2) * PUBLISH_SLOTS);
         void *dv = nullptr;
-        if (cudaHostGetDevicePointer(&dv, ctx->h_sc, 0) == cudaSuccess) {
-            ctx->h_sc_dev = static_cast<DevScalars *>(dv);
-            ctx->h_seq_dev = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(dv) + ((sizeof(DevScalars) + 15) & ~size_t(15)));
-        } else {
-            cudaGetLastError();
-        }
+        if (cudaHostGetDevicePointer(&dv, ctx->h_slots, 0) == cudaSuccess) ctx->h_slots_dev = static_cast<ulonglong2 *>(dv);
+        else cudaGetLastError();
     }
     CU(nullptr, cudaFuncSetAttribute(k_merge_long, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LONG_SMEM)));
     CU(nullptr, cudaFuncSetAttribute(k_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dense_smem(DENSE_MAX_COLS))));
@@ -484,6 +488,7 @@ void osp_destroy(osp_ctx *ctx) {
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
+    if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);

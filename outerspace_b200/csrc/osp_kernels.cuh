@@ -144,17 +144,16 @@ struct U32Out {           // column pointers of the task list (nnzA < 2^32 is ch
 // =====================================================================================
 // Small utility kernels
 // =====================================================================================
-// Hands the device scalars to the host without a copy-engine round trip: one warp writes them into mapped
-// pinned memory, fences at system scope and raises the sequence number the host is polling.
-__global__ void k_publish(const DevScalars *d, DevScalars *h, unsigned long long *h_seq, unsigned long long seq) {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(d);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(h);
-    for (unsigned int i = threadIdx.x; i < sizeof(DevScalars) / 4; i += 32) dst[i] = __ldcg(src + i);
-    __threadfence_system();
-    __syncwarp();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long *>(h_seq) = seq;
+// Hands the device scalars to the host without a copy-engine round trip and without a fence: every 8-byte word
+// travels in its own 16-byte slot {word, sequence number}, written with ONE 16-byte store into mapped pinned
+// memory.  The host polls until every slot carries the sequence number of this hand-over; the kernel retires at
+// once, so the launches queued behind it do not wait for a system-scope fence to drain.
+constexpr int PUBLISH_SLOTS = int((sizeof(DevScalars) + 7) / 8);
+__global__ void k_publish(const DevScalars *d, ulonglong2 *h_slots, unsigned long long seq) {
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(d);
+    if (threadIdx.x < PUBLISH_SLOTS) {
+        const unsigned long long v = __ldcg(src + threadIdx.x);
+        asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(h_slots + threadIdx.x), "l"(v), "l"(seq) : "memory");
     }
 }
 __global__ void k_max_idx(const Elem *d, uint64_t nnz, DevScalars *sc) {
