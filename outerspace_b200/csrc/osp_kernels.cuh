@@ -8,9 +8,12 @@
 //   k_plan                  partitions the output rows into merge tiles and queues long rows
 //   k_multiply              TaskProvider::multiplyPhase SimOuterSPACE.cpp:74-97 with the intended
 //                           semantics of cscMulcsr SimSpGEMM.cpp:265-281 (true column ids)
-//   k_merge_tiles/long/xl   TaskProvider::mergePhase SimOuterSPACE.cpp:98-132 with the intended
-//                           semantics of deduplicateCOO SimSpGEMM.cpp:519-535 (sum equal columns),
-//                           writing CSRMatrix mergedResult (SimOuterSPACE.cpp:140) directly
+//   k_merge_chain           TaskProvider::mergePhase SimOuterSPACE.cpp:98-132 with the intended
+//   (+ k_merge_long/xl/dense  semantics of deduplicateCOO SimSpGEMM.cpp:519-535 (sum equal columns),
+//    for long rows)         writing CSRMatrix mergedResult (SimOuterSPACE.cpp:140) directly, in one pass
+//   k_fused_dense           multiply + merge in one kernel (dense shared-memory accumulator per output row)
+//   k_multiply_peer         the multiply of the k-sharded path, storing into the owning GPU's memory
+//   k_hist_*/k_scatter_*    bucket scatters of the stable conversions (osp_csr2csc, osp_coo2csr_device)
 #pragma once
 #include "osp_device.cuh"
 #include <cstddef>
@@ -421,7 +424,7 @@ k_multiply(Src src, uint64_t t0, uint64_t t1, const Elem *__restrict__ b_data, E
 // Merge, long rows (MT_LONG < len <= MT_XL): one CTA sorts one row's partial products by
 // (col, arrival position) with a bitonic network in shared memory, left-folds equal columns in
 // arrival (= k) order with separately rounded adds, and writes the compacted row back to the
-// start of its bin; uniq[row] = surviving entries.  k_merge_tiles copies it into C.
+// start of its bin; uniq[row] = surviving entries.  k_merge_chain copies it into C.
 // Shared: uint64 keys[cap] | float vals[cap] | uint32 warp_sums[33]
 // =====================================================================================
 __device__ __forceinline__ void bitonic_sort_shared(uint64_t *keys, uint32_t N) {
@@ -1346,20 +1349,6 @@ k_fused_dense(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_dat
         }
     }
 }
-
-// uniq[] -> C.pos for rows [r_lo, r_hi): exclusive scan plus the running total of the earlier row blocks
-// (carry_in), whose successor is left in carry_out; the last block also closes C.pos.
-struct U64OutCarry {
-    uint64_t *y;
-    const unsigned long long *carry_in;
-    unsigned long long *carry_out;
-    uint64_t n;
-    __device__ void operator()(uint64_t i, uint64_t v, uint64_t) const {
-        const uint64_t c = *carry_in;
-        y[i] = c + v;
-        if (i == n) *carry_out = c + v;
-    }
-};
 
 // Duplicate check of the stable conversion: a bucket that shrank while folding held a duplicate.
 __global__ void k_check_same(const uint64_t *a, const uint64_t *b, uint64_t n, DevScalars *sc) {
