@@ -135,6 +135,7 @@ cudaEvent_t next_event(osp_ctx *ctx) {
         if (_m0) (ctx)->marks.push_back({#kernel, _m0, next_event(ctx)});                       \
     } while (0)
 
+constexpr uint64_t XL_LONG_MAX_COLS = 131072;   // up to here k_merge_xl also takes the rows of MT_LONG .. MT_XL partials
 constexpr size_t LONG_SMEM = size_t(MT_XL) * 12 + 34 * 4;
 
 unsigned int grid_for(uint64_t items, unsigned int per_block, unsigned int max_blocks) {
@@ -229,13 +230,14 @@ int reserve_merge(osp_ctx *ctx, const MergeJob &job, unsigned int &xl_ctas) {
     CU(ctx, ctx->tile_state.reserve((uint64_t(job.n_tiles) + 1) * 8));
     CU(ctx, ctx->uniq.reserve(std::max<uint64_t>(job.rows, 1) * 4));
     xl_ctas = 0;
-    if (job.n_xl && job.idx_range > DENSE_MAX_COLS) {
+    const uint64_t n_acc_rows = uint64_t(job.n_xl) + (job.idx_range <= XL_LONG_MAX_COLS ? job.n_long : 0u);
+    if (n_acc_rows && job.idx_range > DENSE_MAX_COLS) {
         const uint64_t words = (job.idx_range + 31) / 32;
         const uint64_t per_cta = job.idx_range * 4 + words * 4;
         const uint64_t budget = std::max<uint64_t>(ctx->total_mem / 16, 1ull << 28);
         const uint64_t max_ctas = budget / std::max<uint64_t>(per_cta, 1);
         if (max_ctas < 1) return fail(ctx, OSP_ERR_UNSUPPORTED, "long-row accumulator does not fit: column range too large");
-        xl_ctas = unsigned(std::min<uint64_t>({max_ctas, uint64_t(ctx->sm_count) * 4, uint64_t(job.n_xl)}));
+        xl_ctas = unsigned(std::min<uint64_t>({max_ctas, uint64_t(ctx->sm_count) * 4, n_acc_rows}));
         CU(ctx, ctx->xl_acc.reserve(uint64_t(xl_ctas) * job.idx_range * 4));
         CU(ctx, ctx->xl_bits.reserve(uint64_t(xl_ctas) * words * 4));
         CU(ctx, cudaMemsetAsync(ctx->xl_bits.p, 0, uint64_t(xl_ctas) * words * 4, ctx->stream));
@@ -260,12 +262,16 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
                    sm, row_bin, bin_base, bins, uniq, ctx->long_list.as<uint32_t>(), ctx->xl_list.as<uint32_t>(), ctx->d_sc,
                    uint32_t(job.idx_range), row_lo, row_hi);
         } else {
-            if (job.n_long)
+            // moderate column ranges: the arbitration kernel takes the medium rows too (compacting a bitmap of
+            // <= 4096 words beats a 4096-key shared-memory sort); huge ranges keep the sort for them
+            const bool xl_takes_long = job.idx_range <= XL_LONG_MAX_COLS && xl_ctas > 0;
+            if (job.n_long && !xl_takes_long)
                 LAUNCH(ctx, k_merge_long, std::min<unsigned>(job.n_long, unsigned(ctx->sm_count) * 4u), 256, LONG_SMEM, row_bin,
                        bin_base, bins, uniq, ctx->long_list.as<uint32_t>(), ctx->d_sc, row_lo, row_hi);
-            if (job.n_xl)
+            if (job.n_xl || (job.n_long && xl_takes_long))
                 LAUNCH(ctx, k_merge_xl, xl_ctas, XL_THREADS, 0, row_bin, bin_base, bins, uniq, ctx->xl_list.as<uint32_t>(),
-                       ctx->d_sc, ctx->xl_acc.as<float>(), ctx->xl_bits.as<uint32_t>(), job.idx_range, row_lo, row_hi);
+                       xl_takes_long ? ctx->long_list.as<uint32_t>() : nullptr, ctx->d_sc, ctx->xl_acc.as<float>(),
+                       ctx->xl_bits.as<uint32_t>(), job.idx_range, row_lo, row_hi);
         }
     }
     // one pass from the bins to C: tiles in row order, chained by a decoupled look-back (C.pos on the way)

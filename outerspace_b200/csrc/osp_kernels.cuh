@@ -524,8 +524,8 @@ constexpr int XL_THREADS = 512;
 constexpr uint32_t XL_HASH_BITS = 12;
 __global__ void __launch_bounds__(XL_THREADS)
 k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, uint32_t *uniq,
-           const uint32_t *xl_list, const DevScalars *sc, float *acc_all, uint32_t *bits_all, uint64_t cols_b,
-           uint64_t row_lo, uint64_t row_hi) {
+           const uint32_t *xl_list, const uint32_t *long_list, const DevScalars *sc, float *acc_all, uint32_t *bits_all,
+           uint64_t cols_b, uint64_t row_lo, uint64_t row_hi) {
     __shared__ uint32_t owner[1u << XL_HASH_BITS];
     __shared__ uint32_t warp_sums[33];
     const uint32_t tid = threadIdx.x;
@@ -533,18 +533,22 @@ k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, 
     const uint64_t words = (cols_b + 31) >> 5;
     float *acc = acc_all + uint64_t(blockIdx.x) * cols_b;
     uint32_t *bits = bits_all + uint64_t(blockIdx.x) * words;
-    const uint32_t n_xl = sc->n_xl;
+    // the longest rows first, then (when the caller passes them: moderate column ranges, where compacting the
+    // bitmap is cheaper than a shared-memory sort) the rows of MT_LONG .. MT_XL partial products
+    const uint32_t n_xl = sc->n_xl, n_all = n_xl + (long_list ? sc->n_long : 0u);
     __syncthreads();
-    for (uint32_t x = blockIdx.x; x < n_xl; x += gridDim.x) {
-        const uint64_t row = xl_list[x];
+    for (uint32_t x = blockIdx.x; x < n_all; x += gridDim.x) {
+        const uint64_t row = x < n_xl ? xl_list[x] : long_list[x - n_xl];
         if (row < row_lo || row >= row_hi) continue;
         const uint64_t len = row_bin[row + 1] - row_bin[row];
         Elem *bin = bins + (row_bin[row] - bin_base);
+        Elem nxt; nxt.idx = 0; nxt.val = 0.f;
+        if (tid < len) nxt = bin[tid];                                   // the next chunk is always in flight
         for (uint64_t c0 = 0; c0 < len; c0 += XL_THREADS) {
             const uint64_t p = c0 + tid;
             bool pending = p < len;
-            Elem e; e.idx = 0; e.val = 0.f;
-            if (pending) e = bin[p];
+            const Elem e = nxt;
+            if (p + XL_THREADS < len) nxt = bin[p + XL_THREADS];
             const uint32_t h = (e.idx * 2654435761u) >> (32 - XL_HASH_BITS);
             while (__syncthreads_or(pending)) {
                 if (pending) atomicMin(&owner[h], tid);
@@ -553,8 +557,10 @@ k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, 
                 if (win) {
                     uint32_t *w = bits + (e.idx >> 5);
                     const uint32_t bit = 1u << (e.idx & 31);
-                    if (__ldcg(w) & bit) {
-                        acc[e.idx] = __fadd_rn(acc[e.idx], e.val);
+                    const uint32_t seen = __ldcg(w);                     // the two loads go out together
+                    const float old = __ldcg(acc + e.idx);
+                    if (seen & bit) {
+                        acc[e.idx] = __fadd_rn(old, e.val);
                     } else {
                         acc[e.idx] = e.val;
                         atomicOr(w, bit);
