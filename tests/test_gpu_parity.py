@@ -321,3 +321,41 @@ def test_coo_ingest_on_device(engine):
     empty = api.COO(np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.float32))
     got = engine.coo2csr(empty, 4)
     assert got.nnz == 0 and np.array_equal(got.pos, np.zeros(5, np.uint64))
+
+
+def test_config2_full_size_bit_exact(engine):
+    """BASELINE.json configs[1] at its full size (ER 16384^2, density 1e-3; P = 4.4e6): the oracle still finishes in
+    a second, so the whole result is compared bit for bit, in both multiply orders."""
+    a, b, dims = synth.build_workload("er16k", 1)
+    a_csc = synth.transpose_host(a, dims["n_k"])
+    want, prod = oracle_spgemm(a_csc, b)
+    for flags in (api.OSP_KSLICE_ORDER, api.OSP_ROWWISE_ORDER):
+        res = engine.spgemm(a, b, a_is_csr=True, cols_b=dims["cols"], flags=flags)
+        got = res.to_host(); st = res.stats(); res.free()
+        assert st["products"] == prod
+        assert_bit_exact(got, want, f"er16k full flags={flags}")
+
+
+def test_config4_shape_properties(engine):
+    """configs[3] shape (ER, 8 nnz/row) at 1/8 linear scale, P = 6.7e7 -- too large for an element-wise oracle in a
+    test, so size-independent properties: CSR invariants, nnz(C) <= P, C.pos[m] = nnz, and the checksum identity
+    sum_ij C_ij = sum_k colsum_A[k] * rowsum_B[k] (float64, relative 1e-5: fp32 products and adds)."""
+    a, b, dims = synth.build_workload("er8m", 8)
+    res = engine.spgemm(a, b, a_is_csr=True, cols_b=dims["cols"])
+    got = res.to_host(); st = res.stats(); res.free()
+    check_csr_invariants(got, dims["cols"])
+    assert got.nnz <= st["products"] and int(got.pos[-1]) == got.nnz and got.NRow() == dims["rows"]
+    colsum_a = np.bincount(a.data["idx"], weights=a.data["val"].astype(np.float64), minlength=dims["n_k"])
+    rows_b = np.repeat(np.arange(b.NRow()), np.diff(b.pos.astype(np.int64)))
+    rowsum_b = np.bincount(rows_b, weights=b.data["val"].astype(np.float64), minlength=dims["n_k"])
+    want_sum = float(np.dot(colsum_a, rowsum_b))
+    got_sum = float(got.data["val"].astype(np.float64).sum())
+    scale = float(np.dot(np.bincount(a.data["idx"], weights=np.abs(a.data["val"]).astype(np.float64), minlength=dims["n_k"]),
+                         np.bincount(rows_b, weights=np.abs(b.data["val"]).astype(np.float64), minlength=dims["n_k"])))
+    assert abs(got_sum - want_sum) <= 1e-5 * scale, (got_sum, want_sum, scale)
+    # the per-row structure is exactly the union of the B rows selected by A's row: spot-check 64 rows
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, dims["rows"], size=64):
+        ks = a.data["idx"][int(a.pos[i]):int(a.pos[i + 1])]
+        cols = np.unique(np.concatenate([b.data["idx"][int(b.pos[k]):int(b.pos[k + 1])] for k in ks])) if ks.size else np.zeros(0, np.uint32)
+        assert np.array_equal(got.data["idx"][int(got.pos[i]):int(got.pos[i + 1])], cols), f"row {i}"
