@@ -302,6 +302,15 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             res, _ = step(api.OSP_PROFILE_KERNELS)
             kernel_rows.append(res.kernel_times())
             res.free()
+        # ---- the outer-product (k-slice) order of north_star, same workload and timing rules, for the record ----
+        ks_ms = []
+        for i in range(3 + max(3, min(args.steps, 10))):
+            flush_l2()
+            res, ms = step(api.OSP_KSLICE_ORDER)
+            res.free()
+            if i >= 3:
+                ks_ms.append(ms)
+        kslice_ms = sum(ks_ms) / len(ks_ms)
         kname, k_ms, k_launches, k_share, k_table = dominant_kernel(kernel_rows, st)
         k_bytes, k_formula = kernel_algorithmic_bytes(kname, st)
         k_bytes_per_launch = k_bytes / max(k_launches, 1.0)
@@ -336,6 +345,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         eng.close()
         products = st["products"]
         alg_bytes = st["algorithmic_bytes"]
+        n1_same = None
     else:
         from outerspace_b200 import distributed as osd
         out = osd.bench_sharded(a, b, dims, args, rank, world, local_rank, flush_l2, sampler)
@@ -345,6 +355,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         achieved = k_bytes_per_launch / (k_ms * 1e-3) / 1e9
         e2e_ms_step, h2d, d2h = out["e2e_ms"], out["h2d"], out["d2h"]
         n1_same = out.get("n1_same_workload")
+        kslice_ms = None
         products, alg_bytes = st["products"], st["algorithmic_bytes"]
 
     if world > 1:
@@ -384,6 +395,10 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         }
         if world > 1 and n1_same:
             line["n1_same_workload"] = n1_same
+        if world == 1:
+            line["multiply_order"] = {"default": "row order of A (automatic)", "ms_per_step": round(ms_per_step, 5),
+                                      "kslice_order_ms_per_step": round(kslice_ms, 5),
+                                      "note": "OSP_KSLICE_ORDER = the reference's outer-product order incl. the device CSR->CSC task list; same bits"}
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:

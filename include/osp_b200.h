@@ -44,12 +44,11 @@ extern "C" {
 #define OSP_A_IS_CSR         1u  /* a_pos/a_data hold CSR(A) (a_slices = rows of A, idx = k): the engine
                                     runs the device CSR->CSC conversion (coo2csr<true>, SimSpGEMM.cpp:878) */
 #define OSP_DEVICE_POINTERS  2u  /* all operand pointers are device pointers (HBM-resident operands) */
-#define OSP_ROWWISE_ORDER    4u  /* force the multiply to emit partial products in row order of A (B rows gathered,
-                                    bins written as one stream); same bins, same result */
-#define OSP_KSLICE_ORDER    32u  /* force the outer-product order: k-slice after k-slice, column k of A (CSC)
-                                    against row k of B (B streamed once, bins scattered).  With neither flag the
-                                    engine picks k-slice order while the bins are expected to stay in L2 and row
-                                    order beyond (DESIGN.md "multiply order") */
+#define OSP_ROWWISE_ORDER    4u  /* the multiply emits partial products in row order of A (rows of B gathered, bins
+                                    written as one stream, no task list): the default, measured faster on every config */
+#define OSP_KSLICE_ORDER    32u  /* the outer-product order of the reference: k-slice after k-slice, column k of A (CSC,
+                                    built on the device) against row k of B (B streamed once, bins scattered).  Same
+                                    bins, same result bit for bit (DESIGN.md "multiply order") */
 #define OSP_NO_FUSED_DENSE  64u  /* keep the bins even when every row is long over a small column range (see
                                     DESIGN.md "fused dense rows"): multiply -> bins -> k_merge_dense */
 #define OSP_PROFILE_PHASES   8u  /* synchronise between phases so that stats.ms_* are per-phase times */

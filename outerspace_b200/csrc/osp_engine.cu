@@ -565,14 +565,12 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     const uint64_t m_plan = std::max<uint64_t>({m_a, args->rows_c, 1});
     const uint64_t limit_elems = std::max<uint64_t>(ctx->ws_limit / 8, 1);
 
-    // ---- multiply order: outer-product (k-slice) order while the bins are expected to stay in L2 -- B is
-    // streamed once and the scattered 8-byte bin writes are absorbed by L2 -- and row order beyond, where the
-    // bins are written as ONE stream and the rows of B are gathered instead (measured: profiles/README.md).
-    // Expected P = nnz(A) nnz(B) / n_k (exact in expectation for uniform operands).
-    if (!(args->flags & (OSP_ROWWISE_ORDER | OSP_KSLICE_ORDER))) {
-        const double p_est = n_k ? double(nnz_a) * double(nnz_b) / double(n_k) : 0.0;
-        rowwise = p_est * 8.0 > double(ctx->l2_bytes) * 0.5;
-    }
+    // ---- multiply order.  The outer-product (k-slice) order of the reference streams B once and scatters 8-byte
+    // partial products over the bins; row order of A writes the bins as ONE stream, gathers the rows of B and needs
+    // no CSR->CSC task list.  Measured (profiles/README.md): row order wins on every config -- config 2 (bins
+    // L2-resident) 0.141 vs 0.161 ms per call, config 4 9.1 vs 16.6 ms -- so it is the automatic choice;
+    // OSP_KSLICE_ORDER selects the outer-product order (same bins, same bits).
+    if (!(args->flags & (OSP_ROWWISE_ORDER | OSP_KSLICE_ORDER))) rowwise = true;
     // ---- fused dense rows: when the column range is small and the rows are expected to be long (config 5), the
     // per-row bin is a dense accumulator in shared memory and no partial product ever reaches HBM.
     bool fused = false;
