@@ -387,7 +387,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
         if (rc) return bail(rc);
         LAUNCH(ctx, k_plan<RowBinStrided>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinStrided{d->dst_off.as<uint64_t>(), uint64_t(G)}, RL,
                cols_b, ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
-               ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(cols_b));
+               ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(cols_b), ctx->tile_state.as<uint64_t>());
         rc = sync_scalars(ctx);
         if (rc) return bail(rc);
         job.n_tiles = ctx->h_sc->n_tiles; job.n_long = ctx->h_sc->n_long; job.n_xl = ctx->h_sc->n_xl;

@@ -205,6 +205,7 @@ int sync_scalars(osp_ctx *ctx) {
 int reserve_plan(osp_ctx *ctx, uint64_t rows, uint64_t max_long) {
     CU(ctx, ctx->row_bin.reserve((rows + 1) * 8));
     CU(ctx, ctx->tile_row.reserve((rows + 2) * 4));
+    CU(ctx, ctx->tile_state.reserve((rows + 2) * 8));      // look-back states of the merge chain, zeroed by the plan
     CU(ctx, ctx->long_list.reserve(std::max<uint64_t>(max_long, 1) * 4));
     CU(ctx, ctx->xl_list.reserve(std::max<uint64_t>(max_long, 1) * 4));
     return OSP_OK;
@@ -227,7 +228,6 @@ struct MergeJob {
 // Scratch that depends on the plan's results: look-back states of the tile chain, survivor counts of the
 // long rows, the dense accumulators of the longest rows.
 int reserve_merge(osp_ctx *ctx, const MergeJob &job, unsigned int &xl_ctas) {
-    CU(ctx, ctx->tile_state.reserve((uint64_t(job.n_tiles) + 1) * 8));
     CU(ctx, ctx->uniq.reserve(std::max<uint64_t>(job.rows, 1) * 4));
     xl_ctas = 0;
     const uint64_t n_acc_rows = uint64_t(job.n_xl) + (job.idx_range <= XL_LONG_MAX_COLS ? job.n_long : 0u);
@@ -276,8 +276,10 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
     }
     // one pass from the bins to C: tiles in row order, chained by a decoupled look-back (C.pos on the way)
     const uint32_t n_chain = t1 - t0;
-    CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, uint64_t(n_chain) * 8, ctx->stream));
-    CU(ctx, cudaMemsetAsync(&ctx->d_sc->tile_ticket, 0, 4, ctx->stream));
+    if (block > 0) {             // the first block's states were zeroed by the plan, its ticket by the arena memset
+        CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, uint64_t(n_chain) * 8, ctx->stream));
+        CU(ctx, cudaMemsetAsync(&ctx->d_sc->tile_ticket, 0, 4, ctx->stream));
+    }
     const int carry_slot = int(block & 1);
     // small column range: rows of more than 128 partial products are merged by bitmap rank instead of a sort
     const uint32_t bm_words = job.idx_range <= 32ull * BM_WORDS ? uint32_t((job.idx_range + 31) / 32) : 0u;
@@ -327,7 +329,7 @@ int csr2csc_device(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint6
     if (rc) return rc;
     LAUNCH(ctx, k_plan<RowBinDirect>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinDirect{d_pos_out}, n_minor, n_major,
            ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
-           ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(std::max<uint64_t>(n_major, 1)));
+           ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(std::max<uint64_t>(n_major, 1)), ctx->tile_state.as<uint64_t>());
     rc = sync_scalars(ctx);
     if (rc) return rc;
     if (ctx->h_sc->err) return fail(ctx, OSP_ERR_INDEX, "index out of range in operand");
@@ -626,7 +628,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     if (rc) return rc;
     LAUNCH(ctx, k_plan<RowBinFromRuns>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinFromRuns{dA_pos, m_a, run_off, nnz_a}, m_plan,
            cols_b, ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
-           ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(cols_b));
+           ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(cols_b), ctx->tile_state.as<uint64_t>());
     cudaEvent_t ev_sym = next_event(ctx);
     rc = sync_scalars(ctx);                       // the one mid-pipeline sync: sizes of the bins and of C
     if (rc) return rc;

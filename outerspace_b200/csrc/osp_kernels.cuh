@@ -205,7 +205,8 @@ struct RowBinDirect {
 template <class RB>
 __global__ void __launch_bounds__(PLAN_BLOCK)
 k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *tile_row, uint32_t *long_list,
-       uint32_t *xl_list, uint64_t *tile_state, DevScalars *sc, int ticket_slot, uint32_t long_thresh) {
+       uint32_t *xl_list, uint64_t *tile_state, DevScalars *sc, int ticket_slot, uint32_t long_thresh,
+       uint64_t *chain_state) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[33];
     __shared__ uint64_t s_bound[PLAN_BLOCK / 32];
@@ -278,7 +279,7 @@ k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *ti
     uint64_t o = s_excl + rank;
 #pragma unroll
     for (int it = 0; it < PLAN_ITEMS; it++)
-        if (flag[it]) tile_row[o++] = uint32_t(i0 + it);
+        if (flag[it]) { chain_state[o] = 0; tile_row[o++] = uint32_t(i0 + it); }   // (look-back state of the merge chain)
 }
 
 // =====================================================================================
