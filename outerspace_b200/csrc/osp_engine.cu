@@ -630,39 +630,39 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
            cols_b, ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
            ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(cols_b), ctx->tile_state.as<uint64_t>());
     cudaEvent_t ev_sym = next_event(ctx);
-    rc = sync_scalars(ctx);                       // the one mid-pipeline sync: sizes of the bins and of C
-    if (rc) return rc;
-    if (ctx->h_sc->err == 6) return fail(ctx, OSP_ERR_UNSUPPORTED, "osp_spgemm: a row of B holds >= 2^24 non-zeros");
-    if (ctx->h_sc->err) return fail(ctx, OSP_ERR_INDEX, "osp_spgemm: index of A out of range of the inner dimension");
+    // ---- result object; C.pos is allocated while the device is still busy with the symbolic pass and the plan ----
+    osp_result *res = new osp_result();
+    res->ctx = ctx;
+    std::memset(&res->stats, 0, sizeof(res->stats));
+    auto bail = [&](int code) { osp_result_free(res); return code; };
+    if (cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_pos), (m_plan + 1) * 8, ctx->stream); e != cudaSuccess) {
+        cudaGetLastError();
+        bail(0);
+        return fail(ctx, OSP_ERR_OOM, std::string("result allocation: ") + cudaGetErrorString(e));
+    }
+    rc = sync_scalars(ctx);                       // the one mid-pipeline hand-over: sizes of the bins and of C
+    if (rc) return bail(rc);
+    if (ctx->h_sc->err == 6) return bail(fail(ctx, OSP_ERR_UNSUPPORTED, "osp_spgemm: a row of B holds >= 2^24 non-zeros"));
+    if (ctx->h_sc->err) return bail(fail(ctx, OSP_ERR_INDEX, "osp_spgemm: index of A out of range of the inner dimension"));
     const uint64_t P = ctx->h_sc->products;
-    if (P >> 40) return fail(ctx, OSP_ERR_UNSUPPORTED, "osp_spgemm: more than 2^40 partial products");
+    if (P >> 40) return bail(fail(ctx, OSP_ERR_UNSUPPORTED, "osp_spgemm: more than 2^40 partial products"));
     if (!cols_b) cols_b = uint64_t(ctx->h_sc->max_idx) + 1;
     const uint64_t min_rows = std::max<uint64_t>(ctx->h_sc->last_nonempty, 1);
     // reference rule numRows = max row id of A + 1 (SimOuterSPACE.cpp:49-53): the last row of A holding a
     // non-zero, whether or not it meets a non-empty row of B
     const uint64_t rows_c = args->rows_c ? args->rows_c : min_rows;
     if (rows_c < ctx->h_sc->last_nonempty)
-        return fail(ctx, OSP_ERR_INDEX, "osp_spgemm: rows_c is smaller than the largest row id of A + 1");
+        return bail(fail(ctx, OSP_ERR_INDEX, "osp_spgemm: rows_c is smaller than the largest row id of A + 1"));
 
     MergeJob job;
     job.rows = m_plan; job.idx_range = std::max<uint64_t>(cols_b, 1); job.long_thresh = plan_long_thresh(args->cols_b);
     job.n_tiles = ctx->h_sc->n_tiles; job.n_long = ctx->h_sc->n_long; job.n_xl = ctx->h_sc->n_xl;
     const uint64_t cap_bound = args->cols_b ? ctx->h_sc->cap_bound : std::min<uint64_t>(ctx->h_sc->cap_bound, P);
-
-    // ---- result object ------------------------------------------------------------------------------
-    osp_result *res = new osp_result();
-    res->ctx = ctx;
-    std::memset(&res->stats, 0, sizeof(res->stats));
-    auto bail = [&](int code) { osp_result_free(res); return code; };
-    {
-        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_pos), (m_plan + 1) * 8, ctx->stream);
-        if (e == cudaSuccess)
-            e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_data), std::max<uint64_t>(cap_bound, 1) * 8, ctx->stream);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            bail(0);
-            return fail(ctx, OSP_ERR_OOM, std::string("result allocation: ") + cudaGetErrorString(e));
-        }
+    if (cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_data), std::max<uint64_t>(cap_bound, 1) * 8, ctx->stream);
+        e != cudaSuccess) {
+        cudaGetLastError();
+        bail(0);
+        return fail(ctx, OSP_ERR_OOM, std::string("result allocation: ") + cudaGetErrorString(e));
     }
     job.c_pos = res->d_pos; job.c_data = res->d_data; job.c_cap = std::max<uint64_t>(cap_bound, 1);
     unsigned int xl_ctas = 0;
@@ -730,7 +730,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     } else
     for (size_t b = 0; b < n_blocks; b++) {
         const uint64_t bin0 = blk_bin[b], p_block = blk_bin[b + 1] - bin0;
-        ev_blocks.push_back(next_event(ctx));
+        ev_blocks.push_back(b == 0 ? ev_sym : next_event(ctx));     // nothing is recorded between the hand-over and the multiply
         if (forked && b == 0) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
         if (rowwise) rc = launch_multiply(ctx, TaskSrcSoA{dA_data, run_off, task_bs}, blk_e[b], blk_e[b + 1], p_block, dB_data, bins, bin0);
         else rc = launch_multiply(ctx, TaskSrcAoS{ctx->tasks.as<Task>()}, 0, nnz_a, p_block, dB_data, bins, bin0);
