@@ -176,6 +176,7 @@ int sync_scalars(osp_ctx *ctx) {
         // microseconds less GPU idle time than a copy + stream synchronisation at every hand-over)
         const unsigned long long seq = ++ctx->seq;
         k_publish<<<1, 32, 0, ctx->stream>>>(ctx->d_sc, ctx->h_slots_dev, seq);
+        ctx->launches++;
         CU(ctx, cudaGetLastError());
         volatile unsigned long long *slots = reinterpret_cast<volatile unsigned long long *>(ctx->h_slots);
         unsigned long long *dst = reinterpret_cast<unsigned long long *>(ctx->h_sc);
