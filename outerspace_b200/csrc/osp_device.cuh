@@ -107,54 +107,6 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *state, uint32_t
     return exclusive;
 }
 
-// The same walk with 32*W predecessors per step: the W windows of a step are loaded together (one L2 round
-// trip), then consumed nearest first and only as far as the first inclusive prefix.  For chains whose
-// aggregates appear late in a tile's life (the merge: after the sort), where hundreds of tiles are between
-// "aggregate published" and "prefix published" at any time.
-template <int W>
-__device__ __forceinline__ uint64_t lookback_exclusive_wide(uint64_t *state, uint32_t tile, uint64_t aggregate, uint64_t carry) {
-    const unsigned int lane = lane_id();
-    if (tile == 0) {
-        if (lane == 0) st_relaxed_u64(state, LB_FLAG_PREFIX | (carry + aggregate));
-        return carry;
-    }
-    if (lane == 0) st_relaxed_u64(state + tile, LB_FLAG_AGG | aggregate);
-    uint64_t exclusive = 0;
-    int64_t base = int64_t(tile) - 1;
-    bool done = false;
-    while (!done) {
-        uint64_t word[W];
-#pragma unroll
-        for (int w = 0; w < W; w++) {
-            const int64_t idx = base - (w * 32 + int(lane));
-            word[w] = idx >= 0 ? ld_relaxed_u64(state + idx) : LB_FLAG_PREFIX;   // before the chain: prefix 0
-        }
-#pragma unroll
-        for (int w = 0; w < W; w++) {
-            if (!done) {
-                const int64_t idx = base - (w * 32 + int(lane));
-                uint64_t x = word[w];
-                unsigned int ns = 32;
-                while ((x >> 62) == 0) {              // predecessor still merging (idx >= 0 here): back off
-                    __nanosleep(ns);
-                    if (ns < 512) ns <<= 1;
-                    x = ld_relaxed_u64(state + idx);
-                }
-                const unsigned int has_prefix = __ballot_sync(FULL, (x >> 62) == 2);
-                const unsigned int firstp = has_prefix ? (__ffs(has_prefix) - 1) : 31;
-                uint64_t v = (lane <= firstp) ? (x & LB_VALUE_MASK) : 0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-                exclusive += v;
-                done = has_prefix != 0;
-            }
-        }
-        base -= 32 * W;
-    }
-    if (lane == 0) st_relaxed_u64(state + tile, LB_FLAG_PREFIX | (exclusive + aggregate));   // tile 0's prefix carries `carry`
-    return exclusive;
-}
-
 // ---- warp / block scans -----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t x) {
     const unsigned int lane = lane_id();
