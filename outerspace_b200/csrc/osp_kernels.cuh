@@ -843,8 +843,9 @@ __device__ __forceinline__ uint32_t merge_rows_grouped(const uint32_t row_off, c
 // folded row); the earliest arrival of a column (atomicMin over arrival positions) opens that place and the
 // later arrivals are added one by one in arrival (= k) order with separately rounded adds.  S 32-element
 // slots of the row live in registers, every pass works on all of them at once (independent shared-memory
-// operations, five warp-level syncs per row).  One instantiation per size class only: more variants (slot counts
-// fitted to the row) ran 50 % slower on config 2 -- warps in different unrolled bodies thrash the instruction cache.
+// operations, five warp-level syncs per row).  ONE 16-slot instantiation serves every row up to 512 partial products
+// (a 20-slot one the rare rows up to 640): slot counts fitted to the row ran up to 50 % slower on config 2 -- warps
+// in different unrolled bodies thrash the instruction cache.
 constexpr uint32_t BM_WORDS = 512;                         // bitmap words per warp: columns < 16384
 constexpr uint32_t BM_SCRATCH = BM_WORDS * 4 + BM_WORDS * 2;   // per warp: bitmap | exclusive popcount prefix per word (u16)
 __device__ __forceinline__ uint4 &smem_u4_at(uint32_t off) { return *reinterpret_cast<uint4 *>(osp_smem + off); }
@@ -1195,8 +1196,7 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
                 uint32_t u;
                 if (BM && c >= 5) {       // small column range: rows of > 128 partial products skip the sort
                     const uint32_t scr_off = uint32_t(offsetof(Smem, bm_scratch)) + warp * BM_SCRATCH;
-                    if (c == 5) u = merge_row_bitmap<8>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);
-                    else if (c == 6) u = merge_row_bitmap<16>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);
+                    if (c <= 6) u = merge_row_bitmap<16>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);   // one hot body (instruction cache)
                     else u = merge_row_bitmap<MT_LONG_BM / 32>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);   // 513..640
                 } else
                 switch (c) {
