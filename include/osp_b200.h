@@ -164,6 +164,14 @@ int  osp_coo2csr(uint64_t nnz, const uint32_t *rows, const uint32_t *cols, const
 int  osp_coo2csr_device(osp_ctx *ctx, uint64_t nnz, const uint32_t *rows, const uint32_t *cols, const float *vals,
                         uint64_t N, uint64_t n_other, int transpose, uint32_t flags, uint64_t *pos, void *data);
 
+/* ---- layer chaining: relu(C + bias) kept sparse ------------------------------------------------------------- */
+/* What a layer of the reference's MLP applies between two products (x = relu(fc(x)), NN_models/models.py:18-31):
+ * out(i,c) = C(i,c) + bias[c] (one rounded fp32 add; bias[c] alone where C has no entry), kept where > 0.
+ * bias: cols floats (host, or device with OSP_DEVICE_POINTERS), NULL = no bias (then only C's entries > 0 stay).
+ * 1 <= cols <= 16384 (the row is densified in shared memory).  *out is a new result: its device CSR
+ * (osp_result_device) is the A operand of the next layer's osp_spgemm (OSP_A_IS_CSR | OSP_DEVICE_POINTERS). */
+int  osp_bias_relu(osp_ctx *ctx, const osp_result *c, uint64_t cols, const float *bias, uint32_t flags, osp_result **out);
+
 const char *osp_version(void);
 
 #ifdef __cplusplus

@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "osp_device_count", "osp_create", "osp_destroy", "osp_last_error", "osp_set_workspace_limit", "osp_stream",
     "osp_spgemm", "osp_result_dims", "osp_result_copy", "osp_result_device", "osp_result_stats", "osp_result_kernels", "osp_result_free",
     "osp_task_sizes", "osp_csr2csc", "osp_readcoo", "osp_readcoo_buffer", "osp_coo_dims", "osp_coo_copy", "osp_coo_free", "osp_coo2csr",
-    "osp_coo2csr_device",
+    "osp_coo2csr_device", "osp_bias_relu",
     "osp_version", "osp_dist_unique_id", "osp_dist_create", "osp_dist_destroy", "osp_dist_rows", "osp_dist_spgemm",
 ]
 
@@ -132,6 +132,7 @@ def load_library() -> C.CDLL:
     lib.osp_coo_free.restype = None
     lib.osp_coo2csr.argtypes = [u64, vp, vp, vp, u64, i32, vp, vp]
     lib.osp_coo2csr_device.argtypes = [vp, u64, vp, vp, vp, u64, u64, i32, u32, vp, vp]
+    lib.osp_bias_relu.argtypes = [vp, vp, u64, vp, u32, C.POINTER(vp)]
     lib.osp_dist_unique_id.argtypes = [vp]
     lib.osp_dist_create.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
     lib.osp_dist_destroy.argtypes = [vp]
@@ -310,6 +311,15 @@ class Engine:
         self._check(self._lib.osp_csr2csc(self._h, m.NRow(), n_minor, m.pos.ctypes.data, _ptr(m.data), 0,
                                           out.pos.ctypes.data, _ptr(out.data)))
         return out
+
+    def bias_relu(self, c: "Result", cols: int, bias: Optional[np.ndarray] = None) -> "Result":
+        """relu(C + bias) kept sparse, on the device: the step between two layers (NN_models/models.py:18-31)."""
+        b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+        if b is not None and b.size != cols:
+            raise ValueError("bias must hold one value per column")
+        h = C.c_void_p()
+        self._check(self._lib.osp_bias_relu(self._h, c._h, cols, None if b is None else b.ctypes.data, 0, C.byref(h)))
+        return Result(self, h)
 
     def coo2csr(self, coo: "COO", N: int, transpose: bool = False, n_other: int = 0) -> CSRMatrix:
         """coo2csr<transpose> + dupcheck on the GPU (SimSpGEMM.cpp:43-53,102-152); raises DuplicateEntry (233)."""

@@ -459,6 +459,7 @@ int osp_create(int device, osp_ctx **out) {
     CU(nullptr, cudaFuncSetAttribute(k_merge_long, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LONG_SMEM)));
     CU(nullptr, cudaFuncSetAttribute(k_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dense_smem(DENSE_MAX_COLS))));
     CU(nullptr, cudaFuncSetAttribute(k_fused_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_dense_smem(DENSE_MAX_COLS))));
+    CU(nullptr, cudaFuncSetAttribute(k_bias_relu, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DENSE_MAX_COLS * 4 + 256)));
     {
         auto k32 = k_merge_chain<uint32_t, false>;
         auto k64 = k_merge_chain<uint64_t, false>;
@@ -907,6 +908,72 @@ int osp_csr2csc(osp_ctx *ctx, uint64_t n_major, uint64_t n_minor, const uint64_t
     CU(ctx, cudaMemcpyAsync(pos_out, ctx->conv_pos.p, (n_minor + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (nnz) CU(ctx, cudaMemcpyAsync(data_out, ctx->conv_data.p, nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return OSP_OK;
+}
+
+// relu(C + bias) kept sparse: the step between two layers of the reference's MLP.
+int osp_bias_relu(osp_ctx *ctx, const osp_result *c, uint64_t cols, const float *bias, uint32_t flags, osp_result **out) {
+    if (!ctx || !c || !out) return fail(ctx, OSP_ERR_INVALID, "osp_bias_relu: NULL argument");
+    *out = nullptr;
+    if (cols == 0 || cols > DENSE_MAX_COLS) return fail(ctx, OSP_ERR_UNSUPPORTED, "osp_bias_relu: the row is densified in shared memory: 1 <= cols <= 16384");
+    if (c->rows >= (1ull << 32)) return fail(ctx, OSP_ERR_INVALID, "osp_bias_relu: too many rows");
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    ctx->events_used = 0;
+    ctx->call_id++;
+    ctx->marks.clear();
+    ctx->profile_kernels = false;
+    const uint64_t rows = c->rows;
+    Arena ar;
+    const uint64_t st0[4] = {0, 0, 0, 0};
+    int rc = prepare_arena(ctx, st0, 0, ar);
+    if (rc) return rc;
+    const float *d_bias = bias;
+    if (bias && !(flags & OSP_DEVICE_POINTERS)) {
+        CU(ctx, ctx->op_a_data.reserve(cols * 4));
+        CU(ctx, cudaMemcpyAsync(ctx->op_a_data.p, bias, cols * 4, cudaMemcpyHostToDevice, ctx->stream));
+        d_bias = ctx->op_a_data.as<float>();
+    }
+    osp_result *res = new osp_result();
+    res->ctx = ctx;
+    std::memset(&res->stats, 0, sizeof(res->stats));
+    auto bail = [&](int code) { osp_result_free(res); return code; };
+    const uint64_t cap = std::max<uint64_t>(bias ? rows * cols : c->nnz, 1);
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_pos), (rows + 1) * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_data), cap * 8, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        bail(0);
+        return fail(ctx, OSP_ERR_OOM, std::string("result allocation: ") + cudaGetErrorString(e));
+    }
+    rc = [&]() -> int {
+        cudaEvent_t ev0 = next_event(ctx);
+        if (rows == 0) {
+            CU(ctx, cudaMemsetAsync(res->d_pos, 0, 8, ctx->stream));
+        } else {
+            CU(ctx, ctx->tile_state.reserve((rows + 1) * 8));
+            CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, (rows + 1) * 8, ctx->stream));
+            const size_t sm = size_t((cols + 15) & ~15ull) * 4 + 64 * 4;
+            int occ = 1;
+            CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bias_relu, BR_THREADS, sm));
+            const unsigned grid = unsigned(std::min<uint64_t>(rows, uint64_t(ctx->sm_count) * std::max(occ, 1)));
+            LAUNCH(ctx, k_bias_relu, grid, BR_THREADS, sm, c->d_pos, c->d_data, rows, uint32_t(cols), d_bias,
+                   ctx->tile_state.as<uint64_t>(), ctx->d_sc, res->d_pos, res->d_data);
+        }
+        cudaEvent_t ev1 = next_event(ctx);
+        res->call_id = ctx->call_id;
+        res->spans.push_back({&res->stats.ms_total, nullptr, ev0, ev1});
+        return OSP_OK;
+    }();
+    if (rc) return bail(rc);
+    rc = sync_scalars(ctx);
+    if (rc) return bail(rc);
+    if (ctx->h_sc->err) return bail(fail(ctx, OSP_ERR_INDEX, "osp_bias_relu: a column id of C is not below cols"));
+    res->rows = rows;
+    res->nnz = rows ? ctx->h_sc->nnz_c[1] : 0;
+    res->stats.rows_c = rows; res->stats.cols_b = cols; res->stats.nnz_c = res->nnz;
+    res->stats.kernel_launches = ctx->launches;
+    *out = res;
     return OSP_OK;
 }
 

@@ -1357,6 +1357,62 @@ k_fused_dense(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_dat
     }
 }
 
+// =====================================================================================
+// Layer chaining: relu(C + bias) kept sparse -- what a layer of the reference's MLP applies
+// between two products (x = relu(fc(x)), NN_models/models.py:18-31) -- so that act_i -> fc_i -> act_{i+1} stays
+// on the device in CSR.  One row at a time per CTA, rows in ticket order: the row is densified in shared memory
+// (dense[c] = bias[c], then C(i,c) + bias[c] with one rounded add where C has an entry), the entries > 0 are
+// counted, the count goes through the decoupled look-back and the row streams to its final place.
+// =====================================================================================
+constexpr int BR_THREADS = 256;
+__global__ void __launch_bounds__(BR_THREADS)
+k_bias_relu(const uint64_t *__restrict__ c_pos, const Elem *__restrict__ c_data, const uint64_t rows, const uint32_t cols,
+            const float *__restrict__ bias, uint64_t *tile_state, DevScalars *sc, uint64_t *__restrict__ o_pos,
+            Elem *__restrict__ o_data) {
+    float *dense = reinterpret_cast<float *>(osp_smem);
+    uint32_t *warp_sums = reinterpret_cast<uint32_t *>(osp_smem + size_t((cols + 15) & ~15u) * 4);
+    uint32_t *s_ticket = warp_sums + 34;
+    uint64_t *s_base = reinterpret_cast<uint64_t *>(warp_sums + 36);
+    const unsigned int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const uint32_t per = (cols + BR_THREADS - 1) / BR_THREADS;
+    const uint32_t cb = min(tid * per, cols), ce = min(cb + per, cols);
+    while (true) {
+        __syncthreads();
+        if (tid == 0) *s_ticket = atomicAdd(&sc->tile_ticket, 1u);
+        __syncthreads();
+        const uint64_t row = *s_ticket;
+        if (row >= rows) break;
+        for (uint32_t c = tid; c < cols; c += BR_THREADS) dense[c] = bias ? bias[c] : 0.f;
+        __syncthreads();
+        const uint64_t p0 = c_pos[row], p1 = c_pos[row + 1];
+        for (uint64_t p = p0 + tid; p < p1; p += BR_THREADS) {
+            const Elem e = c_data[p];
+            if (e.idx < cols) dense[e.idx] = bias ? __fadd_rn(e.val, bias[e.idx]) : e.val;    // columns are distinct in a row
+            else atomicMax(&sc->err, 4u);
+        }
+        __syncthreads();
+        uint32_t cnt = 0;
+        for (uint32_t c = cb; c < ce; c++) cnt += dense[c] > 0.f;
+        uint32_t total;
+        uint32_t o = block_exclusive_scan(cnt, warp_sums, total);
+        if (warp == 0) {
+            lb_publish(tile_state, uint32_t(row), total, 0);
+            const uint64_t excl = lb_resolve(tile_state, uint32_t(row), total, 0);
+            if (lane == 0) *s_base = excl;
+        }
+        __syncthreads();
+        const uint64_t base = *s_base;
+        if (tid == 0) {
+            o_pos[row] = base;
+            if (row + 1 == rows) { o_pos[rows] = base + total; sc->nnz_c[1] = base + total; }
+        }
+        for (uint32_t c = cb; c < ce; c++) {
+            const float v = dense[c];
+            if (v > 0.f) { Elem r; r.idx = c; r.val = v; o_data[base + o++] = r; }
+        }
+    }
+}
+
 // Duplicate check of the stable conversion: a bucket that shrank while folding held a duplicate.
 __global__ void k_check_same(const uint64_t *a, const uint64_t *b, uint64_t n, DevScalars *sc) {
     uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;

@@ -359,3 +359,53 @@ def test_config4_shape_properties(engine):
         ks = a.data["idx"][int(a.pos[i]):int(a.pos[i + 1])]
         cols = np.unique(np.concatenate([b.data["idx"][int(b.pos[k]):int(b.pos[k + 1])] for k in ks])) if ks.size else np.zeros(0, np.uint32)
         assert np.array_equal(got.data["idx"][int(got.pos[i]):int(got.pos[i + 1])], cols), f"row {i}"
+
+
+def _bias_relu_host(c: "CSRMatrix", cols: int, bias):
+    """numpy restatement of the step between two layers (NN_models/models.py:18-31: x = relu(fc(x))) on the engine's
+    definition: out = C + bias with ONE rounded fp32 add per entry (bias alone where C has no entry), kept where > 0."""
+    rows = c.NRow()
+    pos = np.zeros(rows + 1, np.uint64)
+    idx_all, val_all = [], []
+    for i in range(rows):
+        dense = np.array(bias, np.float32, copy=True) if bias is not None else np.zeros(cols, np.float32)
+        lo, hi = int(c.pos[i]), int(c.pos[i + 1])
+        ci, cv = c.data["idx"][lo:hi].astype(np.int64), c.data["val"][lo:hi]
+        dense[ci] = (cv + np.asarray(bias, np.float32)[ci]).astype(np.float32) if bias is not None else cv
+        keep = np.nonzero(dense > 0)[0]
+        idx_all.append(keep.astype(np.uint32)); val_all.append(dense[keep])
+        pos[i + 1] = pos[i] + keep.size
+    from outerspace_b200.formats import CSRMatrix
+    return CSRMatrix.from_arrays(pos, np.concatenate(idx_all) if idx_all else np.zeros(0, np.uint32),
+                                 np.concatenate(val_all) if val_all else np.zeros(0, np.float32))
+
+
+def test_layer_chaining_two_layers(engine):
+    """act_0 -> fc1 -> relu -> fc2 -> relu with sparse activations and pruned weights, everything on the device between
+    the layers (the result's device CSR is the next product's A operand); checked bit for bit against
+    oracle SpGEMM + the numpy epilogue, layer by layer."""
+    rng = np.random.default_rng(5)
+    x = synth.pruned_dense(40, 600, 0.12, seed=11, nonneg=True)            # act_0: 40 x 600
+    w1 = synth.pruned_dense(500, 600, 0.10, seed=12)                       # fc1.weight: 500 x 600
+    w2 = synth.pruned_dense(300, 500, 0.15, seed=13)                       # fc2.weight: 300 x 500
+    b1 = rng.standard_normal(500).astype(np.float32) * 0.5
+    w1t, w2t = synth.transpose_host(w1, 600), synth.transpose_host(w2, 500)   # B = W^T in CSR: 600 x 500, 500 x 300
+    # oracle chain
+    c1, _ = oracle_spgemm(synth.transpose_host(x, 600), w1t, rows_override=40)
+    a1 = _bias_relu_host(c1, 500, b1)
+    c2, _ = oracle_spgemm(synth.transpose_host(a1, 500), w2t, rows_override=40)
+    a2 = _bias_relu_host(c2, 300, None)
+    # engine chain, device resident between the steps
+    r1 = engine.spgemm(x, w1t, a_is_csr=True, rows_c=40, cols_b=500)
+    g1 = engine.bias_relu(r1, 500, b1)
+    assert_bit_exact(g1.to_host(), a1, "layer 1: relu(x W1^T + b1)")
+    import torch
+    dev = torch.device("cuda:0")
+    tb = [torch.from_numpy(v.view(np.uint8).reshape(-1).copy()).to(dev) for v in (w2t.pos, w2t.data)]
+    p_ptr, d_ptr = g1.device_pointers()
+    r2 = engine.spgemm_device(40, p_ptr, d_ptr, 500, tb[0].data_ptr(), tb[1].data_ptr(), a_is_csr=True, rows_c=40, cols_b=300,
+                              a_nnz=g1.nnz, b_nnz=w2t.nnz)
+    g2 = engine.bias_relu(r2, 300, None)
+    assert_bit_exact(g2.to_host(), a2, "layer 2: relu(a1 W2^T)")
+    for r in (r1, g1, r2, g2):
+        r.free()
