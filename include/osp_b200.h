@@ -102,12 +102,21 @@ void osp_destroy(osp_ctx *ctx);
 const char *osp_last_error(const osp_ctx *ctx);     /* message of the last failing call on ctx (or global) */
 int  osp_set_workspace_limit(osp_ctx *ctx, uint64_t bytes); /* cap on partial-product workspace; larger
                                                        products are processed in output-row blocks */
+int  osp_set_result_limit(osp_ctx *ctx, uint64_t bytes);    /* cap on the up-front allocation of C's data; 0 (default) =
+                                                       what the device can spare.  C is allocated at the plan's bound
+                                                       sum_i min(partials of row i, cols) when that fits; otherwise at the
+                                                       cap, and the call runs in row blocks, each admitted against the cap
+                                                       with the exact nnz(C) so far (OSP_ERR_OOM when a block cannot fit) */
 void *osp_stream(osp_ctx *ctx);                     /* the cudaStream_t every kernel of ctx runs on */
 
 /* ---- the hot path: TaskProvider(lmatCSC, rmatCSR) ------------------------------------- */
 int  osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out);
 int  osp_result_dims(const osp_result *r, uint64_t *rows, uint64_t *nnz);
 int  osp_result_copy(osp_result *r, uint64_t *pos, void *data);  /* into CSRMatrix::pos / ::data storage */
+/* Rows [row_begin, row_end) of C: pos gets row_end - row_begin + 1 absolute offsets into C's data, data the
+ * pos[last] - pos[0] elements of those rows (data = NULL: offsets only, to size the buffer).  For results larger than
+ * the caller's host memory (config 3 at full scale holds tens of GB of C). */
+int  osp_result_copy_rows(osp_result *r, uint64_t row_begin, uint64_t row_end, uint64_t *pos, void *data, uint64_t data_capacity);
 int  osp_result_device(const osp_result *r, const uint64_t **d_pos, const void **d_data);
 int  osp_result_stats(const osp_result *r, osp_stats *stats);
 /* Per-launch device times of a call made with OSP_PROFILE_KERNELS, in launch order (two-call pattern:

@@ -38,8 +38,8 @@ OSP_PROFILE_KERNELS = 16
 
 # every symbol include/osp_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "osp_device_count", "osp_create", "osp_destroy", "osp_last_error", "osp_set_workspace_limit", "osp_stream",
-    "osp_spgemm", "osp_result_dims", "osp_result_copy", "osp_result_device", "osp_result_stats", "osp_result_kernels", "osp_result_free",
+    "osp_device_count", "osp_create", "osp_destroy", "osp_last_error", "osp_set_workspace_limit", "osp_set_result_limit", "osp_stream",
+    "osp_spgemm", "osp_result_dims", "osp_result_copy", "osp_result_copy_rows", "osp_result_device", "osp_result_stats", "osp_result_kernels", "osp_result_free",
     "osp_task_sizes", "osp_csr2csc", "osp_readcoo", "osp_readcoo_buffer", "osp_coo_dims", "osp_coo_copy", "osp_coo_free", "osp_coo2csr",
     "osp_coo2csr_device", "osp_bias_relu",
     "osp_version", "osp_dist_unique_id", "osp_dist_create", "osp_dist_destroy", "osp_dist_rows", "osp_dist_spgemm",
@@ -113,11 +113,13 @@ def load_library() -> C.CDLL:
     lib.osp_last_error.argtypes = [vp]
     lib.osp_last_error.restype = C.c_char_p
     lib.osp_set_workspace_limit.argtypes = [vp, u64]
+    lib.osp_set_result_limit.argtypes = [vp, u64]
     lib.osp_stream.argtypes = [vp]
     lib.osp_stream.restype = vp
     lib.osp_spgemm.argtypes = [vp, C.POINTER(SpgemmArgs), C.POINTER(vp)]
     lib.osp_result_dims.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     lib.osp_result_copy.argtypes = [vp, vp, vp]
+    lib.osp_result_copy_rows.argtypes = [vp, u64, u64, vp, vp, u64]
     lib.osp_result_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     lib.osp_result_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.osp_result_kernels.argtypes = [vp, C.POINTER(u64), vp, vp]
@@ -221,6 +223,21 @@ class Result:
         self.copy_into(out.pos, out.data)
         return out
 
+    def pos_to_host(self) -> np.ndarray:
+        """C.pos alone (row pointer, rows + 1 offsets)."""
+        pos = np.empty(self.rows + 1, np.uint64)
+        self._engine._check(self._engine._lib.osp_result_copy_rows(self._h, 0, self.rows, pos.ctypes.data, None, 0))
+        return pos
+
+    def rows_to_host(self, row_begin: int, row_end: int) -> CSRMatrix:
+        """Rows [row_begin, row_end) of C as a CSRMatrix of their own (pos rebased to 0)."""
+        pos = np.empty(row_end - row_begin + 1, np.uint64)
+        lib = self._engine._lib
+        self._engine._check(lib.osp_result_copy_rows(self._h, row_begin, row_end, pos.ctypes.data, None, 0))
+        data = np.empty(int(pos[-1] - pos[0]), ELEM)
+        self._engine._check(lib.osp_result_copy_rows(self._h, row_begin, row_end, pos.ctypes.data, _ptr(data), len(data)))
+        return CSRMatrix(pos - pos[0], data)
+
     def free(self) -> None:
         if self._h is not None:
             self._engine._lib.osp_result_free(self._h)
@@ -264,6 +281,10 @@ class Engine:
 
     def set_workspace_limit(self, nbytes: int) -> None:
         self._check(self._lib.osp_set_workspace_limit(self._h, nbytes))
+
+    def set_result_limit(self, nbytes: int) -> None:
+        """Cap on the up-front allocation of C's data (0 = automatic): see osp_set_result_limit."""
+        self._check(self._lib.osp_set_result_limit(self._h, nbytes))
 
     @property
     def stream(self) -> int:

@@ -46,6 +46,7 @@ struct osp_ctx {
     cudaStream_t stream2 = nullptr;      // the CSR->CSC task list is built beside the merge plan
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint64_t ws_limit = 0;          // bytes of partial-product bins per row block
+    uint64_t result_limit = 0;      // cap on the up-front allocation of C's data (0 = what the device can spare)
     uint64_t launches = 0;
     uint64_t call_id = 0;
     std::string err;
@@ -142,6 +143,23 @@ unsigned int grid_for(uint64_t items, unsigned int per_block, unsigned int max_b
     uint64_t b = (items + per_block - 1) / per_block;
     if (b < 1) b = 1;
     return unsigned(std::min<uint64_t>(b, max_blocks));
+}
+
+// Device memory a call can still obtain: free memory plus what the stream-ordered pool holds but does not use.
+uint64_t device_available(osp_ctx *ctx) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    uint64_t avail = free_b;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+        uint64_t reserved = 0, used = 0;
+        if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+            avail += reserved - used;
+        else
+            cudaGetLastError();
+    }
+    return avail;
 }
 
 uint64_t scan_tiles(uint64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
@@ -512,6 +530,12 @@ int osp_set_workspace_limit(osp_ctx *ctx, uint64_t bytes) {
     return OSP_OK;
 }
 
+int osp_set_result_limit(osp_ctx *ctx, uint64_t bytes) {
+    if (!ctx) return fail(ctx, OSP_ERR_INVALID, "osp_set_result_limit: NULL context");
+    ctx->result_limit = bytes;
+    return OSP_OK;
+}
+
 void *osp_stream(osp_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
 
 int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
@@ -659,28 +683,51 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     MergeJob job;
     job.rows = m_plan; job.idx_range = std::max<uint64_t>(cols_b, 1); job.long_thresh = plan_long_thresh(args->cols_b);
     job.n_tiles = ctx->h_sc->n_tiles; job.n_long = ctx->h_sc->n_long; job.n_xl = ctx->h_sc->n_xl;
-    const uint64_t cap_bound = args->cols_b ? ctx->h_sc->cap_bound : std::min<uint64_t>(ctx->h_sc->cap_bound, P);
-    if (cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_data), std::max<uint64_t>(cap_bound, 1) * 8, ctx->stream);
-        e != cudaSuccess) {
+    const uint64_t cap_bound = std::max<uint64_t>(args->cols_b ? ctx->h_sc->cap_bound : std::min<uint64_t>(ctx->h_sc->cap_bound, P), 1);
+    unsigned int xl_ctas = 0;
+    rc = reserve_merge(ctx, job, xl_ctas);
+    if (rc) return bail(rc);
+    // ---- capacity of C.  The plan only knows the bound sum_i min(len_i, cols) of nnz(C).  On skewed inputs the bound
+    // is far above nnz(C) and can exceed the device (config 3 at full scale: 154 GB of bound next to 167 GB of partial
+    // products): then C gets what the device can spare, the call runs in small row blocks, and every block is admitted
+    // against that capacity with the exact nnz(C) of the blocks before it (carried by the merge chain anyway).
+    bool bounded = false;
+    uint64_t c_cap = cap_bound, block_limit = limit_elems;
+    if (!fused) {
+        if (ctx->result_limit) {
+            bounded = cap_bound * 8 > ctx->result_limit;
+            if (bounded) c_cap = std::max<uint64_t>(ctx->result_limit / 8, 1);
+        } else if ((cap_bound + std::min(P, limit_elems)) * 8 > ctx->total_mem / 4) {      // small calls never ask the driver
+            const uint64_t slack = (1ull << 30) + ctx->total_mem / 64;
+            const uint64_t avail = device_available(ctx);
+            auto bins_extra = [&](uint64_t elems) { const uint64_t b = std::min(P, elems) * 8 + 16; return b > ctx->bins.cap ? b + b / 8 : 0; };
+            if (cap_bound * 8 + bins_extra(limit_elems) + slack > avail) {
+                bounded = true;
+                block_limit = std::min<uint64_t>(limit_elems, std::max<uint64_t>(ctx->total_mem / 128, 1ull << 20));   // 1/16 of the device per block
+                const uint64_t rest = bins_extra(block_limit) + slack;
+                c_cap = std::min<uint64_t>(cap_bound, avail > rest ? (avail - rest) / 8 : 1);
+            }
+        }
+    }
+    if (cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_data), c_cap * 8, ctx->stream); e != cudaSuccess) {
         cudaGetLastError();
         bail(0);
         return fail(ctx, OSP_ERR_OOM, std::string("result allocation: ") + cudaGetErrorString(e));
     }
-    job.c_pos = res->d_pos; job.c_data = res->d_data; job.c_cap = std::max<uint64_t>(cap_bound, 1);
-    unsigned int xl_ctas = 0;
-    rc = reserve_merge(ctx, job, xl_ctas);
-    if (rc) return bail(rc);
+    job.c_pos = res->d_pos; job.c_data = res->d_data; job.c_cap = c_cap;
 
     // ---- row blocks: tiles [tb[b], tb[b+1]) ---------------------------------------------------------------
     std::vector<uint32_t> tb;            // tile boundaries of the blocks
     std::vector<uint64_t> blk_row, blk_bin, blk_e;   // per boundary: row, bin offset, offset into A's data
-    if (fused || P <= limit_elems) {
+    std::vector<uint64_t> h_row_bin;     // host copy of the bin offsets (blocked calls only)
+    if (fused || (P <= block_limit && !bounded)) {
         tb = {0u, job.n_tiles};
         blk_row = {0, m_plan}; blk_bin = {0, P}; blk_e = {0, nnz_a};
     } else {
         rowwise = true;                  // blocks are row ranges: their tasks are taken in row order of A
         std::vector<uint32_t> h_tile_row(job.n_tiles + 1);
-        std::vector<uint64_t> h_row_bin(m_plan + 1), h_a_pos(m_a + 1);
+        std::vector<uint64_t> h_a_pos(m_a + 1);
+        h_row_bin.resize(m_plan + 1);
         CU(ctx, cudaMemcpyAsync(h_tile_row.data(), ctx->tile_row.p, (job.n_tiles + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaMemcpyAsync(h_row_bin.data(), ctx->row_bin.p, (m_plan + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaMemcpyAsync(h_a_pos.data(), dA_pos, (m_a + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -694,7 +741,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         while (t < job.n_tiles) {
             const uint64_t start = h_row_bin[h_tile_row[t]];
             uint32_t u = t + 1;
-            while (u < job.n_tiles && h_row_bin[h_tile_row[u + 1]] - start <= limit_elems) u++;
+            while (u < job.n_tiles && h_row_bin[h_tile_row[u + 1]] - start <= block_limit) u++;
             push(u);
             t = u;
         }
@@ -732,6 +779,20 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     } else
     for (size_t b = 0; b < n_blocks; b++) {
         const uint64_t bin0 = blk_bin[b], p_block = blk_bin[b + 1] - bin0;
+        if (bounded) {
+            // admit the block: nnz(C) of the blocks before it (exact) + this block's bound must fit C's capacity
+            uint64_t carry = 0, bound_b = 0;
+            if (b > 0) {
+                rc = sync_scalars(ctx);
+                if (rc) return bail(rc);
+                carry = ctx->h_sc->nnz_c[b & 1];
+            }
+            for (uint64_t r = blk_row[b]; r < blk_row[b + 1]; r++) bound_b += std::min<uint64_t>(h_row_bin[r + 1] - h_row_bin[r], job.idx_range);
+            if (carry + bound_b > c_cap)
+                return bail(fail(ctx, OSP_ERR_OOM, "osp_spgemm: C does not fit the device: " + std::to_string(carry) + " non-zeros in the first " +
+                                 std::to_string(b) + " of " + std::to_string(n_blocks) + " row blocks + a bound of " + std::to_string(bound_b) +
+                                 " for the next exceed the capacity of " + std::to_string(c_cap)));
+        }
         ev_blocks.push_back(b == 0 ? ev_sym : next_event(ctx));     // nothing is recorded between the hand-over and the multiply
         if (forked && b == 0) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
         if (rowwise) rc = launch_multiply(ctx, TaskSrcSoA{dA_data, run_off, task_bs}, blk_e[b], blk_e[b + 1], p_block, dB_data, bins, bin0);
@@ -798,6 +859,24 @@ int osp_result_copy(osp_result *r, uint64_t *pos, void *data) {
     cudaEvent_t e1 = next_event(ctx);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&r->stats.ms_d2h, e0, e1);
+    return OSP_OK;
+}
+
+int osp_result_copy_rows(osp_result *r, uint64_t row_begin, uint64_t row_end, uint64_t *pos, void *data, uint64_t data_capacity) {
+    if (!r || !pos) return fail(nullptr, OSP_ERR_INVALID, "osp_result_copy_rows: NULL argument");
+    osp_ctx *ctx = r->ctx;
+    if (row_begin > row_end || row_end > r->rows) return fail(ctx, OSP_ERR_INDEX, "osp_result_copy_rows: row range outside C");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = row_end - row_begin;
+    CU(ctx, cudaMemcpyAsync(pos, r->d_pos + row_begin, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint64_t cnt = pos[n] - pos[0];
+    if (!data) return OSP_OK;
+    if (cnt > data_capacity) return fail(ctx, OSP_ERR_INVALID, "osp_result_copy_rows: data_capacity is smaller than the rows' non-zeros");
+    if (cnt) {
+        CU(ctx, cudaMemcpyAsync(data, r->d_data + pos[0], cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return OSP_OK;
 }
 

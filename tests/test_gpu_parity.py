@@ -147,6 +147,47 @@ def test_row_chunking_gives_same_bits(engine):
         eng.close()
 
 
+def test_bounded_result_capacity(engine):
+    """C allocated below the plan's bound (what config 3 needs at full scale, where the bound exceeds HBM): row
+    blocks are admitted one by one against the capacity with the exact nnz(C) so far -- same bits; a capacity
+    that cannot hold C is OSP_ERR_OOM, never a write past the allocation."""
+    a, b, dims = synth.build_workload("rmat20", scale_down=256)         # skewed rows: bound well above nnz(C)
+    want_pos, want_data, prod = oracle.spgemm_rowblocks(a.pos, a.data, b.pos, b.data, 4096)
+    want = pack(want_pos, want_data)
+    nnz_c, rows = len(want_data), len(want_pos) - 1
+    cs = np.concatenate([[0], np.cumsum(np.diff(b.pos.astype(np.int64))[a.data["idx"]])])
+    plen = cs[a.pos[1:].astype(np.int64)] - cs[a.pos[:-1].astype(np.int64)]      # partial products per output row
+    bound = int(np.minimum(plen, dims["cols"]).sum())
+    block = max(int(plen.max()), prod // 24)                            # ~24 row blocks
+    cap = nnz_c + block + 64                                            # C + the last block's bound
+    assert cap < bound, "the workload must leave room between nnz(C) and the plan's bound"
+    eng = osp.Engine(0)
+    try:
+        eng.set_workspace_limit(block * 8)
+        eng.set_result_limit(cap * 8)
+        for is_csr, op in ((True, a), (False, synth.transpose_host(a, dims["n_k"]))):
+            res = eng.spgemm(op, b, a_is_csr=is_csr, cols_b=dims["cols"])
+            got = res.to_host(); st = res.stats()
+            assert st["row_chunks"] > 8 and st["products"] == prod and st["nnz_c"] == nnz_c
+            assert_bit_exact(got, want, f"bounded C, a_is_csr={is_csr}")
+            mid = rows // 3
+            part = res.rows_to_host(mid, mid + 500)                     # osp_result_copy_rows
+            lo, hi = int(want_pos[mid]), int(want_pos[mid + 500])
+            assert np.array_equal(part.pos, want_pos[mid:mid + 501] - want_pos[mid])
+            assert np.array_equal(part.data.view(np.uint64), want_data[lo:hi].view(np.uint64))
+            res.free()
+        eng.set_result_limit(nnz_c * 8 // 2)                            # half of C: must fail cleanly
+        with pytest.raises(osp.OspError) as ei:
+            eng.spgemm(a, b, a_is_csr=True, cols_b=dims["cols"])
+        assert ei.value.code == api.OSP_ERR_OOM and "does not fit" in str(ei.value)
+        eng.set_result_limit(0)                                         # the engine is still usable afterwards
+        res = eng.spgemm(a, b, a_is_csr=True, cols_b=dims["cols"])
+        got = res.to_host(); res.free()
+        assert_bit_exact(got, want, "after the failed call")
+    finally:
+        eng.close()
+
+
 def test_edge_cases(engine):
     E = osp.ELEM
     # empty A (reference: maxRowId = 0 -> one empty output row)
