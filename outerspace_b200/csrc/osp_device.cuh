@@ -41,7 +41,7 @@ struct DevScalars {
     unsigned int tile_ticket;          // dynamic tile ids of the merge kernel
     unsigned int scan_ticket[4];       // dynamic tile ids of the look-back scans (one per scan of a call)
     unsigned int n_dups;               // rows that shrank while folding (duplicate check of csr2csc)
-    unsigned int pad;
+    unsigned int xl_ticket;            // dynamic row ids of k_merge_xl (zeroed before every launch)
 };
 
 constexpr unsigned int FULL = 0xffffffffu;

@@ -287,10 +287,12 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
             if (job.n_long && !xl_takes_long)
                 LAUNCH(ctx, k_merge_long, std::min<unsigned>(job.n_long, unsigned(ctx->sm_count) * 4u), 256, LONG_SMEM, row_bin,
                        bin_base, bins, uniq, ctx->long_list.as<uint32_t>(), ctx->d_sc, row_lo, row_hi);
-            if (job.n_xl || (job.n_long && xl_takes_long))
+            if (job.n_xl || (job.n_long && xl_takes_long)) {
+                CU(ctx, cudaMemsetAsync(&ctx->d_sc->xl_ticket, 0, 4, ctx->stream));
                 LAUNCH(ctx, k_merge_xl, xl_ctas, XL_THREADS, 0, row_bin, bin_base, bins, uniq, ctx->xl_list.as<uint32_t>(),
                        xl_takes_long ? ctx->long_list.as<uint32_t>() : nullptr, ctx->d_sc, ctx->xl_acc.as<float>(),
                        ctx->xl_bits.as<uint32_t>(), job.idx_range, row_lo, row_hi);
+            }
         }
     }
     // one pass from the bins to C: tiles in row order, chained by a decoupled look-back (C.pos on the way)

@@ -515,46 +515,73 @@ k_merge_long(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins
 }
 
 // Rows longer than MT_XL over a large column range: a dense per-CTA accumulator acc[cols_b] in global
-// memory (L2-resident: one row at a time per CTA) with a presence bitmap.  The row is consumed XL_THREADS
-// partial products at a time in arrival order; products of one chunk that hit the same column are
-// serialised by an arbitration on a hashed owner table in shared memory (the lowest position goes first;
-// a hash collision between different columns only delays the later one), so every column is still summed
-// in ascending arrival (= k) order with separately rounded adds.  No sort.  The accumulator is then
-// compacted in ascending column order over the start of the row's bin and the bitmap is cleared.
+// memory (one row at a time per CTA) with a presence bitmap.  The row is consumed XL_THREADS partial
+// products at a time in arrival order.  Products of one chunk that hit the SAME column are serialised: every
+// product enters an open-addressing table in shared memory keyed by its exact column (different columns never
+// share a slot, so they never wait for each other), the lowest position of a slot goes first, so every column
+// is still summed in ascending arrival (= k) order with separately rounded adds.  A chunk without a repeated
+// column -- almost all of them: the runs of a row are duplicate-free -- takes one round.  No sort.  The
+// accumulator is then compacted in ascending column order over the start of the row's bin and the bitmap is
+// cleared.  Rows are handed out by a ticket (sc->xl_ticket, zeroed before the launch): row lengths span three
+// orders of magnitude on power-law inputs, a static assignment left the longest CTA with 2-4x the mean work.
 constexpr int XL_THREADS = 512;
-constexpr uint32_t XL_HASH_BITS = 12;
+constexpr uint32_t XL_SLOTS = 2048;                    // slots of the column table: load <= 1/4
+constexpr uint32_t XL_EMPTY = 0xFFFFFFFFu;             // no column id (ids are < cols_b < 2^32 - 1) and no thread id
 __global__ void __launch_bounds__(XL_THREADS)
 k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, uint32_t *uniq,
-           const uint32_t *xl_list, const uint32_t *long_list, const DevScalars *sc, float *acc_all, uint32_t *bits_all,
+           const uint32_t *xl_list, const uint32_t *long_list, DevScalars *sc, float *acc_all, uint32_t *bits_all,
            uint64_t cols_b, uint64_t row_lo, uint64_t row_hi) {
-    __shared__ uint32_t owner[1u << XL_HASH_BITS];
+    __shared__ uint32_t key[XL_SLOTS];                 // column held by the slot
+    __shared__ uint32_t owner[XL_SLOTS];               // lowest pending position of that column
     __shared__ uint32_t warp_sums[33];
+    __shared__ uint32_t s_x;
     const uint32_t tid = threadIdx.x;
-    for (uint32_t i = tid; i < (1u << XL_HASH_BITS); i += XL_THREADS) owner[i] = 0xFFFFFFFFu;
+    for (uint32_t i = tid; i < XL_SLOTS; i += XL_THREADS) { key[i] = XL_EMPTY; owner[i] = XL_EMPTY; }
     const uint64_t words = (cols_b + 31) >> 5;
     float *acc = acc_all + uint64_t(blockIdx.x) * cols_b;
     uint32_t *bits = bits_all + uint64_t(blockIdx.x) * words;
     // the longest rows first, then (when the caller passes them: moderate column ranges, where compacting the
     // bitmap is cheaper than a shared-memory sort) the rows of MT_LONG .. MT_XL partial products
     const uint32_t n_xl = sc->n_xl, n_all = n_xl + (long_list ? sc->n_long : 0u);
-    __syncthreads();
-    for (uint32_t x = blockIdx.x; x < n_all; x += gridDim.x) {
+    while (true) {
+        __syncthreads();                               // the table is initialised / the previous row is finished
+        if (tid == 0) {
+            uint32_t x;
+            while (true) {                             // next listed row of this row block
+                x = atomicAdd(&sc->xl_ticket, 1u);
+                if (x >= n_all) break;
+                const uint64_t r = x < n_xl ? xl_list[x] : long_list[x - n_xl];
+                if (r >= row_lo && r < row_hi) break;
+            }
+            s_x = x;
+        }
+        __syncthreads();
+        const uint32_t x = s_x;
+        if (x >= n_all) break;
         const uint64_t row = x < n_xl ? xl_list[x] : long_list[x - n_xl];
-        if (row < row_lo || row >= row_hi) continue;
         const uint64_t len = row_bin[row + 1] - row_bin[row];
         Elem *bin = bins + (row_bin[row] - bin_base);
         Elem nxt; nxt.idx = 0; nxt.val = 0.f;
         if (tid < len) nxt = bin[tid];                                   // the next chunk is always in flight
         for (uint64_t c0 = 0; c0 < len; c0 += XL_THREADS) {
             const uint64_t p = c0 + tid;
-            bool pending = p < len;
+            const bool active = p < len;
+            bool pending = active;
             const Elem e = nxt;
             if (p + XL_THREADS < len) nxt = bin[p + XL_THREADS];
-            const uint32_t h = (e.idx * 2654435761u) >> (32 - XL_HASH_BITS);
-            while (__syncthreads_or(pending)) {
-                if (pending) atomicMin(&owner[h], tid);
-                __syncthreads();
-                const bool win = pending && owner[h] == tid;
+            uint32_t slot = 0;
+            if (active) {
+                slot = (e.idx * 2654435761u) >> 21;                      // 11 bits
+                while (true) {
+                    const uint32_t prev = atomicCAS(&key[slot], XL_EMPTY, e.idx);
+                    if (prev == XL_EMPTY || prev == e.idx) break;
+                    slot = (slot + 1) & (XL_SLOTS - 1);
+                }
+                atomicMin(&owner[slot], tid);
+            }
+            __syncthreads();
+            while (true) {
+                const bool win = pending && owner[slot] == tid;
                 if (win) {
                     uint32_t *w = bits + (e.idx >> 5);
                     const uint32_t bit = 1u << (e.idx & 31);
@@ -568,11 +595,15 @@ k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, 
                     }
                     pending = false;
                 }
+                __syncthreads();                                         // every owner[] has been read; the adds are visible
+                if (win) owner[slot] = XL_EMPTY;
+                if (!__syncthreads_or(pending)) break;
+                if (pending) atomicMin(&owner[slot], tid);               // next position of a repeated column
                 __syncthreads();
-                if (win) owner[h] = 0xFFFFFFFFu;
             }
+            if (active) { key[slot] = XL_EMPTY; owner[slot] = XL_EMPTY; }
+            __syncthreads();
         }
-        __syncthreads();
         // ordered compaction of the accumulator over the (fully consumed) bin
         uint64_t produced = 0;
         for (uint64_t w0 = 0; w0 < words; w0 += XL_THREADS) {
@@ -592,7 +623,6 @@ k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, 
             produced += total;
         }
         if (tid == 0) uniq[row] = uint32_t(produced);
-        __syncthreads();
     }
 }
 

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--sample-rows", type=int, default=256)
     ap.add_argument("--heavy-rows", type=int, default=4)
     ap.add_argument("--kernels", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="timing only (runs under ncu)")
     args = ap.parse_args()
     t0 = time.time()
     a, b, dims = synth.build_workload(args.workload, args.scale_down)
@@ -72,6 +73,11 @@ def main():
                     agg.setdefault(name, [0, 0.0]); agg[name][0] += 1; agg[name][1] += ms
                 for name, (n, ms) in agg.items():
                     print(f"   {ms:10.3f} ms  x{n:<4d} {name}", flush=True)
+                per = [round(ms, 1) for name, ms in res.kernel_times() if "k_merge_xl" in name]
+                if len(per) > 1:
+                    print("   k_merge_xl per row block (ms):", per, flush=True)
+        if args.no_check:
+            return
         # ---- global invariants ----
         ok = st["products"] == P
         pos = res.pos_to_host().astype(np.int64)
