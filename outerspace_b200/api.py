@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Optional, Tuple
 
 import numpy as np
@@ -193,6 +194,7 @@ class Result:
     def __init__(self, engine: "Engine", handle: C.c_void_p):
         self._engine = engine
         self._h = handle
+        engine._results.add(self)              # a result must not outlive its context (Engine.close frees what is left)
         rows, nnz = C.c_uint64(), C.c_uint64()
         engine._lib.osp_result_dims(handle, C.byref(rows), C.byref(nnz))
         self.rows, self.nnz = rows.value, nnz.value
@@ -261,9 +263,12 @@ class Engine:
             raise OspError(rc, (self._lib.osp_last_error(None) or b"").decode())
         self._h = h
         self.device = device
+        self._results = weakref.WeakSet()
 
     def close(self) -> None:
         if self._h is not None:
+            for r in list(self._results):
+                r.free()
             self._lib.osp_destroy(self._h)
             self._h = None
 

@@ -365,7 +365,8 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     osp_result *res = new osp_result();
     res->ctx = ctx;
     std::memset(&res->stats, 0, sizeof(res->stats));
-    auto bail = [&](int code) { osp_result_free(res); return code; };
+    ResultGuard guard{res};                      // every early return below (LAUNCH / CU included) frees the result
+    auto bail = [&](int code) { return code; };
     MergeJob job;
     job.rows = std::max<uint64_t>(RL, 1); job.idx_range = cols_b; job.long_thresh = plan_long_thresh(cols_b);
     uint64_t nnz_c = 0;
@@ -435,6 +436,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     stt.exchange_bytes_out = 8 * (P_local - (bound(me, me + 1) - bound(me, me)));
     for (const auto &mk : ctx->marks) res->spans.push_back({nullptr, mk.name, mk.e0, mk.e1});
     ctx->profile_kernels = false;
+    guard.r = nullptr;
     *out = res;
     return OSP_OK;
 }

@@ -105,6 +105,11 @@ int fail(osp_ctx *ctx, int code, const std::string &msg) {
     return code;
 }
 
+struct ResultGuard {
+    osp_result *r;
+    ~ResultGuard() { if (r) osp_result_free(r); }
+};
+
 cudaEvent_t next_event(osp_ctx *ctx) {
     if (ctx->events_used == ctx->events.size()) {
         cudaEvent_t e;
@@ -662,7 +667,8 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     osp_result *res = new osp_result();
     res->ctx = ctx;
     std::memset(&res->stats, 0, sizeof(res->stats));
-    auto bail = [&](int code) { osp_result_free(res); return code; };
+    ResultGuard guard{res};                      // every early return below (CU included) frees the result
+    auto bail = [&](int code) { return code; };
     if (cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_pos), (m_plan + 1) * 8, ctx->stream); e != cudaSuccess) {
         cudaGetLastError();
         bail(0);
@@ -830,6 +836,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     }
     for (const auto &m : ctx->marks) res->spans.push_back({nullptr, m.name, m.e0, m.e1});
     ctx->profile_kernels = false;
+    guard.r = nullptr;
     *out = res;
     return OSP_OK;
 }
@@ -1018,7 +1025,8 @@ int osp_bias_relu(osp_ctx *ctx, const osp_result *c, uint64_t cols, const float 
     osp_result *res = new osp_result();
     res->ctx = ctx;
     std::memset(&res->stats, 0, sizeof(res->stats));
-    auto bail = [&](int code) { osp_result_free(res); return code; };
+    ResultGuard guard{res};                      // every early return below (CU included) frees the result
+    auto bail = [&](int code) { return code; };
     const uint64_t cap = std::max<uint64_t>(bias ? rows * cols : c->nnz, 1);
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_pos), (rows + 1) * 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_data), cap * 8, ctx->stream);
@@ -1054,6 +1062,7 @@ int osp_bias_relu(osp_ctx *ctx, const osp_result *c, uint64_t cols, const float 
     res->nnz = rows ? ctx->h_sc->nnz_c[1] : 0;
     res->stats.rows_c = rows; res->stats.cols_b = cols; res->stats.nnz_c = res->nnz;
     res->stats.kernel_launches = ctx->launches;
+    guard.r = nullptr;
     *out = res;
     return OSP_OK;
 }

@@ -104,3 +104,30 @@ def test_no_cpu_fallback():
     import sys
     src = open(os.path.join(ROOT, "outerspace_b200", "api.py")).read()
     assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_results_do_not_outlive_their_engine():
+    """Engine.close() frees the results still alive (an osp_result keeps a pointer to its osp_ctx) before it
+    destroys the context; freeing twice is harmless.  Host logic only: the library calls are recorded."""
+    calls = []
+
+    class FakeLib:
+        def osp_result_dims(self, h, rows, nnz):
+            return 0
+
+        def osp_result_free(self, h):
+            calls.append(("free", h))
+
+        def osp_destroy(self, h):
+            calls.append(("destroy", h))
+
+    import weakref
+    eng = object.__new__(api.Engine)
+    eng._lib, eng._h, eng.device, eng._results = FakeLib(), 1234, 0, weakref.WeakSet()
+    r1, r2 = api.Result(eng, 1), api.Result(eng, 2)
+    r1.free()
+    eng.close()
+    assert calls[0] == ("free", 1) and calls[-1] == ("destroy", 1234)
+    assert sorted(calls[1:-1]) == [("free", 2)]
+    r2.free(); eng.close()                                   # idempotent
+    assert len(calls) == 3
