@@ -1,0 +1,56 @@
+"""BASELINE.json configs[2] and configs[4] at their FULL sizes on one B200 (P = 2.1e10 and 1.1e10 partial products).
+
+An element-wise oracle cannot finish these, so parity is checked through size-independent properties
+(tools/fullscale_check.py): P equals the host's count, CSR invariants, every row within min(partials, cols), and a
+seeded sample of rows plus the heaviest rows recomputed by the oracle from A[rows, :] and B, compared bit for bit.
+Runs last (file name) and needs a GPU with >= 150 GB: config 3 holds 77.6 GB of C next to row blocks of bins.
+"""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def _big_gpu():
+    import torch
+    return torch.cuda.is_available() and torch.cuda.get_device_properties(0).total_memory >= 150e9
+
+
+def _run(workload, **kw):
+    import outerspace_b200 as osp
+    from outerspace_b200 import api
+    import fullscale_check
+    lines = []
+    try:
+        out = fullscale_check.run_check(workload, log=lambda *xs: lines.append(" ".join(str(x) for x in xs)), **kw)
+    except osp.OspError as e:
+        if e.code == api.OSP_ERR_OOM:
+            pytest.skip(f"device memory not available for {workload} at full size: {e}")
+        raise
+    print("\n".join(lines))
+    return out
+
+
+def test_config5_mlp_batch_full_size():
+    """65536 x 4096 activations @ 10 % times 4096 x 4096 weights^T @ 10 %: fused dense rows, no bins."""
+    if not _big_gpu():
+        pytest.skip("needs a >= 150 GB GPU")
+    out = _run("mlp_batch", iters=1, sample_rows=12, heavy_rows=2)
+    assert out["stats"]["products"] > 1.0e10 and out["stats"]["nnz_c"] == 65536 * 4096
+    assert out["invariants_ok"] and out["bad_rows"] == 0 and out["rows_checked"] >= 12
+
+
+def test_config3_rmat20_full_size():
+    """R-MAT scale 20, edge factor 16, C = A*A: bins (167 GB) and the bound of C (154 GB) exceed the device -- row
+    blocks admitted against the capacity of C -- 295 801 rows through the long-row kernel."""
+    if not _big_gpu():
+        pytest.skip("needs a >= 150 GB GPU")
+    out = _run("rmat20", iters=1, sample_rows=192, heavy_rows=3)
+    st = out["stats"]
+    assert st["products"] > 2.0e10 and st["row_chunks"] > 1 and st["rows_long"] > 100000
+    assert out["invariants_ok"] and out["bad_rows"] == 0 and out["rows_checked"] >= 150
