@@ -7,7 +7,11 @@
 //               of B starts, and with the offset and length of its run of partial products inside the
 //               output-row bins (one LDG.128 per task, no further look-ups in the multiply).
 #pragma once
+#ifdef OSP_CUSIM                      // tests/cusim: the same source on the CPU emulation of the execution model (tests only)
+#include "cusim.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace osp {
@@ -59,6 +63,10 @@ constexpr uint64_t LB_FLAG_AGG = 1ull << 62;
 constexpr uint64_t LB_FLAG_PREFIX = 2ull << 62;
 constexpr uint64_t LB_VALUE_MASK = (1ull << 62) - 1;
 
+#ifdef OSP_CUSIM
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) { return *static_cast<const volatile uint64_t *>(p); }
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) { *static_cast<volatile uint64_t *>(p) = v; }
+#else
 __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
     uint64_t v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -67,6 +75,7 @@ __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
 __device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+#endif
 
 // Called by every lane of ONE warp.  Publishes this tile's aggregate, walks back over the
 // predecessors 32 at a time until an inclusive prefix is found, publishes the tile's own

@@ -1,0 +1,226 @@
+// osp_longrows.cuh -- fused band sweep for long output rows over wide column ranges.
+//
+// STATUS: logic validated on the CPU emulation of the execution model (tests/cusim, tests/test_longrows_sim.py: bit-exact
+// against the oracle, every band / run-group / thread-count combination); compiled for sm_100a with the rest of the
+// engine; NOT yet launched by osp_spgemm -- the host integration and the GPU parity + timing runs are the first item of
+// the next round, when a GPU is available again.  Until then long rows go through k_multiply + k_merge_xl.
+//
+// Why: a long row of C = A*B (config 3: 295 801 rows carry 98.7 % of the 2.09e10 partial products) is made of FEW LONG
+// SORTED runs -- run r = A(i,k_r) * B(k_r,:), ascending k, columns ascending and distinct inside a run.  Writing those
+// partial products to bins and folding them through a per-CTA accumulator of `cols` floats in global memory costs a
+// random DRAM sector per product (profiles/README.md).  Here nothing is materialised: the row is swept one band of
+// LR_BAND columns at a time with the accumulator in shared memory; a run contributes to a band the contiguous
+// segment found by a per-run cursor (runs are sorted), so every element of B is read once per use, from L2.
+//   k_long_count: the sweep with a bitmap only -> the exact number of non-zeros of every long row, so that C is
+//                 allocated exactly and every long row's place in C is known before any value is computed.
+//   k_long_fill:  the sweep with values.  Products of a chunk that hit the same column are serialised by the
+//                 racing-minimum arbitration of k_merge_dense (lowest flat position = lowest (k, position) first), so
+//                 every column is summed in ascending k with separately rounded products and adds: the bits of the
+//                 reference's left fold.  acc[] starts at -0.0f (x + -0 = x for every x): no first-touch test on the add.
+// Runs are taken in groups of LR_RUNS (their cursors' segment prefix lives in shared memory); groups of a band are
+// visited in ascending k, which keeps the order.
+#pragma once
+#include "osp_device.cuh"
+
+namespace osp {
+
+#ifdef OSP_CUSIM
+#define OSP_DYN_SMEM(name) unsigned char *name = cusim::dyn_smem()
+#else
+#define OSP_DYN_SMEM(name)                                       \
+    extern __shared__ __align__(16) unsigned char name##_dyn[];  \
+    unsigned char *name = name##_dyn
+#endif
+
+// First position p in [lo, len] with p == len or run[p].idx >= band_hi; run[lo .. p) lies below band_hi.
+// Galloping from the cursor: a segment of s elements costs ~2 log2(s) probes.
+__device__ __forceinline__ uint32_t lr_advance(const Elem *__restrict__ run, uint32_t lo, uint32_t len, uint64_t band_hi) {
+    if (lo >= len || run[lo].idx >= band_hi) return lo;
+    uint32_t a = lo, step = 1, hi;                       // run[a].idx < band_hi
+    while (true) {
+        const uint64_t b = uint64_t(a) + step;
+        if (b >= len) { hi = len; break; }
+        if (run[b].idx >= band_hi) { hi = uint32_t(b); break; }
+        a = uint32_t(b);
+        step <<= 1;
+    }
+    while (hi - a > 1) {                                 // run[a] < band_hi <= run[hi] (or hi == len)
+        const uint32_t mid = a + (hi - a) / 2;
+        if (run[mid].idx < band_hi) a = mid; else hi = mid;
+    }
+    return hi;
+}
+
+// Shared-memory layout of one CTA: band accumulator | owner | presence bitmap | run group | scan scratch
+template <int BAND, int RUNS, bool VALUES> struct LongRowSmem {
+    static constexpr size_t acc = 0;                                              // float[BAND]      (VALUES)
+    static constexpr size_t owner = acc + (VALUES ? size_t(BAND) * 4 : 0);        // uint16_t[BAND]   (VALUES)
+    static constexpr size_t bits = owner + (VALUES ? size_t(BAND) * 2 : 0);       // uint32_t[BAND/32]
+    static constexpr size_t pre = bits + size_t(BAND) / 8;                        // uint32_t[RUNS+1] exclusive prefix of the segment lengths
+    static constexpr size_t lo = pre + size_t(RUNS + 1) * 4;                      // uint32_t[RUNS]   segment start inside row k of B (absolute in b_data)
+    static constexpr size_t aval = lo + size_t(RUNS) * 4;                         // float[RUNS]      A(i,k)  (VALUES)
+    static constexpr size_t sums = aval + (VALUES ? size_t(RUNS) * 4 : 0);        // uint32_t[34]
+    static constexpr size_t bytes = sums + 36 * 4;
+};
+
+// One CTA per listed row, rows handed out by ticket.  cursors: gridDim.x * cursor_stride uint32 (>= the longest listed
+// row of A).  VALUES=false: count[x] = nnz of listed row x.  VALUES=true: the row is written to out[out_off[x] ...].
+template <int THREADS, int BAND, int RUNS, bool VALUES>
+__device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data,
+                                                const uint64_t *__restrict__ b_pos, const Elem *__restrict__ b_data,
+                                                const uint64_t cols, const uint32_t *__restrict__ rows, const uint32_t n_rows,
+                                                unsigned int *ticket, uint32_t *cursors, const uint64_t cursor_stride,
+                                                uint32_t *count, const uint64_t *__restrict__ out_off, Elem *out) {
+    static_assert(BAND % 32 == 0 && BAND <= 65536 && RUNS >= 1, "the band is a bitmap of whole words");
+    static_assert(THREADS <= 1024 && THREADS % 32 == 0, "whole warps");
+    using L = LongRowSmem<BAND, RUNS, VALUES>;
+    OSP_DYN_SMEM(smem);
+    float *acc = reinterpret_cast<float *>(smem + L::acc);
+    uint16_t *owner = reinterpret_cast<uint16_t *>(smem + L::owner);
+    uint32_t *bits = reinterpret_cast<uint32_t *>(smem + L::bits);
+    uint32_t *s_pre = reinterpret_cast<uint32_t *>(smem + L::pre);
+    uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem + L::lo);
+    float *s_a = reinterpret_cast<float *>(smem + L::aval);
+    uint32_t *warp_sums = reinterpret_cast<uint32_t *>(smem + L::sums);
+    uint32_t *s_x = warp_sums + 34;
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t WORDS = BAND / 32;
+    for (uint32_t w = tid; w < WORDS; w += THREADS) bits[w] = 0u;
+    if (VALUES)
+        for (uint32_t c = tid; c < BAND; c += THREADS) { acc[c] = -0.0f; owner[c] = 0xFFFF; }
+    uint32_t *cursor = cursors + uint64_t(blockIdx.x) * cursor_stride;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) *s_x = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t x = *s_x;
+        if (x >= n_rows) break;
+        const uint64_t row = rows[x];
+        const uint64_t p0 = a_pos[row];
+        const uint64_t R = a_pos[row + 1] - p0;
+        for (uint64_t r = tid; r < R; r += THREADS) cursor[r] = 0u;
+        __syncthreads();                            // a cursor is not always read by the thread that reset it
+        uint32_t my_count = 0;                      // VALUES=false: columns seen, summed over this thread's bitmap words
+        uint64_t produced = 0;                      // VALUES=true: elements of the row already written
+        for (uint64_t band_lo = 0; band_lo < cols; band_lo += BAND) {
+            const uint64_t band_hi = min(cols, band_lo + uint64_t(BAND));
+            for (uint64_t g0 = 0; g0 < R; g0 += RUNS) {
+                const uint32_t G = uint32_t(min(uint64_t(RUNS), R - g0));
+                // ---- the segment of every run of the group inside this band (cursor -> first column >= band_hi) ----
+                uint32_t carry = 0;
+                for (uint32_t r0 = 0; r0 < G; r0 += THREADS) {
+                    const uint32_t r = r0 + tid;
+                    uint32_t seg = 0;
+                    if (r < G) {
+                        const Elem ak = a_data[p0 + g0 + r];
+                        const uint64_t bs = b_pos[ak.idx];
+                        const uint32_t len = uint32_t(b_pos[ak.idx + 1] - bs);
+                        const uint32_t lo = cursor[g0 + r];
+                        const uint32_t hi = lr_advance(b_data + bs, lo, len, band_hi);
+                        cursor[g0 + r] = hi;
+                        seg = hi - lo;
+                        s_lo[r] = uint32_t(bs) + lo;                       // nnz(B) < 2^32
+                        if (VALUES) s_a[r] = ak.val;
+                    }
+                    uint32_t total;
+                    const uint32_t rank = block_exclusive_scan(seg, warp_sums, total);
+                    if (r < G) s_pre[r] = carry + rank;
+                    carry += total;
+                    __syncthreads();                                       // warp_sums is reused by the next pass
+                }
+                if (tid == 0) s_pre[G] = carry;
+                __syncthreads();
+                const uint32_t T = carry;                                  // elements of the group inside the band, in (k, column) order
+                // ---- consume them THREADS at a time ----
+                for (uint32_t c0 = 0; c0 < T; c0 += THREADS) {
+                    const uint32_t f = c0 + tid;
+                    bool pending = f < T;
+                    uint32_t col = 0;
+                    float val = 0.f;
+                    if (pending) {
+                        uint32_t a = 0, b = G;                             // s_pre[a] <= f < s_pre[b]
+                        while (b - a > 1) {
+                            const uint32_t mid = (a + b) >> 1;
+                            if (s_pre[mid] <= f) a = mid; else b = mid;
+                        }
+                        const Elem e = b_data[uint64_t(s_lo[a]) + (f - s_pre[a])];
+                        col = uint32_t(e.idx - band_lo);
+                        if (VALUES) val = __fmul_rn(s_a[a], e.val);
+                    }
+                    if (!VALUES) {
+                        if (pending) atomicOr(&bits[col >> 5], 1u << (col & 31));
+                    } else {
+                        while (__syncthreads_or(pending)) {
+                            // the lowest pending position of every column wins this round (racing minimum, re-checked)
+                            bool want = pending;
+                            do {
+                                if (want && owner[col] > tid) owner[col] = uint16_t(tid);
+                                __syncthreads();
+                                want = pending && owner[col] > tid;
+                            } while (__syncthreads_or(want));
+                            if (pending && owner[col] == tid) {
+                                acc[col] = __fadd_rn(acc[col], val);
+                                atomicOr(&bits[col >> 5], 1u << (col & 31));
+                                owner[col] = 0xFFFF;
+                                pending = false;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();                                           // s_pre / s_lo are rewritten by the next group
+            }
+            // ---- the band is complete: count or emit its columns, reset it ----
+            if (!VALUES) {
+                for (uint32_t w = tid; w < WORDS; w += THREADS) {
+                    my_count += __popc(bits[w]);
+                    bits[w] = 0u;
+                }
+            } else {
+                for (uint32_t w0 = 0; w0 < WORDS; w0 += THREADS) {
+                    const uint32_t w = w0 + tid;
+                    uint32_t bm = w < WORDS ? bits[w] : 0u;
+                    uint32_t total;
+                    const uint32_t rank = block_exclusive_scan(uint32_t(__popc(bm)), warp_sums, total);
+                    uint64_t o = out_off[x] + produced + rank;
+                    if (bm) bits[w] = 0u;
+                    while (bm) {
+                        const uint32_t bit = __ffs(bm) - 1;
+                        bm &= bm - 1;
+                        const uint32_t c = w * 32 + bit;
+                        Elem e; e.idx = uint32_t(band_lo + c); e.val = acc[c];
+                        out[o++] = e;
+                        acc[c] = -0.0f;
+                    }
+                    produced += total;
+                    __syncthreads();                                       // warp_sums is reused
+                }
+            }
+            __syncthreads();
+        }
+        if (!VALUES) {
+            uint32_t total;
+            block_exclusive_scan(my_count, warp_sums, total);
+            if (tid == 0) count[x] = total;
+        }
+    }
+}
+
+template <int THREADS, int BAND, int RUNS>
+__global__ void __launch_bounds__(THREADS)
+k_long_count(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data, const uint64_t *__restrict__ b_pos,
+             const Elem *__restrict__ b_data, uint64_t cols, const uint32_t *__restrict__ rows, uint32_t n_rows,
+             unsigned int *ticket, uint32_t *cursors, uint64_t cursor_stride, uint32_t *count) {
+    long_rows_sweep<THREADS, BAND, RUNS, false>(a_pos, a_data, b_pos, b_data, cols, rows, n_rows, ticket, cursors, cursor_stride,
+                                                count, nullptr, nullptr);
+}
+
+template <int THREADS, int BAND, int RUNS>
+__global__ void __launch_bounds__(THREADS)
+k_long_fill(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data, const uint64_t *__restrict__ b_pos,
+            const Elem *__restrict__ b_data, uint64_t cols, const uint32_t *__restrict__ rows, uint32_t n_rows,
+            unsigned int *ticket, uint32_t *cursors, uint64_t cursor_stride, const uint64_t *__restrict__ out_off, Elem *out) {
+    long_rows_sweep<THREADS, BAND, RUNS, true>(a_pos, a_data, b_pos, b_data, cols, rows, n_rows, ticket, cursors, cursor_stride,
+                                               nullptr, out_off, out);
+}
+
+}  // namespace osp

@@ -1,0 +1,258 @@
+// cusim.h -- a small CPU emulation of the CUDA execution model, for TESTS ONLY.
+//
+// It lets a kernel written in plain CUDA C++ (no inline PTX) run on the host so that its logic -- index arithmetic,
+// barrier structure, warp collectives, arbitration loops -- can be checked against the oracle in the `-m "not gpu"`
+// suite, where no GPU exists.  It is NOT a product path and nothing under outerspace_b200/ links it: the kernels are
+// compiled by nvcc for sm_100a as always; a test translation unit defines OSP_CUSIM, includes this header instead of
+// <cuda_runtime.h>, and calls cusim::launch().
+//
+// Model: the thread blocks of a launch run one after the other; the threads of a block are fibers (ucontext) scheduled
+// round-robin on one OS thread, switching only inside the synchronising built-ins (__syncthreads*, warp collectives,
+// __nanosleep).  That is a legal CUDA schedule, so a kernel that is correct under every schedule is correct here; the
+// reverse does not hold (data races between barriers go unnoticed), which is why GPU parity tests stay the gate.
+// Persistent kernels that hand out work by ticket run to completion in the first block (later blocks find no work);
+// kernels that need co-resident blocks to make progress cannot be emulated.
+#pragma once
+#include <ucontext.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+inline dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+namespace cusim {
+
+struct Fiber {
+    ucontext_t ctx;
+    std::unique_ptr<char[]> stack;
+    unsigned tid = 0;
+    bool done = false;
+};
+
+struct Warp {
+    unsigned arrived = 0, gen = 0;
+    uint64_t slot[2][32];
+};
+
+struct Block {
+    std::vector<Fiber> fibers;
+    unsigned alive = 0, bar_count = 0, bar_gen = 0;
+    int bar_or = 0, bar_and = 1, bar_cnt = 0;
+    int res_or[2] = {0, 0}, res_and[2] = {0, 0}, res_cnt[2] = {0, 0};
+    Warp warps[32];
+    std::vector<unsigned char> dyn;
+    std::function<void()> body;
+};
+
+inline Block *g_block = nullptr;
+inline Fiber *g_fiber = nullptr;
+inline ucontext_t g_sched;
+inline unsigned long long g_progress = 0, g_switches = 0;
+
+inline void yield() {
+    Fiber *me = g_fiber;
+    g_switches++;
+    swapcontext(&me->ctx, &g_sched);
+    g_fiber = me;
+    threadIdx.x = me->tid;
+}
+
+inline void release_barrier(Block &b) {
+    const unsigned g = b.bar_gen & 1;
+    b.res_or[g] = b.bar_or; b.res_and[g] = b.bar_and; b.res_cnt[g] = b.bar_cnt;
+    b.bar_or = 0; b.bar_and = 1; b.bar_cnt = 0; b.bar_count = 0;
+    b.bar_gen++;
+    g_progress++;
+}
+
+// mode 0: plain, 1: or, 2: and, 3: count
+inline int barrier(int pred, int mode) {
+    Block &b = *g_block;
+    const unsigned gen = b.bar_gen;
+    b.bar_or |= pred != 0; b.bar_and &= pred != 0; b.bar_cnt += pred != 0;
+    if (++b.bar_count == b.alive) release_barrier(b);
+    else while (b.bar_gen == gen) yield();
+    const unsigned g = gen & 1;
+    return mode == 1 ? b.res_or[g] : mode == 2 ? b.res_and[g] : mode == 3 ? b.res_cnt[g] : 0;
+}
+
+inline unsigned live_lanes(unsigned warp) {
+    Block &b = *g_block;
+    unsigned m = 0;
+    for (unsigned l = 0; l < 32; l++) {
+        const unsigned t = warp * 32 + l;
+        if (t < b.fibers.size() && !b.fibers[t].done) m |= 1u << l;
+    }
+    return m;
+}
+
+// Every lane named in `mask` deposits a word and gets the warp's 32 words back.
+inline const uint64_t *exchange(unsigned mask, uint64_t v) {
+    Block &b = *g_block;
+    const unsigned tid = g_fiber->tid, w = tid >> 5, lane = tid & 31;
+    Warp &wp = b.warps[w];
+    const unsigned gen = wp.gen;
+    wp.slot[gen & 1][lane] = v;
+    wp.arrived |= 1u << lane;
+    const unsigned need = mask & live_lanes(w);
+    if ((wp.arrived & need) == need) { wp.arrived = 0; wp.gen++; g_progress++; }
+    else while (wp.gen == gen) yield();
+    return wp.slot[gen & 1];
+}
+
+template <class T> inline uint64_t to_word(T v) { static_assert(sizeof(T) <= 8, ""); uint64_t w = 0; std::memcpy(&w, &v, sizeof(T)); return w; }
+template <class T> inline T from_word(uint64_t w) { T v; std::memcpy(&v, &w, sizeof(T)); return v; }
+
+inline unsigned char *dyn_smem() { return g_block->dyn.data(); }
+
+inline void trampoline() {
+    Fiber *me = g_fiber;
+    g_block->body();
+    me->done = true;
+    Block &b = *g_block;
+    b.alive--;
+    g_progress++;
+    if (b.alive && b.bar_count == b.alive) release_barrier(b);       // the others were waiting for this thread only
+    for (unsigned w = 0; w < 32; w++) {                               // likewise for a warp collective
+        Warp &wp = b.warps[w];
+        const unsigned need = live_lanes(w);
+        if (wp.arrived && (wp.arrived & need) == need) { wp.arrived = 0; wp.gen++; }
+    }
+    swapcontext(&me->ctx, &g_sched);
+}
+
+constexpr size_t STACK_BYTES = 256 << 10;
+
+// Runs `body` (a call of the kernel function) once per thread of a grid x block launch, x dimension only.
+template <class F> inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, F &&body) {
+    gridDim = dim3(grid); blockDim = dim3(block);
+    for (unsigned bx = 0; bx < grid; bx++) {
+        Block b;
+        b.fibers.resize(block);
+        b.alive = block;
+        b.dyn.assign(dyn_bytes + 16, 0xCD);
+        b.body = body;
+        g_block = &b;
+        blockIdx = dim3(bx);
+        for (unsigned t = 0; t < block; t++) {
+            Fiber &f = b.fibers[t];
+            f.tid = t;
+            f.stack.reset(new char[STACK_BYTES]);
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack.get();
+            f.ctx.uc_stack.ss_size = STACK_BYTES;
+            f.ctx.uc_link = nullptr;
+            makecontext(&f.ctx, trampoline, 0);
+        }
+        unsigned idle_passes = 0;
+        while (b.alive) {
+            const unsigned long long before = g_progress;
+            for (unsigned t = 0; t < block; t++) {
+                Fiber &f = b.fibers[t];
+                if (f.done) continue;
+                g_fiber = &f;
+                threadIdx = dim3(t);
+                swapcontext(&g_sched, &f.ctx);
+            }
+            if (g_progress == before) {
+                if (++idle_passes > 1000) {
+                    std::fprintf(stderr, "cusim: deadlock in block %u (%u threads alive, %u at the barrier)\n", bx, b.alive, b.bar_count);
+                    std::abort();
+                }
+            } else {
+                idle_passes = 0;
+            }
+        }
+        g_block = nullptr;
+    }
+}
+
+}  // namespace cusim
+
+// ---- synchronising built-ins -----------------------------------------------------------------------------------
+inline void __syncthreads() { cusim::barrier(0, 0); }
+inline int __syncthreads_or(int p) { return cusim::barrier(p, 1); }
+inline int __syncthreads_and(int p) { return cusim::barrier(p, 2); }
+inline int __syncthreads_count(int p) { return cusim::barrier(p, 3); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { cusim::exchange(mask, 0); }
+inline void __nanosleep(unsigned) { cusim::yield(); }
+inline void __threadfence() {}
+inline void __threadfence_block() {}
+
+template <class T> inline T __shfl_sync(unsigned mask, T v, int src) {
+    const uint64_t *s = cusim::exchange(mask, cusim::to_word(v));
+    return cusim::from_word<T>(s[src & 31]);
+}
+template <class T> inline T __shfl_up_sync(unsigned mask, T v, unsigned d) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t *s = cusim::exchange(mask, cusim::to_word(v));
+    return lane >= d ? cusim::from_word<T>(s[lane - d]) : v;
+}
+template <class T> inline T __shfl_down_sync(unsigned mask, T v, unsigned d) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t *s = cusim::exchange(mask, cusim::to_word(v));
+    return lane + d < 32 ? cusim::from_word<T>(s[lane + d]) : v;
+}
+template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int x) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t *s = cusim::exchange(mask, cusim::to_word(v));
+    return cusim::from_word<T>(s[(lane ^ unsigned(x)) & 31]);
+}
+inline unsigned __ballot_sync(unsigned mask, int p) {
+    const unsigned live = mask & cusim::live_lanes(threadIdx.x >> 5);
+    const uint64_t *s = cusim::exchange(mask, p ? 1 : 0);
+    unsigned r = 0;
+    for (unsigned l = 0; l < 32; l++) if (((live >> l) & 1) && s[l]) r |= 1u << l;
+    return r;
+}
+inline int __any_sync(unsigned mask, int p) { return __ballot_sync(mask, p) != 0; }
+inline int __all_sync(unsigned mask, int p) { return __ballot_sync(mask, !p) == 0; }
+template <class T> inline unsigned __match_any_sync(unsigned mask, T v) {
+    const unsigned live = mask & cusim::live_lanes(threadIdx.x >> 5);
+    const uint64_t mine = cusim::to_word(v);
+    const uint64_t *s = cusim::exchange(mask, mine);
+    unsigned r = 0;
+    for (unsigned l = 0; l < 32; l++) if (((live >> l) & 1) && s[l] == mine) r |= 1u << l;
+    return r;
+}
+
+// ---- arithmetic and memory built-ins ---------------------------------------------------------------------------
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+inline int __clz(int v) { return v ? __builtin_clz(unsigned(v)) : 32; }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+template <class T> inline T __ldcg(const T *p) { return *p; }
+template <class T> inline T __ldg(const T *p) { return *p; }
+
+template <class T> inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T atomicMin(T *p, T v) { T o = *p; *p = std::min(o, v); return o; }
+template <class T> inline T atomicMax(T *p, T v) { T o = *p; *p = std::max(o, v); return o; }
+template <class T> inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
+template <class T> inline T atomicAnd(T *p, T v) { T o = *p; *p = o & v; return o; }
+template <class T> inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
+template <class T> inline T atomicCAS(T *p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
+
+using std::max;
+using std::min;
