@@ -51,6 +51,12 @@ extern "C" {
                                     bins, same result bit for bit (DESIGN.md "multiply order") */
 #define OSP_NO_FUSED_DENSE  64u  /* keep the bins even when every row is long over a small column range (see
                                     DESIGN.md "fused dense rows"): multiply -> bins -> k_merge_dense */
+#define OSP_LONGROW_SWEEP  128u  /* EXPERIMENTAL, off by default, not yet run on a B200 (validated on the CPU emulation
+                                    of tests/cusim only): rows of more than 4096 partial products over more than 16384
+                                    columns skip the bins -- a fused band sweep (k_long_fill)
+                                    computes and merges them in shared memory.  Same bits.  Ignored with
+                                    OSP_KSLICE_ORDER.  Environment: OSP_LONGROW_SWEEP=1 turns it on for every call of a
+                                    context, OSP_LONGROW_SWEEP_MIN=<partial products> raises the row threshold */
 #define OSP_PROFILE_PHASES   8u  /* synchronise between phases so that stats.ms_* are per-phase times */
 
 #define OSP_PROFILE_KERNELS 16u  /* record a CUDA-event pair around every kernel launch (osp_result_kernels) */

@@ -4,6 +4,7 @@
 // fails with OSP_ERR_NO_DEVICE / OSP_ERR_CUDA otherwise.
 #include "../../include/osp_b200.h"
 #include "osp_kernels.cuh"
+#include "osp_longrows.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -61,6 +62,12 @@ struct osp_ctx {
     // symbolic / plan / conversion scratch
     DevBuf task_bs, run_off, row_bin, tile_row, long_list, xl_list, uniq, col_ptr, tasks, tile_state, xl_acc, xl_bits;
     DevBuf bins;
+    // fused band sweep of the long rows (opt-in, osp_longrows.cuh): task bitmap for the multiply, per-CTA run cursors
+    DevBuf swept, lr_cursors;
+    bool sweep_ok = false;                  // the device accepted the kernel's shared-memory size
+    bool sweep_env = false;                 // OSP_LONGROW_SWEEP=1
+    uint64_t sweep_min = 0;                 // OSP_LONGROW_SWEEP_MIN: fewest partial products of a swept row (0: every xl row)
+    int sweep_occ = 1;                      // resident CTAs per SM of k_long_fill
     std::vector<cudaEvent_t> events;
     size_t events_used = 0;
     // OSP_PROFILE_KERNELS: one event pair per launch
@@ -247,14 +254,26 @@ struct MergeJob {
     uint64_t *c_pos = nullptr;
     Elem *c_data = nullptr;
     uint64_t c_cap = 0;
+    // fused band sweep (osp_spgemm only): rows of the xl list with >= sweep_min partial products never reached the bins
+    bool sweep = false;
+    uint64_t sweep_min = ~0ull;             // what k_merge_xl leaves alone (~0: nothing)
+    uint64_t cursor_stride = 0;
+    const uint64_t *a_pos = nullptr, *b_pos = nullptr;
+    const Elem *a_data = nullptr, *b_data = nullptr;
 };
+
+// Template arguments of the long-row sweep on a B200: 512 threads, a band of 16384 columns (64 KB accumulator + 32 KB
+// arbitration + 2 KB bitmap), 512 runs per group: 104.6 KB per CTA, two CTAs per SM.
+constexpr int LR_THREADS = 512, LR_BAND = 16384, LR_RUNS = 512;
+constexpr size_t LR_SMEM = LongRowSmem<LR_BAND, LR_RUNS, true>::bytes;
 
 // Scratch that depends on the plan's results: look-back states of the tile chain, survivor counts of the
 // long rows, the dense accumulators of the longest rows.
 int reserve_merge(osp_ctx *ctx, const MergeJob &job, unsigned int &xl_ctas) {
     CU(ctx, ctx->uniq.reserve(std::max<uint64_t>(job.rows, 1) * 4));
     xl_ctas = 0;
-    const uint64_t n_acc_rows = uint64_t(job.n_xl) + (job.idx_range <= XL_LONG_MAX_COLS ? job.n_long : 0u);
+    // with the sweep taking EVERY xl row the global accumulators are only needed for the medium rows
+    const uint64_t n_acc_rows = uint64_t(job.sweep && job.sweep_min <= MT_XL ? 0u : job.n_xl) + (job.idx_range <= XL_LONG_MAX_COLS ? job.n_long : 0u);
     if (n_acc_rows && job.idx_range > DENSE_MAX_COLS) {
         const uint64_t words = (job.idx_range + 31) / 32;
         const uint64_t per_cta = job.idx_range * 4 + words * 4;
@@ -265,6 +284,10 @@ int reserve_merge(osp_ctx *ctx, const MergeJob &job, unsigned int &xl_ctas) {
         CU(ctx, ctx->xl_acc.reserve(uint64_t(xl_ctas) * job.idx_range * 4));
         CU(ctx, ctx->xl_bits.reserve(uint64_t(xl_ctas) * words * 4));
         CU(ctx, cudaMemsetAsync(ctx->xl_bits.p, 0, uint64_t(xl_ctas) * words * 4, ctx->stream));
+    }
+    if (job.sweep) {
+        const uint64_t ctas = std::min<uint64_t>(job.n_xl, uint64_t(ctx->sm_count) * ctx->sweep_occ);
+        CU(ctx, ctx->lr_cursors.reserve(std::max<uint64_t>(ctas * job.cursor_stride, 1) * 4));
     }
     return OSP_OK;
 }
@@ -292,11 +315,21 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
             if (job.n_long && !xl_takes_long)
                 LAUNCH(ctx, k_merge_long, std::min<unsigned>(job.n_long, unsigned(ctx->sm_count) * 4u), 256, LONG_SMEM, row_bin,
                        bin_base, bins, uniq, ctx->long_list.as<uint32_t>(), ctx->d_sc, row_lo, row_hi);
-            if (job.n_xl || (job.n_long && xl_takes_long)) {
+            if (job.sweep) {
+                // these rows' bins are still untouched (k_multiply skipped their tasks): computed, merged and left at
+                // the start of the bin in one sweep, uniq[row] = nnz -- what the chain expects of a long row
+                CU(ctx, cudaMemsetAsync(&ctx->d_sc->xl_ticket, 0, 4, ctx->stream));
+                const unsigned grid = unsigned(std::min<uint64_t>(job.n_xl, uint64_t(ctx->sm_count) * ctx->sweep_occ));
+                const LongRowsInBins rows{ctx->xl_list.as<uint32_t>(), ctx->d_sc, row_bin, bin_base, bins, uniq, row_lo, row_hi,
+                                          job.sweep_min};
+                LAUNCH(ctx, (k_long_fill<LR_THREADS, LR_BAND, LR_RUNS, LongRowsInBins>), grid, LR_THREADS, LR_SMEM, job.a_pos, job.a_data,
+                       job.b_pos, job.b_data, job.idx_range, rows, ctx->lr_cursors.as<uint32_t>(), job.cursor_stride, &ctx->d_sc->err);
+            }
+            if (xl_ctas && ((job.n_xl && !(job.sweep && job.sweep_min <= MT_XL)) || (job.n_long && xl_takes_long))) {
                 CU(ctx, cudaMemsetAsync(&ctx->d_sc->xl_ticket, 0, 4, ctx->stream));
                 LAUNCH(ctx, k_merge_xl, xl_ctas, XL_THREADS, 0, row_bin, bin_base, bins, uniq, ctx->xl_list.as<uint32_t>(),
                        xl_takes_long ? ctx->long_list.as<uint32_t>() : nullptr, ctx->d_sc, ctx->xl_acc.as<float>(),
-                       ctx->xl_bits.as<uint32_t>(), job.idx_range, row_lo, row_hi);
+                       ctx->xl_bits.as<uint32_t>(), job.idx_range, row_lo, row_hi, job.sweep ? job.sweep_min : ~0ull);
             }
         }
     }
@@ -498,6 +531,17 @@ int osp_create(int device, osp_ctx **out) {
         CU(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->chain_occ[2], kbm, MC_THREADS, sizeof(MergeChainSmem<true>)));
         for (int &o : ctx->chain_occ) o = std::max(o, 1);
     }
+    {   // fused band sweep of the long rows: opt-in (include/osp_b200.h, OSP_LONGROW_SWEEP); a device that cannot give
+        // it its shared memory simply never takes that path
+        auto kfill = k_long_fill<LR_THREADS, LR_BAND, LR_RUNS, LongRowsInBins>;
+        ctx->sweep_ok = cudaFuncSetAttribute(kfill, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LR_SMEM)) == cudaSuccess &&
+                        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sweep_occ, kfill, LR_THREADS, LR_SMEM) == cudaSuccess &&
+                        ctx->sweep_occ >= 1;
+        if (!ctx->sweep_ok) { cudaGetLastError(); ctx->sweep_occ = 1; }
+        const char *env = std::getenv("OSP_LONGROW_SWEEP");
+        ctx->sweep_env = env && env[0] && env[0] != '0';
+        if (const char *m = std::getenv("OSP_LONGROW_SWEEP_MIN")) ctx->sweep_min = std::strtoull(m, nullptr, 10);
+    }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = ~0ull;
@@ -519,7 +563,7 @@ void osp_destroy(osp_ctx *ctx) {
     for (DevBuf *b : {&ctx->arena, &ctx->op_a_pos, &ctx->op_a_data, &ctx->op_b_pos, &ctx->op_b_data, &ctx->conv_pos,
                       &ctx->conv_data, &ctx->conv_tmp, &ctx->conv_chk, &ctx->task_bs, &ctx->run_off, &ctx->row_bin, &ctx->tile_row,
                       &ctx->long_list, &ctx->xl_list, &ctx->uniq, &ctx->col_ptr, &ctx->tasks, &ctx->tile_state,
-                      &ctx->xl_acc, &ctx->xl_bits, &ctx->bins})
+                      &ctx->xl_acc, &ctx->xl_bits, &ctx->bins, &ctx->swept, &ctx->lr_cursors})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
@@ -691,10 +735,31 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     MergeJob job;
     job.rows = m_plan; job.idx_range = std::max<uint64_t>(cols_b, 1); job.long_thresh = plan_long_thresh(args->cols_b);
     job.n_tiles = ctx->h_sc->n_tiles; job.n_long = ctx->h_sc->n_long; job.n_xl = ctx->h_sc->n_xl;
+    // ---- fused band sweep of the long rows (opt-in): their tasks are flagged for the multiply, which emits nothing for
+    // them; k_long_fill computes and merges them straight into the start of their bins (launch_merge)
+    const bool sweep = ctx->sweep_ok && ((args->flags & OSP_LONGROW_SWEEP) || ctx->sweep_env) && !(args->flags & OSP_KSLICE_ORDER) &&
+                       rowwise && !fused && job.n_xl > 0 && job.idx_range > DENSE_MAX_COLS;
+    if (sweep) {
+        job.sweep = true;
+        job.sweep_min = ctx->sweep_min;
+        job.cursor_stride = std::max<uint64_t>(std::min<uint64_t>(nnz_a, std::max<uint64_t>(n_k, 1)), 1);   // a row of A holds <= n_k distinct columns
+        job.a_pos = dA_pos; job.a_data = dA_data; job.b_pos = dB_pos; job.b_data = dB_data;
+    }
     const uint64_t cap_bound = std::max<uint64_t>(args->cols_b ? ctx->h_sc->cap_bound : std::min<uint64_t>(ctx->h_sc->cap_bound, P), 1);
     unsigned int xl_ctas = 0;
     rc = reserve_merge(ctx, job, xl_ctas);
     if (rc) return bail(rc);
+    if (sweep) {
+        rc = [&]() -> int {
+            const uint64_t words = (nnz_a + 31) / 32 + 1;
+            CU(ctx, ctx->swept.reserve(words * 4));
+            CU(ctx, cudaMemsetAsync(ctx->swept.p, 0, words * 4, ctx->stream));
+            LAUNCH(ctx, k_mark_swept, grid_for(uint64_t(job.n_xl) * 32, 256, unsigned(ctx->sm_count) * 8u), 256, 0, dA_pos,
+                   ctx->xl_list.as<uint32_t>(), ctx->d_sc, ctx->row_bin.as<uint64_t>(), job.sweep_min, ctx->swept.as<uint32_t>());
+            return OSP_OK;
+        }();
+        if (rc) return bail(rc);
+    }
     // ---- capacity of C.  The plan only knows the bound sum_i min(len_i, cols) of nnz(C).  On skewed inputs the bound
     // is far above nnz(C) and can exceed the device (config 3 at full scale: 154 GB of bound next to 167 GB of partial
     // products): then C gets what the device can spare, the call runs in small row blocks, and every block is admitted
@@ -803,7 +868,10 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         }
         ev_blocks.push_back(b == 0 ? ev_sym : next_event(ctx));     // nothing is recorded between the hand-over and the multiply
         if (forked && b == 0) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-        if (rowwise) rc = launch_multiply(ctx, TaskSrcSoA{dA_data, run_off, task_bs}, blk_e[b], blk_e[b + 1], p_block, dB_data, bins, bin0);
+        if (rowwise && sweep)
+            rc = launch_multiply(ctx, TaskSrcSoASwept{TaskSrcSoA{dA_data, run_off, task_bs}, ctx->swept.as<uint32_t>()}, blk_e[b], blk_e[b + 1],
+                                 p_block, dB_data, bins, bin0);
+        else if (rowwise) rc = launch_multiply(ctx, TaskSrcSoA{dA_data, run_off, task_bs}, blk_e[b], blk_e[b + 1], p_block, dB_data, bins, bin0);
         else rc = launch_multiply(ctx, TaskSrcAoS{ctx->tasks.as<Task>()}, 0, nnz_a, p_block, dB_data, bins, bin0);
         if (rc) return bail(rc);
         ev_blocks.push_back(next_event(ctx));

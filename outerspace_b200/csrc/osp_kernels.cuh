@@ -374,6 +374,14 @@ struct TaskSrcSoA {
         bs = task_bs[i];
     }
 };
+struct TaskSrcSoASwept {        // row order of A minus the tasks of the rows the fused band sweep takes (osp_longrows.cuh)
+    TaskSrcSoA src;
+    const uint32_t *swept;      // one bit per task, set by k_mark_swept
+    __device__ __forceinline__ void load(uint64_t i, uint32_t &bs, float &a, uint64_t &off, uint32_t &len) const {
+        src.load(i, bs, a, off, len);
+        if ((swept[i >> 5] >> (i & 31)) & 1u) len = 0;
+    }
+};
 
 template <class Src>
 __global__ void __launch_bounds__(256)
@@ -530,7 +538,7 @@ constexpr uint32_t XL_EMPTY = 0xFFFFFFFFu;             // no column id (ids are 
 __global__ void __launch_bounds__(XL_THREADS)
 k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, uint32_t *uniq,
            const uint32_t *xl_list, const uint32_t *long_list, DevScalars *sc, float *acc_all, uint32_t *bits_all,
-           uint64_t cols_b, uint64_t row_lo, uint64_t row_hi) {
+           uint64_t cols_b, uint64_t row_lo, uint64_t row_hi, uint64_t sweep_min) {
     __shared__ uint32_t key[XL_SLOTS];                 // column held by the slot
     __shared__ uint32_t owner[XL_SLOTS];               // lowest pending position of that column
     __shared__ uint32_t warp_sums[33];
@@ -551,7 +559,8 @@ k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, 
                 x = atomicAdd(&sc->xl_ticket, 1u);
                 if (x >= n_all) break;
                 const uint64_t r = x < n_xl ? xl_list[x] : long_list[x - n_xl];
-                if (r >= row_lo && r < row_hi) break;
+                // rows of sweep_min partial products or more belong to the fused band sweep (~0: none)
+                if (r >= row_lo && r < row_hi && row_bin[r + 1] - row_bin[r] < sweep_min) break;
             }
             s_x = x;
         }

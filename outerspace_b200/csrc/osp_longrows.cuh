@@ -2,8 +2,9 @@
 //
 // STATUS: logic validated on the CPU emulation of the execution model (tests/cusim, tests/test_longrows_sim.py: bit-exact
 // against the oracle, every band / run-group / thread-count combination); compiled for sm_100a with the rest of the
-// engine; NOT yet launched by osp_spgemm -- the host integration and the GPU parity + timing runs are the first item of
-// the next round, when a GPU is available again.  Until then long rows go through k_multiply + k_merge_xl.
+// engine and launched by osp_spgemm ONLY when the caller opts in (OSP_LONGROW_SWEEP flag or environment variable, see
+// include/osp_b200.h): the round's GPU budget was spent before it could be run on a B200, so the default path still
+// sends long rows through k_multiply + k_merge_xl.  GPU parity tests for the opt-in path: tests/test_gpu_zzz_sweep.py.
 //
 // Why: a long row of C = A*B (config 3: 295 801 rows carry 98.7 % of the 2.09e10 partial products) is made of FEW LONG
 // SORTED runs -- run r = A(i,k_r) * B(k_r,:), ascending k, columns ascending and distinct inside a run.  Writing those
@@ -59,18 +60,51 @@ template <int BAND, int RUNS, bool VALUES> struct LongRowSmem {
     static constexpr size_t pre = bits + size_t(BAND) / 8;                        // uint32_t[RUNS+1] exclusive prefix of the segment lengths
     static constexpr size_t lo = pre + size_t(RUNS + 1) * 4;                      // uint32_t[RUNS]   segment start inside row k of B (absolute in b_data)
     static constexpr size_t aval = lo + size_t(RUNS) * 4;                         // float[RUNS]      A(i,k)  (VALUES)
-    static constexpr size_t sums = aval + (VALUES ? size_t(RUNS) * 4 : 0);        // uint32_t[34]
-    static constexpr size_t bytes = sums + 36 * 4;
+    static constexpr size_t sums = aval + (VALUES ? size_t(RUNS) * 4 : 0);        // uint32_t[34] scan scratch | ticket, more | row (uint64)
+    static constexpr size_t bytes = ((sums + 36 * 4 + 7) & ~size_t(7)) + 8;
 };
 
-// One CTA per listed row, rows handed out by ticket.  cursors: gridDim.x * cursor_stride uint32 (>= the longest listed
-// row of A).  VALUES=false: count[x] = nnz of listed row x.  VALUES=true: the row is written to out[out_off[x] ...].
-template <int THREADS, int BAND, int RUNS, bool VALUES>
+// Where the rows come from and where they go.
+//   next(x, row): called by thread 0 -- the next listed row, false when the list is exhausted;
+//   out(x, row):  where the merged row is written (VALUES);  done(x, row, n): called by thread 0 with the row's nnz.
+struct LongRowsListed {                 // an explicit list with explicit places (tests; exact allocation of C)
+    const uint32_t *rows; uint32_t n_rows; unsigned int *ticket;
+    uint32_t *count; const uint64_t *out_off; Elem *base;
+    __device__ __forceinline__ bool next(uint32_t &x, uint64_t &row) const {
+        x = atomicAdd(ticket, 1u);
+        if (x >= n_rows) return false;
+        row = rows[x];
+        return true;
+    }
+    __device__ __forceinline__ Elem *out(uint32_t x, uint64_t) const { return base + out_off[x]; }
+    __device__ __forceinline__ void done(uint32_t x, uint64_t, uint64_t n) const { if (count) count[x] = uint32_t(n); }
+};
+struct LongRowsInBins {                 // the engine: rows of the plan's xl list inside [row_lo, row_hi) with at least
+    const uint32_t *xl_list;            // min_len partial products; the merged row goes to the start of the row's
+    DevScalars *sc;                     // (untouched) bin and uniq[row] = nnz, which is where k_merge_chain expects a
+    const uint64_t *row_bin;            // long row -- the same hand-over as k_merge_xl
+    uint64_t bin_base; Elem *bins; uint32_t *uniq;
+    uint64_t row_lo, row_hi, min_len;
+    __device__ __forceinline__ bool next(uint32_t &x, uint64_t &row) const {
+        const uint32_t n = sc->n_xl;
+        while (true) {
+            x = atomicAdd(&sc->xl_ticket, 1u);
+            if (x >= n) return false;
+            row = xl_list[x];
+            if (row >= row_lo && row < row_hi && row_bin[row + 1] - row_bin[row] >= min_len) return true;
+        }
+    }
+    __device__ __forceinline__ Elem *out(uint32_t, uint64_t row) const { return bins + (row_bin[row] - bin_base); }
+    __device__ __forceinline__ void done(uint32_t, uint64_t row, uint64_t n) const { uniq[row] = uint32_t(n); }
+};
+
+// One CTA per listed row, rows handed out by ticket.  cursors: gridDim.x * cursor_stride uint32; a listed row of A with
+// more than cursor_stride non-zeros raises *err (the host sizes the stride from the operand).
+template <int THREADS, int BAND, int RUNS, bool VALUES, class Rows>
 __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data,
                                                 const uint64_t *__restrict__ b_pos, const Elem *__restrict__ b_data,
-                                                const uint64_t cols, const uint32_t *__restrict__ rows, const uint32_t n_rows,
-                                                unsigned int *ticket, uint32_t *cursors, const uint64_t cursor_stride,
-                                                uint32_t *count, const uint64_t *__restrict__ out_off, Elem *out) {
+                                                const uint64_t cols, const Rows rows, uint32_t *cursors,
+                                                const uint64_t cursor_stride, unsigned int *err) {
     static_assert(BAND % 32 == 0 && BAND <= 65536 && RUNS >= 1, "the band is a bitmap of whole words");
     static_assert(THREADS <= 1024 && THREADS % 32 == 0, "whole warps");
     using L = LongRowSmem<BAND, RUNS, VALUES>;
@@ -82,7 +116,8 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
     uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem + L::lo);
     float *s_a = reinterpret_cast<float *>(smem + L::aval);
     uint32_t *warp_sums = reinterpret_cast<uint32_t *>(smem + L::sums);
-    uint32_t *s_x = warp_sums + 34;
+    uint32_t *s_x = warp_sums + 34;                                        // [0] ticket, [1] 1 while there is a row
+    uint64_t *s_row = reinterpret_cast<uint64_t *>(smem + L::bytes - 8);
     const uint32_t tid = threadIdx.x;
     constexpr uint32_t WORDS = BAND / 32;
     for (uint32_t w = tid; w < WORDS; w += THREADS) bits[w] = 0u;
@@ -91,13 +126,22 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
     uint32_t *cursor = cursors + uint64_t(blockIdx.x) * cursor_stride;
     while (true) {
         __syncthreads();
-        if (tid == 0) *s_x = atomicAdd(ticket, 1u);
+        if (tid == 0) {
+            uint32_t tx = 0; uint64_t trow = 0;
+            s_x[1] = rows.next(tx, trow) ? 1u : 0u;
+            s_x[0] = tx; *s_row = trow;
+        }
         __syncthreads();
-        const uint32_t x = *s_x;
-        if (x >= n_rows) break;
-        const uint64_t row = rows[x];
+        if (!s_x[1]) break;
+        const uint32_t x = s_x[0];
+        const uint64_t row = *s_row;
         const uint64_t p0 = a_pos[row];
         const uint64_t R = a_pos[row + 1] - p0;
+        if (R > cursor_stride) {                    // not reachable when the host sized the stride from this operand
+            if (tid == 0) { atomicMax(err, 2u); rows.done(x, row, 0); }
+            continue;
+        }
+        Elem *out = VALUES ? rows.out(x, row) : nullptr;
         for (uint64_t r = tid; r < R; r += THREADS) cursor[r] = 0u;
         __syncthreads();                            // a cursor is not always read by the thread that reset it
         uint32_t my_count = 0;                      // VALUES=false: columns seen, summed over this thread's bitmap words
@@ -181,7 +225,7 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
                     uint32_t bm = w < WORDS ? bits[w] : 0u;
                     uint32_t total;
                     const uint32_t rank = block_exclusive_scan(uint32_t(__popc(bm)), warp_sums, total);
-                    uint64_t o = out_off[x] + produced + rank;
+                    uint64_t o = produced + rank;
                     if (bm) bits[w] = 0u;
                     while (bm) {
                         const uint32_t bit = __ffs(bm) - 1;
@@ -200,27 +244,39 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
         if (!VALUES) {
             uint32_t total;
             block_exclusive_scan(my_count, warp_sums, total);
-            if (tid == 0) count[x] = total;
+            if (tid == 0) rows.done(x, row, total);
+        } else if (tid == 0) {
+            rows.done(x, row, produced);
         }
     }
 }
 
-template <int THREADS, int BAND, int RUNS>
+template <int THREADS, int BAND, int RUNS, class Rows>
 __global__ void __launch_bounds__(THREADS)
 k_long_count(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data, const uint64_t *__restrict__ b_pos,
-             const Elem *__restrict__ b_data, uint64_t cols, const uint32_t *__restrict__ rows, uint32_t n_rows,
-             unsigned int *ticket, uint32_t *cursors, uint64_t cursor_stride, uint32_t *count) {
-    long_rows_sweep<THREADS, BAND, RUNS, false>(a_pos, a_data, b_pos, b_data, cols, rows, n_rows, ticket, cursors, cursor_stride,
-                                                count, nullptr, nullptr);
+             const Elem *__restrict__ b_data, uint64_t cols, Rows rows, uint32_t *cursors, uint64_t cursor_stride, unsigned int *err) {
+    long_rows_sweep<THREADS, BAND, RUNS, false>(a_pos, a_data, b_pos, b_data, cols, rows, cursors, cursor_stride, err);
 }
 
-template <int THREADS, int BAND, int RUNS>
+template <int THREADS, int BAND, int RUNS, class Rows>
 __global__ void __launch_bounds__(THREADS)
 k_long_fill(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data, const uint64_t *__restrict__ b_pos,
-            const Elem *__restrict__ b_data, uint64_t cols, const uint32_t *__restrict__ rows, uint32_t n_rows,
-            unsigned int *ticket, uint32_t *cursors, uint64_t cursor_stride, const uint64_t *__restrict__ out_off, Elem *out) {
-    long_rows_sweep<THREADS, BAND, RUNS, true>(a_pos, a_data, b_pos, b_data, cols, rows, n_rows, ticket, cursors, cursor_stride,
-                                               nullptr, out_off, out);
+            const Elem *__restrict__ b_data, uint64_t cols, Rows rows, uint32_t *cursors, uint64_t cursor_stride, unsigned int *err) {
+    long_rows_sweep<THREADS, BAND, RUNS, true>(a_pos, a_data, b_pos, b_data, cols, rows, cursors, cursor_stride, err);
+}
+
+// The tasks (non-zeros of A) of the rows the sweep takes: one bit per task, read by k_multiply (TaskSrcSoASwept), which
+// then emits nothing for them -- their bins stay untouched until k_long_fill writes the merged row there.
+// One warp per listed row; `swept` is zeroed by the host.
+__global__ void k_mark_swept(const uint64_t *__restrict__ a_pos, const uint32_t *__restrict__ xl_list, const DevScalars *sc,
+                             const uint64_t *__restrict__ row_bin, uint64_t min_len, uint32_t *swept) {
+    const uint32_t n = sc->n_xl;
+    const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5, nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t x = warp; x < n; x += nwarps) {
+        const uint64_t row = xl_list[x];
+        if (row_bin[row + 1] - row_bin[row] < min_len) continue;
+        for (uint64_t e = a_pos[row] + lane_id(); e < a_pos[row + 1]; e += 32) atomicOr(&swept[e >> 5], 1u << (e & 31));
+    }
 }
 
 }  // namespace osp

@@ -35,6 +35,8 @@ def sim(tmp_path_factory):
     vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
     lib.lr_sim.restype = C.c_int
     lib.lr_sim.argtypes = [C.c_int, vp, vp, vp, vp, u64, vp, u32, C.c_uint, vp, vp, vp, u64]
+    lib.lr_sim_bins.restype = C.c_int
+    lib.lr_sim_bins.argtypes = [C.c_int, vp, vp, vp, vp, u64, vp, u32, vp, u64, vp, vp, u64, u64, u64, vp, u64, C.c_uint]
     return lib
 
 
@@ -134,3 +136,69 @@ def test_long_runs_gallop(sim):
     B = rand_sparse(rng, 6, 5000, 0.6)
     check(sim, 3, A, B)
     check(sim, 1, A, B)
+
+
+@pytest.mark.parametrize("config", [0, 1])
+def test_engine_hand_over_into_the_bins(sim, config):
+    """LongRowsInBins + k_mark_swept: listed rows of a row block with at least min_len partial products are merged
+    into the start of their own bins (uniq[row] = nnz) and their tasks are flagged for the multiply; every other
+    bin, uniq entry and task bit stays untouched."""
+    rng = np.random.default_rng(21)
+    A = rand_sparse(rng, 16, 24, 0.4)
+    B = rand_sparse(rng, 24, 400, 0.3)
+    a_csc, a_csr, b_csr = operands(A, B)
+    want, _ = oracle_spgemm(a_csc, b_csr)
+    b_len = np.diff(b_csr.pos.astype(np.int64))
+    a_pos = a_csr.pos.astype(np.int64)
+    row_len = np.array([int(b_len[a_csr.data["idx"][a_pos[r]:a_pos[r + 1]]].sum()) for r in range(16)], np.int64)
+    row_bin = np.concatenate([[0], np.cumsum(row_len)]).astype(np.uint64)
+    row_lo, row_hi, min_len = 3, 13, int(np.median(row_len))
+    bin_base = int(row_bin[row_lo])
+    xl_list = np.array([12, 1, 5, 9, 3, 14, 7], np.uint32)           # unordered, some outside the block
+    bins = np.zeros(int(row_bin[row_hi]) - bin_base, ELEM)
+    bins["idx"] = 0xABABABAB
+    uniq = np.full(16, 0xEEEEEEEE, np.uint32)
+    swept = np.zeros((a_csr.nnz + 31) // 32 + 1, np.uint32)
+    ptr = lambda x: x.ctypes.data_as(C.c_void_p)
+    stride = int(np.diff(a_pos).max())
+    rc = sim.lr_sim_bins(config, ptr(a_csr.pos), ptr(a_csr.data), ptr(b_csr.pos), ptr(b_csr.data), 400, ptr(xl_list), len(xl_list),
+                         ptr(row_bin), bin_base, ptr(bins), ptr(uniq), row_lo, row_hi, min_len, ptr(swept), stride, 2)
+    assert rc == 0
+    wpos = want.pos.astype(np.int64)
+    marked = np.unpackbits(swept.view(np.uint8), bitorder="little")[: a_csr.nnz].astype(bool)
+    for r in range(16):
+        listed_long = r in xl_list and row_len[r] >= min_len
+        assert marked[a_pos[r]:a_pos[r + 1]].all() == listed_long or a_pos[r] == a_pos[r + 1]
+        assert marked[a_pos[r]:a_pos[r + 1]].any() == (listed_long and a_pos[r] < a_pos[r + 1])
+        taken = listed_long and row_lo <= r < row_hi
+        if row_lo <= r < row_hi:
+            b = bins[int(row_bin[r]) - bin_base: int(row_bin[r + 1]) - bin_base]
+            if taken:
+                n = wpos[r + 1] - wpos[r]
+                assert uniq[r] == n
+                assert np.array_equal(b[:n]["idx"], want.data["idx"][wpos[r]:wpos[r + 1]])
+                assert np.array_equal(b[:n]["val"].view(np.uint32), want.data["val"][wpos[r]:wpos[r + 1]].view(np.uint32))
+                assert np.all(b[n:]["idx"] == 0xABABABAB)
+            else:
+                assert np.all(b["idx"] == 0xABABABAB)
+        if not taken:
+            assert uniq[r] == 0xEEEEEEEE
+
+
+def test_row_of_a_longer_than_the_cursor_stride_is_reported(sim):
+    rng = np.random.default_rng(22)
+    A = rand_sparse(rng, 4, 24, 0.9)
+    B = rand_sparse(rng, 24, 100, 0.3)
+    a_csc, a_csr, b_csr = operands(A, B)
+    b_len = np.diff(b_csr.pos.astype(np.int64))
+    a_pos = a_csr.pos.astype(np.int64)
+    row_len = np.array([int(b_len[a_csr.data["idx"][a_pos[r]:a_pos[r + 1]]].sum()) for r in range(4)], np.int64)
+    row_bin = np.concatenate([[0], np.cumsum(row_len)]).astype(np.uint64)
+    xl_list = np.arange(4, dtype=np.uint32)
+    bins = np.zeros(int(row_bin[-1]), ELEM)
+    uniq = np.full(4, 0xEEEEEEEE, np.uint32)
+    swept = np.zeros((a_csr.nnz + 31) // 32 + 1, np.uint32)
+    ptr = lambda x: x.ctypes.data_as(C.c_void_p)
+    rc = sim.lr_sim_bins(0, ptr(a_csr.pos), ptr(a_csr.data), ptr(b_csr.pos), ptr(b_csr.data), 100, ptr(xl_list), 4,
+                         ptr(row_bin), 0, ptr(bins), ptr(uniq), 0, 4, 0, ptr(swept), int(np.diff(a_pos).max()) - 1, 1)
+    assert rc == 2
