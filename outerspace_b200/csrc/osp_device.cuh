@@ -14,6 +14,13 @@
 #endif
 #include <stdint.h>
 
+// Dynamic shared memory of a kernel.  (tests/cusim: the block's emulated shared memory.)
+#ifdef OSP_CUSIM
+#define OSP_EXTERN_SMEM(name) unsigned char *name = cusim::dyn_smem()
+#else
+#define OSP_EXTERN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 namespace osp {
 
 struct __align__(8) Elem {

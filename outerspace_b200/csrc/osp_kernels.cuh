@@ -156,7 +156,11 @@ __global__ void k_publish(const DevScalars *d, ulonglong2 *h_slots, unsigned lon
     const unsigned long long *src = reinterpret_cast<const unsigned long long *>(d);
     if (threadIdx.x < PUBLISH_SLOTS) {
         const unsigned long long v = __ldcg(src + threadIdx.x);
+#ifdef OSP_CUSIM
+        h_slots[threadIdx.x] = ulonglong2{v, seq};
+#else
         asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(h_slots + threadIdx.x), "l"(v), "l"(seq) : "memory");
+#endif
     }
 }
 __global__ void k_max_idx(const Elem *d, uint64_t nnz, DevScalars *sc) {
@@ -494,7 +498,7 @@ __device__ __forceinline__ uint32_t fold_sorted(const uint64_t *keys, const floa
 __global__ void __launch_bounds__(256)
 k_merge_long(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, uint32_t *uniq,
              const uint32_t *long_list, const DevScalars *sc, uint64_t row_lo, uint64_t row_hi) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    OSP_EXTERN_SMEM(smem);
     uint64_t *keys = reinterpret_cast<uint64_t *>(smem);
     float *vals = reinterpret_cast<float *>(keys + MT_XL);
     uint32_t *warp_sums = reinterpret_cast<uint32_t *>(vals + MT_XL);
@@ -652,7 +656,7 @@ __global__ void __launch_bounds__(DENSE_THREADS)
 k_merge_dense(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, uint32_t *uniq,
               const uint32_t *long_list, const uint32_t *xl_list, const DevScalars *sc, uint32_t cols,
               uint64_t row_lo, uint64_t row_hi) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    OSP_EXTERN_SMEM(smem);
     const uint32_t cpad = (cols + 15) & ~15u;
     float *acc = reinterpret_cast<float *>(smem);
     uint16_t *owner = reinterpret_cast<uint16_t *>(smem + size_t(cpad) * 4);
@@ -732,7 +736,11 @@ __device__ __forceinline__ uint32_t swz(uint32_t s) { return s ^ ((s >> 4) & 15u
 // the in-lane stages have compile-time partners and directions (two VIMNMX per pair), the cross-lane stages
 // one shuffle and a min-or-max per key.  Levels up to E run inside a lane; T more levels cross lanes.
 // T is a template parameter: the whole network is straight-line code, no register moves at loop edges.
+#ifdef OSP_CUSIM
+#define osp_smem (cusim::dyn_smem())
+#else
 extern __shared__ __align__(16) unsigned char osp_smem[];     // the dynamic shared memory of every kernel here
+#endif
 __device__ __forceinline__ uint32_t &smem_u32_at(uint32_t off) { return *reinterpret_cast<uint32_t *>(osp_smem + off); }
 __device__ __forceinline__ float &smem_f32_at(uint32_t off) { return *reinterpret_cast<float *>(osp_smem + off); }
 __device__ __forceinline__ uint2 &smem_u2_at(uint32_t off) { return *reinterpret_cast<uint2 *>(osp_smem + off); }
@@ -967,6 +975,12 @@ __device__ __forceinline__ uint32_t merge_row_bitmap(const uint32_t row_off, con
 }
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) and its mbarrier ---------------------------------------
+#ifdef OSP_CUSIM   // tests/cusim: a bulk copy that completes at once is one legal schedule of the asynchronous one
+__device__ __forceinline__ void mbar_init(uint64_t *, uint32_t) {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *, uint32_t) {}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *) { std::memcpy(dst_smem, src_gmem, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t *, uint32_t) {}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -986,6 +1000,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
+#endif
 
 // =====================================================================================
 // Merge, the main kernel: one pass from the partial-product bins to CSR C.
@@ -1119,7 +1134,9 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
         if (tid == 0 && d.idx < n_chain && !d.is_long && d.n_in) {
             const uint32_t shift = uint32_t(d.g0 & 1);              // the window starts one element early when g0 is odd
             const uint32_t bytes = ((d.n_in + shift) * 8 + 15) & ~15u;
+#ifndef OSP_CUSIM
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the stage
+#endif
             mbar_expect_tx(&sm.mbar, bytes);
             tma_load_1d(sm.stage, bins + (d.g0 - shift), bytes, &sm.mbar);
         }

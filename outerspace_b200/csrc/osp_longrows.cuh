@@ -25,14 +25,6 @@
 
 namespace osp {
 
-#ifdef OSP_CUSIM
-#define OSP_DYN_SMEM(name) unsigned char *name = cusim::dyn_smem()
-#else
-#define OSP_DYN_SMEM(name)                                       \
-    extern __shared__ __align__(16) unsigned char name##_dyn[];  \
-    unsigned char *name = name##_dyn
-#endif
-
 // First position p in [lo, len] with p == len or run[p].idx >= band_hi; run[lo .. p) lies below band_hi.
 // Galloping from the cursor: a segment of s elements costs ~2 log2(s) probes.
 __device__ __forceinline__ uint32_t lr_advance(const Elem *__restrict__ run, uint32_t lo, uint32_t len, uint64_t band_hi) {
@@ -108,7 +100,7 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
     static_assert(BAND % 32 == 0 && BAND <= 65536 && RUNS >= 1, "the band is a bitmap of whole words");
     static_assert(THREADS <= 1024 && THREADS % 32 == 0, "whole warps");
     using L = LongRowSmem<BAND, RUNS, VALUES>;
-    OSP_DYN_SMEM(smem);
+    OSP_EXTERN_SMEM(smem);
     float *acc = reinterpret_cast<float *>(smem + L::acc);
     uint16_t *owner = reinterpret_cast<uint16_t *>(smem + L::owner);
     uint32_t *bits = reinterpret_cast<uint32_t *>(smem + L::bits);

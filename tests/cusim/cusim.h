@@ -40,6 +40,12 @@ struct dim3 {
 };
 inline dim3 threadIdx, blockIdx, blockDim, gridDim;
 
+struct uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(16) ulonglong2 { unsigned long long x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+
 namespace cusim {
 
 struct Fiber {
@@ -227,6 +233,27 @@ inline unsigned __ballot_sync(unsigned mask, int p) {
 }
 inline int __any_sync(unsigned mask, int p) { return __ballot_sync(mask, p) != 0; }
 inline int __all_sync(unsigned mask, int p) { return __ballot_sync(mask, !p) == 0; }
+template <class T> inline T __reduce_max_sync(unsigned mask, T v) {
+    const unsigned live = mask & cusim::live_lanes(threadIdx.x >> 5);
+    const uint64_t *s = cusim::exchange(mask, cusim::to_word(v));
+    T r = v;
+    for (unsigned l = 0; l < 32; l++) if ((live >> l) & 1) r = std::max(r, cusim::from_word<T>(s[l]));
+    return r;
+}
+template <class T> inline T __reduce_min_sync(unsigned mask, T v) {
+    const unsigned live = mask & cusim::live_lanes(threadIdx.x >> 5);
+    const uint64_t *s = cusim::exchange(mask, cusim::to_word(v));
+    T r = v;
+    for (unsigned l = 0; l < 32; l++) if ((live >> l) & 1) r = std::min(r, cusim::from_word<T>(s[l]));
+    return r;
+}
+template <class T> inline T __reduce_add_sync(unsigned mask, T v) {
+    const unsigned live = mask & cusim::live_lanes(threadIdx.x >> 5);
+    const uint64_t *s = cusim::exchange(mask, cusim::to_word(v));
+    T r = 0;
+    for (unsigned l = 0; l < 32; l++) if ((live >> l) & 1) r += cusim::from_word<T>(s[l]);
+    return r;
+}
 template <class T> inline unsigned __match_any_sync(unsigned mask, T v) {
     const unsigned live = mask & cusim::live_lanes(threadIdx.x >> 5);
     const uint64_t mine = cusim::to_word(v);
@@ -241,12 +268,17 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __clz(int v) { return v ? __builtin_clz(unsigned(v)) : 32; }
 inline int __ffs(int v) { return __builtin_ffs(v); }
+inline float __uint_as_float(unsigned v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned v; std::memcpy(&v, &f, 4); return v; }
+inline int __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); return v; }
+inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 template <class T> inline T __ldcg(const T *p) { return *p; }
 template <class T> inline T __ldg(const T *p) { return *p; }
 
 template <class T> inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T atomicSub(T *p, T v) { T o = *p; *p = o - v; return o; }
 template <class T> inline T atomicMin(T *p, T v) { T o = *p; *p = std::min(o, v); return o; }
 template <class T> inline T atomicMax(T *p, T v) { T o = *p; *p = std::max(o, v); return o; }
 template <class T> inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
