@@ -138,11 +138,18 @@ cudaEvent_t next_event(osp_ctx *ctx) {
         }                                                                                       \
     } while (0)
 
+// The one place a kernel is launched from.  (tests/cusim runs the same call on the CPU emulation of the execution model.)
+#ifdef OSP_CUSIM
+#define OSP_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) cusim::launch((grid), (block), (smem), [&] { kernel(__VA_ARGS__); })
+#else
+#define OSP_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                                             \
     do {                                                                                        \
         cudaEvent_t _m0 = nullptr;                                                              \
         if ((ctx)->profile_kernels) _m0 = next_event(ctx);                                      \
-        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                        \
+        OSP_KERNEL_LAUNCH(kernel, grid, block, smem, (ctx)->stream, __VA_ARGS__);               \
         (ctx)->launches++;                                                                      \
         CU(ctx, cudaGetLastError());                                                            \
         if (_m0) (ctx)->marks.push_back({#kernel, _m0, next_event(ctx)});                       \
@@ -205,7 +212,7 @@ int sync_scalars(osp_ctx *ctx) {
         // the scalars arrive by stores from the device; the host polls the slots' sequence numbers (a few
         // microseconds less GPU idle time than a copy + stream synchronisation at every hand-over)
         const unsigned long long seq = ++ctx->seq;
-        k_publish<<<1, 32, 0, ctx->stream>>>(ctx->d_sc, ctx->h_slots_dev, seq);
+        OSP_KERNEL_LAUNCH(k_publish, 1, 32, 0, ctx->stream, ctx->d_sc, ctx->h_slots_dev, seq);
         ctx->launches++;
         CU(ctx, cudaGetLastError());
         volatile unsigned long long *slots = reinterpret_cast<volatile unsigned long long *>(ctx->h_slots);
@@ -1177,4 +1184,6 @@ int osp_coo2csr_device(osp_ctx *ctx, uint64_t nnz, const uint32_t *rows, const u
 
 }  // extern "C"
 
+#ifndef OSP_CUSIM            // the multi-GPU path needs peers and NCCL: not part of the emulated build
 #include "osp_dist.inl"
+#endif

@@ -6,14 +6,16 @@
 // compiled by nvcc for sm_100a as always; a test translation unit defines OSP_CUSIM, includes this header instead of
 // <cuda_runtime.h>, and calls cusim::launch().
 //
-// Model: the thread blocks of a launch run one after the other; the threads of a block are fibers (ucontext) scheduled
+// Model: the thread blocks of a launch run one after the other; the threads of a block are fibers scheduled
 // round-robin on one OS thread, switching only inside the synchronising built-ins (__syncthreads*, warp collectives,
 // __nanosleep).  That is a legal CUDA schedule, so a kernel that is correct under every schedule is correct here; the
 // reverse does not hold (data races between barriers go unnoticed), which is why GPU parity tests stay the gate.
 // Persistent kernels that hand out work by ticket run to completion in the first block (later blocks find no work);
 // kernels that need co-resident blocks to make progress cannot be emulated.
 #pragma once
+#if !defined(__x86_64__)
 #include <ucontext.h>
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -48,9 +50,57 @@ inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return
 
 namespace cusim {
 
+// Context switch.  On x86-64 a dozen instructions (callee-saved registers + stack pointer): swapcontext() makes two
+// signal-mask system calls per switch, and a barrier of a 512-thread block is 512 switches.
+#if defined(__x86_64__)
+extern "C" void cusim_swap(void **save_sp, void *load_sp);
+asm(R"(
+    .text
+    .type cusim_swap,@function
+cusim_swap:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size cusim_swap, .-cusim_swap
+)");
+struct Context {
+    void *sp = nullptr;
+    void prepare(char *stack, size_t bytes, void (*entry)()) {
+        uintptr_t top = (reinterpret_cast<uintptr_t>(stack) + bytes) & ~uintptr_t(15);
+        void **p = reinterpret_cast<void **>(top);
+        *--p = nullptr;                                   // return address of `entry` (never used: entry does not return)
+        *--p = reinterpret_cast<void *>(entry);           // popped by the first `ret`
+        for (int i = 0; i < 6; i++) *--p = nullptr;       // rbp rbx r12 r13 r14 r15
+        sp = p;
+    }
+};
+inline void switch_context(Context &from, Context &to) { cusim_swap(&from.sp, to.sp); }
+#else
+struct Context {
+    ucontext_t uc;
+    void prepare(char *stack, size_t bytes, void (*entry)()) {
+        getcontext(&uc);
+        uc.uc_stack.ss_sp = stack; uc.uc_stack.ss_size = bytes; uc.uc_link = nullptr;
+        makecontext(&uc, entry, 0);
+    }
+};
+inline void switch_context(Context &from, Context &to) { swapcontext(&from.uc, &to.uc); }
+#endif
+
 struct Fiber {
-    ucontext_t ctx;
-    std::unique_ptr<char[]> stack;
+    Context ctx;
     unsigned tid = 0;
     bool done = false;
 };
@@ -72,13 +122,13 @@ struct Block {
 
 inline Block *g_block = nullptr;
 inline Fiber *g_fiber = nullptr;
-inline ucontext_t g_sched;
+inline Context g_sched;
 inline unsigned long long g_progress = 0, g_switches = 0;
 
 inline void yield() {
     Fiber *me = g_fiber;
     g_switches++;
-    swapcontext(&me->ctx, &g_sched);
+    switch_context(me->ctx, g_sched);
     g_fiber = me;
     threadIdx.x = me->tid;
 }
@@ -144,10 +194,11 @@ inline void trampoline() {
         const unsigned need = live_lanes(w);
         if (wp.arrived && (wp.arrived & need) == need) { wp.arrived = 0; wp.gen++; }
     }
-    swapcontext(&me->ctx, &g_sched);
+    switch_context(me->ctx, g_sched);
 }
 
 constexpr size_t STACK_BYTES = 256 << 10;
+inline std::vector<std::unique_ptr<char[]>> &stack_pool() { static std::vector<std::unique_ptr<char[]>> p; return p; }
 
 // Runs `body` (a call of the kernel function) once per thread of a grid x block launch, x dimension only.
 template <class F> inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, F &&body) {
@@ -163,12 +214,9 @@ template <class F> inline void launch(unsigned grid, unsigned block, size_t dyn_
         for (unsigned t = 0; t < block; t++) {
             Fiber &f = b.fibers[t];
             f.tid = t;
-            f.stack.reset(new char[STACK_BYTES]);
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = f.stack.get();
-            f.ctx.uc_stack.ss_size = STACK_BYTES;
-            f.ctx.uc_link = nullptr;
-            makecontext(&f.ctx, trampoline, 0);
+            auto &pool = stack_pool();                                // stacks are reused across blocks and launches
+            while (pool.size() <= t) pool.emplace_back(new char[STACK_BYTES]);
+            f.ctx.prepare(pool[t].get(), STACK_BYTES, trampoline);
         }
         unsigned idle_passes = 0;
         while (b.alive) {
@@ -178,7 +226,7 @@ template <class F> inline void launch(unsigned grid, unsigned block, size_t dyn_
                 if (f.done) continue;
                 g_fiber = &f;
                 threadIdx = dim3(t);
-                swapcontext(&g_sched, &f.ctx);
+                switch_context(g_sched, f.ctx);
             }
             if (g_progress == before) {
                 if (++idle_passes > 1000) {
@@ -288,3 +336,5 @@ template <class T> inline T atomicCAS(T *p, T cmp, T v) { T o = *p; if (o == cmp
 
 using std::max;
 using std::min;
+
+#include "cusim_runtime.h"
