@@ -263,7 +263,8 @@ struct MergeJob {
     uint64_t c_cap = 0;
     // fused band sweep (osp_spgemm only): rows of the xl list with >= sweep_min partial products never reached the bins
     bool sweep = false;
-    uint64_t sweep_min = ~0ull;             // what k_merge_xl leaves alone (~0: nothing)
+    uint64_t sweep_min = ~0ull;             // fewest partial products of a swept row, > MT_XL (k_merge_xl leaves those alone)
+    bool sweeps_every_xl() const { return sweep && sweep_min <= MT_XL + 1; }
     uint64_t cursor_stride = 0;
     const uint64_t *a_pos = nullptr, *b_pos = nullptr;
     const Elem *a_data = nullptr, *b_data = nullptr;
@@ -273,6 +274,7 @@ struct MergeJob {
 // arbitration + 2 KB bitmap), 512 runs per group: 104.6 KB per CTA, two CTAs per SM.
 constexpr int LR_THREADS = 512, LR_BAND = 16384, LR_RUNS = 512;
 constexpr size_t LR_SMEM = LongRowSmem<LR_BAND, LR_RUNS, true>::bytes;
+constexpr uint64_t LR_MIN_PER_BAND = 64;
 
 // Scratch that depends on the plan's results: look-back states of the tile chain, survivor counts of the
 // long rows, the dense accumulators of the longest rows.
@@ -280,7 +282,7 @@ int reserve_merge(osp_ctx *ctx, const MergeJob &job, unsigned int &xl_ctas) {
     CU(ctx, ctx->uniq.reserve(std::max<uint64_t>(job.rows, 1) * 4));
     xl_ctas = 0;
     // with the sweep taking EVERY xl row the global accumulators are only needed for the medium rows
-    const uint64_t n_acc_rows = uint64_t(job.sweep && job.sweep_min <= MT_XL ? 0u : job.n_xl) + (job.idx_range <= XL_LONG_MAX_COLS ? job.n_long : 0u);
+    const uint64_t n_acc_rows = uint64_t(job.sweeps_every_xl() ? 0u : job.n_xl) + (job.idx_range <= XL_LONG_MAX_COLS ? job.n_long : 0u);
     if (n_acc_rows && job.idx_range > DENSE_MAX_COLS) {
         const uint64_t words = (job.idx_range + 31) / 32;
         const uint64_t per_cta = job.idx_range * 4 + words * 4;
@@ -332,7 +334,7 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
                 LAUNCH(ctx, (k_long_fill<LR_THREADS, LR_BAND, LR_RUNS, LongRowsInBins>), grid, LR_THREADS, LR_SMEM, job.a_pos, job.a_data,
                        job.b_pos, job.b_data, job.idx_range, rows, ctx->lr_cursors.as<uint32_t>(), job.cursor_stride, &ctx->d_sc->err);
             }
-            if (xl_ctas && ((job.n_xl && !(job.sweep && job.sweep_min <= MT_XL)) || (job.n_long && xl_takes_long))) {
+            if (xl_ctas && ((job.n_xl && !job.sweeps_every_xl()) || (job.n_long && xl_takes_long))) {
                 CU(ctx, cudaMemsetAsync(&ctx->d_sc->xl_ticket, 0, 4, ctx->stream));
                 LAUNCH(ctx, k_merge_xl, xl_ctas, XL_THREADS, 0, row_bin, bin_base, bins, uniq, ctx->xl_list.as<uint32_t>(),
                        xl_takes_long ? ctx->long_list.as<uint32_t>() : nullptr, ctx->d_sc, ctx->xl_acc.as<float>(),
@@ -748,7 +750,11 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
                        rowwise && !fused && job.n_xl > 0 && job.idx_range > DENSE_MAX_COLS;
     if (sweep) {
         job.sweep = true;
-        job.sweep_min = ctx->sweep_min;
+        // only rows of the xl list are ever swept, and only where a band sees enough of the row to pay for its barriers:
+        // a row must bring LR_MIN_PER_BAND partial products per band on average (16 M columns = 1024 bands: rows from
+        // 65 536 partial products), shorter rows stay with k_multiply + k_merge_xl.  (Unmeasured starting point.)
+        const uint64_t bands = (job.idx_range + LR_BAND - 1) / LR_BAND;
+        job.sweep_min = std::max<uint64_t>({ctx->sweep_min, MT_XL + 1, LR_MIN_PER_BAND * bands});
         job.cursor_stride = std::max<uint64_t>(std::min<uint64_t>(nnz_a, std::max<uint64_t>(n_k, 1)), 1);   // a row of A holds <= n_k distinct columns
         job.a_pos = dA_pos; job.a_data = dA_data; job.b_pos = dB_pos; job.b_data = dB_data;
     }

@@ -140,6 +140,7 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
         uint64_t produced = 0;                      // VALUES=true: elements of the row already written
         for (uint64_t band_lo = 0; band_lo < cols; band_lo += BAND) {
             const uint64_t band_hi = min(cols, band_lo + uint64_t(BAND));
+            bool touched = false;                                          // uniform: some run has an element in this band
             for (uint64_t g0 = 0; g0 < R; g0 += RUNS) {
                 const uint32_t G = uint32_t(min(uint64_t(RUNS), R - g0));
                 // ---- the segment of every run of the group inside this band (cursor -> first column >= band_hi) ----
@@ -167,6 +168,7 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
                 if (tid == 0) s_pre[G] = carry;
                 __syncthreads();
                 const uint32_t T = carry;                                  // elements of the group inside the band, in (k, column) order
+                touched |= T > 0;
                 // ---- consume them THREADS at a time ----
                 for (uint32_t c0 = 0; c0 < T; c0 += THREADS) {
                     const uint32_t f = c0 + tid;
@@ -206,6 +208,7 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
                 __syncthreads();                                           // s_pre / s_lo are rewritten by the next group
             }
             // ---- the band is complete: count or emit its columns, reset it ----
+            if (!touched) continue;                                        // nothing was set: bitmap and accumulator are still clean
             if (!VALUES) {
                 for (uint32_t w = tid; w < WORDS; w += THREADS) {
                     my_count += __popc(bits[w]);

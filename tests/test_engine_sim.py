@@ -62,3 +62,73 @@ test_error_codes = gp.test_error_codes
 test_csr2csc_device_stable = gp.test_csr2csc_device_stable
 test_csr2csc_random_and_duplicates = gp.test_csr2csc_random_and_duplicates
 test_coo_ingest_on_device = gp.test_coo_ingest_on_device
+test_er_config2_scaled = gp.test_er_config2_scaled
+test_rmat_small = gp.test_rmat_small
+test_mlp_batch_small = gp.test_mlp_batch_small
+test_every_row_length_class = gp.test_every_row_length_class
+
+
+def test_device_pointer_operands(engine):
+    """OSP_DEVICE_POINTERS: operands already on the device (here: the emulated device = host memory), nothing staged."""
+    rng = np.random.default_rng(77)
+    A, B = rand_sparse(rng, 200, 150, 0.05), rand_sparse(rng, 150, 180, 0.05)
+    a_csc, a_csr, b_csr = operands(A, B)
+    want, _ = oracle_spgemm(a_csc, b_csr)
+    res = engine.spgemm_device(a_csr.NRow(), a_csr.pos.ctypes.data, a_csr.data.ctypes.data, b_csr.NRow(), b_csr.pos.ctypes.data,
+                               b_csr.data.ctypes.data, a_is_csr=True)
+    got = res.to_host()
+    assert all(res.device_pointers())
+    res.free()
+    assert_bit_exact(got, want, "device operands")
+
+
+# ---- the opt-in long-row sweep (OSP_LONGROW_SWEEP), end to end: the tests a B200 will run with OSP_TEST_SWEEP=1 ------
+import test_gpu_zzz_sweep as sw
+
+test_every_row_length_class_through_the_sweep = sw.test_every_row_length_class_through_the_sweep
+test_sweep_threshold_from_the_environment = sw.test_sweep_threshold_from_the_environment
+
+
+def test_sweep_with_row_blocks_and_bounded_capacity():
+    """Row blocks (workspace limit) and C allocated below the plan's bound: swept rows are taken block by block, the
+    multiply skips their tasks in every block, the chain's carry of nnz(C) stays exact."""
+    rng = np.random.default_rng(31)
+    lens = [5000, 3, 0, 20000, 700, 4097, 129, 9000, 12, 6000, 300, 4500, 45, 8000] * 2
+    cols = 1 << 16
+    A, B = gp._row_lengths_case(rng, lens, cols, 0.3)
+    a_csc, a_csr, b_csr = operands(A, B)
+    want, prod = oracle_spgemm(a_csc, b_csr)
+    eng = osp.Engine(0)
+    try:
+        eng.set_workspace_limit(25000 * 8)
+        eng.set_result_limit((want.nnz + 25000 + 64) * 8)
+        for flags in (api.OSP_LONGROW_SWEEP, 0):
+            res = eng.spgemm(a_csr, b_csr, a_is_csr=True, cols_b=cols, flags=flags | api.OSP_PROFILE_KERNELS)
+            got = res.to_host(); st = res.stats(); names = {n for n, _ in res.kernel_times()}; res.free()
+            assert st["row_chunks"] > 4 and st["nnz_c"] == want.nnz
+            assert any("k_long_fill" in n for n in names) == bool(flags)
+            assert_bit_exact(got, want, f"row blocks, flags={flags}")
+        res = eng.spgemm(a_csc, b_csr, cols_b=cols, flags=api.OSP_LONGROW_SWEEP)       # A arrives as CSC: converted on the device first
+        got = res.to_host(); res.free()
+        assert_bit_exact(got, want, "row blocks, sweep, CSC(A)")
+    finally:
+        eng.close()
+
+
+def test_sweep_stays_out_where_it_does_not_apply(engine):
+    """<= 16384 columns (k_merge_dense / fused dense rows own that range) and calls without a long row."""
+    rng = np.random.default_rng(32)
+    A, B = gp._row_lengths_case(rng, [5000, 100, 6000], 1 << 14, 0.3)
+    a_csc, a_csr, b_csr = operands(A, B)
+    want, _ = oracle_spgemm(a_csc, b_csr)
+    res = engine.spgemm(a_csr, b_csr, a_is_csr=True, cols_b=1 << 14, flags=api.OSP_LONGROW_SWEEP | api.OSP_PROFILE_KERNELS)
+    got = res.to_host(); names = {n for n, _ in res.kernel_times()}; res.free()
+    assert not any("k_long_fill" in n or "k_mark_swept" in n for n in names), names
+    assert_bit_exact(got, want, "small column range")
+    A, B = gp._row_lengths_case(rng, [500, 100, 4096], 1 << 18, 0.3)
+    a_csc, a_csr, b_csr = operands(A, B)
+    want, _ = oracle_spgemm(a_csc, b_csr)
+    res = engine.spgemm(a_csr, b_csr, a_is_csr=True, cols_b=1 << 18, flags=api.OSP_LONGROW_SWEEP | api.OSP_PROFILE_KERNELS)
+    got = res.to_host(); names = {n for n, _ in res.kernel_times()}; res.free()
+    assert not any("k_long_fill" in n for n in names), names
+    assert_bit_exact(got, want, "no row above 4096 partial products")

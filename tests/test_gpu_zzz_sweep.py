@@ -50,7 +50,8 @@ def test_every_row_length_class_through_the_sweep(engine, cols, dup_rate):
     """Short, medium and swept rows side by side in the same call; column ranges on both sides of the limit up to
     which k_merge_xl takes the medium rows (131072), bands that end inside the last word, 64-bit chain keys."""
     rng = np.random.default_rng(cols % 1000 + int(dup_rate * 10))
-    lens = [0, 1, 8, 33, 129, 512, 513, 700, 1500, 4096, 4097, 5000, 9000, 40000] * 3
+    big = 30000 if cols < (1 << 17) else 70000          # 2^24 columns = 1025 bands: only rows from 65 600 partial products are swept
+    lens = [0, 1, 8, 33, 129, 512, 513, 700, 1500, 4096, 4097, 5000, 9000, big] * 3
     rng.shuffle(lens)
     A, B = _row_lengths_case(rng, lens, cols, dup_rate)
     a_csc, a_csr, b_csr = operands(A, B)
