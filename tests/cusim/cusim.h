@@ -200,6 +200,24 @@ inline void trampoline() {
 constexpr size_t STACK_BYTES = 256 << 10;
 inline std::vector<std::unique_ptr<char[]>> &stack_pool() { static std::vector<std::unique_ptr<char[]>> p; return p; }
 
+// The order in which the runnable threads of a block get their turn in one scheduling pass.  Every order is a legal
+// CUDA schedule; CUSIM_SCHEDULE picks it: unset / "forward" = ascending thread id, "reverse" = descending, "random:<seed>"
+// = a fresh permutation of the block's threads every pass (who wins a racing store, an atomicCAS slot or a ticket
+// then differs from pass to pass and from seed to seed).
+inline void schedule_order(std::vector<unsigned> &order, unsigned n) {
+    static int mode = -1;
+    static uint64_t rng = 0x9E3779B97F4A7C15ull;
+    if (mode < 0) {
+        const char *e = std::getenv("CUSIM_SCHEDULE");
+        mode = !e || !std::strcmp(e, "forward") ? 0 : !std::strcmp(e, "reverse") ? 1 : 2;
+        if (mode == 2) { const char *c = std::strchr(e, ':'); rng ^= c ? std::strtoull(c + 1, nullptr, 10) * 0xD1342543DE82EF95ull : 0; }
+    }
+    for (unsigned i = 0; i < n; i++) order[i] = mode == 1 ? n - 1 - i : i;
+    if (mode != 2) return;
+    auto next = [&] { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+    for (unsigned i = n; i > 1; i--) std::swap(order[i - 1], order[next() % i]);
+}
+
 // Runs `body` (a call of the kernel function) once per thread of a grid x block launch, x dimension only.
 template <class F> inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, F &&body) {
     gridDim = dim3(grid); blockDim = dim3(block);
@@ -219,9 +237,12 @@ template <class F> inline void launch(unsigned grid, unsigned block, size_t dyn_
             f.ctx.prepare(pool[t].get(), STACK_BYTES, trampoline);
         }
         unsigned idle_passes = 0;
+        std::vector<unsigned> order(block);
         while (b.alive) {
             const unsigned long long before = g_progress;
-            for (unsigned t = 0; t < block; t++) {
+            schedule_order(order, block);
+            for (unsigned i = 0; i < block; i++) {
+                const unsigned t = order[i];
                 Fiber &f = b.fibers[t];
                 if (f.done) continue;
                 g_fiber = &f;
