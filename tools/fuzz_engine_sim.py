@@ -82,13 +82,13 @@ def main():
     for case in range(args.cases):
         A, B, cols = draw_case(rng)
         a_csc, a_csr, b_csr = operands(A, B)
-        want, prod = oracle_spgemm(a_csc, b_csr)
+        want, prod = oracle_spgemm(a_csc, b_csr, rows_override=A.shape[0])
         flags = int(rng.choice([0, api.OSP_KSLICE_ORDER, api.OSP_ROWWISE_ORDER, api.OSP_LONGROW_SWEEP, api.OSP_LONGROW_SWEEP, api.OSP_NO_FUSED_DENSE]))
         as_csr = bool(rng.integers(0, 2))
         eng = osp.Engine(0)
         try:
             if rng.random() < 0.3 and prod > 64:
-                eng.set_workspace_limit(max(int(prod // rng.integers(2, 9)), 16) * 8)
+                eng.set_workspace_limit(max(int(prod // rng.integers(2, 9)), 512) * 8)
                 if rng.random() < 0.5:
                     eng.set_result_limit((want.nnz + max(int(prod // 2), 64)) * 8)
             try:
