@@ -71,8 +71,8 @@ constexpr uint64_t LB_FLAG_PREFIX = 2ull << 62;
 constexpr uint64_t LB_VALUE_MASK = (1ull << 62) - 1;
 
 #ifdef OSP_CUSIM
-__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) { return *static_cast<const volatile uint64_t *>(p); }
-__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) { *static_cast<volatile uint64_t *>(p) = v; }
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
 #else
 __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
     uint64_t v;

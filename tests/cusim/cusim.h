@@ -6,12 +6,15 @@
 // compiled by nvcc for sm_100a as always; a test translation unit defines OSP_CUSIM, includes this header instead of
 // <cuda_runtime.h>, and calls cusim::launch().
 //
-// Model: the thread blocks of a launch run one after the other; the threads of a block are fibers scheduled
-// round-robin on one OS thread, switching only inside the synchronising built-ins (__syncthreads*, warp collectives,
-// __nanosleep).  That is a legal CUDA schedule, so a kernel that is correct under every schedule is correct here; the
-// reverse does not hold (data races between barriers go unnoticed), which is why GPU parity tests stay the gate.
-// Persistent kernels that hand out work by ticket run to completion in the first block (later blocks find no work);
-// kernels that need co-resident blocks to make progress cannot be emulated.
+// Model: the threads of a block are fibers scheduled round-robin on one OS thread, switching only inside the
+// synchronising built-ins (__syncthreads*, warp collectives, __nanosleep).  That is a legal CUDA schedule, so a kernel
+// that is correct under every schedule is correct here; the reverse does not hold (data races between barriers go
+// unnoticed), which is why GPU parity tests stay the gate.
+// Blocks: CUSIM_RESIDENT (default 1) blocks are resident at a time, each on its own OS thread, the next block of the
+// grid starting when a resident one retires -- like CTAs on SMs.  With 1 the blocks of a launch run one after the
+// other (a persistent kernel takes all its tickets in the first block); with more, blocks really run concurrently:
+// tickets interleave, decoupled look-back chains wait on live predecessors, global atomics are real atomics.  Static
+// __shared__ variables are thread-local statics (one copy per resident block).
 #pragma once
 #if !defined(__x86_64__)
 #include <ucontext.h>
@@ -24,7 +27,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <atomic>
+#include <chrono>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #define __global__
@@ -32,7 +38,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __noinline__
-#define __shared__ static
+#define __shared__ static thread_local
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 
@@ -40,7 +46,8 @@ struct dim3 {
     unsigned x, y, z;
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
-inline dim3 threadIdx, blockIdx, blockDim, gridDim;
+inline thread_local dim3 threadIdx, blockIdx;
+inline dim3 blockDim, gridDim;
 
 struct uint2 { unsigned x, y; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
@@ -120,14 +127,15 @@ struct Block {
     std::function<void()> body;
 };
 
-inline Block *g_block = nullptr;
-inline Fiber *g_fiber = nullptr;
-inline Context g_sched;
-inline unsigned long long g_progress = 0, g_switches = 0;
+inline thread_local Block *g_block = nullptr;
+inline thread_local Fiber *g_fiber = nullptr;
+inline thread_local Context g_sched;
+inline thread_local unsigned long long g_progress = 0;
+inline std::atomic<unsigned long long> g_switches{0};
 
 inline void yield() {
     Fiber *me = g_fiber;
-    g_switches++;
+    g_switches.fetch_add(1, std::memory_order_relaxed);
     switch_context(me->ctx, g_sched);
     g_fiber = me;
     threadIdx.x = me->tid;
@@ -198,15 +206,20 @@ inline void trampoline() {
 }
 
 constexpr size_t STACK_BYTES = 256 << 10;
-inline std::vector<std::unique_ptr<char[]>> &stack_pool() { static std::vector<std::unique_ptr<char[]>> p; return p; }
+inline std::vector<std::unique_ptr<char[]>> &stack_pool() { static thread_local std::vector<std::unique_ptr<char[]>> p; return p; }
+inline unsigned resident_blocks() {
+    const char *e = std::getenv("CUSIM_RESIDENT");
+    const unsigned n = e ? unsigned(std::strtoul(e, nullptr, 10)) : 1u;
+    return n ? n : 1u;
+}
 
 // The order in which the runnable threads of a block get their turn in one scheduling pass.  Every order is a legal
 // CUDA schedule; CUSIM_SCHEDULE picks it: unset / "forward" = ascending thread id, "reverse" = descending, "random:<seed>"
 // = a fresh permutation of the block's threads every pass (who wins a racing store, an atomicCAS slot or a ticket
 // then differs from pass to pass and from seed to seed).
 inline void schedule_order(std::vector<unsigned> &order, unsigned n) {
-    static int mode = -1;
-    static uint64_t rng = 0x9E3779B97F4A7C15ull;
+    static thread_local int mode = -1;
+    static thread_local uint64_t rng = 0x9E3779B97F4A7C15ull;
     if (mode < 0) {
         const char *e = std::getenv("CUSIM_SCHEDULE");
         mode = !e || !std::strcmp(e, "forward") ? 0 : !std::strcmp(e, "reverse") ? 1 : 2;
@@ -218,48 +231,66 @@ inline void schedule_order(std::vector<unsigned> &order, unsigned n) {
     for (unsigned i = n; i > 1; i--) std::swap(order[i - 1], order[next() % i]);
 }
 
+// One block: its threads as fibers on the calling OS thread, until all of them have returned.
+template <class F> inline void run_block(unsigned bx, unsigned block, size_t dyn_bytes, F &body) {
+    Block b;
+    b.fibers.resize(block);
+    b.alive = block;
+    b.dyn.assign(dyn_bytes + 16, 0xCD);
+    b.body = [&body] { body(); };
+    g_block = &b;
+    blockIdx = dim3(bx);
+    auto &pool = stack_pool();                                    // stacks are reused across blocks and launches
+    while (pool.size() < block) pool.emplace_back(new char[STACK_BYTES]);
+    for (unsigned t = 0; t < block; t++) {
+        Fiber &f = b.fibers[t];
+        f.tid = t;
+        f.ctx.prepare(pool[t].get(), STACK_BYTES, trampoline);
+    }
+    std::vector<unsigned> order(block);
+    auto last_progress = std::chrono::steady_clock::now();
+    unsigned idle_passes = 0;
+    while (b.alive) {
+        const unsigned long long before = g_progress;
+        schedule_order(order, block);
+        for (unsigned i = 0; i < block; i++) {
+            const unsigned t = order[i];
+            Fiber &f = b.fibers[t];
+            if (f.done) continue;
+            g_fiber = &f;
+            threadIdx = dim3(t);
+            switch_context(g_sched, f.ctx);
+        }
+        if (g_progress != before) { idle_passes = 0; continue; }
+        // no thread of this block moved: alone on the device that is a deadlock; with other resident blocks it may be a
+        // wait for one of them (look-back), so only a long silence counts
+        if (idle_passes++ == 0) last_progress = std::chrono::steady_clock::now();
+        const bool alone = resident_blocks() == 1;
+        if ((alone && idle_passes > 1000) ||
+            (!alone && (idle_passes & 1023) == 0 && std::chrono::steady_clock::now() - last_progress > std::chrono::seconds(60))) {
+            std::fprintf(stderr, "cusim: deadlock in block %u (%u threads alive, %u at the barrier)\n", bx, b.alive, b.bar_count);
+            std::abort();
+        }
+        if (!alone) std::this_thread::yield();
+    }
+    g_block = nullptr;
+}
+
 // Runs `body` (a call of the kernel function) once per thread of a grid x block launch, x dimension only.
 template <class F> inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, F &&body) {
     gridDim = dim3(grid); blockDim = dim3(block);
-    for (unsigned bx = 0; bx < grid; bx++) {
-        Block b;
-        b.fibers.resize(block);
-        b.alive = block;
-        b.dyn.assign(dyn_bytes + 16, 0xCD);
-        b.body = body;
-        g_block = &b;
-        blockIdx = dim3(bx);
-        for (unsigned t = 0; t < block; t++) {
-            Fiber &f = b.fibers[t];
-            f.tid = t;
-            auto &pool = stack_pool();                                // stacks are reused across blocks and launches
-            while (pool.size() <= t) pool.emplace_back(new char[STACK_BYTES]);
-            f.ctx.prepare(pool[t].get(), STACK_BYTES, trampoline);
-        }
-        unsigned idle_passes = 0;
-        std::vector<unsigned> order(block);
-        while (b.alive) {
-            const unsigned long long before = g_progress;
-            schedule_order(order, block);
-            for (unsigned i = 0; i < block; i++) {
-                const unsigned t = order[i];
-                Fiber &f = b.fibers[t];
-                if (f.done) continue;
-                g_fiber = &f;
-                threadIdx = dim3(t);
-                switch_context(g_sched, f.ctx);
-            }
-            if (g_progress == before) {
-                if (++idle_passes > 1000) {
-                    std::fprintf(stderr, "cusim: deadlock in block %u (%u threads alive, %u at the barrier)\n", bx, b.alive, b.bar_count);
-                    std::abort();
-                }
-            } else {
-                idle_passes = 0;
-            }
-        }
-        g_block = nullptr;
+    const unsigned resident = std::min(resident_blocks(), grid);
+    if (resident <= 1) {
+        for (unsigned bx = 0; bx < grid; bx++) run_block(bx, block, dyn_bytes, body);
+        return;
     }
+    std::atomic<unsigned> next{0};
+    std::vector<std::thread> sms;
+    for (unsigned w = 0; w < resident; w++)
+        sms.emplace_back([&] {
+            for (unsigned bx = next.fetch_add(1); bx < grid; bx = next.fetch_add(1)) run_block(bx, block, dyn_bytes, body);
+        });
+    for (auto &t : sms) t.join();
 }
 
 }  // namespace cusim
@@ -271,8 +302,8 @@ inline int __syncthreads_and(int p) { return cusim::barrier(p, 2); }
 inline int __syncthreads_count(int p) { return cusim::barrier(p, 3); }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { cusim::exchange(mask, 0); }
 inline void __nanosleep(unsigned) { cusim::yield(); }
-inline void __threadfence() {}
-inline void __threadfence_block() {}
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 template <class T> inline T __shfl_sync(unsigned mask, T v, int src) {
     const uint64_t *s = cusim::exchange(mask, cusim::to_word(v));
@@ -346,14 +377,23 @@ inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 template <class T> inline T __ldcg(const T *p) { return *p; }
 template <class T> inline T __ldg(const T *p) { return *p; }
 
-template <class T> inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
-template <class T> inline T atomicSub(T *p, T v) { T o = *p; *p = o - v; return o; }
-template <class T> inline T atomicMin(T *p, T v) { T o = *p; *p = std::min(o, v); return o; }
-template <class T> inline T atomicMax(T *p, T v) { T o = *p; *p = std::max(o, v); return o; }
-template <class T> inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
-template <class T> inline T atomicAnd(T *p, T v) { T o = *p; *p = o & v; return o; }
-template <class T> inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
-template <class T> inline T atomicCAS(T *p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
+// Atomics are real ones: with CUSIM_RESIDENT > 1 blocks run on different OS threads.
+template <class T> inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+template <class T> inline T atomicSub(T *p, T v) { return __atomic_fetch_sub(p, v, __ATOMIC_RELAXED); }
+template <class T> inline T atomicOr(T *p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+template <class T> inline T atomicAnd(T *p, T v) { return __atomic_fetch_and(p, v, __ATOMIC_RELAXED); }
+template <class T> inline T atomicExch(T *p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+template <class T> inline T atomicCAS(T *p, T cmp, T v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED); return cmp; }
+template <class T> inline T atomicMin(T *p, T v) {
+    T o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < o && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return o;
+}
+template <class T> inline T atomicMax(T *p, T v) {
+    T o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > o && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return o;
+}
 
 using std::max;
 using std::min;

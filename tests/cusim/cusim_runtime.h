@@ -53,7 +53,7 @@ inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ?
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = std::getenv("CUSIM_NO_DEVICE") ? 0 : 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
-    p->multiProcessorCount = 2; p->totalGlobalMem = cusim::device_total(); p->l2CacheSize = 1 << 20;
+    { const char *e = std::getenv("CUSIM_SMS"); p->multiProcessorCount = e ? std::max(1, std::atoi(e)) : 2; } p->totalGlobalMem = cusim::device_total(); p->l2CacheSize = 1 << 20;
     return cudaSuccess;
 }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new cusimStream{0}; return cudaSuccess; }

@@ -132,3 +132,33 @@ def test_sweep_stays_out_where_it_does_not_apply(engine):
     got = res.to_host(); names = {n for n, _ in res.kernel_times()}; res.free()
     assert not any("k_long_fill" in n for n in names), names
     assert_bit_exact(got, want, "no row above 4096 partial products")
+
+
+def test_concurrent_blocks(monkeypatch):
+    """CUSIM_RESIDENT=4: four blocks of every launch run at the same time on four OS threads (the emulated device has
+    four SMs), so tickets interleave, the decoupled look-back chains of the scans and of the merge wait on live
+    predecessors, and global atomics race for real.  Same bits."""
+    monkeypatch.setenv("CUSIM_RESIDENT", "4")
+    monkeypatch.setenv("CUSIM_SMS", "4")
+    eng = osp.Engine(0)
+    try:
+        a, b, dims = synth.build_workload("er16k", scale_down=4)                 # hundreds of merge tiles through the chain
+        want, _ = oracle_spgemm(synth.transpose_host(a, dims["n_k"]), b)
+        for flags in (api.OSP_ROWWISE_ORDER, api.OSP_KSLICE_ORDER):
+            res = eng.spgemm(a, b, a_is_csr=True, cols_b=dims["cols"], flags=flags)
+            got = res.to_host(); st = res.stats(); res.free()
+            assert st["merge_tiles"] > 100
+            assert_bit_exact(got, want, f"er16k/4, four resident blocks, flags={flags}")
+        rng = np.random.default_rng(41)
+        lens = [5000, 3, 0, 20000, 700, 4097, 129, 9000, 12, 6000, 300, 4500, 45, 8000, 513, 2000] * 2
+        A, B = gp._row_lengths_case(rng, lens, 1 << 17, 0.3)
+        a_csc, a_csr, b_csr = operands(A, B)
+        want, _ = oracle_spgemm(a_csc, b_csr)
+        for flags in (0, api.OSP_LONGROW_SWEEP):
+            res = eng.spgemm(a_csc, b_csr, cols_b=1 << 17, flags=flags)          # CSC(A): device conversion first
+            got = res.to_host(); res.free()
+            assert_bit_exact(got, want, f"long rows, four resident blocks, flags={flags}")
+        csc = eng.csr2csc(a_csr, A.shape[1])
+        assert np.array_equal(csc.pos, a_csc.pos) and np.array_equal(csc.data, a_csc.data)
+    finally:
+        eng.close()

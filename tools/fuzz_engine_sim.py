@@ -2,7 +2,7 @@
 """Fuzz campaign: the emulated engine (tests/cusim, the product's sources on the CPU emulation of the CUDA execution
 model) against the oracle on random operands of every shape class -- a campaign the GPU budget never has room for.
 
-    python tools/fuzz_engine_sim.py --cases 300 --seed 1 [--schedule random:7]
+    python tools/fuzz_engine_sim.py --cases 300 --seed 1 [--schedule random:7] [--resident 4]
 
 Every case draws: dimensions, densities, a column range (small: bitmap/dense kernels; medium; > 2^23: 64-bit chain
 keys), a few rows made long on purpose (medium and xl rows), duplicates-free operands in the reference layout, CSR or
@@ -66,9 +66,12 @@ def main():
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--schedule", default="")
+    ap.add_argument("--resident", type=int, default=1, help="blocks resident at a time (CUSIM_RESIDENT = CUSIM_SMS): > 1 runs them on OS threads")
     args = ap.parse_args()
     if args.schedule:
         os.environ["CUSIM_SCHEDULE"] = args.schedule
+    if args.resident > 1:
+        os.environ["CUSIM_RESIDENT"] = os.environ["CUSIM_SMS"] = str(args.resident)
     tmp = tempfile.mkdtemp(prefix="osp_fuzz_")
     lib = os.path.join(tmp, "libosp_b200_cusim.so")
     build(lib)
@@ -110,7 +113,7 @@ def main():
             seen["products"] += prod
         finally:
             eng.close()
-    print(f"fuzz ok: {args.cases} cases, seed {args.seed}, schedule '{args.schedule or 'forward'}', {time.time() - t0:.0f} s; "
+    print(f"fuzz ok: {args.cases} cases, seed {args.seed}, schedule '{args.schedule or 'forward'}', {args.resident} resident block(s), {time.time() - t0:.0f} s; "
           f"calls with sweep {seen['sweep']}, fused dense {seen['fused']}, row blocks {seen['blocks']}, xl rows {seen['xl']}, "
           f"medium rows {seen['long']}; {seen['products']} partial products in total")
 
