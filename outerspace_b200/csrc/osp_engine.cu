@@ -62,8 +62,8 @@ struct osp_ctx {
     // symbolic / plan / conversion scratch
     DevBuf task_bs, run_off, row_bin, tile_row, long_list, xl_list, uniq, col_ptr, tasks, tile_state, xl_acc, xl_bits;
     DevBuf bins;
-    // fused band sweep of the long rows (opt-in, osp_longrows.cuh): task bitmap for the multiply, per-CTA run cursors
-    DevBuf swept, lr_cursors;
+    // fused band sweep of the long rows (opt-in, osp_longrows.cuh): task bitmap for the multiply, band index of B
+    DevBuf swept, lr_bands;
     bool sweep_ok = false;                  // the device accepted the kernel's shared-memory size
     bool sweep_env = false;                 // OSP_LONGROW_SWEEP=1
     uint64_t sweep_min = 0;                 // OSP_LONGROW_SWEEP_MIN: fewest partial products of a swept row (0: every xl row)
@@ -265,8 +265,8 @@ struct MergeJob {
     bool sweep = false;
     uint64_t sweep_min = ~0ull;             // fewest partial products of a swept row, > MT_XL (k_merge_xl leaves those alone)
     bool sweeps_every_xl() const { return sweep && sweep_min <= MT_XL + 1; }
-    uint64_t cursor_stride = 0;
-    const uint64_t *a_pos = nullptr, *b_pos = nullptr;
+    const uint32_t *bandptr = nullptr;      // band index of B (k_long_bands)
+    const uint64_t *a_pos = nullptr;
     const Elem *a_data = nullptr, *b_data = nullptr;
 };
 
@@ -293,10 +293,6 @@ int reserve_merge(osp_ctx *ctx, const MergeJob &job, unsigned int &xl_ctas) {
         CU(ctx, ctx->xl_acc.reserve(uint64_t(xl_ctas) * job.idx_range * 4));
         CU(ctx, ctx->xl_bits.reserve(uint64_t(xl_ctas) * words * 4));
         CU(ctx, cudaMemsetAsync(ctx->xl_bits.p, 0, uint64_t(xl_ctas) * words * 4, ctx->stream));
-    }
-    if (job.sweep) {
-        const uint64_t ctas = std::min<uint64_t>(job.n_xl, uint64_t(ctx->sm_count) * ctx->sweep_occ);
-        CU(ctx, ctx->lr_cursors.reserve(std::max<uint64_t>(ctas * job.cursor_stride, 1) * 4));
     }
     return OSP_OK;
 }
@@ -332,7 +328,7 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
                 const LongRowsInBins rows{ctx->xl_list.as<uint32_t>(), ctx->d_sc, row_bin, bin_base, bins, uniq, row_lo, row_hi,
                                           job.sweep_min};
                 LAUNCH(ctx, (k_long_fill<LR_THREADS, LR_BAND, LR_RUNS, LongRowsInBins>), grid, LR_THREADS, LR_SMEM, job.a_pos, job.a_data,
-                       job.b_pos, job.b_data, job.idx_range, rows, ctx->lr_cursors.as<uint32_t>(), job.cursor_stride, &ctx->d_sc->err);
+                       job.b_data, job.bandptr, job.idx_range, rows);
             }
             if (xl_ctas && ((job.n_xl && !job.sweeps_every_xl()) || (job.n_long && xl_takes_long))) {
                 CU(ctx, cudaMemsetAsync(&ctx->d_sc->xl_ticket, 0, 4, ctx->stream));
@@ -572,7 +568,7 @@ void osp_destroy(osp_ctx *ctx) {
     for (DevBuf *b : {&ctx->arena, &ctx->op_a_pos, &ctx->op_a_data, &ctx->op_b_pos, &ctx->op_b_data, &ctx->conv_pos,
                       &ctx->conv_data, &ctx->conv_tmp, &ctx->conv_chk, &ctx->task_bs, &ctx->run_off, &ctx->row_bin, &ctx->tile_row,
                       &ctx->long_list, &ctx->xl_list, &ctx->uniq, &ctx->col_ptr, &ctx->tasks, &ctx->tile_state,
-                      &ctx->xl_acc, &ctx->xl_bits, &ctx->bins, &ctx->swept, &ctx->lr_cursors})
+                      &ctx->xl_acc, &ctx->xl_bits, &ctx->bins, &ctx->swept, &ctx->lr_bands})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
@@ -746,17 +742,20 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     job.n_tiles = ctx->h_sc->n_tiles; job.n_long = ctx->h_sc->n_long; job.n_xl = ctx->h_sc->n_xl;
     // ---- fused band sweep of the long rows (opt-in): their tasks are flagged for the multiply, which emits nothing for
     // them; k_long_fill computes and merges them straight into the start of their bins (launch_merge)
+    // The band index of B (4 bytes per row of B and band) must fit a sixteenth of the device, else the call stays on
+    // the default path.
+    const uint64_t lr_bands = (job.idx_range + LR_BAND - 1) / LR_BAND;
+    const uint64_t lr_index_bytes = std::max<uint64_t>(n_k, 1) * (lr_bands + 1) * 4;
     const bool sweep = ctx->sweep_ok && ((args->flags & OSP_LONGROW_SWEEP) || ctx->sweep_env) && !(args->flags & OSP_KSLICE_ORDER) &&
-                       rowwise && !fused && job.n_xl > 0 && job.idx_range > DENSE_MAX_COLS;
+                       rowwise && !fused && job.n_xl > 0 && job.idx_range > DENSE_MAX_COLS &&
+                       lr_index_bytes <= std::max<uint64_t>(ctx->total_mem / 16, 256ull << 20);
     if (sweep) {
         job.sweep = true;
         // only rows of the xl list are ever swept, and only where a band sees enough of the row to pay for its barriers:
         // a row must bring LR_MIN_PER_BAND partial products per band on average (16 M columns = 1024 bands: rows from
         // 65 536 partial products), shorter rows stay with k_multiply + k_merge_xl.  (Unmeasured starting point.)
-        const uint64_t bands = (job.idx_range + LR_BAND - 1) / LR_BAND;
-        job.sweep_min = std::max<uint64_t>({ctx->sweep_min, MT_XL + 1, LR_MIN_PER_BAND * bands});
-        job.cursor_stride = std::max<uint64_t>(std::min<uint64_t>(nnz_a, std::max<uint64_t>(n_k, 1)), 1);   // a row of A holds <= n_k distinct columns
-        job.a_pos = dA_pos; job.a_data = dA_data; job.b_pos = dB_pos; job.b_data = dB_data;
+        job.sweep_min = std::max<uint64_t>({ctx->sweep_min, MT_XL + 1, LR_MIN_PER_BAND * lr_bands});
+        job.a_pos = dA_pos; job.a_data = dA_data; job.b_data = dB_data;
     }
     const uint64_t cap_bound = std::max<uint64_t>(args->cols_b ? ctx->h_sc->cap_bound : std::min<uint64_t>(ctx->h_sc->cap_bound, P), 1);
     unsigned int xl_ctas = 0;
@@ -769,6 +768,10 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
             CU(ctx, cudaMemsetAsync(ctx->swept.p, 0, words * 4, ctx->stream));
             LAUNCH(ctx, k_mark_swept, grid_for(uint64_t(job.n_xl) * 32, 256, unsigned(ctx->sm_count) * 8u), 256, 0, dA_pos,
                    ctx->xl_list.as<uint32_t>(), ctx->d_sc, ctx->row_bin.as<uint64_t>(), job.sweep_min, ctx->swept.as<uint32_t>());
+            CU(ctx, ctx->lr_bands.reserve(lr_index_bytes));
+            LAUNCH(ctx, k_long_bands, grid_for(n_k * (lr_bands + 1), 256, 1u << 30), 256, 0, dB_pos, dB_data, n_k, uint32_t(LR_BAND),
+                   uint32_t(lr_bands), ctx->lr_bands.as<uint32_t>());
+            job.bandptr = ctx->lr_bands.as<uint32_t>();
             return OSP_OK;
         }();
         if (rc) return bail(rc);

@@ -10,38 +10,43 @@
 // SORTED runs -- run r = A(i,k_r) * B(k_r,:), ascending k, columns ascending and distinct inside a run.  Writing those
 // partial products to bins and folding them through a per-CTA accumulator of `cols` floats in global memory costs a
 // random DRAM sector per product (profiles/README.md).  Here nothing is materialised: the row is swept one band of
-// LR_BAND columns at a time with the accumulator in shared memory; a run contributes to a band the contiguous
-// segment found by a per-run cursor (runs are sorted), so every element of B is read once per use, from L2.
+// LR_BAND columns at a time with the accumulator in shared memory; a run contributes to a band one contiguous
+// segment (runs are sorted) whose bounds come from a band index of B built once per call (k_long_bands: for every
+// row k of B the position of the first column of every band -- two adjacent 4-byte loads per (run, band), no search
+// and no per-run state during the sweep), so every element of B is read once per use, from L2.
 //   k_long_count: the sweep with a bitmap only -> the exact number of non-zeros of every long row, so that C is
 //                 allocated exactly and every long row's place in C is known before any value is computed.
 //   k_long_fill:  the sweep with values.  Products of a chunk that hit the same column are serialised by the
 //                 racing-minimum arbitration of k_merge_dense (lowest flat position = lowest (k, position) first), so
 //                 every column is summed in ascending k with separately rounded products and adds: the bits of the
 //                 reference's left fold.  acc[] starts at -0.0f (x + -0 = x for every x): no first-touch test on the add.
-// Runs are taken in groups of LR_RUNS (their cursors' segment prefix lives in shared memory); groups of a band are
-// visited in ascending k, which keeps the order.
+// Runs are taken in groups of LR_RUNS (the prefix of their segment lengths lives in shared memory); groups of a band
+// are visited in ascending k, which keeps the order.  The elements of the next chunk are loaded before the current one
+// is arbitrated.
 #pragma once
 #include "osp_device.cuh"
 
 namespace osp {
 
-// First position p in [lo, len] with p == len or run[p].idx >= band_hi; run[lo .. p) lies below band_hi.
-// Galloping from the cursor: a segment of s elements costs ~2 log2(s) probes.
-__device__ __forceinline__ uint32_t lr_advance(const Elem *__restrict__ run, uint32_t lo, uint32_t len, uint64_t band_hi) {
-    if (lo >= len || run[lo].idx >= band_hi) return lo;
-    uint32_t a = lo, step = 1, hi;                       // run[a].idx < band_hi
-    while (true) {
-        const uint64_t b = uint64_t(a) + step;
-        if (b >= len) { hi = len; break; }
-        if (run[b].idx >= band_hi) { hi = uint32_t(b); break; }
-        a = uint32_t(b);
-        step <<= 1;
+// Band index of B: bandptr[k * (n_bands + 1) + b] = position in b_data of the first element of row k whose column is
+// >= b * band (b = n_bands: the end of the row).  One thread per entry, a binary search inside the row.
+__global__ void k_long_bands(const uint64_t *__restrict__ b_pos, const Elem *__restrict__ b_data, uint64_t n_k, uint32_t band,
+                             uint32_t n_bands, uint32_t *__restrict__ bandptr) {
+    const uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    const uint64_t nb1 = uint64_t(n_bands) + 1;
+    if (t >= n_k * nb1) return;
+    const uint64_t k = t / nb1, b = t % nb1;
+    uint64_t lo = b_pos[k], hi = b_pos[k + 1];
+    if (b < n_bands) {
+        const uint64_t target = b * uint64_t(band);
+        while (lo < hi) {
+            const uint64_t mid = lo + (hi - lo) / 2;
+            if (b_data[mid].idx < target) lo = mid + 1; else hi = mid;
+        }
+    } else {
+        lo = hi;
     }
-    while (hi - a > 1) {                                 // run[a] < band_hi <= run[hi] (or hi == len)
-        const uint32_t mid = a + (hi - a) / 2;
-        if (run[mid].idx < band_hi) a = mid; else hi = mid;
-    }
-    return hi;
+    bandptr[t] = uint32_t(lo);                                             // nnz(B) < 2^32
 }
 
 // Shared-memory layout of one CTA: band accumulator | owner | presence bitmap | run group | scan scratch
@@ -90,13 +95,11 @@ struct LongRowsInBins {                 // the engine: rows of the plan's xl lis
     __device__ __forceinline__ void done(uint32_t, uint64_t row, uint64_t n) const { uniq[row] = uint32_t(n); }
 };
 
-// One CTA per listed row, rows handed out by ticket.  cursors: gridDim.x * cursor_stride uint32; a listed row of A with
-// more than cursor_stride non-zeros raises *err (the host sizes the stride from the operand).
+// One CTA per listed row, rows handed out by ticket.  bandptr: the band index of B for bands of BAND columns.
 template <int THREADS, int BAND, int RUNS, bool VALUES, class Rows>
 __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data,
-                                                const uint64_t *__restrict__ b_pos, const Elem *__restrict__ b_data,
-                                                const uint64_t cols, const Rows rows, uint32_t *cursors,
-                                                const uint64_t cursor_stride, unsigned int *err) {
+                                                const Elem *__restrict__ b_data, const uint32_t *__restrict__ bandptr,
+                                                const uint64_t cols, const Rows rows) {
     static_assert(BAND % 32 == 0 && BAND <= 65536 && RUNS >= 1, "the band is a bitmap of whole words");
     static_assert(THREADS <= 1024 && THREADS % 32 == 0, "whole warps");
     using L = LongRowSmem<BAND, RUNS, VALUES>;
@@ -115,7 +118,8 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
     for (uint32_t w = tid; w < WORDS; w += THREADS) bits[w] = 0u;
     if (VALUES)
         for (uint32_t c = tid; c < BAND; c += THREADS) { acc[c] = -0.0f; owner[c] = 0xFFFF; }
-    uint32_t *cursor = cursors + uint64_t(blockIdx.x) * cursor_stride;
+    const uint32_t n_bands = uint32_t((cols + BAND - 1) / BAND);
+    const uint64_t nb1 = uint64_t(n_bands) + 1;
     while (true) {
         __syncthreads();
         if (tid == 0) {
@@ -129,34 +133,25 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
         const uint64_t row = *s_row;
         const uint64_t p0 = a_pos[row];
         const uint64_t R = a_pos[row + 1] - p0;
-        if (R > cursor_stride) {                    // not reachable when the host sized the stride from this operand
-            if (tid == 0) { atomicMax(err, 2u); rows.done(x, row, 0); }
-            continue;
-        }
         Elem *out = VALUES ? rows.out(x, row) : nullptr;
-        for (uint64_t r = tid; r < R; r += THREADS) cursor[r] = 0u;
-        __syncthreads();                            // a cursor is not always read by the thread that reset it
         uint32_t my_count = 0;                      // VALUES=false: columns seen, summed over this thread's bitmap words
         uint64_t produced = 0;                      // VALUES=true: elements of the row already written
-        for (uint64_t band_lo = 0; band_lo < cols; band_lo += BAND) {
-            const uint64_t band_hi = min(cols, band_lo + uint64_t(BAND));
+        for (uint32_t band = 0; band < n_bands; band++) {
+            const uint64_t band_lo = uint64_t(band) * BAND;
             bool touched = false;                                          // uniform: some run has an element in this band
             for (uint64_t g0 = 0; g0 < R; g0 += RUNS) {
                 const uint32_t G = uint32_t(min(uint64_t(RUNS), R - g0));
-                // ---- the segment of every run of the group inside this band (cursor -> first column >= band_hi) ----
+                // ---- the segment of every run of the group inside this band ----
                 uint32_t carry = 0;
                 for (uint32_t r0 = 0; r0 < G; r0 += THREADS) {
                     const uint32_t r = r0 + tid;
                     uint32_t seg = 0;
                     if (r < G) {
                         const Elem ak = a_data[p0 + g0 + r];
-                        const uint64_t bs = b_pos[ak.idx];
-                        const uint32_t len = uint32_t(b_pos[ak.idx + 1] - bs);
-                        const uint32_t lo = cursor[g0 + r];
-                        const uint32_t hi = lr_advance(b_data + bs, lo, len, band_hi);
-                        cursor[g0 + r] = hi;
-                        seg = hi - lo;
-                        s_lo[r] = uint32_t(bs) + lo;                       // nnz(B) < 2^32
+                        const uint32_t *bp = bandptr + uint64_t(ak.idx) * nb1 + band;
+                        const uint32_t lo = bp[0];
+                        seg = bp[1] - lo;
+                        s_lo[r] = lo;
                         if (VALUES) s_a[r] = ak.val;
                     }
                     uint32_t total;
@@ -169,22 +164,29 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
                 __syncthreads();
                 const uint32_t T = carry;                                  // elements of the group inside the band, in (k, column) order
                 touched |= T > 0;
-                // ---- consume them THREADS at a time ----
+                // ---- consume them THREADS at a time; the next chunk's elements are in flight during the arbitration ----
+                // element f of the group: run a with s_pre[a] <= f < s_pre[a + 1], element f - s_pre[a] of its segment
+                auto locate = [&](uint32_t f, Elem &e, uint32_t &a) {
+                    a = 0;
+                    uint32_t b = G;
+                    while (b - a > 1) {
+                        const uint32_t mid = (a + b) >> 1;
+                        if (s_pre[mid] <= f) a = mid; else b = mid;
+                    }
+                    e = b_data[uint64_t(s_lo[a]) + (f - s_pre[a])];
+                };
+                Elem e_next; e_next.idx = 0; e_next.val = 0.f;
+                uint32_t a_next = 0;
+                if (tid < T) locate(tid, e_next, a_next);
                 for (uint32_t c0 = 0; c0 < T; c0 += THREADS) {
                     const uint32_t f = c0 + tid;
                     bool pending = f < T;
-                    uint32_t col = 0;
+                    const Elem e = e_next;
+                    const uint32_t a = a_next;
+                    if (f + THREADS < T) locate(f + THREADS, e_next, a_next);
+                    const uint32_t col = pending ? uint32_t(e.idx - band_lo) : 0u;
                     float val = 0.f;
-                    if (pending) {
-                        uint32_t a = 0, b = G;                             // s_pre[a] <= f < s_pre[b]
-                        while (b - a > 1) {
-                            const uint32_t mid = (a + b) >> 1;
-                            if (s_pre[mid] <= f) a = mid; else b = mid;
-                        }
-                        const Elem e = b_data[uint64_t(s_lo[a]) + (f - s_pre[a])];
-                        col = uint32_t(e.idx - band_lo);
-                        if (VALUES) val = __fmul_rn(s_a[a], e.val);
-                    }
+                    if (VALUES && pending) val = __fmul_rn(s_a[a], e.val);
                     if (!VALUES) {
                         if (pending) atomicOr(&bits[col >> 5], 1u << (col & 31));
                     } else {
@@ -248,16 +250,16 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
 
 template <int THREADS, int BAND, int RUNS, class Rows>
 __global__ void __launch_bounds__(THREADS)
-k_long_count(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data, const uint64_t *__restrict__ b_pos,
-             const Elem *__restrict__ b_data, uint64_t cols, Rows rows, uint32_t *cursors, uint64_t cursor_stride, unsigned int *err) {
-    long_rows_sweep<THREADS, BAND, RUNS, false>(a_pos, a_data, b_pos, b_data, cols, rows, cursors, cursor_stride, err);
+k_long_count(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data, const Elem *__restrict__ b_data,
+             const uint32_t *__restrict__ bandptr, uint64_t cols, Rows rows) {
+    long_rows_sweep<THREADS, BAND, RUNS, false>(a_pos, a_data, b_data, bandptr, cols, rows);
 }
 
 template <int THREADS, int BAND, int RUNS, class Rows>
 __global__ void __launch_bounds__(THREADS)
-k_long_fill(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data, const uint64_t *__restrict__ b_pos,
-            const Elem *__restrict__ b_data, uint64_t cols, Rows rows, uint32_t *cursors, uint64_t cursor_stride, unsigned int *err) {
-    long_rows_sweep<THREADS, BAND, RUNS, true>(a_pos, a_data, b_pos, b_data, cols, rows, cursors, cursor_stride, err);
+k_long_fill(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data, const Elem *__restrict__ b_data,
+            const uint32_t *__restrict__ bandptr, uint64_t cols, Rows rows) {
+    long_rows_sweep<THREADS, BAND, RUNS, true>(a_pos, a_data, b_data, bandptr, cols, rows);
 }
 
 // The tasks (non-zeros of A) of the rows the sweep takes: one bit per task, read by k_multiply (TaskSrcSoASwept), which

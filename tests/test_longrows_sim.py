@@ -3,7 +3,7 @@ execution model (tests/cusim), bit for bit against the oracle.
 
 The very source nvcc compiles for sm_100a is compiled here by g++ with OSP_CUSIM defined; the threads of a
 block run as fibers that switch at the synchronising built-ins, which is one legal CUDA schedule.  This
-checks the kernel's LOGIC (cursors, run groups, band hand-over, arbitration order = the reference's left
+checks the kernel's LOGIC (band index, run groups, band hand-over, arbitration order = the reference's left
 fold in ascending k, SimSpGEMM.cpp:265-281 + :519-535) where no GPU exists; it cannot see data races, so
 the GPU parity tests (tests/test_gpu_parity.py) stay the gate for the product.
 """
@@ -34,9 +34,9 @@ def sim(tmp_path_factory):
     lib = C.CDLL(out)
     vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
     lib.lr_sim.restype = C.c_int
-    lib.lr_sim.argtypes = [C.c_int, vp, vp, vp, vp, u64, vp, u32, C.c_uint, vp, vp, vp, u64]
+    lib.lr_sim.argtypes = [C.c_int, vp, vp, vp, vp, u64, u64, vp, u32, C.c_uint, vp, vp, vp, u64]
     lib.lr_sim_bins.restype = C.c_int
-    lib.lr_sim_bins.argtypes = [C.c_int, vp, vp, vp, vp, u64, vp, u32, vp, u64, vp, vp, u64, u64, u64, vp, u64, C.c_uint]
+    lib.lr_sim_bins.argtypes = [C.c_int, vp, vp, vp, vp, u64, u64, vp, u32, vp, u64, vp, vp, u64, u64, u64, vp, C.c_uint]
     return lib
 
 
@@ -50,7 +50,7 @@ def run_sim(lib, config, a_csr, b_csr, cols, rows, grid=2):
     out = np.zeros(bound, ELEM)
     out["idx"] = 0xABABABAB
     ptr = lambda x: x.ctypes.data_as(C.c_void_p)
-    rc = lib.lr_sim(config, ptr(a_csr.pos), ptr(a_csr.data), ptr(b_csr.pos), ptr(b_csr.data), cols, ptr(rows), n, grid,
+    rc = lib.lr_sim(config, ptr(a_csr.pos), ptr(a_csr.data), ptr(b_csr.pos), ptr(b_csr.data), b_csr.NRow(), cols, ptr(rows), n, grid,
                     ptr(count), ptr(off), ptr(out), bound)
     assert rc == 0, rc
     return count, off, out
@@ -129,8 +129,8 @@ def test_columns_not_a_multiple_of_the_band_and_last_band_single_column(sim):
             check(sim, config, A, B)
 
 
-def test_long_runs_gallop(sim):
-    """Runs much longer than a band: the cursor gallops over hundreds of elements per band."""
+def test_long_runs(sim):
+    """Runs much longer than a band: hundreds of elements per (run, band) segment, several chunks per group."""
     rng = np.random.default_rng(13)
     A = rand_sparse(rng, 2, 6, 0.9)
     B = rand_sparse(rng, 6, 5000, 0.6)
@@ -160,9 +160,8 @@ def test_engine_hand_over_into_the_bins(sim, config):
     uniq = np.full(16, 0xEEEEEEEE, np.uint32)
     swept = np.zeros((a_csr.nnz + 31) // 32 + 1, np.uint32)
     ptr = lambda x: x.ctypes.data_as(C.c_void_p)
-    stride = int(np.diff(a_pos).max())
-    rc = sim.lr_sim_bins(config, ptr(a_csr.pos), ptr(a_csr.data), ptr(b_csr.pos), ptr(b_csr.data), 400, ptr(xl_list), len(xl_list),
-                         ptr(row_bin), bin_base, ptr(bins), ptr(uniq), row_lo, row_hi, min_len, ptr(swept), stride, 2)
+    rc = sim.lr_sim_bins(config, ptr(a_csr.pos), ptr(a_csr.data), ptr(b_csr.pos), ptr(b_csr.data), 24, 400, ptr(xl_list), len(xl_list),
+                         ptr(row_bin), bin_base, ptr(bins), ptr(uniq), row_lo, row_hi, min_len, ptr(swept), 2)
     assert rc == 0
     wpos = want.pos.astype(np.int64)
     marked = np.unpackbits(swept.view(np.uint8), bitorder="little")[: a_csr.nnz].astype(bool)
@@ -183,22 +182,3 @@ def test_engine_hand_over_into_the_bins(sim, config):
                 assert np.all(b["idx"] == 0xABABABAB)
         if not taken:
             assert uniq[r] == 0xEEEEEEEE
-
-
-def test_row_of_a_longer_than_the_cursor_stride_is_reported(sim):
-    rng = np.random.default_rng(22)
-    A = rand_sparse(rng, 4, 24, 0.9)
-    B = rand_sparse(rng, 24, 100, 0.3)
-    a_csc, a_csr, b_csr = operands(A, B)
-    b_len = np.diff(b_csr.pos.astype(np.int64))
-    a_pos = a_csr.pos.astype(np.int64)
-    row_len = np.array([int(b_len[a_csr.data["idx"][a_pos[r]:a_pos[r + 1]]].sum()) for r in range(4)], np.int64)
-    row_bin = np.concatenate([[0], np.cumsum(row_len)]).astype(np.uint64)
-    xl_list = np.arange(4, dtype=np.uint32)
-    bins = np.zeros(int(row_bin[-1]), ELEM)
-    uniq = np.full(4, 0xEEEEEEEE, np.uint32)
-    swept = np.zeros((a_csr.nnz + 31) // 32 + 1, np.uint32)
-    ptr = lambda x: x.ctypes.data_as(C.c_void_p)
-    rc = sim.lr_sim_bins(0, ptr(a_csr.pos), ptr(a_csr.data), ptr(b_csr.pos), ptr(b_csr.data), 100, ptr(xl_list), 4,
-                         ptr(row_bin), 0, ptr(bins), ptr(uniq), 0, 4, 0, ptr(swept), int(np.diff(a_pos).max()) - 1, 1)
-    assert rc == 2
