@@ -190,7 +190,9 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
                     if (!VALUES) {
                         if (pending) atomicOr(&bits[col >> 5], 1u << (col & 31));
                     } else {
-                        while (__syncthreads_or(pending)) {
+                        // A chunk holds at least one product (c0 < T) and follows a barrier, so the first round needs no
+                        // vote: three barriers for a chunk without a repeated column.
+                        do {
                             // the lowest pending position of every column wins this round (racing minimum, re-checked)
                             bool want = pending;
                             do {
@@ -204,7 +206,7 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
                                 owner[col] = 0xFFFF;
                                 pending = false;
                             }
-                        }
+                        } while (__syncthreads_or(pending));
                     }
                 }
                 __syncthreads();                                           // s_pre / s_lo are rewritten by the next group
