@@ -172,6 +172,19 @@ void osp_coo_free(osp_coo *c);
 int  osp_coo2csr(uint64_t nnz, const uint32_t *rows, const uint32_t *cols, const float *vals,
                  uint64_t N, int transpose, uint64_t *pos, void *data);
 
+/* Compact COO (CompactCOOMatrix, common.h:52-56; the reference's alternative operand format for the multiply,
+ * compactMulcsr SimSpGEMM.cpp:247-263).  Triplets are returned as three arrays like osp_coo_copy.
+ * osp_csr2compact = csr2compact (SimSpGEMM.cpp:154-219): group j = the (j+1)-th non-zero of every slice that has
+ * one, slices ascending; *n_groups = the longest slice.  Call with group_pos = NULL for n_groups alone, then with
+ * group_pos[n_groups + 1] and rows/cols/vals[nnz].  A matrix without non-zeros has 0 groups (undefined behaviour in
+ * the reference).  osp_csc2rawcompact = csc2rawcompact (SimSpGEMM.cpp:221-243): one group per slice (group_pos =
+ * pos), row = the element's index, col = the slice id.
+ * A compact operand enters the engine as the triplet list it is: osp_coo2csr_device(rows, cols, vals) -> osp_spgemm
+ * gives the merged equivalent of compactMulcsr (tests/test_compact.py). */
+int  osp_csr2compact(uint64_t n_major, const uint64_t *pos, const void *data, uint64_t *n_groups, uint64_t *group_pos,
+                     uint32_t *rows, uint32_t *cols, float *vals);
+int  osp_csc2rawcompact(uint64_t n_major, const uint64_t *pos, const void *data, uint32_t *rows, uint32_t *cols, float *vals);
+
 /* The same conversion on the GPU (histogram -> scan -> bucket scatter -> per-slice sort with the merge machinery;
  * a slice that shrinks while folding held a duplicate -> OSP_ERR_DUPLICATE = the reference's throw(233)).
  * N = number of slices (rows for CSR, columns when transpose); n_other = range of the other index (0 = derive it;

@@ -12,6 +12,11 @@
 //                      getMultiplyTasks()/getMergeTasks() give the task SIZES the timing models read (:176-196);
 //                      mergedResult is public and holds the intended (cscMulcsr + deduplicateCOO) result
 //   SimSpGEMM.cpp:884-891 mulflops_ref                    mulflops(csc, csr)
+//   common.h:52-56   CompactCOOMatrix{pos,data}           same
+//   SimSpGEMM.cpp:154  csr2compact(csr)                   same signature
+//   SimSpGEMM.cpp:221  csc2rawcompact(csc)                same signature
+//   SimSpGEMM.cpp:247  compactMulcsr(compact, csr)        Engine::compactMulcsr: the MERGED product (the reference returns
+//                                                         the unmerged partial products of every group)
 //
 // Errors: the reference asserts (abort) on a k-dimension mismatch and throws the int 233 on duplicate
 // entries.  Here coo2csr throws 233 as well (so existing catch sites keep working); everything else
@@ -98,6 +103,41 @@ CSRMatrix coo2csr(COOMatrix coo, size_t N) {
     return out;
 }
 
+struct CompactCOOMatrix {
+    std::vector<size_t> pos;
+    std::vector<COOElement> data;
+};
+
+inline CompactCOOMatrix from_triplets(std::vector<size_t> pos, const std::vector<uint32_t> &r, const std::vector<uint32_t> &c,
+                                      const std::vector<float> &v) {
+    CompactCOOMatrix out;
+    out.pos = std::move(pos);
+    out.data.resize(r.size());
+    for (size_t i = 0; i < r.size(); i++) out.data[i] = COOElement{r[i], c[i], v[i]};
+    return out;
+}
+
+inline CompactCOOMatrix csr2compact(const CSRMatrix &csr) {
+    if (csr.pos.empty()) return CompactCOOMatrix();
+    uint64_t groups = 0;
+    const uint64_t *pos = reinterpret_cast<const uint64_t *>(csr.pos.data());
+    check(osp_csr2compact(csr.NRow(), pos, csr.data.data(), &groups, nullptr, nullptr, nullptr, nullptr), nullptr, "csr2compact");
+    std::vector<size_t> gpos(groups + 1, 0);
+    std::vector<uint32_t> r(csr.data.size()), c(csr.data.size());
+    std::vector<float> v(csr.data.size());
+    check(osp_csr2compact(csr.NRow(), pos, csr.data.data(), &groups, reinterpret_cast<uint64_t *>(gpos.data()), r.data(), c.data(), v.data()),
+          nullptr, "csr2compact");
+    return from_triplets(std::move(gpos), r, c, v);
+}
+
+inline CompactCOOMatrix csc2rawcompact(const CSRMatrix &csc) {
+    std::vector<uint32_t> r(csc.data.size()), c(csc.data.size());
+    std::vector<float> v(csc.data.size());
+    check(osp_csc2rawcompact(csc.NRow(), reinterpret_cast<const uint64_t *>(csc.pos.data()), csc.data.data(), r.data(), c.data(), v.data()),
+          nullptr, "csc2rawcompact");
+    return from_triplets(csc.pos, r, c, v);
+}
+
 inline size_t mulflops(const CSRMatrix &csc, const CSRMatrix &csr) {
     size_t f = 0;
     for (size_t i = 0; i + 1 < csr.pos.size() && i + 1 < csc.pos.size(); i++)
@@ -152,6 +192,28 @@ public:
         }
         osp_result_free(res);
         return c;
+    }
+
+    // compactMulcsr (SimSpGEMM.cpp:247-263), merged: the compact operand is a triplet list, so it enters through the
+    // device COO ingest (coo2csr + dupcheck on the GPU) and the product runs like any other.  rows_a = rows of A
+    // (0: largest row id + 1).  The reference returns the unmerged partial products of every group; merging them in
+    // group order (= ascending k inside every output row) gives exactly this result.
+    CSRMatrix compactMulcsr(const CompactCOOMatrix &compact, const CSRMatrix &csr, size_t rows_a = 0) {
+        const size_t n = compact.data.size();
+        std::vector<uint32_t> r(n), c(n);
+        std::vector<float> v(n);
+        for (size_t i = 0; i < n; i++) {
+            r[i] = compact.data[i].row; c[i] = compact.data[i].col; v[i] = compact.data[i].val;
+            if (size_t(r[i]) + 1 > rows_a) rows_a = size_t(r[i]) + 1;
+        }
+        CSRMatrix a;
+        a.pos.assign(rows_a + 1, 0);
+        a.data.resize(n);
+        int rc = osp_coo2csr_device(ctx_, n, r.data(), c.data(), v.data(), rows_a, csr.NRow(), 0, 0,
+                                    reinterpret_cast<uint64_t *>(a.pos.data()), a.data.data());
+        if (rc == OSP_ERR_DUPLICATE) throw(233);            // compactMulcsr's dupcheck, SimSpGEMM.cpp:260
+        check(rc, ctx_, "compactMulcsr: ingest");
+        return spgemm(a, csr, /*a_is_csr=*/true);
     }
 
 private:

@@ -90,6 +90,10 @@ def ref_libs() -> Tuple[C.CDLL, C.CDLL]:
         a.ref_result_dims.argtypes = [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(C.c_double)]
         a.ref_result_copy.argtypes = [_vp, _vp, _vp]
         a.ref_result_free.argtypes = [_vp]
+        a.ref_compact.restype = _u64
+        a.ref_compact.argtypes = [C.c_int, _u64, _vp, _vp, _vp, _vp, _vp, _vp]
+        a.ref_compact_spgemm.restype = _vp
+        a.ref_compact_spgemm.argtypes = [_u64, _vp, _vp, _vp, _vp, _u64, _vp, _vp, C.POINTER(C.c_int)]
         b.ref_taskprovider.restype = _vp
         b.ref_taskprovider.argtypes = [_u64, _vp, _vp, _vp, _vp]
         b.ref_tp_dims.argtypes = [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64),
@@ -189,6 +193,40 @@ def spgemm_rowblocks(a_csr_pos, a_csr_data, b_pos, b_data, rows_per_block: int =
     pos, data = np.zeros(rows.value + 1, np.uint64), np.zeros(nnz.value, ELEM)
     lib.orc_result_copy(h, _p(pos), _p(data))
     lib.orc_result_free(h)
+    return pos, data, prod.value
+
+
+def ref_compact(pos, data, raw: bool = False):
+    """The reference's csr2compact (SimSpGEMM.cpp:154-219) or, with raw, csc2rawcompact (:221-243), unmodified
+    -> (group_pos u64, rows u32, cols u32, vals f32)."""
+    pos, data = _c(pos, np.uint64), _c(data, ELEM)
+    lib = ref_libs()[0]
+    n = len(pos) - 1
+    npos = lib.ref_compact(int(raw), n, _p(pos), _p(data), None, None, None, None)
+    gpos = np.zeros(npos, np.uint64)
+    nnz = len(data)
+    rows, cols, vals = np.zeros(nnz, np.uint32), np.zeros(nnz, np.uint32), np.zeros(nnz, np.float32)
+    lib.ref_compact(int(raw), n, _p(pos), _p(data), _p(gpos), _p(rows), _p(cols), _p(vals))
+    return gpos, rows, cols, vals
+
+
+def ref_compact_spgemm(group_pos, rows, cols, vals, b_pos, b_data):
+    """The reference's compactMulcsr (SimSpGEMM.cpp:247-263) on a compact operand, its partial products folded by the
+    deduplicateCOO rule with a stable sort -> (pos u64, data ELEM, products).  Raises ValueError(233) when its
+    dupcheck throws."""
+    group_pos, b_pos, b_data = _c(group_pos, np.uint64), _c(b_pos, np.uint64), _c(b_data, ELEM)
+    rows, cols, vals = _c(rows, np.uint32), _c(cols, np.uint32), _c(vals, np.float32)
+    lib = ref_libs()[0]
+    status = C.c_int()
+    h = lib.ref_compact_spgemm(len(group_pos) - 1, _p(group_pos), _p(rows), _p(cols), _p(vals), len(b_pos) - 1, _p(b_pos), _p(b_data),
+                               C.byref(status))
+    if not h:
+        raise ValueError(status.value)
+    nrows, nnz, prod, sec = _u64(), _u64(), _u64(), C.c_double()
+    lib.ref_result_dims(h, C.byref(nrows), C.byref(nnz), C.byref(prod), C.byref(sec))
+    pos, data = np.zeros(nrows.value + 1, np.uint64), np.zeros(nnz.value, ELEM)
+    lib.ref_result_copy(h, _p(pos), _p(data))
+    lib.ref_result_free(h)
     return pos, data, prod.value
 
 

@@ -93,6 +93,63 @@ int ref_coo2csr(uint64_t nnz, const uint32_t *rows, const uint32_t *cols, const 
     return 0;
 }
 
+// reference csr2compact (SimSpGEMM.cpp:154-219) / csc2rawcompact (:221-243), unmodified.  First call with
+// group_pos == nullptr returns the number of groups + 1 (pos.size()).
+uint64_t ref_compact(int raw, uint64_t n, const uint64_t *pos, const void *data, uint64_t *group_pos,
+                     uint32_t *rows, uint32_t *cols, float *vals) {
+    CSRMatrix m = wrap(n, pos, data);
+    // csr2compact reports its run time on std::cout (TIMER, SimSpGEMM.cpp:38,162): muted for the call -- the stream of
+    // a dlopen'ed library built with a newer libstdc++ than the host process may not have its locale set up
+    const std::ios_base::iostate saved = std::cout.rdstate();
+    std::cout.setstate(std::ios_base::failbit);
+    CompactCOOMatrix c = raw ? csc2rawcompact(m) : csr2compact(m);
+    std::cout.clear(saved);
+    if (!group_pos) return c.pos.size();
+    for (size_t i = 0; i < c.pos.size(); i++) group_pos[i] = c.pos[i];
+    for (size_t i = 0; i < c.data.size(); i++) { rows[i] = c.data[i].row; cols[i] = c.data[i].col; vals[i] = c.data[i].val; }
+    return c.pos.size();
+}
+
+// reference compactMulcsr (SimSpGEMM.cpp:247-263) on a compact operand given as group_pos + triplets: the partial
+// products of all groups in group order, then the deduplicateCOO fold with a stable sort (a row's entries appear in
+// ascending k over the groups, so this is the k-ordered merge).  233 when its dupcheck throws.
+void *ref_compact_spgemm(uint64_t n_groups, const uint64_t *group_pos, const uint32_t *rows, const uint32_t *cols,
+                         const float *vals, uint64_t n_k, const uint64_t *b_pos, const void *b_data, int *status) {
+    CompactCOOMatrix c;
+    c.pos.assign(group_pos, group_pos + n_groups + 1);
+    c.data.resize(group_pos[n_groups]);
+    for (size_t i = 0; i < c.data.size(); i++) c.data[i] = COOElement{rows[i], cols[i], vals[i]};
+    CSRMatrix csr = wrap(n_k, b_pos, b_data);
+    auto *res = new RefResult();
+    std::vector<COOMatrix> per_group;
+    try {
+        per_group = compactMulcsr(c, csr);
+    } catch (int code) {
+        *status = code;
+        delete res;
+        return nullptr;
+    }
+    *status = 0;
+    COOMatrix flat;
+    for (auto &m : per_group) flat.insert(flat.end(), m.begin(), m.end());
+    res->products = flat.size();
+    std::stable_sort(flat.begin(), flat.end());
+    index_t maxRow = 0;
+    for (auto &e : c.data) maxRow = std::max(maxRow, e.row);
+    const size_t nrows = c.data.empty() ? 0 : size_t(maxRow) + 1;
+    res->pos.assign(nrows + 1, 0);
+    for (size_t i = 0; i < flat.size();) {
+        size_t j = i;
+        value_t sum = flat[i].val;
+        for (j = i + 1; j < flat.size() && flat[j].row == flat[i].row && flat[j].col == flat[i].col; j++) sum += flat[j].val;
+        res->data.push_back(CSRElement{flat[i].col, sum});
+        res->pos[flat[i].row + 1]++;
+        i = j;
+    }
+    for (size_t r = 0; r < nrows; r++) res->pos[r + 1] += res->pos[r];
+    return res;
+}
+
 // reference cscMulcsr (SimSpGEMM.cpp:265-281), flattened in k order, then the
 // deduplicateCOO fold with a stable sort, rows = maxRowId+1.
 void *ref_spgemm(uint64_t n_k, const uint64_t *a_pos, const void *a_data,

@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "osp_device_count", "osp_create", "osp_destroy", "osp_last_error", "osp_set_workspace_limit", "osp_set_result_limit", "osp_stream",
     "osp_spgemm", "osp_result_dims", "osp_result_copy", "osp_result_copy_rows", "osp_result_device", "osp_result_stats", "osp_result_kernels", "osp_result_free",
     "osp_task_sizes", "osp_csr2csc", "osp_readcoo", "osp_readcoo_buffer", "osp_coo_dims", "osp_coo_copy", "osp_coo_free", "osp_coo2csr",
-    "osp_coo2csr_device", "osp_bias_relu",
+    "osp_coo2csr_device", "osp_bias_relu", "osp_csr2compact", "osp_csc2rawcompact",
     "osp_version", "osp_dist_unique_id", "osp_dist_create", "osp_dist_destroy", "osp_dist_rows", "osp_dist_spgemm",
 ]
 
@@ -136,6 +136,8 @@ def load_library() -> C.CDLL:
     lib.osp_coo_free.restype = None
     lib.osp_coo2csr.argtypes = [u64, vp, vp, vp, u64, i32, vp, vp]
     lib.osp_coo2csr_device.argtypes = [vp, u64, vp, vp, vp, u64, u64, i32, u32, vp, vp]
+    lib.osp_csr2compact.argtypes = [u64, vp, vp, C.POINTER(u64), vp, vp, vp, vp]
+    lib.osp_csc2rawcompact.argtypes = [u64, vp, vp, vp, vp, vp]
     lib.osp_bias_relu.argtypes = [vp, vp, u64, vp, u32, C.POINTER(vp)]
     lib.osp_dist_unique_id.argtypes = [vp]
     lib.osp_dist_create.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
@@ -184,6 +186,31 @@ def coo2csr(coo: COO, N: int, transpose: bool = False) -> CSRMatrix:
     if rc != OSP_OK:
         raise OspError(rc, "coo2csr failed")
     return out
+
+
+def csr2compact(m: CSRMatrix) -> Tuple[np.ndarray, COO]:
+    """csr2compact (SimSpGEMM.cpp:154-219): (group_pos, triplets) -- group j = the (j+1)-th non-zero of every slice."""
+    lib = load_library()
+    n = C.c_uint64()
+    rc = lib.osp_csr2compact(m.NRow(), m.pos.ctypes.data, _ptr(m.data), C.byref(n), None, None, None, None)
+    if rc != OSP_OK:
+        raise OspError(rc, "csr2compact failed")
+    gpos = np.zeros(n.value + 1, np.uint64)
+    rows, cols, vals = np.empty(m.nnz, np.uint32), np.empty(m.nnz, np.uint32), np.empty(m.nnz, np.float32)
+    rc = lib.osp_csr2compact(m.NRow(), m.pos.ctypes.data, _ptr(m.data), C.byref(n), gpos.ctypes.data, _ptr(rows), _ptr(cols), _ptr(vals))
+    if rc != OSP_OK:
+        raise OspError(rc, "csr2compact failed")
+    return gpos, COO(rows, cols, vals)
+
+
+def csc2rawcompact(m: CSRMatrix) -> Tuple[np.ndarray, COO]:
+    """csc2rawcompact (SimSpGEMM.cpp:221-243): (group_pos = pos, triplets with row = idx, col = slice id)."""
+    lib = load_library()
+    rows, cols, vals = np.empty(m.nnz, np.uint32), np.empty(m.nnz, np.uint32), np.empty(m.nnz, np.float32)
+    rc = lib.osp_csc2rawcompact(m.NRow(), m.pos.ctypes.data, _ptr(m.data), _ptr(rows), _ptr(cols), _ptr(vals))
+    if rc != OSP_OK:
+        raise OspError(rc, "csc2rawcompact failed")
+    return m.pos.copy(), COO(rows, cols, vals)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -8,6 +8,9 @@
 //               output-row bins (one LDG.128 per task, no further look-ups in the multiply).
 #pragma once
 #ifdef OSP_CUSIM                      // tests/cusim: the same source on the CPU emulation of the execution model (tests only)
+#ifdef __CUDACC__
+#error "OSP_CUSIM is for the g++ test build under tests/cusim only: the product is compiled by nvcc for sm_100a and has no CPU path"
+#endif
 #include "cusim.h"
 #else
 #include <cuda_runtime.h>

@@ -369,4 +369,59 @@ int osp_coo2csr(uint64_t nnz, const uint32_t *rows, const uint32_t *cols, const 
     return OSP_OK;
 }
 
+// ---- compact COO (CompactCOOMatrix, common.h:52-56) -------------------------------------------------------------
+// csr2compact (SimSpGEMM.cpp:154-219): group j holds the (j+1)-th non-zero of every slice that has one, slices in
+// ascending order; n_groups = the longest slice.  The reference counts the slices per length, suffix-sums the counts
+// and walks the slices with one cursor per group; here the suffix sum is the same and the scatter is a direct
+// computation of every element's place -- element j of slice i goes to group_pos[j] + (slices before i that hold
+// more than j non-zeros) -- found with one counting pass per group length class, no cursors.
+// A matrix without any non-zero gives zero groups (the reference indexes statNNZR[-1] there: undefined behaviour).
+int osp_csr2compact(uint64_t n_major, const uint64_t *pos, const void *data, uint64_t *n_groups, uint64_t *group_pos,
+                    uint32_t *rows, uint32_t *cols, float *vals) {
+    if (!n_groups || (n_major && !pos)) return OSP_ERR_INVALID;
+    uint64_t longest = 0;
+    for (uint64_t i = 0; i < n_major; i++) {
+        if (pos[i + 1] < pos[i]) return OSP_ERR_INVALID;
+        longest = std::max(longest, pos[i + 1] - pos[i]);
+    }
+    *n_groups = longest;
+    if (!group_pos) return OSP_OK;                        // size query
+    const uint64_t nnz = n_major ? pos[n_major] - pos[0] : 0;
+    if (nnz && (!data || !rows || !cols || !vals)) return OSP_ERR_INVALID;
+    // at_least[j] = slices with more than j non-zeros (SimSpGEMM.cpp:172-185)
+    std::vector<uint64_t> at_least(longest + 1, 0);
+    for (uint64_t i = 0; i < n_major; i++) {
+        const uint64_t len = pos[i + 1] - pos[i];
+        if (len) at_least[len - 1]++;
+    }
+    for (uint64_t j = longest; j-- > 1;) at_least[j - 1] += at_least[j];
+    group_pos[0] = 0;
+    for (uint64_t j = 0; j < longest; j++) group_pos[j + 1] = group_pos[j] + at_least[j];
+    const HostElem *in = static_cast<const HostElem *>(data);
+    std::vector<uint64_t> fill(group_pos, group_pos + longest);          // next free place of every group
+    for (uint64_t i = 0; i < n_major; i++) {
+        const HostElem *e = in + pos[i];
+        const uint64_t len = pos[i + 1] - pos[i];
+        for (uint64_t j = 0; j < len; j++) {
+            const uint64_t o = fill[j]++;
+            rows[o] = uint32_t(i); cols[o] = e[j].idx; vals[o] = e[j].val;
+        }
+    }
+    return OSP_OK;
+}
+
+// csc2rawcompact (SimSpGEMM.cpp:221-243): the COO view of a compressed matrix, one group per slice (group_pos = pos):
+// row = the element's index, col = the slice id.
+int osp_csc2rawcompact(uint64_t n_major, const uint64_t *pos, const void *data, uint32_t *rows, uint32_t *cols, float *vals) {
+    if (n_major && !pos) return OSP_ERR_INVALID;
+    const uint64_t nnz = n_major ? pos[n_major] - pos[0] : 0;
+    if (nnz && (!data || !rows || !cols || !vals)) return OSP_ERR_INVALID;
+    const HostElem *in = static_cast<const HostElem *>(data);
+    for (uint64_t s = 0; s < n_major; s++)
+        for (uint64_t e = pos[s]; e < pos[s + 1]; e++) {
+            rows[e - pos[0]] = in[e].idx; cols[e - pos[0]] = uint32_t(s); vals[e - pos[0]] = in[e].val;
+        }
+    return OSP_OK;
+}
+
 }  // extern "C"

@@ -1,5 +1,6 @@
 // Host-only check of include/osp_b200.hpp (no GPU): readcoo + coo2csr<> through the C++ shim.
-// usage: shim_host_check file.mtx  -> prints NRow NCol nnz, then csr pos/data, then csc pos/data
+// usage: shim_host_check file.mtx  -> prints NRow NCol nnz, then csr pos/data, then csc pos/data, then the compact
+// forms (csr2compact of the CSR, csc2rawcompact of the CSC) as "cpos ..." / "cdata row:col:val ..."
 #include <cstdio>
 #include <fstream>
 
@@ -15,6 +16,14 @@ static void print(const CSRMatrix &m) {
     std::printf("\n");
 }
 
+static void print(const CompactCOOMatrix &m) {
+    std::printf("cpos");
+    for (size_t p : m.pos) std::printf(" %zu", p);
+    std::printf("\ncdata");
+    for (auto &e : m.data) std::printf(" %u:%u:%a", e.row, e.col, (double)e.val);
+    std::printf("\n");
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) return 2;
     std::ifstream fin(argv[1]);
@@ -22,8 +31,11 @@ int main(int argc, char **argv) {
     COOMatrix coo = readcoo(fin, NRow, NCol, argc > 2);
     std::printf("%zu %zu %zu\n", NRow, NCol, coo.size());
     try {
-        print(coo2csr(coo, NRow));
-        print(coo2csr<true>(coo, NCol));
+        const CSRMatrix csr = coo2csr(coo, NRow), csc = coo2csr<true>(coo, NCol);
+        print(csr);
+        print(csc);
+        print(csr2compact(csr));
+        print(csc2rawcompact(csc));
     } catch (int code) {
         std::printf("throw %d\n", code);
     }

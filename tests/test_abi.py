@@ -104,6 +104,13 @@ def test_no_cpu_fallback():
     import sys
     src = open(os.path.join(ROOT, "outerspace_b200", "api.py")).read()
     assert "import oracle" not in src and "from oracle" not in src
+    # nor does the product library carry the test-only CPU emulation (tests/cusim): no such symbol, no OSP_CUSIM in the
+    # build recipe, and nvcc refuses the macro (osp_device.cuh)
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", api._LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "cusim" not in syms
+    assert "OSP_CUSIM" not in open(os.path.join(ROOT, "outerspace_b200", "csrc", "Makefile")).read()
+    assert "cusim" not in "".join(open(os.path.join(ROOT, "outerspace_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "outerspace_b200")) if f.endswith(".py"))
 
 
 def test_results_do_not_outlive_their_engine():

@@ -49,6 +49,18 @@ def test_shim_loaders_match_python_mirror_and_oracle(name, sym):
         assert np.array_equal(pos, want.pos) and np.array_equal(data, want.data)
         rc, opos, odata = oracle.coo2csr(coo.rows, coo.cols, coo.vals, N, transpose=tr)
         assert rc == 0 and np.array_equal(pos, opos) and np.array_equal(data, odata)
+    # compact forms (csr2compact / csc2rawcompact, SimSpGEMM.cpp:154-243) through the shim = the Python mirror = the reference
+    csr, csc = osp.coo2csr(coo, nrow), osp.coo2csr(coo, ncol, transpose=True)
+    for k, (m, fn, raw) in enumerate(((csr, osp.csr2compact, False), (csc, osp.csc2rawcompact, True))):
+        cpos = np.array(out[5 + 2 * k].split()[1:], dtype=np.uint64)
+        trip = [t.split(":") for t in out[6 + 2 * k].split()[1:]]
+        gpos, want = fn(m)
+        assert np.array_equal(cpos, gpos)
+        assert [int(t[0]) for t in trip] == list(want.rows) and [int(t[1]) for t in trip] == list(want.cols)
+        assert np.array_equal(np.array([float.fromhex(t[2]) for t in trip], np.float32).view(np.uint32), want.vals.view(np.uint32))
+        if oracle.ref_available():
+            rpos, rr, rc_, rv = oracle.ref_compact(m.pos, m.data, raw=raw)
+            assert np.array_equal(gpos, rpos) and np.array_equal(want.rows, rr) and np.array_equal(want.cols, rc_)
 
 
 @pytest.mark.gpu

@@ -162,3 +162,9 @@ def test_concurrent_blocks(monkeypatch):
         assert np.array_equal(csc.pos, a_csc.pos) and np.array_equal(csc.data, a_csc.data)
     finally:
         eng.close()
+
+
+def test_compact_operand_product(engine):
+    """SURVEY 8a row a16 on the emulated engine: compactMulcsr's merged equivalent (tests/test_compact.py)."""
+    from test_compact import compact_product_check
+    compact_product_check(engine)
