@@ -134,11 +134,26 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
         const uint64_t p0 = a_pos[row];
         const uint64_t R = a_pos[row + 1] - p0;
         Elem *out = VALUES ? rows.out(x, row) : nullptr;
+        // Rows whose runs fit one group and one pass (the common case: <= min(RUNS, THREADS) non-zeros in the row of A)
+        // keep their run in registers: A's element, the row of the band index, and the segment bounds of the current
+        // band -- the bound of the band after is loaded one band ahead, so no load sits between two bands.
+        const bool one_group = R <= uint64_t(RUNS < THREADS ? RUNS : THREADS);
+        Elem my_ak; my_ak.idx = 0; my_ak.val = 0.f;
+        const uint32_t *my_bp = bandptr;
+        uint32_t cur_lo = 0, cur_hi = 0;
+        if (one_group && tid < R) {
+            my_ak = a_data[p0 + tid];
+            my_bp = bandptr + uint64_t(my_ak.idx) * nb1;
+            cur_lo = my_bp[0];
+            cur_hi = n_bands ? my_bp[1] : cur_lo;
+        }
         uint32_t my_count = 0;                      // VALUES=false: columns seen, summed over this thread's bitmap words
         uint64_t produced = 0;                      // VALUES=true: elements of the row already written
         for (uint32_t band = 0; band < n_bands; band++) {
             const uint64_t band_lo = uint64_t(band) * BAND;
             bool touched = false;                                          // uniform: some run has an element in this band
+            uint32_t nxt_hi = 0;
+            if (one_group && tid < R && band + 2 <= n_bands) nxt_hi = my_bp[band + 2];
             for (uint64_t g0 = 0; g0 < R; g0 += RUNS) {
                 const uint32_t G = uint32_t(min(uint64_t(RUNS), R - g0));
                 // ---- the segment of every run of the group inside this band ----
@@ -146,7 +161,11 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
                 for (uint32_t r0 = 0; r0 < G; r0 += THREADS) {
                     const uint32_t r = r0 + tid;
                     uint32_t seg = 0;
-                    if (r < G) {
+                    if (r < G && one_group) {
+                        seg = cur_hi - cur_lo;
+                        s_lo[r] = cur_lo;
+                        if (VALUES) s_a[r] = my_ak.val;
+                    } else if (r < G) {
                         const Elem ak = a_data[p0 + g0 + r];
                         const uint32_t *bp = bandptr + uint64_t(ak.idx) * nb1 + band;
                         const uint32_t lo = bp[0];
@@ -211,6 +230,7 @@ __device__ __forceinline__ void long_rows_sweep(const uint64_t *__restrict__ a_p
                 }
                 __syncthreads();                                           // s_pre / s_lo are rewritten by the next group
             }
+            cur_lo = cur_hi; cur_hi = nxt_hi;                              // (one_group) the next band's segment
             // ---- the band is complete: count or emit its columns, reset it ----
             if (!touched) continue;                                        // nothing was set: bitmap and accumulator are still clean
             if (!VALUES) {
