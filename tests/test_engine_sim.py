@@ -16,6 +16,7 @@ import subprocess
 
 import numpy as np
 import pytest
+import scipy.sparse as sp
 
 import oracle
 import outerspace_b200 as osp
@@ -168,3 +169,24 @@ def test_compact_operand_product(engine):
     """SURVEY 8a row a16 on the emulated engine: compactMulcsr's merged equivalent (tests/test_compact.py)."""
     from test_compact import compact_product_check
     compact_product_check(engine)
+
+
+def test_sweep_row_with_more_runs_than_a_group(engine):
+    """A row of A with more non-zeros than the sweep takes in one group (512): two and three groups per band, the
+    group boundary inside a band, next to rows that fit one group (kept in registers)."""
+    rng = np.random.default_rng(51)
+    k, cols = 1400, 1 << 16
+    A = sp.lil_matrix((6, k), dtype=np.float32)
+    for r, n in enumerate((1300, 40, 513, 512, 0, 1024)):
+        sel = rng.choice(k, size=n, replace=False)
+        A[r, sel] = (rng.standard_normal(n) + 2).astype(np.float32)
+    B = rand_sparse(rng, k, cols, 12.0 / cols).tolil()
+    for kk in rng.choice(k, size=30, replace=False):                       # a few long rows of B: segments of many elements
+        c = rng.choice(cols, size=400, replace=False)
+        B[kk, c] = rng.standard_normal(400).astype(np.float32)
+    a_csc, a_csr, b_csr = operands(A.tocsr(), B.tocsr())
+    want, prod = oracle_spgemm(a_csc, b_csr, rows_override=6)
+    res = engine.spgemm(a_csr, b_csr, a_is_csr=True, cols_b=cols, rows_c=6, flags=api.OSP_LONGROW_SWEEP | api.OSP_PROFILE_KERNELS)
+    got = res.to_host(); st = res.stats(); names = {n for n, _ in res.kernel_times()}; res.free()
+    assert any("k_long_fill" in n for n in names) and st["rows_long"] >= 3
+    assert_bit_exact(got, want, "rows of A with up to 1300 runs")
