@@ -3,7 +3,7 @@ reference functions compiled into oracle/_ref, and the engine's product from a c
 reference's compactMulcsr (SimSpGEMM.cpp:247-263) with its partial products folded in group order.
 
 The format conversions are host code in the reference and host code here (C ABI: osp_csr2compact,
-osp_csc2rawcompact); the product is the GPU engine (test_compact_product_on_gpu) -- the same test body runs on the
+osp_csc2rawcompact); the product is the GPU engine (tests/test_gpu_zzy_compact.py) -- the same test body runs on the
 emulated engine in the CPU suite (tests/test_engine_sim.py)."""
 import numpy as np
 import pytest
@@ -96,8 +96,3 @@ def compact_product_check(engine):
     dup = COO(np.array([0, 1, 1], np.uint32), np.array([2, 3, 3], np.uint32), np.ones(3, np.float32))
     with pytest.raises(osp.DuplicateEntry):
         engine.coo2csr(dup, 2, n_other=4)
-
-
-@pytest.mark.gpu
-def test_compact_product_on_gpu(engine):
-    compact_product_check(engine)
