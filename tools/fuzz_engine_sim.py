@@ -31,7 +31,27 @@ def build(out):
                     os.path.join(sim, "engine_sim.cpp"), os.path.join(csrc, "osp_host.cpp"), "-lpthread"], check=True)
 
 
+def draw_wide_case(rng):
+    """A few rows of A with hundreds to > 1000 non-zeros (more runs than one sweep group of 512) over a wide column range."""
+    k = int(rng.integers(600, 1500))
+    cols = int(rng.choice([rng.integers(16385, 70000), rng.integers(70000, 300000)]))
+    m = int(rng.integers(2, 8))
+    A = sp.lil_matrix((m, k), dtype=np.float32)
+    for r in range(m):
+        n = int(rng.choice([0, rng.integers(1, 60), rng.integers(400, 520), rng.integers(513, k)]))
+        sel = rng.choice(k, size=n, replace=False)
+        A[r, sel] = (rng.standard_normal(n) + 2).astype(np.float32)
+    B = sp.random(k, cols, density=float(rng.choice([4, 12, 30])) / cols, format="csr", random_state=int(rng.integers(1 << 31)), dtype=np.float32,
+                  data_rvs=lambda n: (rng.standard_normal(n) * 2 + 0.1).astype(np.float32))
+    A = sp.csr_matrix(A)
+    A.eliminate_zeros()
+    B.eliminate_zeros()
+    return A, B, cols
+
+
 def draw_case(rng):
+    if rng.random() < 0.1:
+        return draw_wide_case(rng)
     cols = int(rng.choice([rng.integers(1, 64), rng.integers(64, 4096), rng.integers(4096, 16385), rng.integers(16385, 200000),
                            rng.integers(200000, 1 << 21), (1 << 23) + int(rng.integers(1, 1 << 22))]))
     m = int(rng.integers(1, 120))
