@@ -25,7 +25,7 @@ struct cudaDeviceProp { int multiProcessorCount; size_t totalGlobalMem; int l2Ca
 namespace cusim {
 inline size_t &device_bytes() { static size_t b = 0; return b; }          // live "device" allocations
 inline size_t device_total() {
-    if (const char *e = std::getenv("CUSIM_DEVICE_MB")) return size_t(std::strtoull(e, nullptr, 10)) << 20;
+    if (const char *e = std::getenv("CUSIM_DEVICE_MB")) return size_t(std::strtod(e, nullptr) * double(1 << 20));
     return size_t(4) << 30;
 }
 inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }

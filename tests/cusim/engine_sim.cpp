@@ -14,4 +14,5 @@ void osp_dist_destroy(osp_dist *) {}
 int osp_dist_rows(const osp_dist *, uint64_t, uint64_t *, uint64_t *) { return OSP_ERR_UNSUPPORTED; }
 int osp_dist_spgemm(osp_dist *, const osp_spgemm_args *, osp_result **) { return OSP_ERR_UNSUPPORTED; }
 const char *cusim_marker(void) { return "tests/cusim build: CPU emulation, test infrastructure only"; }
+unsigned long long cusim_device_bytes(void) { return cusim::device_bytes(); }      // live "device" allocations (leak checks)
 }

@@ -190,3 +190,69 @@ def test_sweep_row_with_more_runs_than_a_group(engine):
     got = res.to_host(); st = res.stats(); names = {n for n, _ in res.kernel_times()}; res.free()
     assert any("k_long_fill" in n for n in names) and st["rows_long"] >= 3
     assert_bit_exact(got, want, "rows of A with up to 1300 runs")
+
+
+def _live_bytes(lib):
+    lib.cusim_device_bytes.restype = __import__("ctypes").c_ulonglong
+    return int(lib.cusim_device_bytes())
+
+
+def test_no_device_memory_is_leaked(emulated_library):
+    """Every allocation of a context -- scratch, staged operands, results, including those of calls that fail half
+    way -- is back when the context is destroyed (the emulated runtime counts live bytes; a real device cannot be
+    asked this cheaply)."""
+    before = _live_bytes(emulated_library)
+    rng = np.random.default_rng(61)
+    A, B = rand_sparse(rng, 60, 50, 0.2), rand_sparse(rng, 50, 70000, 0.01)
+    a_csc, a_csr, b_csr = operands(A, B)
+    eng = osp.Engine(0)
+    r1 = eng.spgemm(a_csr, b_csr, a_is_csr=True)
+    r2 = eng.spgemm(a_csc, b_csr, flags=api.OSP_LONGROW_SWEEP)
+    r1.free()
+    with pytest.raises(osp.OspError):                                   # k-dimension mismatch: fails before any launch
+        eng.spgemm(a_csc, pack(b_csr.pos[:-3], b_csr.data[: int(b_csr.pos[-4])]))
+    bad = a_csr.data.copy(); bad["idx"][0] = 10_000                     # index out of range: fails after the symbolic pass
+    with pytest.raises(osp.OspError) as ei:
+        eng.spgemm(pack(a_csr.pos, bad), b_csr, a_is_csr=True)
+    assert ei.value.code == api.OSP_ERR_INDEX
+    eng.set_result_limit(4096)                                          # C cannot fit: fails between two row blocks
+    with pytest.raises(osp.OspError) as ei:
+        eng.spgemm(a_csr, b_csr, a_is_csr=True, cols_b=70000)
+    assert ei.value.code == api.OSP_ERR_OOM
+    eng.set_result_limit(0)
+    B2 = rand_sparse(rng, 50, 90, 0.3)
+    r3 = eng.spgemm(a_csr, operands(A, B2)[2], a_is_csr=True, cols_b=90)
+    r4 = eng.bias_relu(r3, 90, np.linspace(-1, 1, 90, dtype=np.float32))   # noqa: F841 -- left alive on purpose
+    assert _live_bytes(emulated_library) > before
+    eng.close()                                                         # frees r2, r3 and r4, which are still alive
+    assert _live_bytes(emulated_library) == before
+
+
+def test_device_out_of_memory_is_reported_not_fatal(emulated_library, monkeypatch):
+    """A device too small for the call: OSP_ERR_OOM from whichever allocation fails, nothing leaked, and the context
+    works again once there is room."""
+    rng = np.random.default_rng(62)
+    A, B = rand_sparse(rng, 300, 200, 0.2), rand_sparse(rng, 200, 400, 0.2)
+    a_csc, a_csr, b_csr = operands(A, B)
+    want, prod = oracle_spgemm(a_csc, b_csr)
+    eng = osp.Engine(0)
+    try:
+        base = _live_bytes(emulated_library)
+        failures = 0
+        for extra_kb in (16, 64, 256, 1024, 4096, 16384):               # ever larger devices: the call fails at ever later allocations
+            monkeypatch.setenv("CUSIM_DEVICE_MB", str((base + extra_kb * 1024) / (1 << 20)))
+            try:
+                res = eng.spgemm(a_csr, b_csr, a_is_csr=True)
+            except osp.OspError as e:
+                assert e.code == api.OSP_ERR_OOM, str(e)
+                failures += 1
+                continue
+            got = res.to_host(); res.free()
+            assert_bit_exact(got, want, f"device with {extra_kb} KB to spare")
+        assert failures >= 2
+        monkeypatch.delenv("CUSIM_DEVICE_MB")
+        res = eng.spgemm(a_csr, b_csr, a_is_csr=True)
+        got = res.to_host(); res.free()
+        assert_bit_exact(got, want, "after the failed calls")
+    finally:
+        eng.close()
