@@ -25,7 +25,11 @@ struct DevBuf {
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
+#ifdef OSP_CUSIM
+        size_t want = bytes;                 // tests/cusim under AddressSanitizer: no head-room that would hide an overrun
+#else
         size_t want = bytes + bytes / 8 + 256;
+#endif
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
         if (e == cudaSuccess) cap = want; else p = nullptr;

@@ -29,21 +29,24 @@ inline size_t device_total() {
     return size_t(4) << 30;
 }
 inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-struct Header { size_t bytes; size_t pad[7]; };                           // keeps the 64-byte alignment of the payload
+// A "device" allocation: 256 bytes of header (its size), then the payload, 256-byte aligned like cudaMalloc's.  The block
+// ends 16 bytes after the payload -- the slack a bulk copy may read, its size being rounded up to 16 bytes -- so that
+// under AddressSanitizer (tools/fuzz_engine_sim.py --asan) any access of a kernel beyond that is reported.
+constexpr size_t DEV_HEADER = 256, DEV_SLACK = 16;
 inline cudaError_t dev_alloc(void **p, size_t bytes) {
     if (device_bytes() + bytes > device_total()) { *p = nullptr; return cudaErrorMemoryAllocation; }
-    void *raw = std::aligned_alloc(256, ((sizeof(Header) + bytes + 64 + 255) / 256) * 256 + 256);   // slack: bulk copies round up to 16 bytes
-    if (!raw) { *p = nullptr; return cudaErrorMemoryAllocation; }
-    std::memset(raw, 0xCD, sizeof(Header) + bytes + 64);                    // fresh device memory is garbage
-    static_cast<Header *>(raw)->bytes = bytes;
+    void *raw = nullptr;
+    if (posix_memalign(&raw, 256, DEV_HEADER + bytes + DEV_SLACK) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    std::memset(raw, 0xCD, DEV_HEADER + bytes + DEV_SLACK);                 // fresh device memory is garbage
+    *static_cast<size_t *>(raw) = bytes;
     device_bytes() += bytes;
-    *p = static_cast<char *>(raw) + 256;
+    *p = static_cast<char *>(raw) + DEV_HEADER;
     return cudaSuccess;
 }
 inline void dev_free(void *p) {
     if (!p) return;
-    void *raw = static_cast<char *>(p) - 256;
-    device_bytes() -= static_cast<Header *>(raw)->bytes;
+    void *raw = static_cast<char *>(p) - DEV_HEADER;
+    device_bytes() -= *static_cast<size_t *>(raw);
     std::free(raw);
 }
 }  // namespace cusim

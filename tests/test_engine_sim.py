@@ -31,7 +31,9 @@ CSRC = os.path.join(HERE, "..", "outerspace_b200", "csrc")
 @pytest.fixture(scope="module", autouse=True)
 def emulated_library(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("cusim_engine") / "libosp_b200_cusim.so")
-    cmd = ["g++", "-O1", "-std=c++17", "-x", "c++", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas",
+    # CUSIM_ASAN=1 (with LD_PRELOAD=$(g++ -print-file-name=libasan.so) for the interpreter): AddressSanitizer build
+    asan = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("CUSIM_ASAN") == "1" else []
+    cmd = ["g++", "-O1"] + asan + ["-std=c++17", "-x", "c++", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas",
            "-Wno-unused-function", "-I", os.path.join(HERE, "cusim"), "-I", CSRC, "-o", out,
            os.path.join(HERE, "cusim", "engine_sim.cpp"), os.path.join(CSRC, "osp_host.cpp"), "-lpthread"]
     subprocess.run(cmd, check=True)

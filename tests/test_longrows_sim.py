@@ -28,7 +28,9 @@ CONFIGS = {0: (64, 64, 8), 1: (128, 256, 32), 2: (32, 32, 64), 3: (96, 1024, 5)}
 def sim(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("cusim") / "liblongrows_sim.so")
     src = os.path.join(HERE, "cusim", "longrows_sim.cpp")
-    cmd = ["g++", "-O1", "-std=c++17", "-x", "c++", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas",
+    # CUSIM_ASAN=1 (with LD_PRELOAD=$(g++ -print-file-name=libasan.so) for the interpreter): AddressSanitizer build
+    asan = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("CUSIM_ASAN") == "1" else []
+    cmd = ["g++", "-O1"] + asan + ["-std=c++17", "-x", "c++", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas",
            "-I", os.path.join(HERE, "cusim"), "-I", CSRC, "-o", out, src]
     subprocess.run(cmd, check=True)
     lib = C.CDLL(out)

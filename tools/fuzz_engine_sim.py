@@ -2,7 +2,7 @@
 """Fuzz campaign: the emulated engine (tests/cusim, the product's sources on the CPU emulation of the CUDA execution
 model) against the oracle on random operands of every shape class -- a campaign the GPU budget never has room for.
 
-    python tools/fuzz_engine_sim.py --cases 300 --seed 1 [--schedule random:7] [--resident 4]
+    python tools/fuzz_engine_sim.py --cases 300 --seed 1 [--schedule random:7] [--resident 4] [--asan]
 
 Every case draws: dimensions, densities, a column range (small: bitmap/dense kernels; medium; > 2^23: 64-bit chain
 keys), a few rows made long on purpose (medium and xl rows), duplicates-free operands in the reference layout, CSR or
@@ -24,10 +24,10 @@ import numpy as np
 import scipy.sparse as sp
 
 
-def build(out):
+def build(out, asan=False):
     csrc = os.path.join(ROOT, "outerspace_b200", "csrc")
     sim = os.path.join(ROOT, "tests", "cusim")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-x", "c++", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-I", sim, "-I", csrc, "-o", out,
+    subprocess.run(["g++", "-O1"] + (["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []) + ["-std=c++17", "-x", "c++", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-I", sim, "-I", csrc, "-o", out,
                     os.path.join(sim, "engine_sim.cpp"), os.path.join(csrc, "osp_host.cpp"), "-lpthread"], check=True)
 
 
@@ -86,15 +86,21 @@ def main():
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--schedule", default="")
+    ap.add_argument("--asan", action="store_true", help="AddressSanitizer build: every access of a kernel or of the host code outside an "
+                    "allocation of the emulated device aborts the run (re-executes itself with libasan preloaded)")
     ap.add_argument("--resident", type=int, default=1, help="blocks resident at a time (CUSIM_RESIDENT = CUSIM_SMS): > 1 runs them on OS threads")
     args = ap.parse_args()
+    if args.asan and "libasan" not in os.environ.get("LD_PRELOAD", ""):
+        asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True, check=True).stdout.strip()
+        env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1")
+        os.execve(sys.executable, [sys.executable] + sys.argv, env)
     if args.schedule:
         os.environ["CUSIM_SCHEDULE"] = args.schedule
     if args.resident > 1:
         os.environ["CUSIM_RESIDENT"] = os.environ["CUSIM_SMS"] = str(args.resident)
     tmp = tempfile.mkdtemp(prefix="osp_fuzz_")
     lib = os.path.join(tmp, "libosp_b200_cusim.so")
-    build(lib)
+    build(lib, args.asan)
     import outerspace_b200 as osp
     from outerspace_b200 import api
     from helpers import assert_bit_exact, operands, oracle_spgemm
@@ -133,7 +139,7 @@ def main():
             seen["products"] += prod
         finally:
             eng.close()
-    print(f"fuzz ok: {args.cases} cases, seed {args.seed}, schedule '{args.schedule or 'forward'}', {args.resident} resident block(s), {time.time() - t0:.0f} s; "
+    print(f"fuzz ok: {args.cases} cases, seed {args.seed}, schedule '{args.schedule or 'forward'}', {args.resident} resident block(s){', AddressSanitizer' if args.asan else ''}, {time.time() - t0:.0f} s; "
           f"calls with sweep {seen['sweep']}, fused dense {seen['fused']}, row blocks {seen['blocks']}, xl rows {seen['xl']}, "
           f"medium rows {seen['long']}; {seen['products']} partial products in total")
 
