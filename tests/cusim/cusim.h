@@ -236,7 +236,8 @@ template <class F> inline void run_block(unsigned bx, unsigned block, size_t dyn
     Block b;
     b.fibers.resize(block);
     b.alive = block;
-    b.dyn.assign(dyn_bytes + 16, 0xCD);
+    static const int fill = [] { const char *e = std::getenv("CUSIM_FILL"); return e ? int(std::strtol(e, nullptr, 0)) & 0xFF : 0xCD; }();
+    b.dyn.assign(dyn_bytes + 16, (unsigned char)fill);             // shared memory starts as garbage too
     b.body = [&body] { body(); };
     g_block = &b;
     blockIdx = dim3(bx);

@@ -37,7 +37,8 @@ inline cudaError_t dev_alloc(void **p, size_t bytes) {
     if (device_bytes() + bytes > device_total()) { *p = nullptr; return cudaErrorMemoryAllocation; }
     void *raw = nullptr;
     if (posix_memalign(&raw, 256, DEV_HEADER + bytes + DEV_SLACK) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
-    std::memset(raw, 0xCD, DEV_HEADER + bytes + DEV_SLACK);                 // fresh device memory is garbage
+    static const int fill = [] { const char *e = std::getenv("CUSIM_FILL"); return e ? int(std::strtol(e, nullptr, 0)) & 0xFF : 0xCD; }();
+    std::memset(raw, fill, DEV_HEADER + bytes + DEV_SLACK);                 // fresh device memory is garbage (CUSIM_FILL picks which)
     *static_cast<size_t *>(raw) = bytes;
     device_bytes() += bytes;
     *p = static_cast<char *>(raw) + DEV_HEADER;
