@@ -57,6 +57,10 @@ extern "C" {
                                     computes and merges them in shared memory.  Same bits.  Ignored with
                                     OSP_KSLICE_ORDER.  Environment: OSP_LONGROW_SWEEP=1 turns it on for every call of a
                                     context, OSP_LONGROW_SWEEP_MIN=<partial products> raises the row threshold */
+#define OSP_FUSED_SHORT    256u  /* EXPERIMENTAL, off by default, not yet run on a B200 (CPU emulation only): the tiles of short
+                                    rows never go through the bins -- the merge chain computes a tile's partial products
+                                    straight into its shared-memory stage (k_merge_chain_fused), k_multiply only serves the
+                                    long rows.  Same bits.  Ignored with OSP_KSLICE_ORDER.  Environment: OSP_FUSED_SHORT=1 */
 #define OSP_PROFILE_PHASES   8u  /* synchronise between phases so that stats.ms_* are per-phase times */
 
 #define OSP_PROFILE_KERNELS 16u  /* record a CUDA-event pair around every kernel launch (osp_result_kernels) */

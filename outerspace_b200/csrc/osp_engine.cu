@@ -72,6 +72,9 @@ struct osp_ctx {
     bool sweep_env = false;                 // OSP_LONGROW_SWEEP=1
     uint64_t sweep_min = 0;                 // OSP_LONGROW_SWEEP_MIN: fewest partial products of a swept row (0: every xl row)
     int sweep_occ = 1;                      // resident CTAs per SM of k_long_fill
+    // OSP_FUSED_SHORT (opt-in): short-row tiles computed inside the merge chain
+    bool fused_short_ok = false, fused_short_env = false;
+    int chain_fused_occ[3] = {1, 1, 1};
     std::vector<cudaEvent_t> events;
     size_t events_used = 0;
     // OSP_PROFILE_KERNELS: one event pair per launch
@@ -270,6 +273,11 @@ struct MergeJob {
     uint64_t sweep_min = ~0ull;             // fewest partial products of a swept row, > MT_XL (k_merge_xl leaves those alone)
     bool sweeps_every_xl() const { return sweep && sweep_min <= MT_XL + 1; }
     const uint32_t *bandptr = nullptr;      // band index of B (k_long_bands)
+    // OSP_FUSED_SHORT: the chain computes the short rows' partial products itself (k_merge_chain_fused)
+    bool fused_short = false;
+    const uint64_t *run_off = nullptr;
+    const uint32_t *task_bs = nullptr;
+    uint64_t m_a = 0;
     const uint64_t *a_pos = nullptr;
     const Elem *a_data = nullptr, *b_data = nullptr;
 };
@@ -355,6 +363,14 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
 #define MC_ARGS row_bin, bin_base, bins, ctx->tile_row.as<uint32_t>(), t0, n_chain, uniq, ctx->tile_state.as<uint64_t>(), ctx->d_sc, \
                 carry_slot, job.c_pos, job.c_data, bm_wpl, job.long_thresh
     const int variant = bm_words ? 2 : job.idx_range <= (1ull << 23) ? 0 : 1;
+    if (job.fused_short) {
+        const FusedSrc fs{job.a_pos, job.a_data, job.run_off, job.task_bs, job.b_data, job.m_a};
+        const unsigned int gridf = std::min<unsigned>(n_chain, unsigned(ctx->sm_count) * unsigned(ctx->chain_fused_occ[variant]));
+        if (variant == 2) LAUNCH(ctx, (k_merge_chain_fused<uint32_t, true>), gridf, MC_THREADS, sizeof(MergeChainSmem<true>), MC_ARGS, fs);
+        else if (variant == 0) LAUNCH(ctx, (k_merge_chain_fused<uint32_t, false>), gridf, MC_THREADS, sizeof(MergeChainSmem<false>), MC_ARGS, fs);
+        else LAUNCH(ctx, (k_merge_chain_fused<uint64_t, false>), gridf, MC_THREADS, sizeof(MergeChainSmem<false>), MC_ARGS, fs);
+        return OSP_OK;
+    }
     const unsigned int grid = std::min<unsigned>(n_chain, unsigned(ctx->sm_count) * unsigned(ctx->chain_occ[variant]));   // persistent CTAs
     if (variant == 2) LAUNCH(ctx, (k_merge_chain<uint32_t, true>), grid, MC_THREADS, sizeof(MergeChainSmem<true>), MC_ARGS);
     else if (variant == 0) LAUNCH(ctx, (k_merge_chain<uint32_t, false>), grid, MC_THREADS, sizeof(MergeChainSmem<false>), MC_ARGS);
@@ -550,6 +566,22 @@ int osp_create(int device, osp_ctx **out) {
         const char *env = std::getenv("OSP_LONGROW_SWEEP");
         ctx->sweep_env = env && env[0] && env[0] != '0';
         if (const char *m = std::getenv("OSP_LONGROW_SWEEP_MIN")) ctx->sweep_min = std::strtoull(m, nullptr, 10);
+    }
+    {   // OSP_FUSED_SHORT: opt-in as well
+        auto f32 = k_merge_chain_fused<uint32_t, false>;
+        auto f64 = k_merge_chain_fused<uint64_t, false>;
+        auto fbm = k_merge_chain_fused<uint32_t, true>;
+        ctx->fused_short_ok =
+            cudaFuncSetAttribute(f32, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MergeChainSmem<false>))) == cudaSuccess &&
+            cudaFuncSetAttribute(f64, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MergeChainSmem<false>))) == cudaSuccess &&
+            cudaFuncSetAttribute(fbm, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MergeChainSmem<true>))) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->chain_fused_occ[0], f32, MC_THREADS, sizeof(MergeChainSmem<false>)) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->chain_fused_occ[1], f64, MC_THREADS, sizeof(MergeChainSmem<false>)) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->chain_fused_occ[2], fbm, MC_THREADS, sizeof(MergeChainSmem<true>)) == cudaSuccess;
+        if (!ctx->fused_short_ok) cudaGetLastError();
+        for (int &o : ctx->chain_fused_occ) o = std::max(o, 1);
+        const char *env = std::getenv("OSP_FUSED_SHORT");
+        ctx->fused_short_env = env && env[0] && env[0] != '0';
     }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -761,21 +793,41 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         job.sweep_min = std::max<uint64_t>({ctx->sweep_min, MT_XL + 1, LR_MIN_PER_BAND * lr_bands});
         job.a_pos = dA_pos; job.a_data = dA_data; job.b_data = dB_data;
     }
+    // ---- OSP_FUSED_SHORT (opt-in): no bins for the tiles of short rows; the multiply only serves the long rows
+    const bool fused_short = ctx->fused_short_ok && ((args->flags & OSP_FUSED_SHORT) || ctx->fused_short_env) &&
+                             !(args->flags & OSP_KSLICE_ORDER) && rowwise && !fused && nnz_a > 0;
+    if (fused_short) {
+        job.fused_short = true;
+        job.run_off = run_off; job.task_bs = task_bs; job.m_a = m_a;
+        job.a_pos = dA_pos; job.a_data = dA_data; job.b_data = dB_data;
+    }
     const uint64_t cap_bound = std::max<uint64_t>(args->cols_b ? ctx->h_sc->cap_bound : std::min<uint64_t>(ctx->h_sc->cap_bound, P), 1);
     unsigned int xl_ctas = 0;
     rc = reserve_merge(ctx, job, xl_ctas);
     if (rc) return bail(rc);
-    if (sweep) {
+    const bool masked = sweep || fused_short;            // the multiply reads a task bitmap
+    if (masked) {
         rc = [&]() -> int {
             const uint64_t words = (nnz_a + 31) / 32 + 1;
             CU(ctx, ctx->swept.reserve(words * 4));
             CU(ctx, cudaMemsetAsync(ctx->swept.p, 0, words * 4, ctx->stream));
-            LAUNCH(ctx, k_mark_swept, grid_for(uint64_t(job.n_xl) * 32, 256, unsigned(ctx->sm_count) * 8u), 256, 0, dA_pos,
-                   ctx->xl_list.as<uint32_t>(), ctx->d_sc, ctx->row_bin.as<uint64_t>(), job.sweep_min, ctx->swept.as<uint32_t>());
-            CU(ctx, ctx->lr_bands.reserve(lr_index_bytes));
-            LAUNCH(ctx, k_long_bands, grid_for(n_k * (lr_bands + 1), 256, 1u << 30), 256, 0, dB_pos, dB_data, n_k, uint32_t(LR_BAND),
-                   uint32_t(lr_bands), ctx->lr_bands.as<uint32_t>());
-            job.bandptr = ctx->lr_bands.as<uint32_t>();
+            if (fused_short) {
+                // marked = goes to the bins: medium rows, and the xl rows the sweep leaves alone
+                if (job.n_xl + job.n_long)
+                    LAUNCH(ctx, k_mark_binned, grid_for(uint64_t(job.n_xl + job.n_long) * 32, 256, unsigned(ctx->sm_count) * 8u), 256, 0, dA_pos,
+                           ctx->xl_list.as<uint32_t>(), ctx->long_list.as<uint32_t>(), ctx->d_sc, ctx->row_bin.as<uint64_t>(),
+                           sweep ? job.sweep_min : ~0ull, ctx->swept.as<uint32_t>());
+            } else {
+                // marked = swept: computed by k_long_fill, not by the multiply
+                LAUNCH(ctx, k_mark_swept, grid_for(uint64_t(job.n_xl) * 32, 256, unsigned(ctx->sm_count) * 8u), 256, 0, dA_pos,
+                       ctx->xl_list.as<uint32_t>(), ctx->d_sc, ctx->row_bin.as<uint64_t>(), job.sweep_min, ctx->swept.as<uint32_t>());
+            }
+            if (sweep) {
+                CU(ctx, ctx->lr_bands.reserve(lr_index_bytes));
+                LAUNCH(ctx, k_long_bands, grid_for(n_k * (lr_bands + 1), 256, 1u << 30), 256, 0, dB_pos, dB_data, n_k, uint32_t(LR_BAND),
+                       uint32_t(lr_bands), ctx->lr_bands.as<uint32_t>());
+                job.bandptr = ctx->lr_bands.as<uint32_t>();
+            }
             return OSP_OK;
         }();
         if (rc) return bail(rc);
@@ -888,9 +940,11 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         }
         ev_blocks.push_back(b == 0 ? ev_sym : next_event(ctx));     // nothing is recorded between the hand-over and the multiply
         if (forked && b == 0) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-        if (rowwise && sweep)
-            rc = launch_multiply(ctx, TaskSrcSoASwept{TaskSrcSoA{dA_data, run_off, task_bs}, ctx->swept.as<uint32_t>()}, blk_e[b], blk_e[b + 1],
-                                 p_block, dB_data, bins, bin0);
+        if (rowwise && fused_short && job.n_xl + job.n_long == 0)
+            rc = OSP_OK;                                                  // every tile is computed inside the chain
+        else if (rowwise && masked)
+            rc = launch_multiply(ctx, TaskSrcSoASwept{TaskSrcSoA{dA_data, run_off, task_bs}, ctx->swept.as<uint32_t>(), fused_short ? 0u : 1u},
+                                 blk_e[b], blk_e[b + 1], p_block, dB_data, bins, bin0);
         else if (rowwise) rc = launch_multiply(ctx, TaskSrcSoA{dA_data, run_off, task_bs}, blk_e[b], blk_e[b + 1], p_block, dB_data, bins, bin0);
         else rc = launch_multiply(ctx, TaskSrcAoS{ctx->tasks.as<Task>()}, 0, nnz_a, p_block, dB_data, bins, bin0);
         if (rc) return bail(rc);

@@ -378,12 +378,13 @@ struct TaskSrcSoA {
         bs = task_bs[i];
     }
 };
-struct TaskSrcSoASwept {        // row order of A minus the tasks of the rows the fused band sweep takes (osp_longrows.cuh)
-    TaskSrcSoA src;
-    const uint32_t *swept;      // one bit per task, set by k_mark_swept
+struct TaskSrcSoASwept {        // row order of A minus the tasks somebody else computes: the rows of the fused band sweep
+    TaskSrcSoA src;             // (osp_longrows.cuh; bits set by k_mark_swept, skip = 1) or, with OSP_FUSED_SHORT, every
+    const uint32_t *mask;       // task that is NOT marked as belonging to a long row (k_mark_binned, skip = 0)
+    uint32_t skip;              // the bit value of a task that emits nothing
     __device__ __forceinline__ void load(uint64_t i, uint32_t &bs, float &a, uint64_t &off, uint32_t &len) const {
         src.load(i, bs, a, off, len);
-        if ((swept[i >> 5] >> (i & 31)) & 1u) len = 0;
+        if (((mask[i >> 5] >> (i & 31)) & 1u) == skip) len = 0;
     }
 };
 
@@ -1083,12 +1084,27 @@ __device__ __forceinline__ uint64_t lb_resolve(uint64_t *state, uint32_t idx, ui
     return exclusive;
 }
 
-template <class K, bool BM>
-__global__ void __launch_bounds__(MC_THREADS, BM ? 2 : MC_OCC)
-k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, const Elem *__restrict__ bins,
-              const uint32_t *__restrict__ tile_row, const uint32_t t0, const uint32_t n_chain,
-              const uint32_t *__restrict__ uniq, uint64_t *tile_state, DevScalars *sc, const int carry_slot,
-              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, const uint32_t bm_wpl, const uint32_t long_thresh) {
+// FUSED (opt-in, OSP_FUSED_SHORT; not yet run on a B200): the tiles of short rows never go through the bins.  With the
+// row-order multiply a tile's partial products are the runs of consecutive tasks (run_off is the prefix the plan cut
+// the tiles from), so the CTA computes them straight into its stage -- the warp-flat walk of k_multiply with
+// shared-memory stores -- where the default path bulk-copies what k_multiply wrote to HBM.  Long rows (tiles of their
+// own) still come merged from the bins.
+struct FusedSrc {
+    const uint64_t *a_pos;      // CSR(A)
+    const Elem *a_data;
+    const uint64_t *run_off;    // bin offset of every task's run (absolute)
+    const uint32_t *task_bs;    // b_pos[k] of every task
+    const Elem *b_data;
+    uint64_t m_a;               // rows of A (rows beyond hold no task)
+};
+
+template <class K, bool BM, bool FUSED>
+__device__ __forceinline__ void
+merge_chain_body(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, const Elem *__restrict__ bins,
+                 const uint32_t *__restrict__ tile_row, const uint32_t t0, const uint32_t n_chain,
+                 const uint32_t *__restrict__ uniq, uint64_t *tile_state, DevScalars *sc, const int carry_slot,
+                 uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, const uint32_t bm_wpl, const uint32_t long_thresh,
+                 const FusedSrc fs) {
     using Smem = MergeChainSmem<BM>;
     Smem &sm = *reinterpret_cast<Smem *>(osp_smem);
     const unsigned int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
@@ -1130,7 +1146,60 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
         d.n_out = 0;
         return d;
     };
+    // FUSED: the tile's partial products computed into the stage by the whole CTA (tasks of rows r0 .. r0+R, 32 per
+    // warp and turn, the concatenation of their runs walked 64 products at a time as in k_multiply).
+    auto fill_stage = [&](const TileDesc &d) {
+        if (d.idx < n_chain && !d.is_long && d.n_in) {
+            const uint64_t e0 = fs.a_pos[min(d.r0, fs.m_a)], e1 = fs.a_pos[min(d.r0 + d.R, fs.m_a)];
+            Elem *stage = sm.stage + uint32_t(d.g0 & 1);
+            const uint64_t first = d.g0 + bin_base;              // run_off of the tile's first partial product
+            for (uint64_t base = e0 + warp * 32; base < e1; base += (MC_THREADS / 32) * 32) {
+                uint32_t bs = 0, len = 0, off = 0; float a = 0.f;
+                if (base + lane < e1) {
+                    const uint64_t i = base + lane;
+                    const uint64_t ro = fs.run_off[i];
+                    a = fs.a_data[i].val; off = uint32_t(ro - first);
+                    len = uint32_t(fs.run_off[i + 1] - ro);
+                    bs = fs.task_bs[i];
+                }
+                const uint32_t incl = warp_inclusive_scan(len);
+                const uint32_t total = __shfl_sync(FULL, incl, 31);
+                const uint32_t excl = incl - len;
+                const uint32_t dbs = bs - excl, doff = off - excl;
+                for (uint32_t q0 = 0; q0 < total; q0 += 64) {
+                    const uint32_t q[2] = {q0 + lane, q0 + 32 + lane};
+                    uint32_t t[2] = {0, 0};
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            const uint32_t v = __shfl_sync(FULL, incl, t[u] + step - 1);
+                            if (v <= q[u]) t[u] += step;
+                        }
+                    }
+                    float a_t[2]; uint32_t dbs_t[2], doff_t[2]; Elem b[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        a_t[u] = __shfl_sync(FULL, a, t[u] & 31);
+                        dbs_t[u] = __shfl_sync(FULL, dbs, t[u] & 31);
+                        doff_t[u] = __shfl_sync(FULL, doff, t[u] & 31);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; u++)
+                        if (q[u] < total) b[u] = fs.b_data[dbs_t[u] + q[u]];
+#pragma unroll
+                    for (int u = 0; u < 2; u++)
+                        if (q[u] < total) {
+                            Elem o; o.idx = b[u].idx; o.val = __fmul_rn(a_t[u], b[u].val);     // rounded on its own: no FMA
+                            stage[doff_t[u] + q[u]] = o;
+                        }
+                }
+            }
+        }
+        __syncthreads();                                         // the stage is complete (and every warp has left the loop)
+    };
     auto start_copy = [&](const TileDesc &d) {
+        if (FUSED) { fill_stage(d); return; }
         if (tid == 0 && d.idx < n_chain && !d.is_long && d.n_in) {
             const uint32_t shift = uint32_t(d.g0 & 1);              // the window starts one element early when g0 is odd
             const uint32_t bytes = ((d.n_in + shift) * 8 + 15) & ~15u;
@@ -1227,7 +1296,7 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
             Elem *stage = sm.stage + uint32_t(cur.g0 & 1);
             const uint32_t stage_off = uint32_t(offsetof(Smem, stage)) + uint32_t(cur.g0 & 1) * 8;
             const uint32_t ost_off = uint32_t(offsetof(Smem, ostage)) + ob * uint32_t(sizeof(Elem) * MC_STAGE_ELEMS);
-            if (cur.n_in) { mbar_wait(&sm.mbar, n_tma & 1); n_tma++; }
+            if (!FUSED && cur.n_in) { mbar_wait(&sm.mbar, n_tma & 1); n_tma++; }
             if (my_len == 1) ostage[swz(rstart[tid])] = stage[rstart[tid]];
             __syncthreads();                                  // order[] is complete
             const uint32_t n_batches = sm.cls_b0[8];
@@ -1289,6 +1358,27 @@ k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, con
         __syncthreads();
         retire_tile(prev, (it + 2) % 3, (it & 1) ^ 1);
     }
+}
+
+template <class K, bool BM>
+__global__ void __launch_bounds__(MC_THREADS, BM ? 2 : MC_OCC)
+k_merge_chain(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, const Elem *__restrict__ bins,
+              const uint32_t *__restrict__ tile_row, const uint32_t t0, const uint32_t n_chain,
+              const uint32_t *__restrict__ uniq, uint64_t *tile_state, DevScalars *sc, const int carry_slot,
+              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, const uint32_t bm_wpl, const uint32_t long_thresh) {
+    merge_chain_body<K, BM, false>(row_bin, bin_base, bins, tile_row, t0, n_chain, uniq, tile_state, sc, carry_slot, c_pos, c_data, bm_wpl,
+                                   long_thresh, FusedSrc{});
+}
+
+template <class K, bool BM>
+__global__ void __launch_bounds__(MC_THREADS, BM ? 2 : MC_OCC)
+k_merge_chain_fused(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, const Elem *__restrict__ bins,
+                    const uint32_t *__restrict__ tile_row, const uint32_t t0, const uint32_t n_chain,
+                    const uint32_t *__restrict__ uniq, uint64_t *tile_state, DevScalars *sc, const int carry_slot,
+                    uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, const uint32_t bm_wpl, const uint32_t long_thresh,
+                    const FusedSrc fs) {
+    merge_chain_body<K, BM, true>(row_bin, bin_base, bins, tile_row, t0, n_chain, uniq, tile_state, sc, carry_slot, c_pos, c_data, bm_wpl,
+                                  long_thresh, fs);
 }
 
 // =====================================================================================

@@ -298,4 +298,18 @@ __global__ void k_mark_swept(const uint64_t *__restrict__ a_pos, const uint32_t 
     }
 }
 
+// OSP_FUSED_SHORT: the tasks whose partial products still go to the bins -- those of the medium rows (long_list) and of
+// the xl rows the sweep does not take (fewer than sweep_min partial products; ~0 without the sweep).
+__global__ void k_mark_binned(const uint64_t *__restrict__ a_pos, const uint32_t *__restrict__ xl_list,
+                              const uint32_t *__restrict__ long_list, const DevScalars *sc, const uint64_t *__restrict__ row_bin,
+                              uint64_t sweep_min, uint32_t *bits) {
+    const uint32_t n_xl = sc->n_xl, n = n_xl + sc->n_long;
+    const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5, nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t x = warp; x < n; x += nwarps) {
+        const uint64_t row = x < n_xl ? xl_list[x] : long_list[x - n_xl];
+        if (x < n_xl && row_bin[row + 1] - row_bin[row] >= sweep_min) continue;
+        for (uint64_t e = a_pos[row] + lane_id(); e < a_pos[row + 1]; e += 32) atomicOr(&bits[e >> 5], 1u << (e & 31));
+    }
+}
+
 }  // namespace osp

@@ -258,3 +258,61 @@ def test_device_out_of_memory_is_reported_not_fatal(emulated_library, monkeypatc
         assert_bit_exact(got, want, "after the failed calls")
     finally:
         eng.close()
+
+
+# ---- OSP_FUSED_SHORT (opt-in, not yet run on a B200): short-row tiles computed inside the merge chain -------------------
+@pytest.fixture()
+def engine_fused(emulated_library, monkeypatch):
+    monkeypatch.setenv("OSP_FUSED_SHORT", "1")            # read at osp_create: every call of this context takes the fused chain
+    eng = osp.Engine(0)
+    yield eng
+    eng.close()
+
+
+def test_fused_short_rows_golden_and_random(engine_fused):
+    for name in gp.CASES:
+        for a_is_csr in (False, True):
+            gp.test_golden(engine_fused, name, a_is_csr)
+    for seed in range(8):
+        gp.test_random_vs_oracle(engine_fused, seed)
+    gp.test_edge_cases(engine_fused)
+    gp.test_er_config2_scaled(engine_fused)
+    gp.test_mtx_pipeline_like_reference_main(engine_fused)
+
+
+@pytest.mark.parametrize("cols,dup_rate", [(1 << 14, 0.3), (1 << 20, 0.0), (1 << 20, 0.3), ((1 << 24) + 5, 0.2)])
+def test_fused_short_rows_every_row_length_class(engine_fused, cols, dup_rate):
+    """Bitmap variant, 32- and 64-bit sort keys; short rows (computed in the chain) next to medium and long rows (still
+    multiplied into the bins), with and without the long-row sweep."""
+    gp.test_every_row_length_class(engine_fused, cols, dup_rate)
+    if cols > (1 << 14):
+        sw.test_every_row_length_class_through_the_sweep(engine_fused, cols, dup_rate)
+
+
+def test_fused_short_rows_in_row_blocks(engine_fused):
+    rng = np.random.default_rng(71)
+    lens = [5000, 3, 0, 20000, 700, 4097, 129, 9000, 12, 6000, 300, 4500, 45, 8000] * 2
+    A, B = gp._row_lengths_case(rng, lens, 1 << 16, 0.3)
+    a_csc, a_csr, b_csr = operands(A, B)
+    want, prod = oracle_spgemm(a_csc, b_csr)
+    engine_fused.set_workspace_limit(25000 * 8)
+    engine_fused.set_result_limit((want.nnz + 25000 + 64) * 8)
+    for flags in (0, api.OSP_LONGROW_SWEEP):
+        for is_csr, op in ((True, a_csr), (False, a_csc)):
+            res = engine_fused.spgemm(op, b_csr, a_is_csr=is_csr, cols_b=1 << 16, flags=flags | api.OSP_PROFILE_KERNELS)
+            got = res.to_host(); st = res.stats(); names = {n for n, _ in res.kernel_times()}; res.free()
+            assert st["row_chunks"] > 4
+            assert any("k_merge_chain_fused" in n for n in names), names
+            if is_csr:                                   # (the CSC hand-over converts A with the default chain first)
+                assert not any("k_merge_chain<" in n for n in names), names
+            assert_bit_exact(got, want, f"fused short rows in row blocks, flags={flags}, csr={is_csr}")
+    # a call without any long row: no multiply launch at all
+    A2, B2 = rand_sparse(rng, 300, 200, 0.02), rand_sparse(rng, 200, 5000, 0.004)
+    a_csc, a_csr, b_csr = operands(A2, B2)
+    want, _ = oracle_spgemm(a_csc, b_csr)
+    engine_fused.set_workspace_limit(1 << 30)
+    engine_fused.set_result_limit(0)
+    res = engine_fused.spgemm(a_csr, b_csr, a_is_csr=True, flags=api.OSP_PROFILE_KERNELS)
+    got = res.to_host(); names = {n for n, _ in res.kernel_times()}; res.free()
+    assert not any("k_multiply" in n for n in names), names
+    assert_bit_exact(got, want, "no long row: the chain computes everything")

@@ -6,7 +6,7 @@ model) against the oracle on random operands of every shape class -- a campaign 
 
 Every case draws: dimensions, densities, a column range (small: bitmap/dense kernels; medium; > 2^23: 64-bit chain
 keys), a few rows made long on purpose (medium and xl rows), duplicates-free operands in the reference layout, CSR or
-CSC hand-over of A, multiply order, fused-dense on/off, the opt-in long-row sweep, and sometimes a workspace / result
+CSC hand-over of A, multiply order, fused-dense on/off, the opt-in long-row sweep and fused short rows, and sometimes a workspace / result
 limit that forces row blocks.  The result must match the oracle bit for bit.  TEST INFRASTRUCTURE ONLY.
 """
 import argparse
@@ -107,12 +107,13 @@ def main():
     api._LIB_PATH, api._lib = lib, None
     rng = np.random.default_rng(args.seed)
     t0 = time.time()
-    seen = {"sweep": 0, "blocks": 0, "fused": 0, "xl": 0, "long": 0, "products": 0}
+    seen = {"sweep": 0, "blocks": 0, "fused": 0, "xl": 0, "long": 0, "products": 0, "fused_short": 0}
     for case in range(args.cases):
         A, B, cols = draw_case(rng)
         a_csc, a_csr, b_csr = operands(A, B)
         want, prod = oracle_spgemm(a_csc, b_csr, rows_override=A.shape[0])
-        flags = int(rng.choice([0, api.OSP_KSLICE_ORDER, api.OSP_ROWWISE_ORDER, api.OSP_LONGROW_SWEEP, api.OSP_LONGROW_SWEEP, api.OSP_NO_FUSED_DENSE]))
+        flags = int(rng.choice([0, api.OSP_KSLICE_ORDER, api.OSP_ROWWISE_ORDER, api.OSP_LONGROW_SWEEP, api.OSP_LONGROW_SWEEP, api.OSP_NO_FUSED_DENSE,
+                                api.OSP_FUSED_SHORT, api.OSP_FUSED_SHORT | api.OSP_LONGROW_SWEEP, api.OSP_FUSED_SHORT | api.OSP_NO_FUSED_DENSE]))
         as_csr = bool(rng.integers(0, 2))
         eng = osp.Engine(0)
         try:
@@ -133,6 +134,7 @@ def main():
             assert_bit_exact(got, want, what)
             seen["sweep"] += any("k_long_fill" in n for n in names)
             seen["fused"] += any("k_fused_dense" in n for n in names)
+            seen["fused_short"] += any("k_merge_chain_fused" in n for n in names)
             seen["blocks"] += st["row_chunks"] > 1
             seen["xl"] += st["rows_long"] > 0
             seen["long"] += st["rows_medium"] > 0
@@ -140,7 +142,7 @@ def main():
         finally:
             eng.close()
     print(f"fuzz ok: {args.cases} cases, seed {args.seed}, schedule '{args.schedule or 'forward'}', {args.resident} resident block(s){', AddressSanitizer' if args.asan else ''}, {time.time() - t0:.0f} s; "
-          f"calls with sweep {seen['sweep']}, fused dense {seen['fused']}, row blocks {seen['blocks']}, xl rows {seen['xl']}, "
+          f"calls with sweep {seen['sweep']}, fused short rows {seen['fused_short']}, fused dense {seen['fused']}, row blocks {seen['blocks']}, xl rows {seen['xl']}, "
           f"medium rows {seen['long']}; {seen['products']} partial products in total")
 
 

@@ -25,6 +25,18 @@ for min in 32768 262144; do
       > $out/rmat20_sd1_sweep1_min${min}.log 2>&1
   echo "rmat20/1 sweep min=$min rc=$?" | tee -a $out/status.txt
 done
+# the other opt-in path: short-row tiles computed inside the chain (OSP_FUSED_SHORT), configs 2 and 4
+OSP_TEST_FUSED_SHORT=1 timeout 600 python -m pytest tests/test_gpu_zzz_fused_short.py -m gpu -x -q > $out/fused_short_tests.log 2>&1
+echo "fused short tests rc=$?" | tee -a $out/status.txt
+if tail -n 3 $out/fused_short_tests.log | grep -q passed; then
+  for w in "er16k" "er8m --scale-down 8" "er8m"; do
+    for f in 0 1; do
+      OSP_FUSED_SHORT=$f timeout 600 python tools/quick_bench.py --workload $w --iters 4 --flush --kernels --check \
+          > "$out/fused${f}_$(echo $w | tr -d ' -').log" 2>&1
+      echo "$w fused_short=$f rc=$?" | tee -a $out/status.txt
+    done
+  done
+fi
 if ! grep -q "rc=[1-9]" $out/status.txt; then
   OSP_LONGROW_SWEEP=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_long_fill -c 1 \
       -o $out/k_long_fill_rmat16 python tools/fullscale_check.py --workload rmat20 --scale-down 16 --iters 1 --no-check > $out/ncu.log 2>&1
