@@ -377,7 +377,9 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                        "rows": st["rows_c"], "n_k": st["n_k"], "nnz_a": st["nnz_a"], "products": products,
                        "nnz_c": st["nnz_c"], "parallelism": "single" if world == 1 else f"k-shard{world}+alltoallv",
                        "timed_region": "HBM-resident CSR(A),CSR(B) -> HBM-resident CSR(C); CUDA events on the engine stream",
-                       "l2": f"L2 flushed ({L2_FLUSH_BYTES >> 20} MiB write) before every step, outside the event pair"},
+                       "l2": f"L2 flushed ({L2_FLUSH_BYTES >> 20} MiB write) before every step, outside the event pair",
+                       # experimental engine paths are opt-in through the environment; a line measured with one says so
+                       "opt_in": {k.lower(): os.environ.get(k, "0") not in ("", "0") for k in ("OSP_LONGROW_SWEEP", "OSP_FUSED_SHORT")}},
             "algorithmic_gbs": round(alg_bytes / (ms_per_step * 1e-3) / 1e9, 2),
             "algorithmic_frac_of_hbm_peak": round(alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
             "wall_s_timed_region": round(wall, 4),
