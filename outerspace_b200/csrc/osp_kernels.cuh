@@ -1148,6 +1148,7 @@ merge_chain_body(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, 
     };
     // FUSED: the tile's partial products computed into the stage by the whole CTA (tasks of rows r0 .. r0+R, 32 per
     // warp and turn, the concatenation of their runs walked 64 products at a time as in k_multiply).
+    constexpr int FW = 4;                                        // independent 32-product chunks (= loads in flight per lane) per turn
     auto fill_stage = [&](const TileDesc &d) {
         if (d.idx < n_chain && !d.is_long && d.n_in) {
             const uint64_t e0 = fs.a_pos[min(d.r0, fs.m_a)], e1 = fs.a_pos[min(d.r0 + d.R, fs.m_a)];
@@ -1166,29 +1167,30 @@ merge_chain_body(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, 
                 const uint32_t total = __shfl_sync(FULL, incl, 31);
                 const uint32_t excl = incl - len;
                 const uint32_t dbs = bs - excl, doff = off - excl;
-                for (uint32_t q0 = 0; q0 < total; q0 += 64) {
-                    const uint32_t q[2] = {q0 + lane, q0 + 32 + lane};
-                    uint32_t t[2] = {0, 0};
+                for (uint32_t q0 = 0; q0 < total; q0 += 32 * FW) {
+                    uint32_t q[FW], t[FW];
+#pragma unroll
+                    for (int u = 0; u < FW; u++) { q[u] = q0 + 32 * u + lane; t[u] = 0; }
 #pragma unroll
                     for (int step = 16; step > 0; step >>= 1) {
 #pragma unroll
-                        for (int u = 0; u < 2; u++) {
+                        for (int u = 0; u < FW; u++) {
                             const uint32_t v = __shfl_sync(FULL, incl, t[u] + step - 1);
                             if (v <= q[u]) t[u] += step;
                         }
                     }
-                    float a_t[2]; uint32_t dbs_t[2], doff_t[2]; Elem b[2];
+                    float a_t[FW]; uint32_t dbs_t[FW], doff_t[FW]; Elem b[FW];
 #pragma unroll
-                    for (int u = 0; u < 2; u++) {
+                    for (int u = 0; u < FW; u++) {
                         a_t[u] = __shfl_sync(FULL, a, t[u] & 31);
                         dbs_t[u] = __shfl_sync(FULL, dbs, t[u] & 31);
                         doff_t[u] = __shfl_sync(FULL, doff, t[u] & 31);
                     }
 #pragma unroll
-                    for (int u = 0; u < 2; u++)
+                    for (int u = 0; u < FW; u++)
                         if (q[u] < total) b[u] = fs.b_data[dbs_t[u] + q[u]];
 #pragma unroll
-                    for (int u = 0; u < 2; u++)
+                    for (int u = 0; u < FW; u++)
                         if (q[u] < total) {
                             Elem o; o.idx = b[u].idx; o.val = __fmul_rn(a_t[u], b[u].val);     // rounded on its own: no FMA
                             stage[doff_t[u] + q[u]] = o;
