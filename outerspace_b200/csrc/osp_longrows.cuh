@@ -1,7 +1,8 @@
 // osp_longrows.cuh -- fused band sweep for long output rows over wide column ranges.
 //
-// STATUS: logic validated on the CPU emulation of the execution model (tests/cusim, tests/test_longrows_sim.py: bit-exact
-// against the oracle, every band / run-group / thread-count combination); compiled for sm_100a with the rest of the
+// STATUS: logic validated on the CPU emulation of the execution model (tests/cusim: tests/test_longrows_sim.py with small
+// template parameters, tests/test_engine_sim.py and tools/fuzz_engine_sim.py end to end through osp_spgemm with the
+// engine's own instantiation -- bit-exact against the oracle, also under AddressSanitizer); compiled for sm_100a with the rest of the
 // engine and launched by osp_spgemm ONLY when the caller opts in (OSP_LONGROW_SWEEP flag or environment variable, see
 // include/osp_b200.h): the round's GPU budget was spent before it could be run on a B200, so the default path still
 // sends long rows through k_multiply + k_merge_xl.  GPU parity tests for the opt-in path: tests/test_gpu_zzz_sweep.py.
@@ -14,8 +15,9 @@
 // segment (runs are sorted) whose bounds come from a band index of B built once per call (k_long_bands: for every
 // row k of B the position of the first column of every band -- two adjacent 4-byte loads per (run, band), no search
 // and no per-run state during the sweep), so every element of B is read once per use, from L2.
-//   k_long_count: the sweep with a bitmap only -> the exact number of non-zeros of every long row, so that C is
-//                 allocated exactly and every long row's place in C is known before any value is computed.
+//   k_long_count: the sweep with a bitmap only -> the exact number of non-zeros of every long row, so that C can be
+//                 allocated exactly and every long row's place known before any value is computed (not used by the
+//                 engine yet: the first integration hands the merged row over through the start of its bin).
 //   k_long_fill:  the sweep with values.  Products of a chunk that hit the same column are serialised by the
 //                 racing-minimum arbitration of k_merge_dense (lowest flat position = lowest (k, position) first), so
 //                 every column is summed in ascending k with separately rounded products and adds: the bits of the
