@@ -287,6 +287,7 @@ struct MergeJob {
 constexpr int LR_THREADS = 512, LR_BAND = 16384, LR_RUNS = 512;
 constexpr size_t LR_SMEM = LongRowSmem<LR_BAND, LR_RUNS, true>::bytes;
 constexpr uint64_t LR_MIN_PER_BAND = 64;
+constexpr uint64_t LR_HUGE_ROW = 1ull << 20;           // rows from here on are started before the rest of the list
 
 // Scratch that depends on the plan's results: look-back states of the tile chain, survivor counts of the
 // long rows, the dense accumulators of the longest rows.
@@ -338,7 +339,7 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
                 CU(ctx, cudaMemsetAsync(&ctx->d_sc->xl_ticket, 0, 4, ctx->stream));
                 const unsigned grid = unsigned(std::min<uint64_t>(job.n_xl, uint64_t(ctx->sm_count) * ctx->sweep_occ));
                 const LongRowsInBins rows{ctx->xl_list.as<uint32_t>(), ctx->d_sc, row_bin, bin_base, bins, uniq, row_lo, row_hi,
-                                          job.sweep_min};
+                                          job.sweep_min, LR_HUGE_ROW};
                 LAUNCH(ctx, (k_long_fill<LR_THREADS, LR_BAND, LR_RUNS, LongRowsInBins>), grid, LR_THREADS, LR_SMEM, job.a_pos, job.a_data,
                        job.b_data, job.bandptr, job.idx_range, rows);
             }

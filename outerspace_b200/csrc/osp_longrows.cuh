@@ -84,13 +84,17 @@ struct LongRowsInBins {                 // the engine: rows of the plan's xl lis
     const uint64_t *row_bin;            // long row -- the same hand-over as k_merge_xl
     uint64_t bin_base; Elem *bins; uint32_t *uniq;
     uint64_t row_lo, row_hi, min_len;
+    uint64_t huge_len;                  // rows of at least this many partial products are handed out first: the list is in
+                                        // no particular order, and a hub row that starts last is the tail of the launch
     __device__ __forceinline__ bool next(uint32_t &x, uint64_t &row) const {
         const uint32_t n = sc->n_xl;
         while (true) {
-            x = atomicAdd(&sc->xl_ticket, 1u);
-            if (x >= n) return false;
-            row = xl_list[x];
-            if (row >= row_lo && row < row_hi && row_bin[row + 1] - row_bin[row] >= min_len) return true;
+            x = atomicAdd(&sc->xl_ticket, 1u);                 // tickets 0 .. n-1: the huge rows; n .. 2n-1: the others
+            if (x >= 2 * uint64_t(n)) return false;
+            const bool first_pass = x < n;
+            row = xl_list[first_pass ? x : x - n];
+            const uint64_t len = row_bin[row + 1] - row_bin[row];
+            if (row >= row_lo && row < row_hi && len >= min_len && (len >= huge_len) == first_pass) return true;
         }
     }
     __device__ __forceinline__ Elem *out(uint32_t, uint64_t row) const { return bins + (row_bin[row] - bin_base); }

@@ -54,7 +54,7 @@ int run_bins(const uint64_t *a_pos, const Elem *a_data, const uint64_t *b_pos, c
     sc.n_xl = n_xl;
     cusim::launch(2, 64, 0, [&] { k_mark_swept(a_pos, xl_list, &sc, row_bin, min_len, swept); });
     const std::vector<uint32_t> bandptr = band_index<BAND>(b_pos, b_data, n_k, cols);
-    const LongRowsInBins rows{xl_list, &sc, row_bin, bin_base, bins, uniq, row_lo, row_hi, min_len};
+    const LongRowsInBins rows{xl_list, &sc, row_bin, bin_base, bins, uniq, row_lo, row_hi, min_len, 2 * min_len};   // two hand-out passes
     cusim::launch(grid, THREADS, LongRowSmem<BAND, RUNS, true>::bytes, [&] {
         k_long_fill<THREADS, BAND, RUNS>(a_pos, a_data, b_data, bandptr.data(), cols, rows);
     });

@@ -316,3 +316,23 @@ def test_fused_short_rows_in_row_blocks(engine_fused):
     got = res.to_host(); names = {n for n, _ in res.kernel_times()}; res.free()
     assert not any("k_multiply" in n for n in names), names
     assert_bit_exact(got, want, "no long row: the chain computes everything")
+
+
+def test_sweep_hands_out_huge_rows_first(engine):
+    """A row of more than 2^20 partial products (handed out in the first ticket pass) next to ordinary long rows."""
+    rng = np.random.default_rng(81)
+    k, cols = 1400, 70000
+    A = sp.lil_matrix((3, k), dtype=np.float32)
+    for r, n in enumerate((1400, 30, 600)):
+        sel = rng.choice(k, size=n, replace=False)
+        A[r, sel] = (rng.standard_normal(n) + 2).astype(np.float32)
+    B = sp.random(k, cols, density=800.0 / cols, format="csr", random_state=7, dtype=np.float32,
+                  data_rvs=lambda n: (rng.standard_normal(n) * 2 + 0.1).astype(np.float32))
+    B.eliminate_zeros()
+    a_csc, a_csr, b_csr = operands(A.tocsr(), B)
+    want, prod = oracle_spgemm(a_csc, b_csr, rows_override=3)
+    res = engine.spgemm(a_csr, b_csr, a_is_csr=True, cols_b=cols, rows_c=3, flags=api.OSP_LONGROW_SWEEP | api.OSP_PROFILE_KERNELS)
+    got = res.to_host(); names = {n for n, _ in res.kernel_times()}; res.free()
+    plen = np.diff(b_csr.pos.astype(np.int64))[a_csr.data["idx"][: int(a_csr.pos[1])]].sum()
+    assert plen >= (1 << 20) and any("k_long_fill" in n for n in names)
+    assert_bit_exact(got, want, "a huge row and two long ones")
