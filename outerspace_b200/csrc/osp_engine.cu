@@ -839,14 +839,18 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     // against that capacity with the exact nnz(C) of the blocks before it (carried by the merge chain anyway).
     bool bounded = false;
     uint64_t c_cap = cap_bound, block_limit = limit_elems;
+    // OSP_FUSED_SHORT without a single medium or long row: nothing is ever written to the bins, so they cost no memory
+    // and the workspace limit cuts no row blocks (a bounded C still does)
+    const bool no_bins = fused_short && job.n_xl + job.n_long == 0;
+    const uint64_t P_bins = no_bins ? 0 : P;
     if (!fused) {
         if (ctx->result_limit) {
             bounded = cap_bound * 8 > ctx->result_limit;
             if (bounded) c_cap = std::max<uint64_t>(ctx->result_limit / 8, 1);
-        } else if ((cap_bound + std::min(P, limit_elems)) * 8 > ctx->total_mem / 4) {      // small calls never ask the driver
+        } else if ((cap_bound + std::min(P_bins, limit_elems)) * 8 > ctx->total_mem / 4) {      // small calls never ask the driver
             const uint64_t slack = (1ull << 30) + ctx->total_mem / 64;
             const uint64_t avail = device_available(ctx);
-            auto bins_extra = [&](uint64_t elems) { const uint64_t b = std::min(P, elems) * 8 + 16; return b > ctx->bins.cap ? b + b / 8 : 0; };
+            auto bins_extra = [&](uint64_t elems) { const uint64_t b = std::min(P_bins, elems) * 8 + 16; return b > ctx->bins.cap ? b + b / 8 : 0; };
             if (cap_bound * 8 + bins_extra(limit_elems) + slack > avail) {
                 bounded = true;
                 block_limit = std::min<uint64_t>(limit_elems, std::max<uint64_t>(ctx->total_mem / 128, 1ull << 20));   // 1/16 of the device per block
@@ -866,7 +870,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     std::vector<uint32_t> tb;            // tile boundaries of the blocks
     std::vector<uint64_t> blk_row, blk_bin, blk_e;   // per boundary: row, bin offset, offset into A's data
     std::vector<uint64_t> h_row_bin;     // host copy of the bin offsets (blocked calls only)
-    if (fused || (P <= block_limit && !bounded)) {
+    if (fused || (P_bins <= block_limit && !bounded)) {
         tb = {0u, job.n_tiles};
         blk_row = {0, m_plan}; blk_bin = {0, P}; blk_e = {0, nnz_a};
     } else {
@@ -896,7 +900,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     const size_t n_blocks = tb.size() - 1;
     uint64_t max_block = 0;
     for (size_t b = 0; b < n_blocks; b++) max_block = std::max(max_block, blk_bin[b + 1] - blk_bin[b]);
-    rc = [&]() -> int { CU(ctx, ctx->bins.reserve(std::max<uint64_t>(max_block, 1) * 8 + 16)); return OSP_OK; }();
+    rc = [&]() -> int { CU(ctx, ctx->bins.reserve(std::max<uint64_t>(no_bins ? 0 : max_block, 1) * 8 + 16)); return OSP_OK; }();
     if (rc) return bail(rc);
     Elem *bins = ctx->bins.as<Elem>();
 

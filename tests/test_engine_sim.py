@@ -336,3 +336,31 @@ def test_sweep_hands_out_huge_rows_first(engine):
     plen = np.diff(b_csr.pos.astype(np.int64))[a_csr.data["idx"][: int(a_csr.pos[1])]].sum()
     assert plen >= (1 << 20) and any("k_long_fill" in n for n in names)
     assert_bit_exact(got, want, "a huge row and two long ones")
+
+
+def test_fused_short_rows_need_no_bins(emulated_library, monkeypatch):
+    """OSP_FUSED_SHORT on a product without medium or long rows: the bins are never written, so they are not allocated
+    and the workspace limit cuts no row blocks -- the same call needs many blocks on the default path."""
+    rng = np.random.default_rng(91)
+    A, B = rand_sparse(rng, 2000, 400, 0.01), rand_sparse(rng, 400, 30000, 0.0008)
+    a_csc, a_csr, b_csr = operands(A, B)
+    want, prod = oracle_spgemm(a_csc, b_csr)
+    assert prod > 40000
+    for fused_on in (False, True):
+        if fused_on:
+            monkeypatch.setenv("OSP_FUSED_SHORT", "1")
+        eng = osp.Engine(0)
+        try:
+            eng.set_workspace_limit(4096)                                  # 512 partial products per row block
+            before = _live_bytes(emulated_library)
+            res = eng.spgemm(a_csr, b_csr, a_is_csr=True, cols_b=30000)
+            got = res.to_host(); st = res.stats()
+            grown = _live_bytes(emulated_library) - before - (st["nnz_c"] + st["rows_c"] + 1) * 8   # scratch the call added
+            res.free()
+            assert st["rows_medium"] == 0 and st["rows_long"] == 0
+            assert (st["row_chunks"] == 1) == fused_on, st["row_chunks"]
+            if fused_on:
+                assert grown < prod * 8, "the bins were allocated"
+            assert_bit_exact(got, want, f"fused_short={fused_on}")
+        finally:
+            eng.close()
