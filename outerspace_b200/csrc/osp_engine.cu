@@ -589,6 +589,10 @@ int osp_create(int device, osp_ctx **out) {
         uint64_t thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    if (const char *env = std::getenv("OSP_L2_FETCH")) {      // development knob: cudaLimitMaxL2FetchGranularity (32 / 64 / 128)
+        const size_t g = std::strtoull(env, nullptr, 10);
+        if (g) { if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g) != cudaSuccess) cudaGetLastError(); }
+    }
     ctx->ws_limit = uint64_t(double(ctx->total_mem) * 0.35);
     if (const char *env = std::getenv("OSP_WORKSPACE_LIMIT_MB")) {
         uint64_t mb = std::strtoull(env, nullptr, 10);

@@ -1,9 +1,7 @@
 """GPU parity of the OPT-IN fused short rows (OSP_FUSED_SHORT: k_merge_chain_fused computes the tiles of short rows
-straight into its stage, no bins for them).  Like the long-row sweep it was written after the round's GPU budget was
-spent: bit-exact on the CPU emulation (tests/test_engine_sim.py, tools/fuzz_engine_sim.py), NOT yet run on a B200, off
-by default.  Runs only with OSP_TEST_FUSED_SHORT=1:
+straight into its stage, no bins for them).  Round 2: bit-exact on a B200 (profiles/r02_optin_paths.md); runs with
+the rest of the GPU suite.
 
-    OSP_TEST_FUSED_SHORT=1 python -m pytest tests/test_gpu_zzz_fused_short.py -m gpu -x -q
     OSP_FUSED_SHORT=1 python -m pytest tests -m gpu -x -q            # the whole suite through the fused chain
 """
 import os
@@ -13,10 +11,7 @@ import pytest
 import outerspace_b200 as osp
 import test_gpu_parity as gp
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("OSP_TEST_FUSED_SHORT") != "1",
-                                 reason="opt-in path not yet verified on a B200: run with OSP_TEST_FUSED_SHORT=1"),
-              pytest.mark.timeout(300)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
 @pytest.fixture(scope="module")
