@@ -4,10 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
 One "step" = one C = A*A of the named synthetic workload: HBM-resident CSR(A), CSR(B) -> HBM-resident
-CSR(C) (device CSR->CSC conversion + symbolic count + multiply + [exchange] + merge), through the C ABI
-(include/osp_b200.h).  N=1 runs BASELINE.json configs[1] (ER 16384^2, density 1e-3); N>1 runs configs[3]
-(ER 2^23, 8 nnz/row) k-sharded over the ranks with an NCCL all-to-allv of the partial products.
-Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for every field.
+CSR(C) (symbolic count + multiply + [exchange] + merge), through the C ABI (include/osp_b200.h).  Every N runs
+BASELINE.json configs[3] (ER 2^23, 8 nnz/row) -- on one GPU at N=1, k-sharded over the ranks with the exchange of
+the partial products at N>1 -- so the 1 -> 8 curve is one workload; the N=1 line carries a `per_config` table with
+configs[0], [1], [2] and [4] at full size.  Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement".
 
 The oracle (oracle/, oracle/_ref) is used here ONLY for the `cpu_baseline` object and the
 `--impl reference` arm; it is never on the measured GPU path.
@@ -158,9 +158,10 @@ def cpu_reference_run(a_csr, b_csr, n_k, reps: int):
 
 
 def workload_for(n_gpus: int, name: str | None):
-    if name:
-        return name
-    return "er16k" if n_gpus == 1 else "er8m"
+    """The headline workload is the same at every N (BASELINE configs[3], the one the multi-GPU metric is quoted on and
+    the largest ER config that fits one GPU): the driver's 1 -> 8 curve divides like by like.  The other configs are
+    in the N=1 line's `per_config` table."""
+    return name or "er8m"
 
 
 WORKLOAD_DESC = {
@@ -174,24 +175,30 @@ WORKLOAD_DESC = {
 CPU_SAMPLE_SCALE = {"mlp_fc2": 1, "er16k": 1, "rmat20": 64, "er8m": 64, "mlp_batch": 2048}
 
 
+def config_of(wl: str, scale_down: int) -> dict:
+    """The `config` object: identical in both arms (the driver compares them key by key)."""
+    return {"workload": WORKLOAD_DESC[wl], "name": wl, "scale_down": scale_down}
+
+
 def run_reference(args, rank: int, world: int) -> None:
     if rank != 0:
         return
     from outerspace_b200 import synth
     wl = workload_for(args.gpus, args.workload)
-    sd = CPU_SAMPLE_SCALE[wl]
+    sd = CPU_SAMPLE_SCALE[wl] * args.scale_down
     a, b, dims = synth.build_workload(wl, sd)
     secs, kind, prod = cpu_reference_run(a, b, dims["n_k"], args.warmup + args.steps)
     timed = secs[args.warmup:]
     ms = 1e3 * sum(timed) / len(timed)
     value = 2.0 * prod / (ms * 1e-3) / 1e9
-    sample = f"{wl} at 1/{sd} linear scale (rows={dims['rows']}, P={prod}), one TaskProvider ctor per step" if sd > 1 \
+    sample = f"{wl} at 1/{sd} linear scale (rows={dims['rows']}, P={prod}), one TaskProvider ctor per step; GFLOP/s is a per-product " \
+             f"rate, so the sample stands for the full workload" if sd > 1 \
         else f"full {wl} (rows={dims['rows']}, P={prod}), one TaskProvider ctor per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
-        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC[wl], "name": wl, "sample_scale_down": sd},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_of(wl, args.scale_down),
         "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -203,32 +210,170 @@ def run_reference(args, rank: int, world: int) -> None:
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def dominant_kernel(kernel_rows, stats):
-    """kernel_rows: list over steps of [(name, ms)].  -> (name, avg ms per launch, launches/step, share)."""
+def kernel_table(kernel_rows):
+    """kernel_rows: list over steps of [(name, ms)] -> {name: (ms per step, launches per step)} sorted by time."""
     agg, cnt = {}, {}
     for rows in kernel_rows:
         for name, ms in rows:
             agg[name] = agg.get(name, 0.0) + ms
             cnt[name] = cnt.get(name, 0) + 1
-    total = sum(agg.values()) or 1.0
-    name = max(agg, key=agg.get)
-    return name, agg[name] / cnt[name], cnt[name] / len(kernel_rows), agg[name] / total, \
-        {k: round(v / len(kernel_rows), 5) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}
+    n = max(len(kernel_rows), 1)
+    return {k: (agg[k] / n, cnt[k] / n) for k in sorted(agg, key=lambda k: -agg[k])}
 
 
 def kernel_algorithmic_bytes(name: str, st: dict) -> tuple[int, str]:
-    """Algorithmic bytes of ONE launch of the named kernel when it covers the whole workload
-    (DESIGN.md "Kernels": from the reference's DRAM model analyzeMultiplyTask / analyzeMergeTask,
+    """Algorithmic bytes of the named kernel over ONE step (all its launches together) when it covers the whole
+    workload (DESIGN.md "Kernels": from the reference's DRAM model analyzeMultiplyTask / analyzeMergeTask,
     SimOuterSPACE.cpp:176-196)."""
     P, nnz_a, nnz_b, nnz_c = st["products"], st["nnz_a"], st["nnz_b"], st["nnz_c"]
     m, n = st["rows_c"], st["n_k"]
+    if "fused" in name or "chain2" in name:
+        return 8 * nnz_a + 8 * nnz_b + 16 * (n + 1) + 16 * P + 8 * nnz_c + 8 * (m + 1), \
+            "fused multiply+merge: what the two phases move through HBM in the reference's model, 8nnzA + 8nnzB + 16(n+1) + 16P + 8nnzC + 8(m+1)"
     if "multiply" in name:
         return 8 * nnz_a + 8 * nnz_b + 16 * (n + 1) + 8 * P, "multiply: 8nnzA + 8nnzB + 16(n+1) + 8P"
-    if "merge" in name:
+    if "merge" in name or "long_fill" in name:
         return 8 * P + 8 * nnz_c + 8 * (m + 1), "merge: 8P + 8nnzC + 8(m+1)"
-    if "gather" in name:
-        return 16 * nnz_c, "gather: 16 nnzC"
     return 16 * nnz_a + 8 * (m + n + 2), "convert/symbolic: 16nnzA + 8(m+n+2)"
+
+
+def roofline_of(table: dict, st: dict, peak: float, peak_src: str, wl: str) -> dict:
+    """`roofline` object for the dominant kernel of a step (by summed event time)."""
+    kname = next(iter(table))
+    k_ms_step, k_launches = table[kname]
+    k_bytes, k_formula = kernel_algorithmic_bytes(kname, st)
+    total = sum(v[0] for v in table.values()) or 1.0
+    per_launch = k_bytes / max(k_launches, 1.0)
+    avg_launch_ms = k_ms_step / max(k_launches, 1.0)
+    achieved = per_launch / (avg_launch_ms * 1e-3) / 1e9
+    out = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+           "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+           "avg_launch_ms": round(avg_launch_ms, 5), "launches_per_step": k_launches,
+           "algorithmic_bytes_per_launch": int(per_launch), "formula": k_formula,
+           "share_of_kernel_time": round(k_ms_step / total, 4),
+           "kernel_ms_per_step": {k: round(v[0], 5) for k, v in table.items()}}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                tr = json.load(f).get(wl, {})
+            kbase = kname.strip("() ").split("<")[0]
+            if kbase in tr.get("kernels", {}):
+                out["traffic"] = tr["kernels"][kbase]["dram_bytes_per_launch"]
+                out["traffic_source"] = tr.get("source")
+        except (OSError, ValueError, KeyError, AttributeError):
+            pass
+    return out
+
+
+def mlp_fc2_through_mtx():
+    """configs[0] the way the reference gets it: the pruned layer written by scipy.io.mmwrite(csr_matrix) like
+    NN_models/util.py:61-62, read back by readcoo + coo2csr (the loader path of SimSpGEMM.cpp:55-152)."""
+    import tempfile
+
+    import scipy.io
+    import scipy.sparse as sp
+
+    import outerspace_b200 as osp
+    from outerspace_b200 import synth
+    a0, _, dims = synth.build_workload("mlp_fc2")
+    m = sp.csr_matrix((a0.data["val"], a0.data["idx"].astype(np.int64), a0.pos.astype(np.int64)), shape=(dims["rows"], dims["n_k"]))
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "fc2_weight.mtx")
+        scipy.io.mmwrite(path, m)
+        coo, nrow, ncol = osp.readcoo(path)
+    a = osp.coo2csr(coo, nrow)
+    return a, a, dict(rows=nrow, n_k=ncol, cols=ncol)
+
+
+def sampled_parity(res, a, b, dims, n_rows=48, heavy=2, row_lo=0, row_hi=None, seed=7):
+    """Outside every timed region: a seeded sample of rows of C (plus the heaviest) recomputed by the oracle from
+    A[rows, :] and B and compared bit for bit with the engine's rows.  The oracle is the CHECKER here, never measured."""
+    import oracle
+    a_pos = a.pos.astype(np.int64)
+    row_hi = a.NRow() if row_hi is None else row_hi
+    b_len = np.diff(b.pos.astype(np.int64))
+    cs = np.concatenate([[0], np.cumsum(b_len[a.data["idx"]])])
+    plen = (cs[a_pos[1:]] - cs[a_pos[:-1]])[row_lo:row_hi]
+    n = min(row_hi - row_lo, res.rows)
+    if n <= 0:
+        return {"ok": True, "rows_checked": 0, "products_checked": 0}
+    rng = np.random.default_rng(seed)
+    pick = np.unique(np.concatenate([rng.integers(0, n, size=n_rows), np.argsort(plen[:n])[-heavy:]])).astype(np.int64)
+    sub_pos = np.zeros(len(pick) + 1, np.uint64)
+    np.cumsum(a_pos[row_lo + pick + 1] - a_pos[row_lo + pick], out=sub_pos[1:])
+    sub_data = np.concatenate([a.data[a_pos[row_lo + r]:a_pos[row_lo + r + 1]] for r in pick])
+    w_pos, w_data, w_prod = oracle.spgemm_rowblocks(sub_pos, sub_data, b.pos, b.data, 64)
+    w_pos = np.concatenate([w_pos, np.full(len(pick) + 1 - len(w_pos), w_pos[-1], np.uint64)]).astype(np.int64)
+    bad = 0
+    for j, r in enumerate(pick):
+        got = res.rows_to_host(int(r), int(r) + 1)
+        want = w_data[w_pos[j]:w_pos[j + 1]]
+        if len(got.data) != len(want) or not np.array_equal(got.data.view(np.uint64), want.view(np.uint64)):
+            bad += 1
+    return {"ok": bad == 0, "rows_checked": int(len(pick)), "products_checked": int(w_prod), "bad_rows": bad,
+            "how": "seeded sample of rows + the heaviest, engine rows vs oracle rows, bit for bit"}
+
+
+def measure_single(eng, torch, dev, wl, scale_down, steps, warmup, flush_l2, peak, peak_src, operands=None):
+    """One workload on one GPU, HBM-resident operands: device time per step (CUDA events on the engine's stream, L2
+    flushed before every step), per-kernel table, sampled-row parity.  Returns (summary dict, operands, last stats)."""
+    from outerspace_b200 import api, synth
+    a, b, dims = operands if operands is not None else synth.build_workload(wl, scale_down)
+
+    def up(x):
+        return torch.from_numpy(x.view(np.uint8).reshape(-1)).to(dev)
+    t = [up(a.pos), up(a.data), up(b.pos), up(b.data)]
+    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+
+    def step(flags=0, keep=False):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res = eng.spgemm_device(a.NRow(), t[0].data_ptr(), t[1].data_ptr(), b.NRow(), t[2].data_ptr(),
+                                t[3].data_ptr(), a_is_csr=True, cols_b=dims["cols"], flags=flags, a_nnz=a.nnz, b_nnz=b.nnz)
+        e1.record(stream)
+        e1.synchronize()
+        return res, e0.elapsed_time(e1)
+
+    for _ in range(warmup):
+        flush_l2()
+        res, _ = step()
+        res.free()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    ms_steps, launches, st = [], 0, None
+    for _ in range(steps):
+        flush_l2()
+        res, ms = step()
+        st = res.stats()
+        launches += st["kernel_launches"]
+        ms_steps.append(ms)
+        res.free()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    ms_per_step = sum(ms_steps) / len(ms_steps)
+    kernel_rows = []
+    for _ in range(3):
+        flush_l2()
+        res, _ = step(api.OSP_PROFILE_KERNELS)
+        kernel_rows.append(res.kernel_times())
+        res.free()
+    table = kernel_table(kernel_rows)
+    flush_l2()
+    res, _ = step()
+    par = sampled_parity(res, a, b, dims)
+    res.free()
+    roof = roofline_of(table, st, peak, peak_src, wl)
+    alg = st["algorithmic_bytes"]
+    summary = {
+        "name": wl, "workload": WORKLOAD_DESC[wl], "scale_down": scale_down, "steps": steps, "ms_per_step": round(ms_per_step, 5),
+        "gflops": round(2.0 * st["products"] / (ms_per_step * 1e-3) / 1e9, 3), "products": st["products"], "nnz_c": st["nnz_c"],
+        "rows": st["rows_c"], "row_chunks": st["row_chunks"],
+        "algorithmic_gbs": round(alg / (ms_per_step * 1e-3) / 1e9, 2), "algorithmic_frac_of_hbm_peak": round(alg / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+        "dominant_kernel": roof["kernel"], "dominant_kernel_frac": roof["frac"], "dominant_kernel_share": roof["share_of_kernel_time"],
+        "kernel_ms_per_step": roof["kernel_ms_per_step"], "parity": par,
+    }
+    return summary, (a, b, dims), st, dict(ms_per_step=ms_per_step, wall=wall, launches=launches, roofline=roof, t=t, step=step)
 
 
 def run_ours(args, rank: int, world: int, local_rank: int) -> None:
@@ -246,12 +391,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         dist.init_process_group("nccl", device_id=dev)
 
     wl = workload_for(args.gpus, args.workload)
-    a, b, dims = synth.build_workload(wl, args.scale_down)
     peak, peak_src = peaks()
-
-    def up(x):
-        return torch.from_numpy(x.view(np.uint8).reshape(-1)).to(dev)
-
     flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
     def flush_l2():
@@ -259,62 +399,25 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
+    per_config, parity = None, None
 
     if world == 1:
-        t = [up(a.pos), up(a.data), up(b.pos), up(b.data)]
         eng = osp.Engine(local_rank)
-        stream = torch.cuda.ExternalStream(eng.stream, device=dev)
-
-        def step(flags=0):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            res = eng.spgemm_device(a.NRow(), t[0].data_ptr(), t[1].data_ptr(), b.NRow(), t[2].data_ptr(),
-                                    t[3].data_ptr(), a_is_csr=True, cols_b=dims["cols"], flags=flags, a_nnz=a.nnz, b_nnz=b.nnz)
-            e1.record(stream)
-            e1.synchronize()
-            return res, e0.elapsed_time(e1)
-
-        for _ in range(args.warmup):
-            flush_l2()
-            res, _ = step()
-            res.free()
-        # ---- timed region: K steps, L2 flushed before each, device time per step from CUDA events ----
-        torch.cuda.synchronize()
-        sampler.start()
-        wall0 = time.perf_counter()
-        ms_steps, launches, st = [], 0, None
-        for _ in range(args.steps):
-            flush_l2()
-            res, ms = step()
-            st = res.stats()
-            launches += st["kernel_launches"]
-            ms_steps.append(ms)
-            res.free()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - wall0
+        sampler.start()                               # sampled through warm-up and the timed steps (>= 50 samples)
+        summary, (a, b, dims), st, m = measure_single(eng, torch, dev, wl, args.scale_down, args.steps, args.warmup, flush_l2, peak, peak_src)
         clocks = sampler.stop()
-        ms_per_step = sum(ms_steps) / len(ms_steps)
-
-        # ---- per-kernel durations (event pair per launch), a separate short pass ----
-        kernel_rows = []
-        for _ in range(max(3, min(args.steps, 10))):
-            flush_l2()
-            res, _ = step(api.OSP_PROFILE_KERNELS)
-            kernel_rows.append(res.kernel_times())
-            res.free()
+        ms_per_step, wall, launches, roof = m["ms_per_step"], m["wall"], m["launches"], m["roofline"]
+        parity = summary["parity"]
         # ---- the outer-product (k-slice) order of north_star, same workload and timing rules, for the record ----
         ks_ms = []
-        for i in range(3 + max(3, min(args.steps, 10))):
+        for i in range(6):
             flush_l2()
-            res, ms = step(api.OSP_KSLICE_ORDER)
+            res, ms = m["step"](api.OSP_KSLICE_ORDER)
             res.free()
             if i >= 3:
                 ks_ms.append(ms)
         kslice_ms = sum(ks_ms) / len(ks_ms)
-        kname, k_ms, k_launches, k_share, k_table = dominant_kernel(kernel_rows, st)
-        k_bytes, k_formula = kernel_algorithmic_bytes(kname, st)
-        k_bytes_per_launch = k_bytes / max(k_launches, 1.0)
-        achieved = k_bytes_per_launch / (k_ms * 1e-3) / 1e9
+        del m
 
         # ---- e2e: host CSRMatrix operands (pinned) -> osp_spgemm -> host CSRMatrix result ----
         def pinned_like(x):
@@ -330,31 +433,44 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         out_pos = out_pos_buf.numpy().view(np.uint64)
         out_dat = out_dat_buf.numpy().view(osp.ELEM)
         e2e_ms = []
-        for i in range(args.warmup + args.steps):
+        n_e2e = min(args.steps, 10)
+        for i in range(2 + n_e2e):
             flush_l2()
             t0 = time.perf_counter()
             res = eng.spgemm(ha, hb, a_is_csr=True, cols_b=dims["cols"])
             res.copy_into(out_pos[: res.rows + 1], out_dat[: res.nnz])
             dt = time.perf_counter() - t0
             res.free()
-            if i >= args.warmup:
+            if i >= 2:
                 e2e_ms.append(dt * 1e3)
         e2e_ms_step = sum(e2e_ms) / len(e2e_ms)
         h2d = int(a.pos.nbytes + a.data.nbytes + b.pos.nbytes + b.data.nbytes)
         d2h = int((st["rows_c"] + 1) * 8 + st["nnz_c"] * 8)
-        eng.close()
+        del keep, ha, hb, out_pos, out_dat, out_pos_buf, out_dat_buf
         products = st["products"]
         alg_bytes = st["algorithmic_bytes"]
-        n1_same = None
+        # ---- the other BASELINE configs at full size, fewer steps: the same measurement, one entry each ----
+        if not args.no_per_config and args.scale_down == 1 and args.workload is None:
+            per_config = []
+            for name in ("mlp_fc2", "er16k", "rmat20", "mlp_batch"):
+                try:
+                    ops = mlp_fc2_through_mtx() if name == "mlp_fc2" else None
+                    s2, _, _, m2 = measure_single(eng, torch, dev, name, 1, 5 if name != "rmat20" else 3, 3, flush_l2, peak, peak_src, ops)
+                    del m2
+                    per_config.append(s2)
+                except osp.OspError as e:
+                    per_config.append({"name": name, "error": str(e)})
+                torch.cuda.empty_cache()
+        eng.close()
     else:
         from outerspace_b200 import distributed as osd
-        out = osd.bench_sharded(a, b, dims, args, rank, world, local_rank, flush_l2, sampler)
+        a, b, dims = synth.build_workload(wl, args.scale_down)
+        out = osd.bench_sharded(a, b, dims, args, rank, world, local_rank, flush_l2, sampler, sampled_parity)
         ms_per_step, wall, clocks, launches, st = out["ms_per_step"], out["wall"], out["clocks"], out["launches"], out["stats"]
-        kname, k_ms, k_launches, k_share, k_table = out["kernel"]
-        k_bytes_per_launch, k_formula = out["kernel_bytes"], out["kernel_formula"]
-        achieved = k_bytes_per_launch / (k_ms * 1e-3) / 1e9
+        roof = roofline_of(out["kernel_table"], out["rank_stats"], peak, peak_src, wl)
+        roof["formula"] += " (this rank's share)"
         e2e_ms_step, h2d, d2h = out["e2e_ms"], out["h2d"], out["d2h"]
-        n1_same = out.get("n1_same_workload")
+        parity = out["parity"]
         kslice_ms = None
         products, alg_bytes = st["products"], st["algorithmic_bytes"]
 
@@ -372,49 +488,35 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
-            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC[wl], "name": wl, "scale_down": args.scale_down,
-                       "rows": st["rows_c"], "n_k": st["n_k"], "nnz_a": st["nnz_a"], "products": products,
-                       "nnz_c": st["nnz_c"], "parallelism": "single" if world == 1 else f"k-shard{world}+alltoallv",
-                       "timed_region": "HBM-resident CSR(A),CSR(B) -> HBM-resident CSR(C); CUDA events on the engine stream",
-                       "l2": f"L2 flushed ({L2_FLUSH_BYTES >> 20} MiB write) before every step, outside the event pair",
-                       # experimental engine paths are opt-in through the environment; a line measured with one says so
-                       "opt_in": {k.lower(): os.environ.get(k, "0") not in ("", "0") for k in ("OSP_LONGROW_SWEEP", "OSP_FUSED_SHORT")}},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(wl, args.scale_down),
+            "workload_detail": {"rows": st["rows_c"], "n_k": st["n_k"], "nnz_a": st["nnz_a"], "products": products,
+                                "nnz_c": st["nnz_c"], "parallelism": "single" if world == 1 else f"k-shard{world}+alltoallv",
+                                "timed_region": "HBM-resident CSR(A),CSR(B) -> HBM-resident CSR(C); CUDA events on the engine stream",
+                                "l2": f"L2 flushed ({L2_FLUSH_BYTES >> 20} MiB write) before every step, outside the event pair",
+                                # experimental engine paths are opt-in through the environment; a line measured with one says so
+                                "opt_in": {k.lower(): os.environ.get(k, "0") not in ("", "0") for k in ("OSP_LONGROW_SWEEP", "OSP_FUSED_SHORT")}},
             "algorithmic_gbs": round(alg_bytes / (ms_per_step * 1e-3) / 1e9, 2),
             "algorithmic_frac_of_hbm_peak": round(alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
             "wall_s_timed_region": round(wall, 4),
             "phases_ms_rank0": {k: round(float(st.get("ms_" + k, 0.0)), 4) for k in ("convert", "multiply", "exchange", "merge", "total")},
             "clocks": clocks,
             "gpu_launches": int(launches),
+            "parity": parity,
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "ms_per_step": round(e2e_ms_step, 4),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "path": "host CSRMatrix (pinned) -> osp_spgemm -> osp_result_copy to host CSRMatrix"},
-            "roofline": {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                         "avg_launch_ms": round(k_ms, 5), "launches_per_step": k_launches,
-                         "algorithmic_bytes_per_launch": int(k_bytes_per_launch), "formula": k_formula,
-                         "share_of_kernel_time": round(k_share, 4), "kernel_ms_per_step": k_table},
+            "roofline": roof,
         }
-        if world > 1 and n1_same:
-            line["n1_same_workload"] = n1_same
+        if per_config is not None:
+            line["per_config"] = per_config
         if world == 1:
             line["multiply_order"] = {"default": "row order of A (automatic)", "ms_per_step": round(ms_per_step, 5),
                                       "kslice_order_ms_per_step": round(kslice_ms, 5),
                                       "note": "OSP_KSLICE_ORDER = the reference's outer-product order incl. the device CSR->CSC task list; same bits"}
-        prof = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(prof):
-            try:
-                with open(prof) as f:
-                    tr = json.load(f)
-                kbase = kname.strip("() ").split("<")[0]
-                if tr.get("workload") == wl and kbase in tr.get("kernels", {}):
-                    line["roofline"]["traffic"] = tr["kernels"][kbase]["dram_bytes_per_launch"]
-                    line["roofline"]["traffic_source"] = tr.get("source")
-            except (OSError, ValueError, KeyError):
-                pass
         if world == 1 and not args.no_cpu_baseline:
             sd = CPU_SAMPLE_SCALE[wl] if args.scale_down == 1 else 1
-            ca, cb, cdims = (a, b, dims) if sd == 1 else synth.build_workload(wl, sd)
+            ca, cb, cdims = (a, b, dims) if sd == 1 else synth.build_workload(wl, sd * args.scale_down)
             secs, kind, cprod = cpu_reference_run(ca, cb, cdims["n_k"], 3)
             best = min(secs)
             line["cpu_baseline"] = {
@@ -437,6 +539,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=list(WORKLOAD_DESC))
     ap.add_argument("--scale-down", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true", help="skip the per_config table of the N=1 line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))

@@ -134,7 +134,8 @@ class DistEngine:
 # ------------------------------------------------------------------------------------------------
 # bench.py --gpus N
 # ------------------------------------------------------------------------------------------------
-def bench_sharded(a: CSRMatrix, b: CSRMatrix, dims: dict, args, rank: int, world: int, local_rank: int, flush_l2, sampler):
+def bench_sharded(a: CSRMatrix, b: CSRMatrix, dims: dict, args, rank: int, world: int, local_rank: int, flush_l2, sampler,
+                  sampled_parity=None):
     """Strong scaling of one workload over `world` ranks.  Returns the dict bench.py prints from."""
     import torch
     import torch.distributed as dist
@@ -164,13 +165,13 @@ def bench_sharded(a: CSRMatrix, b: CSRMatrix, dims: dict, args, rank: int, world
         dist.barrier()
         torch.cuda.synchronize()
 
+    sampler.start()                                 # sampled through warm-up and the timed steps
     for _ in range(args.warmup):
         flush_l2()
         barrier()
         res, _ = step()
         res.free()
     barrier()
-    sampler.start()
     wall0 = time.perf_counter()
     ms_steps, launches, st = [], 0, None
     for _ in range(args.steps):
@@ -219,27 +220,19 @@ def bench_sharded(a: CSRMatrix, b: CSRMatrix, dims: dict, args, rank: int, world
         if i >= 2:
             e2e.append(float(tm[0]))
 
-    # the same workload on ONE GPU (rank 0, its full operands), so that the scaling of this line can be read
-    # against the same problem: bench.py's N=1 line is BASELINE.json configs[1], a different workload
-    n1 = None
-    if rank == 0:
-        tf = [up(a.pos), up(a.data), up(b.pos), up(b.data)]
-        ms1 = []
-        for i in range(3 + min(args.steps, 5)):
-            flush_l2()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            r1 = eng.spgemm_device(a.NRow(), tf[0].data_ptr(), tf[1].data_ptr(), b.NRow(), tf[2].data_ptr(), tf[3].data_ptr(),
-                                   a_is_csr=True, cols_b=dims["cols"], a_nnz=a.nnz, b_nnz=b.nnz)
-            e1.record(stream)
-            e1.synchronize()
-            if i >= 3:
-                ms1.append(e0.elapsed_time(e1))
-            p1 = r1.stats()["products"]
-            r1.free()
-        n1 = {"ms_per_step": round(sum(ms1) / len(ms1), 5), "value": round(2.0 * p1 / (sum(ms1) / len(ms1) * 1e-3) / 1e9, 3),
-              "unit": "GFLOP/s", "note": "same workload, single-GPU engine on rank 0, same timing rules"}
-        del tf
+    # parity, outside every timed region: sampled rows of THIS rank's block of C against the oracle, every rank's verdict gathered
+    parity = None
+    if sampled_parity is not None:
+        flush_l2()
+        barrier()
+        res, _ = step()
+        r0, r1 = row_block(dims["rows"], world, rank)
+        par = sampled_parity(res, a, b, dims, n_rows=24, heavy=1, row_lo=r0, row_hi=r1, seed=7 + rank)
+        res.free()
+        pt = torch.tensor([0 if par["ok"] else 1, par["rows_checked"], par["products_checked"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(pt)
+        parity = {"ok": int(pt[0]) == 0, "ranks_failing": int(pt[0]), "rows_checked": int(pt[1]), "products_checked": int(pt[2]),
+                  "how": "every rank: seeded sample of rows of its own block + the heaviest, engine rows vs oracle rows, bit for bit"}
     barrier()
 
     # whole-job sums
@@ -254,26 +247,20 @@ def bench_sharded(a: CSRMatrix, b: CSRMatrix, dims: dict, args, rank: int, world
     deng.close()
     eng.close()
 
-    # dominant kernel of this rank, with the algorithmic bytes of THIS rank's launch
+    # per-kernel table of this rank (ms per step, launches per step), sorted by time
     agg, cnt = {}, {}
     for rows in kernel_rows:
         for name, ms in rows:
             agg[name] = agg.get(name, 0.0) + ms
             cnt[name] = cnt.get(name, 0) + 1
-    total_ms = sum(agg.values()) or 1.0
-    kname = max(agg, key=agg.get)
-    table = {k: round(v / len(kernel_rows), 5) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}
-    if "multiply" in kname:
-        kbytes, formula = 8 * st["nnz_a"] + 8 * st["nnz_b"] + 16 * (st["n_k"] + 1) + 8 * st["products"], \
-            "multiply (this rank's k-range): 8nnzA_g + 8nnzB_g + 16(n_g+1) + 8P_g"
-    elif "merge" in kname:
-        p_owned = (st["algorithmic_bytes"] - 8 * st["products"] - 8 * st["nnz_c"] - 24 * st["nnz_a"] - 8 * st["nnz_b"]
-                   - 8 * (2 * st["rows_c"] + 3 * st["n_k"] + 5)) // 8
-        kbytes, formula = 8 * p_owned + 8 * st["nnz_c"] + 8 * (st["rows_c"] + 1), "merge (this rank's rows): 8P_owned + 8nnzC_g + 8(m_g+1)"
-    else:
-        kbytes, formula = 16 * st["nnz_a"] + 8 * (st["rows_c"] + st["n_k"] + 2), "symbolic/plan: 16nnzA_g + 8(m_g+n_g+2)"
-    launches_per_step = cnt[kname] / len(kernel_rows)
+    nk = max(len(kernel_rows), 1)
+    table = {k: (agg[k] / nk, cnt[k] / nk) for k in sorted(agg, key=lambda k: -agg[k])}
+    # this rank's own sizes for the roofline of its dominant kernel: the merge reads what the rank OWNS
+    p_owned = (st["algorithmic_bytes"] - 8 * st["products"] - 8 * st["nnz_c"] - 24 * st["nnz_a"] - 8 * st["nnz_b"]
+               - 8 * (2 * st["rows_c"] + 3 * st["n_k"] + 5)) // 8
+    rank_stats = dict(st)
+    if next(iter(table), "").find("merge") >= 0:
+        rank_stats["products"] = p_owned
     return dict(ms_per_step=sum(ms_steps) / len(ms_steps), wall=wall, clocks=clocks, launches=launches, stats=stats,
-                kernel=(kname, agg[kname] / cnt[kname], launches_per_step, agg[kname] / total_ms, table),
-                kernel_bytes=kbytes / max(launches_per_step, 1.0), kernel_formula=formula,
-                e2e_ms=sum(e2e) / len(e2e), h2d=tot[5], d2h=tot[6], n1_same_workload=n1)
+                kernel_table=table, rank_stats=rank_stats, parity=parity,
+                e2e_ms=sum(e2e) / len(e2e), h2d=tot[5], d2h=tot[6])

@@ -1,6 +1,6 @@
 """GPU suite: the CUDA path (through the C ABI) against the oracle -- bit-exact row_ptr, col_idx AND
 values (the engine's merge is the deterministic k-ordered one).  Sizes here finish in seconds on the
-oracle; full-size configs are covered by the property tests in test_gpu_properties.py."""
+oracle; full-size configs are covered by the property tests in test_gpu_zz_fullsize.py."""
 import os
 
 import numpy as np
@@ -48,6 +48,32 @@ def test_mtx_pipeline_like_reference_main(engine):
     merge = provider.getMergeTasks()
     assert merge.shape[0] == provider.mergedResult.NRow()
     assert np.array_equal(merge[:, 1], np.diff(provider.mergedResult.pos.astype(np.int64)).astype(np.uint32))
+
+
+def test_config1_as_surveyed_through_mtx(engine, tmp_path):
+    """BASELINE configs[0] as SURVEY.md 8d describes it: a 1000 x 1000 layer pruned to 1 % density, written by
+    scipy.io.mmwrite(csr_matrix) exactly like NN_models/util.py:61-62, read back by readcoo (SimSpGEMM.cpp:55-100),
+    turned into CSC(A) / CSR(A) by coo2csr (:102-152), multiplied as A*A on the GPU, compared with the oracle."""
+    import scipy.io
+    a0, _, dims = synth.build_workload("mlp_fc2")
+    dense = sp.csr_matrix((a0.data["val"], a0.data["idx"].astype(np.int64), a0.pos.astype(np.int64)), shape=(1000, 1000))
+    path = str(tmp_path / "fc2_weight.mtx")
+    scipy.io.mmwrite(path, dense)
+    coo, nrow, ncol = osp.readcoo(path)
+    assert (nrow, ncol) == (1000, 1000) and len(coo.rows) == 10000
+    csc = osp.coo2csr(coo, ncol, transpose=True)
+    csr = osp.coo2csr(coo, nrow)
+    want, prod = oracle_spgemm(csc, csr)
+    assert 5e4 < prod < 2e5                                   # SURVEY 8: P ~ 1e5
+    for a, is_csr in ((csc, False), (csr, True)):
+        res = engine.spgemm(a, csr, a_is_csr=is_csr)
+        got = res.to_host()
+        assert res.stats()["products"] == prod
+        res.free()
+        assert_bit_exact(got, want, f"config 1 through .mtx, a_is_csr={is_csr}")
+        check_csr_invariants(got, 1000)
+    provider = osp.TaskProvider(csc, csr, engine=engine)       # the reference's own entry point (SimOuterSPACE.cpp:859-860)
+    assert_bit_exact(provider.mergedResult, want, "config 1 TaskProvider")
 
 
 @pytest.mark.parametrize("seed", range(8))

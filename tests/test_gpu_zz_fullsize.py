@@ -54,3 +54,14 @@ def test_config3_rmat20_full_size():
     st = out["stats"]
     assert st["products"] > 2.0e10 and st["row_chunks"] > 1 and st["rows_long"] > 100000
     assert out["invariants_ok"] and out["bad_rows"] == 0 and out["rows_checked"] >= 150
+
+
+def test_config4_er8m_full_size():
+    """ER 2^23 x 2^23, 8 nnz/row, C = A*A at FULL size on one GPU (the headline workload of bench.py): P = 5.4e8,
+    4.3 GB of C; global invariants plus sampled rows bit for bit against the oracle."""
+    if not _big_gpu():
+        pytest.skip("needs a >= 150 GB GPU")
+    out = _run("er8m", iters=1, sample_rows=256, heavy_rows=4)
+    st = out["stats"]
+    assert st["products"] > 5.3e8 and st["rows_c"] == 1 << 23
+    assert out["invariants_ok"] and out["bad_rows"] == 0 and out["rows_checked"] >= 200
