@@ -5,6 +5,7 @@
 #include "../../include/osp_b200.h"
 #include "osp_kernels.cuh"
 #include "osp_longrows.cuh"
+#include "osp_chain2.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -64,7 +65,7 @@ struct osp_ctx {
     // operand staging (host-pointer calls) and converted operands
     DevBuf op_a_pos, op_a_data, op_b_pos, op_b_data, conv_pos, conv_data, conv_tmp, conv_chk;
     // symbolic / plan / conversion scratch
-    DevBuf task_bs, run_off, row_bin, tile_row, long_list, xl_list, uniq, col_ptr, tasks, tile_state, xl_acc, xl_bits;
+    DevBuf task_bs, run_off, row_bin, tile_row, tile_start, long_list, xl_list, uniq, col_ptr, tasks, tile_state, xl_acc, xl_bits;
     DevBuf bins;
     // fused band sweep of the long rows (opt-in, osp_longrows.cuh): task bitmap for the multiply, band index of B
     DevBuf swept, lr_bands;
@@ -75,6 +76,9 @@ struct osp_ctx {
     // OSP_FUSED_SHORT (opt-in): short-row tiles computed inside the merge chain
     bool fused_short_ok = false, fused_short_env = false;
     int chain_fused_occ[3] = {1, 1, 1};
+    // k_chain2 (osp_chain2.cuh): the warp-specialised fused chain; `chain2_old` (OSP_FUSED_SHORT_OLD=1) keeps k_merge_chain_fused
+    bool chain2_ok = false, chain2_old = false;
+    int chain2_occ[3] = {1, 1, 1};
     std::vector<cudaEvent_t> events;
     size_t events_used = 0;
     // OSP_PROFILE_KERNELS: one event pair per launch
@@ -250,6 +254,7 @@ int sync_scalars(osp_ctx *ctx) {
 int reserve_plan(osp_ctx *ctx, uint64_t rows, uint64_t max_long) {
     CU(ctx, ctx->row_bin.reserve((rows + 1) * 8));
     CU(ctx, ctx->tile_row.reserve((rows + 2) * 4));
+    CU(ctx, ctx->tile_start.reserve((rows + 2) * sizeof(TileStart)));
     CU(ctx, ctx->tile_state.reserve((rows + 2) * 8));      // look-back states of the merge chain, zeroed by the plan
     CU(ctx, ctx->long_list.reserve(std::max<uint64_t>(max_long, 1) * 4));
     CU(ctx, ctx->xl_list.reserve(std::max<uint64_t>(max_long, 1) * 4));
@@ -275,6 +280,7 @@ struct MergeJob {
     const uint32_t *bandptr = nullptr;      // band index of B (k_long_bands)
     // OSP_FUSED_SHORT: the chain computes the short rows' partial products itself (k_merge_chain_fused)
     bool fused_short = false;
+    bool chain2 = false;                    // ... with k_chain2 (producer warps) instead of k_merge_chain_fused
     const uint64_t *run_off = nullptr;
     const uint32_t *task_bs = nullptr;
     uint64_t m_a = 0;
@@ -364,6 +370,20 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
 #define MC_ARGS row_bin, bin_base, bins, ctx->tile_row.as<uint32_t>(), t0, n_chain, uniq, ctx->tile_state.as<uint64_t>(), ctx->d_sc, \
                 carry_slot, job.c_pos, job.c_data, bm_wpl, job.long_thresh
     const int variant = bm_words ? 2 : job.idx_range <= (1ull << 23) ? 0 : 1;
+    if (job.fused_short && job.chain2) {
+        const C2SrcProduct src{job.a_data, job.run_off, job.task_bs, job.b_data};
+        const TileStart *tiles = ctx->tile_start.as<TileStart>();
+        const unsigned int grid2 = std::min<unsigned>(n_chain, unsigned(ctx->sm_count) * unsigned(ctx->chain2_occ[variant == 2 && job.long_thresh != MT_LONG_BM ? 0 : variant]));
+#define C2_ARGS tiles, row_bin, bin_base, bins, t0, n_chain, uniq, ctx->tile_state.as<uint64_t>(), ctx->d_sc, carry_slot, job.c_pos, job.c_data, \
+                bm_wpl, job.long_thresh, src
+        // the bitmap variant needs the smaller tiles the plan cuts when it knows the column range up front
+        const int v2 = variant == 2 && job.long_thresh != MT_LONG_BM ? 0 : variant;
+        if (v2 == 2) LAUNCH(ctx, (k_chain2<uint32_t, true, C2SrcProduct>), grid2, C2_THREADS, sizeof(Chain2Smem<true>), C2_ARGS);
+        else if (v2 == 0) LAUNCH(ctx, (k_chain2<uint32_t, false, C2SrcProduct>), grid2, C2_THREADS, sizeof(Chain2Smem<false>), C2_ARGS);
+        else LAUNCH(ctx, (k_chain2<uint64_t, false, C2SrcProduct>), grid2, C2_THREADS, sizeof(Chain2Smem<false>), C2_ARGS);
+#undef C2_ARGS
+        return OSP_OK;
+    }
     if (job.fused_short) {
         const FusedSrc fs{job.a_pos, job.a_data, job.run_off, job.task_bs, job.b_data, job.m_a};
         const unsigned int gridf = std::min<unsigned>(n_chain, unsigned(ctx->sm_count) * unsigned(ctx->chain_fused_occ[variant]));
@@ -584,14 +604,27 @@ int osp_create(int device, osp_ctx **out) {
         const char *env = std::getenv("OSP_FUSED_SHORT");
         ctx->fused_short_env = env && env[0] && env[0] != '0';
     }
+    {   // k_chain2: the warp-specialised implementation of the same path
+        auto c32 = k_chain2<uint32_t, false, C2SrcProduct>;
+        auto c64 = k_chain2<uint64_t, false, C2SrcProduct>;
+        auto cbm = k_chain2<uint32_t, true, C2SrcProduct>;
+        ctx->chain2_ok =
+            cudaFuncSetAttribute(c32, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(Chain2Smem<false>))) == cudaSuccess &&
+            cudaFuncSetAttribute(c64, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(Chain2Smem<false>))) == cudaSuccess &&
+            cudaFuncSetAttribute(cbm, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(Chain2Smem<true>))) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->chain2_occ[0], c32, C2_THREADS, sizeof(Chain2Smem<false>)) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->chain2_occ[1], c64, C2_THREADS, sizeof(Chain2Smem<false>)) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->chain2_occ[2], cbm, C2_THREADS, sizeof(Chain2Smem<true>)) == cudaSuccess &&
+            ctx->chain2_occ[0] >= 1 && ctx->chain2_occ[1] >= 1 && ctx->chain2_occ[2] >= 1;
+        if (!ctx->chain2_ok) cudaGetLastError();
+        for (int &o : ctx->chain2_occ) o = std::max(o, 1);
+        const char *env = std::getenv("OSP_FUSED_SHORT_OLD");
+        ctx->chain2_old = env && env[0] && env[0] != '0';
+    }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-    if (const char *env = std::getenv("OSP_L2_FETCH")) {      // development knob: cudaLimitMaxL2FetchGranularity (32 / 64 / 128)
-        const size_t g = std::strtoull(env, nullptr, 10);
-        if (g) { if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g) != cudaSuccess) cudaGetLastError(); }
     }
     ctx->ws_limit = uint64_t(double(ctx->total_mem) * 0.35);
     if (const char *env = std::getenv("OSP_WORKSPACE_LIMIT_MB")) {
@@ -608,7 +641,7 @@ void osp_destroy(osp_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->arena, &ctx->op_a_pos, &ctx->op_a_data, &ctx->op_b_pos, &ctx->op_b_data, &ctx->conv_pos,
                       &ctx->conv_data, &ctx->conv_tmp, &ctx->conv_chk, &ctx->task_bs, &ctx->run_off, &ctx->row_bin, &ctx->tile_row,
-                      &ctx->long_list, &ctx->xl_list, &ctx->uniq, &ctx->col_ptr, &ctx->tasks, &ctx->tile_state,
+                      &ctx->tile_start, &ctx->long_list, &ctx->xl_list, &ctx->uniq, &ctx->col_ptr, &ctx->tasks, &ctx->tile_state,
                       &ctx->xl_acc, &ctx->xl_bits, &ctx->bins, &ctx->swept, &ctx->lr_bands})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -749,9 +782,16 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     }
     rc = reserve_plan(ctx, m_plan, std::min(m_plan, std::max<uint64_t>(nnz_a, 1)));
     if (rc) return rc;
+    // ---- OSP_FUSED_SHORT: no bins for the tiles of short rows; the multiply only serves the long rows.  Decided before the
+    // plan: the bitmap variant of k_chain2 takes smaller tiles (shared memory)
+    const bool fused_short = ctx->fused_short_ok && ((args->flags & OSP_FUSED_SHORT) || ctx->fused_short_env) &&
+                             !(args->flags & OSP_KSLICE_ORDER) && rowwise && !fused && nnz_a > 0;
+    const bool chain2 = fused_short && ctx->chain2_ok && !ctx->chain2_old;
+    const int cap_shift_max = chain2 && plan_long_thresh(cols_b) == MT_LONG_BM ? C2_CAP_SHIFT_BM : MT_CAP_SHIFT_MAX;
     LAUNCH(ctx, k_plan<RowBinFromRuns>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinFromRuns{dA_pos, m_a, run_off, nnz_a}, m_plan,
            cols_b, ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
-           ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(cols_b), ctx->tile_state.as<uint64_t>());
+           ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(cols_b), ctx->tile_state.as<uint64_t>(),
+           ctx->tile_start.as<TileStart>(), cap_shift_max);
     cudaEvent_t ev_sym = next_event(ctx);
     // ---- result object; C.pos is allocated while the device is still busy with the symbolic pass and the plan ----
     osp_result *res = new osp_result();
@@ -798,11 +838,8 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         job.sweep_min = std::max<uint64_t>({ctx->sweep_min, MT_XL + 1, LR_MIN_PER_BAND * lr_bands});
         job.a_pos = dA_pos; job.a_data = dA_data; job.b_data = dB_data;
     }
-    // ---- OSP_FUSED_SHORT (opt-in): no bins for the tiles of short rows; the multiply only serves the long rows
-    const bool fused_short = ctx->fused_short_ok && ((args->flags & OSP_FUSED_SHORT) || ctx->fused_short_env) &&
-                             !(args->flags & OSP_KSLICE_ORDER) && rowwise && !fused && nnz_a > 0;
     if (fused_short) {
-        job.fused_short = true;
+        job.fused_short = true; job.chain2 = chain2;
         job.run_off = run_off; job.task_bs = task_bs; job.m_a = m_a;
         job.a_pos = dA_pos; job.a_data = dA_data; job.b_data = dB_data;
     }

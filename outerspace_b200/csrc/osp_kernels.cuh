@@ -187,6 +187,11 @@ constexpr uint32_t MT_STAGE = MT_CAP + MT_LONG_BM;    // hard bound of a tile of
 constexpr uint32_t MT_RMAX = 256;      // rows per tile (one thread per row in the tile's scans)
 constexpr uint32_t MT_XL = 4096;       // longest row sorted in shared memory by one CTA
 
+// What the producer warps of k_chain2 (osp_chain2.cuh) need to open a tile, in one 32-byte load (entries t and t + 1):
+// first row, first task (non-zero of A / segment) and first partial product of the tile.
+struct __align__(16) TileStart { uint32_t r0, e0; uint64_t b0; };
+static_assert(sizeof(TileStart) == 16, "two tile starts are one 32-byte load");
+
 constexpr int PLAN_BLOCK = 256;
 constexpr int PLAN_ITEMS = 4;
 constexpr int PLAN_TILE = PLAN_BLOCK * PLAN_ITEMS;
@@ -199,18 +204,20 @@ struct RowBinFromRuns {        // row i starts where the run of its first non-ze
     __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return run_off[i <= m_a ? a_pos[i] : nnz_a]; }
     // a row counts for numRows = maxRowId + 1 (SimOuterSPACE.cpp:49-53) when A holds a non-zero in it
     __device__ __forceinline__ bool nonempty(uint64_t i) const { return i < m_a && a_pos[i + 1] > a_pos[i]; }
+    __device__ __forceinline__ uint64_t task_begin(uint64_t i) const { return i <= m_a ? a_pos[i] : nnz_a; }   // first non-zero of A of row i
 };
 struct RowBinDirect {
     const uint64_t *pos;
     __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return pos[i]; }
     __device__ __forceinline__ bool nonempty(uint64_t i) const { return pos[i + 1] > pos[i]; }
+    __device__ __forceinline__ uint64_t task_begin(uint64_t) const { return 0; }
 };
 
 template <class RB>
 __global__ void __launch_bounds__(PLAN_BLOCK)
 k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *tile_row, uint32_t *long_list,
        uint32_t *xl_list, uint64_t *tile_state, DevScalars *sc, int ticket_slot, uint32_t long_thresh,
-       uint64_t *chain_state) {
+       uint64_t *chain_state, TileStart *tile_start = nullptr, int cap_shift_max = MT_CAP_SHIFT_MAX) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[33];
     __shared__ uint64_t s_bound[PLAN_BLOCK / 32];
@@ -225,7 +232,7 @@ k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *ti
     // tiles for every persistent CTA of the merge (444 on a B200): 2^cap_shift ~ P / 1024 within [256, MT_CAP]
     const uint64_t p_all = rb(rows);
     int cap_shift = MT_CAP_SHIFT_MIN;
-    while (cap_shift < MT_CAP_SHIFT_MAX && (p_all >> (cap_shift + 1)) >= 1024) cap_shift++;
+    while (cap_shift < cap_shift_max && (p_all >> (cap_shift + 1)) >= 1024) cap_shift++;
 
     uint64_t s[PLAN_ITEMS + 1];
 #pragma unroll
@@ -276,6 +283,7 @@ k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *ti
                 sc->n_tiles = uint32_t(excl + total);
                 tile_row[excl + total] = uint32_t(rows);
                 row_bin[rows] = rb(rows);
+                if (tile_start) tile_start[excl + total] = TileStart{uint32_t(rows), uint32_t(rb.task_begin(rows)), rb(rows)};
             }
         }
     }
@@ -283,7 +291,11 @@ k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *ti
     uint64_t o = s_excl + rank;
 #pragma unroll
     for (int it = 0; it < PLAN_ITEMS; it++)
-        if (flag[it]) { chain_state[o] = 0; tile_row[o++] = uint32_t(i0 + it); }   // (look-back state of the merge chain)
+        if (flag[it]) {
+            chain_state[o] = 0;                                                    // (look-back state of the merge chain)
+            if (tile_start) tile_start[o] = TileStart{uint32_t(i0 + it), uint32_t(rb.task_begin(i0 + it)), s[it]};
+            tile_row[o++] = uint32_t(i0 + it);
+        }
 }
 
 // =====================================================================================
@@ -1602,6 +1614,7 @@ struct RowBinStrided {         // row i of the owner starts at dst_off[i * G]
     uint64_t G;
     __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return off[i * G]; }
     __device__ __forceinline__ bool nonempty(uint64_t i) const { return off[(i + 1) * G] > off[i * G]; }
+    __device__ __forceinline__ uint64_t task_begin(uint64_t i) const { return i * G; }        // segment (row i, source 0)
 };
 // One warp per owned row: the row's G segments (one per source, received source-major) become one contiguous
 // row in the row-major bins, sources in ascending order.  The lanes stride over the ROW's elements -- every
