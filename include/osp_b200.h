@@ -61,6 +61,12 @@ extern "C" {
                                     rows never go through the bins -- the merge chain computes a tile's partial products
                                     straight into its shared-memory stage (k_merge_chain_fused), k_multiply only serves the
                                     long rows.  Same bits.  Ignored with OSP_KSLICE_ORDER.  Environment: OSP_FUSED_SHORT=1 */
+#define OSP_NO_VALIDATE    512u  /* the caller vouches for the operand preconditions (slices ascending and duplicate-free,
+                                    every column id of B below cols_b): skips the validation pass (one streaming read of
+                                    both operands, k_validate).  By default a violation returns OSP_ERR_INVALID (unsorted
+                                    slice, broken pos array), OSP_ERR_DUPLICATE (233) or OSP_ERR_INDEX before any merge
+                                    kernel runs -- where the reference relies on coo2csr's sort + dupcheck
+                                    (SimSpGEMM.cpp:113-123) */
 #define OSP_PROFILE_PHASES   8u  /* synchronise between phases so that stats.ms_* are per-phase times */
 
 #define OSP_PROFILE_KERNELS 16u  /* record a CUDA-event pair around every kernel launch (osp_result_kernels) */

@@ -36,6 +36,7 @@ OSP_KSLICE_ORDER = 32
 OSP_NO_FUSED_DENSE = 64
 OSP_LONGROW_SWEEP = 128     # experimental, off by default (include/osp_b200.h)
 OSP_FUSED_SHORT = 256       # experimental, off by default (include/osp_b200.h)
+OSP_NO_VALIDATE = 512       # the caller vouches for sorted, duplicate-free slices and in-range column ids
 OSP_PROFILE_PHASES = 8
 OSP_PROFILE_KERNELS = 16
 

@@ -56,6 +56,11 @@ struct DevScalars {
     unsigned int scan_ticket[4];       // dynamic tile ids of the look-back scans (one per scan of a call)
     unsigned int n_dups;               // rows that shrank while folding (duplicate check of csr2csc)
     unsigned int xl_ticket;            // dynamic row ids of k_merge_xl (zeroed before every launch)
+    // k_validate (operand preconditions): positions p with d[p].idx <= d[p-1].idx, and how many of them are the first
+    // element of a slice; the same for d[p].idx == d[p-1].idx.  Slices are ascending and duplicate-free exactly when
+    // every descent sits on a slice boundary.
+    unsigned long long v_desc, v_bdesc, v_eq, v_beq;
+    unsigned long long v_bad_pos;      // pos[] entries that decrease or exceed nnz
 };
 
 constexpr unsigned int FULL = 0xffffffffu;

@@ -517,6 +517,23 @@ int launch_multiply(osp_ctx *ctx, Src src, uint64_t t0, uint64_t t1, uint64_t pr
     return OSP_OK;
 }
 
+// Operand preconditions (k_validate): launched into the current arena; check_operands() reads the verdict after the next
+// hand-over of the device scalars.
+int launch_validate(osp_ctx *ctx, const ValidateOp &op0, const ValidateOp &op1, int n_ops) {
+    const uint64_t work = std::max<uint64_t>({op0.nnz, op0.n_slices, n_ops > 1 ? op1.nnz : 0, n_ops > 1 ? op1.n_slices : 0, 1});
+    LAUNCH(ctx, k_validate, grid_for(work, 1024, unsigned(ctx->sm_count) * 8u), 256, 0, op0, op1, n_ops, ctx->d_sc);
+    return OSP_OK;
+}
+int check_operands(osp_ctx *ctx, const char *who) {
+    const DevScalars &h = *ctx->h_sc;
+    if (h.v_bad_pos) return fail(ctx, OSP_ERR_INVALID, std::string(who) + ": a pos array decreases or points past its data array");
+    if (h.v_desc - h.v_eq != h.v_bdesc - h.v_beq)
+        return fail(ctx, OSP_ERR_INVALID, std::string(who) + ": the indices of a slice are not ascending (operands must be sorted inside every slice, "
+                                                             "as coo2csr leaves them, SimSpGEMM.cpp:113-120)");
+    if (h.v_eq != h.v_beq) return fail(ctx, OSP_ERR_DUPLICATE, std::string(who) + ": duplicate (row,col) entry in operand");
+    return OSP_OK;
+}
+
 }  // namespace
 
 // ========================================================================================
@@ -690,6 +707,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     int rc;
 
     const uint64_t n_k = args->n_k;
+    const bool validate = !(args->flags & OSP_NO_VALIDATE);
     Operands op;
     rc = stage_operands(ctx, args, op);
     if (rc) return rc;
@@ -708,9 +726,18 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         const uint64_t st0[4] = {0, 0, 0, 0};
         rc = prepare_arena(ctx, st0, 0, ar0);
         if (rc) return rc;
-        if (nnz_a) LAUNCH(ctx, k_max_idx, grid_for(nnz_a, 1024, unsigned(ctx->sm_count) * 8u), 256, 0, dA_data, nnz_a, ctx->d_sc);
+        if (validate) {             // also leaves the largest row id in max_idx
+            const ValidateOp opa{dA_pos, dA_data, args->a_slices, nnz_a, args->rows_c};
+            rc = launch_validate(ctx, opa, opa, 1);
+            if (rc) return rc;
+        } else if (nnz_a) LAUNCH(ctx, k_max_idx, grid_for(nnz_a, 1024, unsigned(ctx->sm_count) * 8u), 256, 0, dA_data, nnz_a, ctx->d_sc);
         rc = sync_scalars(ctx);
         if (rc) return rc;
+        if (validate) {
+            if (ctx->h_sc->err) return fail(ctx, OSP_ERR_INDEX, "osp_spgemm: rows_c is smaller than the largest row id of A + 1");
+            rc = check_operands(ctx, "osp_spgemm (A)");
+            if (rc) return rc;
+        }
         m_a = uint64_t(ctx->h_sc->max_idx) + 1;
         CU(ctx, ctx->conv_pos.reserve((m_a + 1) * 8));
         CU(ctx, ctx->conv_data.reserve(std::max<uint64_t>(nnz_a, 1) * 8));
@@ -743,7 +770,16 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     rc = prepare_arena(ctx, st, rowwise ? 0 : n_k, ar);
     if (rc) return rc;
     uint64_t cols_b = args->cols_b;
-    if (!cols_b && nnz_b)
+    if (validate) {
+        // B: ascending, duplicate-free rows, column ids below cols_b (or their maximum when cols_b is to be derived);
+        // A in row-compressed form: ascending rows (k < n_k is the symbolic pass's check).  A converted on the device a
+        // moment ago is sorted by construction; A == B (C = A*A on the same arrays) is read once.
+        const ValidateOp opb{dB_pos, dB_data, n_k, nnz_b, cols_b};
+        const ValidateOp opa{dA_pos, dA_data, m_a, nnz_a, 0};
+        const bool same = a_is_csr && dA_pos == dB_pos && dA_data == dB_data && m_a == n_k;
+        rc = a_is_csr && !same ? launch_validate(ctx, opa, opb, 2) : launch_validate(ctx, opb, opb, 1);
+        if (rc) return rc;
+    } else if (!cols_b && nnz_b)
         LAUNCH(ctx, k_max_idx, grid_for(nnz_b, 1024, unsigned(ctx->sm_count) * 8u), 256, 0, dB_data, nnz_b, ctx->d_sc);
     CU(ctx, ctx->run_off.reserve((nnz_a + 1) * 8));
     CU(ctx, ctx->task_bs.reserve(std::max<uint64_t>(nnz_a, 1) * 4));
@@ -787,11 +823,11 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     const bool fused_short = ctx->fused_short_ok && ((args->flags & OSP_FUSED_SHORT) || ctx->fused_short_env) &&
                              !(args->flags & OSP_KSLICE_ORDER) && rowwise && !fused && nnz_a > 0;
     const bool chain2 = fused_short && ctx->chain2_ok && !ctx->chain2_old;
-    const int cap_shift_max = chain2 && plan_long_thresh(cols_b) == MT_LONG_BM ? C2_CAP_SHIFT_BM : MT_CAP_SHIFT_MAX;
+    const uint32_t cap_max = !chain2 ? MT_CAP : plan_long_thresh(cols_b) == MT_LONG_BM ? C2_CAP_BM : C2_CAP;
     LAUNCH(ctx, k_plan<RowBinFromRuns>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinFromRuns{dA_pos, m_a, run_off, nnz_a}, m_plan,
            cols_b, ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
            ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(cols_b), ctx->tile_state.as<uint64_t>(),
-           ctx->tile_start.as<TileStart>(), cap_shift_max);
+           ctx->tile_start.as<TileStart>(), cap_max);
     cudaEvent_t ev_sym = next_event(ctx);
     // ---- result object; C.pos is allocated while the device is still busy with the symbolic pass and the plan ----
     osp_result *res = new osp_result();
@@ -806,8 +842,13 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     }
     rc = sync_scalars(ctx);                       // the one mid-pipeline hand-over: sizes of the bins and of C
     if (rc) return bail(rc);
+    if (validate && ctx->h_sc->v_bad_pos) return bail(check_operands(ctx, "osp_spgemm"));     // (a broken pos array also looks like a huge row)
     if (ctx->h_sc->err == 6) return bail(fail(ctx, OSP_ERR_UNSUPPORTED, "osp_spgemm: a row of B holds >= 2^24 non-zeros"));
-    if (ctx->h_sc->err) return bail(fail(ctx, OSP_ERR_INDEX, "osp_spgemm: index of A out of range of the inner dimension"));
+    if (ctx->h_sc->err) return bail(fail(ctx, OSP_ERR_INDEX, "osp_spgemm: index out of range (k of A beyond the inner dimension, or a column of B beyond cols_b)"));
+    if (validate) {
+        rc = check_operands(ctx, "osp_spgemm");
+        if (rc) return bail(rc);
+    }
     const uint64_t P = ctx->h_sc->products;
     if (P >> 40) return bail(fail(ctx, OSP_ERR_UNSUPPORTED, "osp_spgemm: more than 2^40 partial products"));
     if (!cols_b) cols_b = uint64_t(ctx->h_sc->max_idx) + 1;

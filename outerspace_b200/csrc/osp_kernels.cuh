@@ -171,6 +171,60 @@ __global__ void k_max_idx(const Elem *d, uint64_t nnz, DevScalars *sc) {
     if (lane_id() == 0 && m) atomicMax(&sc->max_idx, m);
 }
 
+// Operand preconditions: "both sorted ascending inside a slice, duplicate-free" -- what coo2csr guarantees
+// in the reference (sort + dupcheck, SimSpGEMM.cpp:113-123) and what the merge kernels rely on (k_band_ptr's binary
+// search, one-round arbitration of a duplicate-free run).  One streaming pass per operand: every position whose index
+// does not exceed its predecessor's is counted, and so is every such position that opens a slice; an operand is valid
+// exactly when the two counts agree.  Also: index range (idx < idx_range when given), max index of operand 1, pos[]
+// monotone and within nnz.
+struct ValidateOp { const uint64_t *pos; const Elem *d; uint64_t n_slices, nnz, idx_range; };
+__global__ void __launch_bounds__(256)
+k_validate(const ValidateOp op0, const ValidateOp op1, const int n_ops, DevScalars *sc) {
+    uint32_t desc = 0, bdesc = 0, eq = 0, beq = 0, badpos = 0, mx = 0;
+    bool range_err = false;
+    const uint64_t t0 = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x, nt = uint64_t(gridDim.x) * blockDim.x;
+    for (int o = 0; o < n_ops; o++) {
+        const ValidateOp &op = o ? op1 : op0;
+        for (uint64_t p0 = t0; p0 < op.nnz; p0 += 4 * nt) {                    // four independent pairs of loads in flight per thread
+            uint32_t cur[4], prv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint64_t p = p0 + u * nt;
+                cur[u] = p < op.nnz ? op.d[p].idx : 0u;
+                prv[u] = p < op.nnz && p ? op.d[p - 1].idx : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint64_t p = p0 + u * nt;
+                if (p >= op.nnz) continue;
+                if (op.idx_range && cur[u] >= op.idx_range) range_err = true;
+                if (o == n_ops - 1) mx = max(mx, cur[u]);
+                if (p) { desc += cur[u] <= prv[u]; eq += cur[u] == prv[u]; }
+            }
+        }
+        for (uint64_t r = t0; r < op.n_slices; r += nt) {
+            const uint64_t s = op.pos[r], e = op.pos[r + 1];
+            if (e < s || e > op.nnz) { badpos++; continue; }
+            if (s < e && s > 0) {
+                const uint32_t cur = op.d[s].idx, prv = op.d[s - 1].idx;
+                bdesc += cur <= prv; beq += cur == prv;
+            }
+        }
+    }
+    desc = __reduce_add_sync(FULL, desc); bdesc = __reduce_add_sync(FULL, bdesc);
+    eq = __reduce_add_sync(FULL, eq); beq = __reduce_add_sync(FULL, beq);
+    badpos = __reduce_add_sync(FULL, badpos); mx = __reduce_max_sync(FULL, mx);
+    if (__any_sync(FULL, range_err) && lane_id() == 0) atomicMax(&sc->err, 4u);                 // OSP_ERR_INDEX
+    if (lane_id() == 0) {
+        if (desc) atomicAdd(&sc->v_desc, (unsigned long long)desc);
+        if (bdesc) atomicAdd(&sc->v_bdesc, (unsigned long long)bdesc);
+        if (eq) atomicAdd(&sc->v_eq, (unsigned long long)eq);
+        if (beq) atomicAdd(&sc->v_beq, (unsigned long long)beq);
+        if (badpos) atomicAdd(&sc->v_bad_pos, (unsigned long long)badpos);
+        if (mx) atomicMax(&sc->max_idx, mx);
+    }
+}
+
 // =====================================================================================
 // Merge plan.  Tiles are runs of consecutive output rows; row i opens a tile when
 //   i == 0, i % MT_RMAX == 0, its bin start crosses a multiple of MT_CAP, or it or its
@@ -217,7 +271,7 @@ template <class RB>
 __global__ void __launch_bounds__(PLAN_BLOCK)
 k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *tile_row, uint32_t *long_list,
        uint32_t *xl_list, uint64_t *tile_state, DevScalars *sc, int ticket_slot, uint32_t long_thresh,
-       uint64_t *chain_state, TileStart *tile_start = nullptr, int cap_shift_max = MT_CAP_SHIFT_MAX) {
+       uint64_t *chain_state, TileStart *tile_start = nullptr, uint32_t cap_max = MT_CAP) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[33];
     __shared__ uint64_t s_bound[PLAN_BLOCK / 32];
@@ -232,7 +286,8 @@ k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *ti
     // tiles for every persistent CTA of the merge (444 on a B200): 2^cap_shift ~ P / 1024 within [256, MT_CAP]
     const uint64_t p_all = rb(rows);
     int cap_shift = MT_CAP_SHIFT_MIN;
-    while (cap_shift < cap_shift_max && (p_all >> (cap_shift + 1)) >= 1024) cap_shift++;
+    while (cap_shift < MT_CAP_SHIFT_MAX && (p_all >> (cap_shift + 1)) >= 1024) cap_shift++;
+    const uint64_t cap = min(1u << cap_shift, cap_max);       // (k_chain2 takes tiles that are not a power of two: shared memory)
 
     uint64_t s[PLAN_ITEMS + 1];
 #pragma unroll
@@ -248,7 +303,7 @@ k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *ti
         if (i < rows) {
             const uint64_t len = s[it + 1] - s[it];
             const uint64_t plen = s[it] - sp;
-            flag[it] = i == 0 || (i % MT_RMAX) == 0 || len > long_thresh || plen > long_thresh || (sp >> cap_shift) != (s[it] >> cap_shift);
+            flag[it] = i == 0 || (i % MT_RMAX) == 0 || len > long_thresh || plen > long_thresh || (sp / cap) != (s[it] / cap);
             row_bin[i] = s[it];
             if (len > MT_XL) xl_list[atomicAdd(&sc->n_xl, 1u)] = uint32_t(i);
             else if (len > long_thresh) long_list[atomicAdd(&sc->n_long, 1u)] = uint32_t(i);
@@ -400,6 +455,19 @@ struct TaskSrcSoASwept {        // row order of A minus the tasks somebody else 
     }
 };
 
+// Gathered rows of B: `ld.global.L2::64B` fetches 64-byte granules where the default fetches up to a whole 128-byte line --
+// a random gather of 64-byte rows moves 111 B per row from DRAM with it, 159 B without (profiles/r02_gather_probe.md).
+#ifdef OSP_CUSIM
+__device__ __forceinline__ Elem ld_gather(const Elem *p) { return *p; }
+#else
+__device__ __forceinline__ Elem ld_gather(const Elem *p) {
+    Elem e; uint32_t v;
+    asm volatile("ld.global.L2::64B.v2.u32 {%0, %1}, [%2];" : "=r"(e.idx), "=r"(v) : "l"(p));
+    e.val = __uint_as_float(v);
+    return e;
+}
+#endif
+
 template <class Src>
 __global__ void __launch_bounds__(256)
 k_multiply(Src src, uint64_t t0, uint64_t t1, const Elem *__restrict__ b_data, Elem *__restrict__ bins, uint64_t bin_base) {
@@ -434,7 +502,7 @@ k_multiply(Src src, uint64_t t0, uint64_t t1, const Elem *__restrict__ b_data, E
             }
 #pragma unroll
             for (int u = 0; u < 2; u++)
-                if (e[u] < total) b[u] = b_data[dbs_t[u] + e[u]];
+                if (e[u] < total) b[u] = ld_gather(b_data + dbs_t[u] + e[u]);
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 if (e[u] < total) {
@@ -810,9 +878,11 @@ __device__ __forceinline__ void sort_grouped(K (&x)[E], const unsigned int lig) 
 // partial products in the tile's input stage (reused as fold scratch once every input is in registers) and
 // the index of the row's first element in the output stage at byte offset `ost_off`.  Returns the row's
 // number of surviving entries.
-template <int E, int T, class K>
+// MUL (k_chain2): the stage holds the raw elements of B; element p of the row is multiplied by the float at shared-memory
+// byte offset arow_off + 4 p (A(i,k) of the run it belongs to) when its value is read -- rounded on its own, no FMA.
+template <int E, int T, class K, bool MUL = false>
 __device__ __forceinline__ uint32_t merge_rows_grouped(const uint32_t row_off, const uint32_t ost_off, const uint32_t o0,
-                                                       const uint32_t len, const unsigned int lane) {
+                                                       const uint32_t len, const unsigned int lane, const uint32_t arow_off = 0) {
     constexpr int LE = ILog2<E>::value;
     constexpr uint32_t G = 1u << T, PB = LE + T, N = uint32_t(E) << T;
     const uint32_t lig = lane & (G - 1);
@@ -834,6 +904,7 @@ __device__ __forceinline__ uint32_t merge_rows_grouped(const uint32_t row_off, c
     for (int e = 0; e < E; e++) {
         col[e] = uint32_t(key[e] >> PB);
         v[e] = smem_f32_at(row_off + 4 + (uint32_t(key[e]) & (N - 1)) * 8);       // padding keys read harmless bytes
+        if (MUL) v[e] = __fmul_rn(smem_f32_at(arow_off + (uint32_t(key[e]) & (N - 1)) * 4), v[e]);
     }
     const uint32_t s0 = lig * E;
     uint32_t prev = __shfl_up_sync(FULL, col[E - 1], 1);
@@ -911,10 +982,10 @@ constexpr uint32_t BM_SCRATCH = BM_WORDS * 4 + BM_WORDS * 2;   // per warp: bitm
 __device__ __forceinline__ uint4 &smem_u4_at(uint32_t off) { return *reinterpret_cast<uint4 *>(osp_smem + off); }
 __device__ __forceinline__ uint16_t &smem_u16_at(uint32_t off) { return *reinterpret_cast<uint16_t *>(osp_smem + off); }
 
-template <int S>
+template <int S, bool MUL = false>
 __device__ __forceinline__ uint32_t merge_row_bitmap(const uint32_t row_off, const uint32_t ost_off, const uint32_t o0,
                                                      const uint32_t len, const uint32_t wpl, const uint32_t scr_off,
-                                                     const unsigned int lane) {
+                                                     const unsigned int lane, const uint32_t arow_off = 0) {
     const uint32_t bm_off = scr_off, pre_off = scr_off + BM_WORDS * 4;
     // lane owns the bitmap words {4*lane + 128*q .. +3}: conflict-free 128-bit accesses
     for (uint32_t q = 0; q < wpl; q += 4) smem_u4_at(bm_off + (4 * lane + 32 * q) * 4) = make_uint4(0, 0, 0, 0);
@@ -924,7 +995,10 @@ __device__ __forceinline__ uint32_t merge_row_bitmap(const uint32_t row_off, con
     for (int s = 0; s < S; s++) {
         const uint32_t p = s * 32 + lane;
         col[s] = 0xFFFFFFFFu; val[s] = 0.f;
-        if (p < len) { const uint2 e = smem_u2_at(row_off + p * 8); col[s] = e.x; val[s] = __uint_as_float(e.y); }
+        if (p < len) {
+            const uint2 e = smem_u2_at(row_off + p * 8); col[s] = e.x; val[s] = __uint_as_float(e.y);
+            if (MUL) val[s] = __fmul_rn(smem_f32_at(arow_off + p * 4), val[s]);
+        }
     }
     __syncwarp();
 #pragma unroll

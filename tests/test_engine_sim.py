@@ -62,6 +62,7 @@ test_task_sizes_match_reference_structure = gp.test_task_sizes_match_reference_s
 test_row_chunking_gives_same_bits = gp.test_row_chunking_gives_same_bits
 test_edge_cases = gp.test_edge_cases
 test_error_codes = gp.test_error_codes
+test_operand_preconditions_are_validated = gp.test_operand_preconditions_are_validated
 test_csr2csc_device_stable = gp.test_csr2csc_device_stable
 test_csr2csc_random_and_duplicates = gp.test_csr2csc_random_and_duplicates
 test_coo_ingest_on_device = gp.test_coo_ingest_on_device

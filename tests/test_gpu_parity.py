@@ -266,6 +266,44 @@ def test_error_codes(engine):
     res.free()
 
 
+def test_operand_preconditions_are_validated(engine):
+    """both operands "sorted ascending inside a slice, duplicate-free" (what coo2csr guarantees in the
+    reference, SimSpGEMM.cpp:113-123) and every column id of B below cols_b: a violation is an error code before any
+    merge kernel runs, never an out-of-bounds access; OSP_NO_VALIDATE skips the pass for callers that vouch for them."""
+    E = osp.ELEM
+    a = pack([0, 2, 3], np.array([(0, 1.0), (1, 2.0), (1, 3.0)], E))            # CSR(A) 2 x 2
+    good = pack([0, 2, 4], np.array([(1, 1.0), (5, 2.0), (0, 3.0), (2, 4.0)], E))
+    want, _ = oracle_spgemm(synth.transpose_host(a, 2), good)
+    for flags in (0, api.OSP_NO_VALIDATE):
+        res = engine.spgemm(a, good, a_is_csr=True, cols_b=6, flags=flags)
+        assert_bit_exact(res.to_host(), want, f"valid operands, flags={flags}")
+        res.free()
+    unsorted_b = pack([0, 2, 4], np.array([(5, 1.0), (1, 2.0), (0, 3.0), (2, 4.0)], E))
+    dup_b = pack([0, 2, 4], np.array([(1, 1.0), (1, 2.0), (0, 3.0), (2, 4.0)], E))
+    unsorted_a = pack([0, 2, 3], np.array([(1, 1.0), (0, 2.0), (1, 3.0)], E))
+    dup_a = pack([0, 2, 3], np.array([(1, 1.0), (1, 2.0), (1, 3.0)], E))
+    bad_pos = osp.CSRMatrix(np.array([0, 3, 2], np.uint64), good.data[:2].copy())
+    for aa, bb, cols, code, what in ((a, unsorted_b, 6, api.OSP_ERR_INVALID, "unsorted row of B"),
+                                     (a, dup_b, 6, api.OSP_ERR_DUPLICATE, "duplicate in a row of B"),
+                                     (unsorted_a, good, 6, api.OSP_ERR_INVALID, "unsorted row of A"),
+                                     (dup_a, good, 6, api.OSP_ERR_DUPLICATE, "duplicate in a row of A"),
+                                     (a, good, 5, api.OSP_ERR_INDEX, "column id 5 with cols_b = 5"),
+                                     (a, bad_pos, 6, api.OSP_ERR_INVALID, "pos array that decreases")):
+        with pytest.raises(osp.OspError) as ei:
+            engine.spgemm(aa, bb, a_is_csr=True, cols_b=cols)
+        assert ei.value.code == code, (what, ei.value.code, str(ei.value))
+    # CSC(A) hand-over: the same checks on the column-compressed operand
+    with pytest.raises(osp.OspError) as ei:
+        engine.spgemm(unsorted_a, good, a_is_csr=False, cols_b=6)
+    assert ei.value.code == api.OSP_ERR_INVALID
+    # a last row of B that is not ascending across the slice boundary only (boundary descents are legal)
+    edge = pack([0, 2, 4], np.array([(3, 1.0), (5, 2.0), (0, 3.0), (1, 4.0)], E))
+    res = engine.spgemm(a, edge, a_is_csr=True, cols_b=6)
+    want, _ = oracle_spgemm(synth.transpose_host(a, 2), edge)
+    assert_bit_exact(res.to_host(), want, "descent across a slice boundary")
+    res.free()
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_csr2csc_device_stable(engine, name):
     """Device CSR->CSC equals coo2csr<true> of the reference (fixture made by the compiled reference)."""
