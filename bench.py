@@ -323,7 +323,8 @@ def measure_single(eng, torch, dev, wl, scale_down, steps, warmup, flush_l2, pea
 
     def up(x):
         return torch.from_numpy(x.view(np.uint8).reshape(-1)).to(dev)
-    t = [up(a.pos), up(a.data), up(b.pos), up(b.data)]
+    t = [up(a.pos), up(a.data)]
+    t += t if b is a else [up(b.pos), up(b.data)]          # C = A*A: both operands are the same arrays in HBM
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
 
     def step(flags=0, keep=False):

@@ -67,6 +67,10 @@ extern "C" {
                                     slice, broken pos array), OSP_ERR_DUPLICATE (233) or OSP_ERR_INDEX before any merge
                                     kernel runs -- where the reference relies on coo2csr's sort + dupcheck
                                     (SimSpGEMM.cpp:113-123) */
+#define OSP_KWAY_MERGE    1024u  /* rows of 4 097 .. 32 768 partial products made of at most 64 ways (runs A(i,k) * B(k,:), each
+                                    sorted by construction) are merged by rank -- a k-way merge of the pre-sorted ways,
+                                    the idea of merge2way / mergeHardware (SimSpGEMM.cpp:306-327, 411-441) -- instead of
+                                    going through the dense accumulator of k_merge_xl.  Same bits.  Environment: OSP_KWAY=1 */
 #define OSP_PROFILE_PHASES   8u  /* synchronise between phases so that stats.ms_* are per-phase times */
 
 #define OSP_PROFILE_KERNELS 16u  /* record a CUDA-event pair around every kernel launch (osp_result_kernels) */

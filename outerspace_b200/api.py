@@ -23,7 +23,7 @@ import numpy as np
 
 from .formats import COO, CSRMatrix, ELEM
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libosp_b200.so")
+_LIB_PATH = os.environ.get("OSP_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libosp_b200.so")   # (OSP_LIB_PATH: development builds)
 
 OSP_OK = 0
 OSP_ERR_INVALID, OSP_ERR_CUDA, OSP_ERR_OOM, OSP_ERR_INDEX, OSP_ERR_IO, OSP_ERR_UNSUPPORTED, OSP_ERR_NO_DEVICE = range(1, 8)
@@ -37,6 +37,7 @@ OSP_NO_FUSED_DENSE = 64
 OSP_LONGROW_SWEEP = 128     # experimental, off by default (include/osp_b200.h)
 OSP_FUSED_SHORT = 256       # experimental, off by default (include/osp_b200.h)
 OSP_NO_VALIDATE = 512       # the caller vouches for sorted, duplicate-free slices and in-range column ids
+OSP_KWAY_MERGE = 1024       # k-way merge of the pre-sorted ways for rows of 4097..32768 partial products in <= 64 ways
 OSP_PROFILE_PHASES = 8
 OSP_PROFILE_KERNELS = 16
 

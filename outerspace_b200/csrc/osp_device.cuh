@@ -61,6 +61,8 @@ struct DevScalars {
     // every descent sits on a slice boundary.
     unsigned long long v_desc, v_bdesc, v_eq, v_beq;
     unsigned long long v_bad_pos;      // pos[] entries that decrease or exceed nnz
+    unsigned int kw_ticket;            // dynamic row ids of k_merge_ways (zeroed before every launch)
+    unsigned int cut_tile;             // k_plan: index of the tile that starts at the requested cut row (k-sharded path: two halves)
 };
 
 constexpr unsigned int FULL = 0xffffffffu;

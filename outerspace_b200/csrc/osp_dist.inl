@@ -94,12 +94,7 @@ uint64_t block_begin(uint64_t rows, int world, int r) { return rows * uint64_t(r
 int map_peer_bins(osp_dist *d, uint64_t bytes) {
     osp_ctx *ctx = d->ctx;
     const int G = d->world, me = d->rank;
-    if (bytes > d->recv_buf.cap) {
-        if (d->retired) { cudaFree(d->retired); d->retired = nullptr; }
-        d->retired = d->recv_buf.p;
-        d->recv_buf.p = nullptr; d->recv_buf.cap = 0;
-        CU(ctx, d->recv_buf.reserve(bytes));
-    }
+    (void)bytes;                                   // (the caller has grown the landing buffer, and every rank knows it succeeded)
     d->peer_ptr[me] = d->recv_buf.p;
     if (G == 1) return OSP_OK;
     if (d->own_exported != d->recv_buf.p) {
@@ -176,7 +171,14 @@ int osp_dist_create(osp_ctx *ctx, const void *id128, int rank, int world, osp_di
         delete d;
         return fail(ctx, OSP_ERR_CUDA, std::string("ncclCommInitRank: ") + api->GetErrorString(r));
     }
-    cudaMallocHost(reinterpret_cast<void **>(&d->h_bounds), size_t(world) * (world + 2) * 8);
+    cudaMallocHost(reinterpret_cast<void **>(&d->h_bounds), size_t(world) * (world + 6) * 8);
+    // the buffers of the per-call agreement exist from here on: a call never has to allocate before it can tell its peers
+    if (!d->h_bounds || d->bounds_idx.reserve((world + 6) * 8) != cudaSuccess || d->bounds_dev.reserve((world + 6) * 8) != cudaSuccess ||
+        d->bounds_all.reserve(size_t(world) * (world + 6) * 8) != cudaSuccess || d->flags_dev.reserve(size_t(world) * 4 + 4) != cudaSuccess) {
+        cudaGetLastError();
+        osp_dist_destroy(d);
+        return fail(ctx, OSP_ERR_OOM, "osp_dist_create: buffers of the per-call agreement");
+    }
     cudaMallocHost(reinterpret_cast<void **>(&d->h_handles), size_t(world) * sizeof(cudaIpcMemHandle_t));
     cudaMallocHost(reinterpret_cast<void **>(&d->h_flags), size_t(world) * 4);
     std::memset(d->peer_handle, 0, sizeof(d->peer_handle));
@@ -218,77 +220,169 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     if (!d || !args || !out) return fail(d ? d->ctx : nullptr, OSP_ERR_INVALID, "osp_dist_spgemm: NULL argument");
     osp_ctx *ctx = d->ctx;
     *out = nullptr;
-    if (!(args->flags & OSP_A_IS_CSR) || !args->rows_c || !args->cols_b || !args->a_pos || !args->b_pos)
-        return fail(ctx, OSP_ERR_INVALID, "osp_dist_spgemm: needs CSR(A) shards, rows_c and cols_b");
-    if (args->a_slices > args->rows_c) return fail(ctx, OSP_ERR_INVALID, "osp_dist_spgemm: shard has more rows than C");
-    if (args->n_k >= (1ull << 32) || args->rows_c >= (1ull << 32) || args->cols_b >= (1ull << 32))
-        return fail(ctx, OSP_ERR_INVALID, "osp_dist_spgemm: dimensions must fit index_t (uint32)");
-    CU(ctx, cudaSetDevice(ctx->device));
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { cudaGetLastError(); return fail(ctx, OSP_ERR_CUDA, "osp_dist_spgemm: cudaSetDevice"); }
     ctx->launches = 0;
     ctx->events_used = 0;
     ctx->call_id++;
     ctx->marks.clear();
     ctx->profile_kernels = args->flags & OSP_PROFILE_KERNELS;
     const int G = d->world, me = d->rank;
+    const uint32_t W = uint32_t(G) + 6;       // record of a rank: G+1 bounds | 3 capacities | host status | device status
     const uint64_t m = args->rows_c, m_a = args->a_slices, n_k = args->n_k, cols_b = args->cols_b;
     const uint64_t R0 = block_begin(m, G, me), R1 = block_begin(m, G, me + 1), RL = R1 - R0;
+    const bool validate = !(args->flags & OSP_NO_VALIDATE);
     int rc;
     Operands op;
-    rc = stage_operands(ctx, args, op);
-    if (rc) return rc;
-    const uint64_t nnz_a = op.nnz_a;
-    cudaEvent_t ev_begin = next_event(ctx);
-
-    // ---- local symbolic pass over the shard ------------------------------------------------------
     Arena ar;
-    const uint64_t st[4] = {scan_tiles(std::max<uint64_t>(nnz_a, 1)), plan_tiles(std::max<uint64_t>(RL, 1)),
-                            scan_tiles(std::max<uint64_t>(RL * G, 1)), scan_tiles(std::max<uint64_t>(RL * G, 1))};
-    rc = prepare_arena(ctx, st, 0, ar);
-    if (rc) return rc;
-    CU(ctx, ctx->run_off.reserve((nnz_a + 1) * 8));
-    CU(ctx, ctx->task_bs.reserve(std::max<uint64_t>(nnz_a, 1) * 4));
-    uint64_t *run_off = ctx->run_off.as<uint64_t>();
-    uint32_t *task_bs = ctx->task_bs.as<uint32_t>();
-    if (nnz_a)
-        LAUNCH(ctx, (k_scan<SymIn, RunOffOut>), unsigned(st[0]), SCAN_BLOCK, 0, SymIn{op.a_data, op.b_pos, n_k, nullptr, ctx->d_sc, task_bs},
-               RunOffOut{run_off, ctx->d_sc, nnz_a}, nnz_a, ar.state[0], &ctx->d_sc->scan_ticket[0]);
-    else
-        CU(ctx, cudaMemsetAsync(run_off, 0, 8, ctx->stream));
-    CU(ctx, ctx->row_bin.reserve((m + 1) * 8));
-    CU(ctx, d->lens_send.reserve(std::max<uint64_t>(m, 1) * 4));
-    uint64_t *row_bin = ctx->row_bin.as<uint64_t>();
-    LAUNCH(ctx, k_shard_rows, grid_for(m + 1, 256, 1u << 30), 256, 0, op.a_pos, m_a, run_off, nnz_a, m, row_bin,
-           d->lens_send.as<uint32_t>(), ctx->d_sc);
-    // send offsets at the owners' row boundaries, all-gathered: bounds_all[s][dst] = row_bin_s[R_dst]
-    // (the last word of a rank's record is the capacity of its landing buffer: every rank can tell who must grow)
-    CU(ctx, d->bounds_idx.reserve((G + 2) * 8));
-    CU(ctx, d->bounds_dev.reserve((G + 2) * 8));
-    CU(ctx, d->bounds_all.reserve(uint64_t(G) * (G + 2) * 8));
+    uint64_t st[4] = {0, 0, 0, 0};
+    uint64_t *run_off = nullptr, *row_bin = nullptr;
+    uint32_t *task_bs = nullptr;
+    cudaEvent_t ev_begin = nullptr;
+
+    // ---- everything a rank can fail at on its own happens in here; the verdict travels in the record, so that either every
+    //      rank goes on to the exchange or none does (a rank that returned early used to leave its peers in the collectives)
+    const int pre_rc = [&]() -> int {
+        if (!(args->flags & OSP_A_IS_CSR) || !args->rows_c || !args->cols_b || !args->a_pos || !args->b_pos)
+            return fail(ctx, OSP_ERR_INVALID, "osp_dist_spgemm: needs CSR(A) shards, rows_c and cols_b");
+        if (args->a_slices > args->rows_c) return fail(ctx, OSP_ERR_INVALID, "osp_dist_spgemm: shard has more rows than C");
+        if (args->n_k >= (1ull << 32) || args->rows_c >= (1ull << 32) || args->cols_b >= (1ull << 32) || RL * uint64_t(G) >= (1ull << 32))
+            return fail(ctx, OSP_ERR_INVALID, "osp_dist_spgemm: dimensions must fit index_t (uint32)");
+        int r = stage_operands(ctx, args, op);
+        if (r) return r;
+        ev_begin = next_event(ctx);
+        st[0] = scan_tiles(std::max<uint64_t>(op.nnz_a, 1)); st[1] = plan_tiles(std::max<uint64_t>(RL, 1));
+        st[2] = scan_tiles(std::max<uint64_t>(RL * G, 1)); st[3] = st[2];
+        r = prepare_arena(ctx, st, 0, ar);
+        if (r) return r;
+        CU(ctx, ctx->run_off.reserve((op.nnz_a + 1) * 8));
+        CU(ctx, ctx->task_bs.reserve(std::max<uint64_t>(op.nnz_a, 1) * 4));
+        CU(ctx, ctx->row_bin.reserve((std::max(m, RL) + 1) * 8));
+        CU(ctx, d->lens_send.reserve(std::max<uint64_t>(m, 1) * 4));
+        CU(ctx, d->lens_recv.reserve(std::max<uint64_t>(RL * G, 1) * 4));
+        CU(ctx, d->src_off.reserve((RL * G + 1) * 8));
+        CU(ctx, d->dst_off.reserve((RL * G + 1) * 8));
+        r = reserve_plan(ctx, std::max<uint64_t>(RL, 1), std::max<uint64_t>(RL, 1));
+        if (r) return r;
+        run_off = ctx->run_off.as<uint64_t>(); task_bs = ctx->task_bs.as<uint32_t>(); row_bin = ctx->row_bin.as<uint64_t>();
+        if (validate) {      // the shard's operands: ascending duplicate-free slices, column ids below cols_b (k < n_k: symbolic pass)
+            const ValidateOp opa{op.a_pos, op.a_data, m_a, op.nnz_a, 0}, opb{op.b_pos, op.b_data, n_k, op.nnz_b, cols_b};
+            r = launch_validate(ctx, opa, opb, 2);
+            if (r) return r;
+        }
+        if (op.nnz_a)
+            LAUNCH(ctx, (k_scan<SymIn, RunOffOut>), unsigned(st[0]), SCAN_BLOCK, 0, SymIn{op.a_data, op.b_pos, n_k, nullptr, ctx->d_sc, task_bs},
+                   RunOffOut{run_off, ctx->d_sc, op.nnz_a}, op.nnz_a, ar.state[0], &ctx->d_sc->scan_ticket[0]);
+        else
+            CU(ctx, cudaMemsetAsync(run_off, 0, 8, ctx->stream));
+        LAUNCH(ctx, k_shard_rows, grid_for(m + 1, 256, 1u << 30), 256, 0, op.a_pos, m_a, run_off, op.nnz_a, m, row_bin,
+               d->lens_send.as<uint32_t>(), ctx->d_sc);
+        return OSP_OK;
+    }();
+    const std::string pre_msg = pre_rc ? ctx->err : std::string();
+    const uint64_t nnz_a = op.nnz_a;
+
+    // ---- the call's all-gather: bounds_all[s][dst] = row_bin_s[R_dst], capacities, status --------------------------------
     {
-        std::vector<uint64_t> idx(G + 2);
-        for (int r = 0; r <= G; r++) idx[r] = block_begin(m, G, r);
-        idx[G + 1] = uint64_t(d->recv_buf.cap);
-        std::memcpy(d->h_bounds, idx.data(), (G + 2) * 8);
-        CU(ctx, cudaMemcpyAsync(d->bounds_idx.p, d->h_bounds, (G + 2) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(d->bounds_dev.as<uint64_t>() + (G + 1), d->bounds_idx.as<uint64_t>() + (G + 1), 8,
-                                cudaMemcpyDeviceToDevice, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));           // h_bounds is reused as the landing buffer below
+        for (int r = 0; r <= G; r++) d->h_bounds[r] = block_begin(m, G, r);
+        d->h_bounds[G + 1] = uint64_t(d->recv_buf.cap);
+        d->h_bounds[G + 2] = uint64_t(d->bins2.cap);
+        d->h_bounds[G + 3] = uint64_t(ctx->bins.cap);
+        d->h_bounds[G + 4] = uint64_t(pre_rc);
+        d->h_bounds[G + 5] = 0;
+        CU(ctx, cudaMemcpyAsync(d->bounds_idx.p, d->h_bounds, W * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (pre_rc == OSP_OK) {
+            OSP_KERNEL_LAUNCH(k_dist_record, 1, 256, 0, ctx->stream, row_bin, d->bounds_idx.as<uint64_t>(), uint32_t(G), W, ctx->d_sc,
+                              d->bounds_dev.as<uint64_t>());
+            ctx->launches++;
+        } else {
+            CU(ctx, cudaMemcpyAsync(d->bounds_dev.p, d->bounds_idx.p, W * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        NC(ctx, d, d->nccl->AllGather(d->bounds_dev.p, d->bounds_all.p, W, ncclUint64, d->comm, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(d->h_bounds, d->bounds_all.p, uint64_t(G) * W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    LAUNCH(ctx, k_pick_u64, 1, 256, 0, row_bin, d->bounds_idx.as<uint64_t>(), uint32_t(G + 1), d->bounds_dev.as<uint64_t>());
-    NC(ctx, d, d->nccl->AllGather(d->bounds_dev.p, d->bounds_all.p, G + 2, ncclUint64, d->comm, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(d->h_bounds, d->bounds_all.p, uint64_t(G) * (G + 2) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    rc = sync_scalars(ctx);
-    if (rc) return rc;
-    if (ctx->h_sc->err == 6) return fail(ctx, OSP_ERR_UNSUPPORTED, "osp_dist_spgemm: a row of one shard holds >= 2^32 partial products");
-    if (ctx->h_sc->err) return fail(ctx, OSP_ERR_INDEX, "osp_dist_spgemm: index of A out of range of the shard's inner dimension");
-    const uint64_t P_local = ctx->h_sc->products;
-    auto bound = [&](int s, int r) { return d->h_bounds[uint64_t(s) * (G + 2) + r]; };
-    std::vector<uint64_t> recv_cnt(G), recv_off(G + 1, 0);
+    auto word = [&](int s, uint32_t i) { return d->h_bounds[uint64_t(s) * W + i]; };
+    auto bound = [&](int s, int r) { return word(s, uint32_t(r)); };
+    for (int r = 0; r < G; r++) {
+        const uint64_t host_code = word(r, uint32_t(G) + 4), dev_code = word(r, uint32_t(G) + 5);
+        if (!host_code && !dev_code) continue;
+        if (r == me) {
+            if (host_code) return fail(ctx, int(host_code), pre_msg);
+            if (dev_code == 233) return fail(ctx, OSP_ERR_DUPLICATE, "osp_dist_spgemm: duplicate (row,col) entry in this rank's shard");
+            if (dev_code == 1) return fail(ctx, OSP_ERR_INVALID, "osp_dist_spgemm: a slice of this rank's shard is not ascending, or a pos array is broken");
+            if (dev_code == 6) return fail(ctx, OSP_ERR_UNSUPPORTED, "osp_dist_spgemm: a row of one shard holds >= 2^32 partial products");
+            return fail(ctx, OSP_ERR_INDEX, "osp_dist_spgemm: index out of range in this rank's shard (k beyond the shard's inner dimension or a column beyond cols_b)");
+        }
+    }
+    for (int r = 0; r < G; r++)
+        if (word(r, uint32_t(G) + 4) || word(r, uint32_t(G) + 5))
+            return fail(ctx, OSP_ERR_INVALID, "osp_dist_spgemm: rank " + std::to_string(r) + " reported an error (code " +
+                                              std::to_string(word(r, uint32_t(G) + 4) ? word(r, uint32_t(G) + 4) : word(r, uint32_t(G) + 5)) +
+                                              "); no rank entered the exchange");
+    const uint64_t P_local = bound(me, G);
+    std::vector<uint64_t> recv_cnt(G), recv_off(G + 1, 0), p_owned(G, 0);
     for (int s = 0; s < G; s++) { recv_cnt[s] = bound(s, me + 1) - bound(s, me); recv_off[s + 1] = recv_off[s] + recv_cnt[s]; }
     const uint64_t P_owned = recv_off[G];
+    for (int r = 0; r < G; r++)
+        for (int s2 = 0; s2 < G; s2++) p_owned[r] += bound(s2, r + 1) - bound(s2, r);
 
-    // ---- per-row counts to the owners; multiply; partial products to the owners --------------------
-    CU(ctx, d->lens_recv.reserve(std::max<uint64_t>(RL * G, 1) * 4));
+    // ---- buffers that depend on the exchanged sizes.  Every rank knows every rank's sizes and capacities, so all agree,
+    //      without talking, on whether anybody allocates; if so the outcome of the allocations goes round before anything else
+    bool direct = d->p2p;
+    {
+        bool any_grow = direct && !d->mapped_once;
+        for (int r = 0; r < G; r++) {
+            const uint64_t need = std::max<uint64_t>(p_owned[r], 1) * 8 + 16;
+            any_grow |= need > word(r, uint32_t(G) + 1) || need > word(r, uint32_t(G) + 2);
+            if (!direct) any_grow |= std::max<uint64_t>(bound(r, G), 1) * 8 > word(r, uint32_t(G) + 3);
+        }
+        if (any_grow) {
+            const uint64_t need = std::max<uint64_t>(P_owned, 1) * 8 + 16;
+            int grow_rc = OSP_OK;
+            if (need > d->bins2.cap && d->bins2.reserve(need) != cudaSuccess) { cudaGetLastError(); grow_rc = OSP_ERR_OOM; }
+            if (!direct) {
+                if (!grow_rc && d->recv_buf.reserve(need) != cudaSuccess) { cudaGetLastError(); grow_rc = OSP_ERR_OOM; }
+                if (!grow_rc && ctx->bins.reserve(std::max<uint64_t>(P_local, 1) * 8) != cudaSuccess) { cudaGetLastError(); grow_rc = OSP_ERR_OOM; }
+            } else if (!grow_rc && need > d->recv_buf.cap) {       // landing buffer: the old one stays until the peers have remapped
+                if (d->retired) { cudaFree(d->retired); d->retired = nullptr; }
+                d->retired = d->recv_buf.p;
+                d->recv_buf.p = nullptr; d->recv_buf.cap = 0;
+                if (d->recv_buf.reserve(need) != cudaSuccess) { cudaGetLastError(); grow_rc = OSP_ERR_OOM; }
+            }
+            // the verdicts go round
+            d->h_flags[me] = uint32_t(grow_rc);
+            CU(ctx, d->flags_dev.reserve(size_t(G) * 4 + 4));
+            uint32_t *fd = d->flags_dev.as<uint32_t>();
+            CU(ctx, cudaMemcpyAsync(fd + me, &d->h_flags[me], 4, cudaMemcpyHostToDevice, ctx->stream));
+            NC(ctx, d, d->nccl->AllGather(fd + me, fd, 1, ncclUint32, d->comm, ctx->stream));
+            CU(ctx, cudaMemcpyAsync(d->h_flags, fd, size_t(G) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int r = 0; r < G; r++)
+                if (d->h_flags[r])
+                    return fail(ctx, r == me ? OSP_ERR_OOM : OSP_ERR_INVALID,
+                                r == me ? std::string("osp_dist_spgemm: device memory for the exchange buffers") :
+                                          "osp_dist_spgemm: rank " + std::to_string(r) + " could not allocate its exchange buffers; no rank entered the exchange");
+            if (direct) {
+                rc = map_peer_bins(d, need);                  // (handles and success flags go round: two more all-gathers)
+                if (rc) return rc;
+                direct = d->p2p;
+                d->mapped_once = true;
+                if (!direct) {                                // some peer is not mappable: every rank takes the staged exchange from now on
+                    const bool ok = ctx->bins.reserve(std::max<uint64_t>(P_local, 1) * 8) == cudaSuccess;
+                    if (!ok) cudaGetLastError();
+                    d->h_flags[me] = ok ? 0u : 1u;
+                    CU(ctx, cudaMemcpyAsync(fd + me, &d->h_flags[me], 4, cudaMemcpyHostToDevice, ctx->stream));
+                    NC(ctx, d, d->nccl->AllGather(fd + me, fd, 1, ncclUint32, d->comm, ctx->stream));
+                    CU(ctx, cudaMemcpyAsync(d->h_flags, fd, size_t(G) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                    CU(ctx, cudaStreamSynchronize(ctx->stream));
+                    for (int r = 0; r < G; r++)
+                        if (d->h_flags[r]) return fail(ctx, OSP_ERR_OOM, "osp_dist_spgemm: device memory for the staged exchange");
+                }
+            }
+        }
+    }
+
+    // ---- per-row counts to the owners --------------------------------------------------------------------------------------
     NC(ctx, d, d->nccl->GroupStart());
     for (int r = 0; r < G; r++) {
         const uint64_t b0 = block_begin(m, G, r), b1 = block_begin(m, G, r + 1);
@@ -296,102 +390,108 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
         if (RL) NC(ctx, d, d->nccl->Recv(d->lens_recv.as<uint32_t>() + uint64_t(r) * RL, RL, ncclUint32, r, d->comm, ctx->stream));
     }
     NC(ctx, d, d->nccl->GroupEnd());
-    cudaEvent_t ev_sym = nullptr, ev_mul = nullptr, ev_xchg = nullptr;
-    // ---- peer-memory exchange: every owner's landing buffer is mapped, the multiply stores into it --------
-    // Every rank knows every owner's partial-product count and landing capacity (the all-gather above), so all
-    // ranks agree, without talking, on whether a buffer grows and the IPC handles must go round again.
-    bool direct = d->p2p;
-    if (direct) {
-        bool remap = !d->mapped_once;
-        std::vector<uint64_t> p_owned(G, 0);
-        for (int r = 0; r < G; r++) {
-            for (int s2 = 0; s2 < G; s2++) p_owned[r] += bound(s2, r + 1) - bound(s2, r);
-            if (std::max<uint64_t>(p_owned[r], 1) * 8 + 16 > d->h_bounds[uint64_t(r) * (G + 2) + G + 1]) remap = true;
+    cudaEvent_t ev_sym = next_event(ctx), ev_mul = nullptr, ev_xchg = nullptr;
+
+    // ---- the owner's plan needs the counts only: it runs on the second stream BESIDE the multiply, whose stores are bound by
+    //      NVLink and leave the SMs mostly idle (scans + plan used to follow the exchange: ~0.35 ms that did not shrink with G).
+    //      The exchange itself goes in TWO HALVES of every owner's rows: while the sources send the second half, the owners
+    //      already regroup and merge the first (row blocks of the merge chain, carried nnz(C) like the single-GPU row blocks).
+    const uint32_t *lens = d->lens_recv.as<uint32_t>();
+    const uint64_t n_seg = RL * G;
+    cudaStream_t main_stream = ctx->stream;
+    const bool side = RL && !ctx->profile_kernels;               // (per-kernel event pairs assume one stream)
+    const int H = (direct && G > 1 && m >= uint64_t(4 * G) && !std::getenv("OSP_DIST_ONE_PHASE")) ? 2 : 1;
+    const uint64_t cut_local = H == 2 ? RL / 2 : ~0ull;          // first row (of this owner's block) of the second half
+    if (RL) {
+        if (side) {
+            CU(ctx, cudaEventRecord(ctx->ev_fork, main_stream));
+            CU(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+            ctx->stream = ctx->stream2;                          // LAUNCH and sync_scalars use ctx->stream
         }
-        if (remap) {
-            rc = map_peer_bins(d, std::max<uint64_t>(P_owned, 1) * 8 + 16);      // (host syncs: handles, success flags)
-            if (rc) return rc;
-            direct = d->p2p;
-            d->mapped_once = true;
-        }
+        const int plan_rc = [&]() -> int {
+            LAUNCH(ctx, (k_scan<U32In, U64Out>), unsigned(st[2]), SCAN_BLOCK, 0, U32In{lens}, U64Out{d->src_off.as<uint64_t>()}, n_seg,
+                   ar.state[2], &ctx->d_sc->scan_ticket[2]);
+            LAUNCH(ctx, (k_scan<TransposedIn, U64Out>), unsigned(st[3]), SCAN_BLOCK, 0, TransposedIn{lens, RL, uint64_t(G)},
+                   U64Out{d->dst_off.as<uint64_t>()}, n_seg, ar.state[3], &ctx->d_sc->scan_ticket[3]);
+            LAUNCH(ctx, k_plan<RowBinStrided>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinStrided{d->dst_off.as<uint64_t>(), uint64_t(G)}, RL,
+                   cols_b, ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
+                   ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(cols_b), ctx->tile_state.as<uint64_t>(),
+                   static_cast<TileStart *>(nullptr), MT_CAP, cut_local);
+            return OSP_OK;
+        }();
+        ctx->stream = main_stream;
+        if (plan_rc) return plan_rc;
     }
+
+    // ---- multiply; partial products to the owners --------------------------------------------------------------------------
+    cudaEvent_t ev_half[2] = {nullptr, nullptr};
     if (direct) {
-        CU(ctx, d->bins2.reserve(std::max<uint64_t>(P_owned, 1) * 8 + 16));
-        ev_sym = next_event(ctx);
-        if (nnz_a && P_local) {
-            PeerDst dst;
-            std::memset(&dst, 0, sizeof(dst));
-            dst.world = G;
-            for (int r = 0; r < G; r++) {
-                dst.base[r] = static_cast<Elem *>(d->peer_ptr[r]);
-                dst.bound[r] = bound(me, r);
-                uint64_t region = 0;                                   // where source `me` lands inside owner r's buffer
-                for (int s2 = 0; s2 < me; s2++) region += bound(s2, r + 1) - bound(s2, r);
-                dst.delta[r] = int64_t(region) - int64_t(bound(me, r));
-            }
-            dst.bound[G] = bound(me, G);
-            const uint64_t first_row = std::min<uint64_t>(block_begin(m, G, (me + 1) % G), m_a);
-            LAUNCH(ctx, k_multiply_peer, grid_for(nnz_a, 256, unsigned(ctx->sm_count) * 32u), 256, 0, op.a_data, run_off, task_bs,
-                   nnz_a, op.b_data, dst, op.a_pos, first_row);
+        PeerDst dst;
+        std::memset(&dst, 0, sizeof(dst));
+        dst.world = G;
+        for (int r = 0; r < G; r++) {
+            dst.base[r] = static_cast<Elem *>(d->peer_ptr[r]);
+            dst.bound[r] = bound(me, r);
+            uint64_t region = 0;                                   // where source `me` lands inside owner r's buffer
+            for (int s2 = 0; s2 < me; s2++) region += bound(s2, r + 1) - bound(s2, r);
+            dst.delta[r] = int64_t(region) - int64_t(bound(me, r));
         }
-        ev_mul = next_event(ctx);
-        // every rank's stores have landed once every rank's multiply has retired: one tiny collective on the stream
-        if (G > 1) {
-            CU(ctx, d->flags_dev.reserve(size_t(G) * 4 + 4));
-            uint32_t *fd = d->flags_dev.as<uint32_t>();
-            NC(ctx, d, d->nccl->AllGather(fd + me, fd, 1, ncclUint32, d->comm, ctx->stream));
+        dst.bound[G] = bound(me, G);
+        uint32_t *fd = d->flags_dev.as<uint32_t>();
+        for (int h = 0; h < H; h++) {
+            if (nnz_a && P_local) {
+                PeerRows rows;
+                std::memset(&rows, 0, sizeof(rows));
+                for (int r = 0; r < G; r++) {
+                    const uint64_t b0 = block_begin(m, G, r), b1 = block_begin(m, G, r + 1), cut = b0 + (b1 - b0) / 2;
+                    rows.lo[r] = H == 1 || h == 0 ? b0 : cut;
+                    rows.hi[r] = H == 1 || h == 1 ? b1 : cut;
+                }
+                LAUNCH(ctx, k_multiply_peer, grid_for(nnz_a / H + 1, 256, unsigned(ctx->sm_count) * 32u), 256, 0, op.a_data, run_off, task_bs,
+                       op.b_data, dst, op.a_pos, m_a, rows, (me + 1) % G);
+            }
+            if (h == H - 1) ev_mul = next_event(ctx);
+            // every rank's stores (of this half) have landed once every rank's multiply has retired: one tiny collective
+            if (G > 1) NC(ctx, d, d->nccl->AllGather(fd + me, fd, 1, ncclUint32, d->comm, ctx->stream));
+            if (side && H == 2) {
+                ev_half[h] = ctx->ev_half[h];
+                CU(ctx, cudaEventRecord(ev_half[h], ctx->stream));
+            }
         }
         ev_xchg = next_event(ctx);
     } else {
-    CU(ctx, ctx->bins.reserve(std::max<uint64_t>(P_local, 1) * 8));
-    CU(ctx, d->recv_buf.reserve(std::max<uint64_t>(P_owned, 1) * 8));
-    CU(ctx, d->bins2.reserve(std::max<uint64_t>(P_owned, 1) * 8 + 16));
-    ev_sym = next_event(ctx);
-    rc = launch_multiply(ctx, TaskSrcSoA{op.a_data, run_off, task_bs}, 0, nnz_a, P_local, op.b_data, ctx->bins.as<Elem>(), 0);
-    if (rc) return rc;
-    ev_mul = next_event(ctx);
-    NC(ctx, d, d->nccl->GroupStart());
-    for (int r = 0; r < G; r++) {
-        const uint64_t cnt = bound(me, r + 1) - bound(me, r);
-        if (cnt) NC(ctx, d, d->nccl->Send(ctx->bins.as<Elem>() + bound(me, r), cnt * 8, ncclUint8, r, d->comm, ctx->stream));
-        if (recv_cnt[r]) NC(ctx, d, d->nccl->Recv(d->recv_buf.as<Elem>() + recv_off[r], recv_cnt[r] * 8, ncclUint8, r, d->comm, ctx->stream));
+        rc = launch_multiply(ctx, TaskSrcSoA{op.a_data, run_off, task_bs}, 0, nnz_a, P_local, op.b_data, ctx->bins.as<Elem>(), 0);
+        if (rc) return rc;
+        ev_mul = next_event(ctx);
+        NC(ctx, d, d->nccl->GroupStart());
+        for (int r = 0; r < G; r++) {
+            const uint64_t cnt = bound(me, r + 1) - bound(me, r);
+            if (cnt) NC(ctx, d, d->nccl->Send(ctx->bins.as<Elem>() + bound(me, r), cnt * 8, ncclUint8, r, d->comm, ctx->stream));
+            if (recv_cnt[r]) NC(ctx, d, d->nccl->Recv(d->recv_buf.as<Elem>() + recv_off[r], recv_cnt[r] * 8, ncclUint8, r, d->comm, ctx->stream));
+        }
+        NC(ctx, d, d->nccl->GroupEnd());
+        ev_xchg = next_event(ctx);
     }
-    NC(ctx, d, d->nccl->GroupEnd());
-    ev_xchg = next_event(ctx);
+    // From here on there is no collective left: a rank that fails below returns on its own.
 
-    }
-
-    // ---- regroup source-major -> row-major, plan, merge ------------------------------------------------
+    // ---- regroup source-major -> row-major, merge ---------------------------------------------------------------------------
     osp_result *res = new osp_result();
     res->ctx = ctx;
     std::memset(&res->stats, 0, sizeof(res->stats));
     ResultGuard guard{res};                      // every early return below (LAUNCH / CU included) frees the result
-    auto bail = [&](int code) { return code; };
+    auto bail = [&](int code) { ctx->stream = main_stream; return code; };
     MergeJob job;
     job.rows = std::max<uint64_t>(RL, 1); job.idx_range = cols_b; job.long_thresh = plan_long_thresh(cols_b);
     uint64_t nnz_c = 0;
+    int n_blocks = 1;
     if (RL) {
-        const uint64_t n = RL * G;
-        if ((rc = [&]() -> int {
-                CU(ctx, d->src_off.reserve((n + 1) * 8));
-                CU(ctx, d->dst_off.reserve((n + 1) * 8));
-                return OSP_OK;
-            }())) return bail(rc);
-        const uint32_t *lens = d->lens_recv.as<uint32_t>();
-        LAUNCH(ctx, (k_scan<U32In, U64Out>), unsigned(st[2]), SCAN_BLOCK, 0, U32In{lens}, U64Out{d->src_off.as<uint64_t>()}, n,
-               ar.state[2], &ctx->d_sc->scan_ticket[2]);
-        LAUNCH(ctx, (k_scan<TransposedIn, U64Out>), unsigned(st[3]), SCAN_BLOCK, 0, TransposedIn{lens, RL, uint64_t(G)},
-               U64Out{d->dst_off.as<uint64_t>()}, n, ar.state[3], &ctx->d_sc->scan_ticket[3]);
-        LAUNCH(ctx, k_regroup, grid_for(RL, 8, unsigned(ctx->sm_count) * 32u), 256, 0, d->recv_buf.as<Elem>(),
-               d->src_off.as<uint64_t>(), d->dst_off.as<uint64_t>(), lens, RL, uint32_t(G), d->bins2.as<Elem>());
-        rc = reserve_plan(ctx, RL, RL);
-        if (rc) return bail(rc);
-        LAUNCH(ctx, k_plan<RowBinStrided>, unsigned(st[1]), PLAN_BLOCK, 0, RowBinStrided{d->dst_off.as<uint64_t>(), uint64_t(G)}, RL,
-               cols_b, ctx->row_bin.as<uint64_t>(), ctx->tile_row.as<uint32_t>(), ctx->long_list.as<uint32_t>(),
-               ctx->xl_list.as<uint32_t>(), ar.state[1], ctx->d_sc, 1, plan_long_thresh(cols_b), ctx->tile_state.as<uint64_t>());
+        // the plan's scalars (second stream): sizes of C and of the merge scratch
+        if (side) ctx->stream = ctx->stream2;
         rc = sync_scalars(ctx);
         if (rc) return bail(rc);
         job.n_tiles = ctx->h_sc->n_tiles; job.n_long = ctx->h_sc->n_long; job.n_xl = ctx->h_sc->n_xl;
+        const uint32_t cut_tile = ctx->h_sc->cut_tile;
+        const bool halves = H == 2 && cut_local > 0 && cut_local < RL && cut_tile > 0 && cut_tile < job.n_tiles;
         const uint64_t cap = std::max<uint64_t>(ctx->h_sc->cap_bound, 1);
         cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_pos), (RL + 1) * 8, ctx->stream);
         if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_data), cap * 8, ctx->stream);
@@ -404,8 +504,33 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
         unsigned int xl_ctas = 0;
         rc = reserve_merge(ctx, job, xl_ctas);
         if (rc) return bail(rc);
-        rc = launch_merge(ctx, job, xl_ctas, d->bins2.as<Elem>(), 0, 0, job.n_tiles, 0, RL, 0);
-        if (rc) return bail(rc);
+        // owner side, on the second stream when there is one: half h as soon as its partial products have landed
+        n_blocks = halves ? 2 : 1;
+        for (int h = 0; h < n_blocks; h++) {
+            const uint64_t r_lo = halves && h == 1 ? cut_local : 0, r_hi = halves && h == 0 ? cut_local : RL;
+            const uint32_t t_lo = halves && h == 1 ? cut_tile : 0u, t_hi = halves && h == 0 ? cut_tile : job.n_tiles;
+            rc = [&]() -> int {
+                if (side) {
+                    // (one phase: everything; two phases whose plan could not be cut: wait for the second half as well)
+                    cudaEvent_t need = H == 2 ? ev_half[halves ? h : 1] : nullptr;
+                    if (need) CU(ctx, cudaStreamWaitEvent(ctx->stream, need, 0));
+                    else { CU(ctx, cudaEventRecord(ctx->ev_half[0], main_stream)); CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_half[0], 0)); }
+                }
+                LAUNCH(ctx, k_regroup, grid_for(r_hi - r_lo, 8, unsigned(ctx->sm_count) * 32u), 256, 0, d->recv_buf.as<Elem>(),
+                       d->src_off.as<uint64_t>(), d->dst_off.as<uint64_t>(), lens, RL, uint32_t(G), d->bins2.as<Elem>(), r_lo, r_hi);
+                return launch_merge(ctx, job, xl_ctas, d->bins2.as<Elem>(), 0, t_lo, t_hi, r_lo, r_hi, unsigned(h));
+            }();
+            if (rc) return bail(rc);
+        }
+        if (side) {
+            rc = [&]() -> int {
+                CU(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+                CU(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
+                return OSP_OK;
+            }();
+            if (rc) return bail(rc);
+        }
+        ctx->stream = main_stream;
     } else {
         cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&res->d_pos), 8, ctx->stream);
         if (e != cudaSuccess) { cudaGetLastError(); bail(0); return fail(ctx, OSP_ERR_OOM, "result allocation"); }
@@ -415,7 +540,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     rc = sync_scalars(ctx);
     if (rc) return bail(rc);
     if (ctx->h_sc->err) return bail(fail(ctx, OSP_ERR_CUDA, "osp_dist_spgemm: internal capacity check failed on the device"));
-    if (RL) nnz_c = ctx->h_sc->nnz_c[1];
+    if (RL) nnz_c = ctx->h_sc->nnz_c[n_blocks & 1];
     res->rows = RL;
     res->nnz = nnz_c;
     osp_stats &stt = res->stats;

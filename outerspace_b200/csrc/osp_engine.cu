@@ -51,6 +51,7 @@ struct osp_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;      // the CSR->CSC task list is built beside the merge plan
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_half[2] = {nullptr, nullptr};      // k-sharded path: a half of the exchange has landed
     uint64_t ws_limit = 0;          // bytes of partial-product bins per row block
     uint64_t result_limit = 0;      // cap on the up-front allocation of C's data (0 = what the device can spare)
     uint64_t launches = 0;
@@ -68,7 +69,8 @@ struct osp_ctx {
     DevBuf task_bs, run_off, row_bin, tile_row, tile_start, long_list, xl_list, uniq, col_ptr, tasks, tile_state, xl_acc, xl_bits;
     DevBuf bins;
     // fused band sweep of the long rows (opt-in, osp_longrows.cuh): task bitmap for the multiply, band index of B
-    DevBuf swept, lr_bands;
+    DevBuf swept, lr_bands, kw_scratch;
+    bool kway_env = false;                  // OSP_KWAY=1: rows of 4097 .. 32768 partial products in <= 64 ways go to k_merge_ways
     bool sweep_ok = false;                  // the device accepted the kernel's shared-memory size
     bool sweep_env = false;                 // OSP_LONGROW_SWEEP=1
     uint64_t sweep_min = 0;                 // OSP_LONGROW_SWEEP_MIN: fewest partial products of a swept row (0: every xl row)
@@ -281,6 +283,7 @@ struct MergeJob {
     // OSP_FUSED_SHORT: the chain computes the short rows' partial products itself (k_merge_chain_fused)
     bool fused_short = false;
     bool chain2 = false;                    // ... with k_chain2 (producer warps) instead of k_merge_chain_fused
+    bool kway = false;                      // k_merge_ways takes the xl rows of few long ways (needs a_pos, run_off)
     const uint64_t *run_off = nullptr;
     const uint32_t *task_bs = nullptr;
     uint64_t m_a = 0;
@@ -349,11 +352,20 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
                 LAUNCH(ctx, (k_long_fill<LR_THREADS, LR_BAND, LR_RUNS, LongRowsInBins>), grid, LR_THREADS, LR_SMEM, job.a_pos, job.a_data,
                        job.b_data, job.bandptr, job.idx_range, rows);
             }
+            if (job.kway && job.n_xl) {
+                // rows of few long sorted ways: ranks by binary search over the ways, no accumulator (osp_kway.cuh)
+                CU(ctx, cudaMemsetAsync(&ctx->d_sc->kw_ticket, 0, 4, ctx->stream));
+                const unsigned gridk = unsigned(std::min<uint64_t>(job.n_xl, uint64_t(ctx->sm_count) * 2));
+                CU(ctx, ctx->kw_scratch.reserve(uint64_t(gridk) * KW_MAX_LEN * 8));
+                LAUNCH(ctx, k_merge_ways, gridk, KW_THREADS, 0, job.a_pos, job.run_off, row_bin, bin_base, bins, uniq,
+                       ctx->xl_list.as<uint32_t>(), ctx->d_sc, ctx->kw_scratch.as<Elem>(), row_lo, row_hi);
+            }
             if (xl_ctas && ((job.n_xl && !job.sweeps_every_xl()) || (job.n_long && xl_takes_long))) {
                 CU(ctx, cudaMemsetAsync(&ctx->d_sc->xl_ticket, 0, 4, ctx->stream));
                 LAUNCH(ctx, k_merge_xl, xl_ctas, XL_THREADS, 0, row_bin, bin_base, bins, uniq, ctx->xl_list.as<uint32_t>(),
                        xl_takes_long ? ctx->long_list.as<uint32_t>() : nullptr, ctx->d_sc, ctx->xl_acc.as<float>(),
-                       ctx->xl_bits.as<uint32_t>(), job.idx_range, row_lo, row_hi, job.sweep ? job.sweep_min : ~0ull);
+                       ctx->xl_bits.as<uint32_t>(), job.idx_range, row_lo, row_hi, job.sweep ? job.sweep_min : ~0ull,
+                       job.kway ? job.a_pos : nullptr);
             }
         }
     }
@@ -566,9 +578,15 @@ int osp_create(int device, osp_ctx **out) {
     ctx->total_mem = prop.totalGlobalMem;
     if (prop.l2CacheSize > 0) ctx->l2_bytes = size_t(prop.l2CacheSize);
     CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    {   // the side stream runs ahead of the main one where both have work (the owner's merge beside the peers' multiply)
+        int prio_lo = 0, prio_hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) { cudaGetLastError(); prio_hi = 0; }
+        CU(nullptr, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi));
+    }
     CU(nullptr, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CU(nullptr, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    CU(nullptr, cudaEventCreateWithFlags(&ctx->ev_half[0], cudaEventDisableTiming));
+    CU(nullptr, cudaEventCreateWithFlags(&ctx->ev_half[1], cudaEventDisableTiming));
     CU(nullptr, cudaMallocHost(reinterpret_cast<void **>(&ctx->h_sc), sizeof(DevScalars)));
     if (!std::getenv("OSP_NO_MAPPED_SYNC")) {
         CU(nullptr, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_slots), sizeof(ulonglong2) * PUBLISH_SLOTS, cudaHostAllocMapped));
@@ -603,6 +621,8 @@ int osp_create(int device, osp_ctx **out) {
         if (!ctx->sweep_ok) { cudaGetLastError(); ctx->sweep_occ = 1; }
         const char *env = std::getenv("OSP_LONGROW_SWEEP");
         ctx->sweep_env = env && env[0] && env[0] != '0';
+        const char *kw = std::getenv("OSP_KWAY");
+        ctx->kway_env = kw && kw[0] && kw[0] != '0';
         if (const char *m = std::getenv("OSP_LONGROW_SWEEP_MIN")) ctx->sweep_min = std::strtoull(m, nullptr, 10);
     }
     {   // OSP_FUSED_SHORT: opt-in as well
@@ -659,13 +679,14 @@ void osp_destroy(osp_ctx *ctx) {
     for (DevBuf *b : {&ctx->arena, &ctx->op_a_pos, &ctx->op_a_data, &ctx->op_b_pos, &ctx->op_b_data, &ctx->conv_pos,
                       &ctx->conv_data, &ctx->conv_tmp, &ctx->conv_chk, &ctx->task_bs, &ctx->run_off, &ctx->row_bin, &ctx->tile_row,
                       &ctx->tile_start, &ctx->long_list, &ctx->xl_list, &ctx->uniq, &ctx->col_ptr, &ctx->tasks, &ctx->tile_state,
-                      &ctx->xl_acc, &ctx->xl_bits, &ctx->bins, &ctx->swept, &ctx->lr_bands})
+                      &ctx->xl_acc, &ctx->xl_bits, &ctx->bins, &ctx->swept, &ctx->lr_bands, &ctx->kw_scratch})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    for (cudaEvent_t e : ctx->ev_half) if (e) cudaEventDestroy(e);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -878,6 +899,13 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         // 65 536 partial products), shorter rows stay with k_multiply + k_merge_xl.  (Unmeasured starting point.)
         job.sweep_min = std::max<uint64_t>({ctx->sweep_min, MT_XL + 1, LR_MIN_PER_BAND * lr_bands});
         job.a_pos = dA_pos; job.a_data = dA_data; job.b_data = dB_data;
+    }
+    // ---- k-way merge of the long rows made of few long ways (opt-in until measured): the multiply writes their bins as
+    // usual, k_merge_ways replaces k_merge_xl for them.  Needs the row-order bins (ways = runs of consecutive tasks).
+    if (((args->flags & OSP_KWAY_MERGE) || ctx->kway_env) && !sweep && rowwise && !fused && job.n_xl > 0 && job.idx_range > DENSE_MAX_COLS &&
+        !(args->flags & OSP_KSLICE_ORDER)) {
+        job.kway = true;
+        job.a_pos = dA_pos; job.run_off = run_off;
     }
     if (fused_short) {
         job.fused_short = true; job.chain2 = chain2;

@@ -16,6 +16,7 @@
 //   k_hist_*/k_scatter_*    bucket scatters of the stable conversions (osp_csr2csc, osp_coo2csr_device)
 #pragma once
 #include "osp_device.cuh"
+#include "osp_kway.cuh"
 #include <cstddef>
 
 namespace osp {
@@ -185,22 +186,38 @@ k_validate(const ValidateOp op0, const ValidateOp op1, const int n_ops, DevScala
     const uint64_t t0 = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x, nt = uint64_t(gridDim.x) * blockDim.x;
     for (int o = 0; o < n_ops; o++) {
         const ValidateOp &op = o ? op1 : op0;
-        for (uint64_t p0 = t0; p0 < op.nnz; p0 += 4 * nt) {                    // four independent pairs of loads in flight per thread
-            uint32_t cur[4], prv[4];
+        // elements two at a time (one 128-bit load; data arrays are 16-byte aligned), four loads in flight per thread;
+        // the predecessor of a pair's first element comes from the neighbouring lane
+        const uint4 *d2 = reinterpret_cast<const uint4 *>(op.d);
+        const bool aligned = (reinterpret_cast<uintptr_t>(op.d) & 15) == 0;
+        const uint64_t n_pairs = aligned ? op.nnz / 2 : 0;
+        for (uint64_t qw = t0 - lane_id(); qw < n_pairs; qw += 4 * nt) {      // warp-uniform bound: the shuffle below needs the whole warp
+            const uint64_t q0 = qw + lane_id();
+            uint4 v[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const uint64_t p = p0 + u * nt;
-                cur[u] = p < op.nnz ? op.d[p].idx : 0u;
-                prv[u] = p < op.nnz && p ? op.d[p - 1].idx : 0u;
+                const uint64_t q = q0 + u * nt;
+                v[u] = q < n_pairs ? d2[q] : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const uint64_t p = p0 + u * nt;
-                if (p >= op.nnz) continue;
-                if (op.idx_range && cur[u] >= op.idx_range) range_err = true;
-                if (o == n_ops - 1) mx = max(mx, cur[u]);
-                if (p) { desc += cur[u] <= prv[u]; eq += cur[u] == prv[u]; }
+                const uint64_t q = q0 + u * nt;
+                const bool live = q < n_pairs;
+                uint32_t prv = __shfl_up_sync(FULL, v[u].z, 1);          // second element of the pair before (lane - 1)
+                if (lane_id() == 0 && live && q) prv = op.d[2 * q - 1].idx;
+                if (!live) continue;
+                const uint32_t c0 = v[u].x, c1 = v[u].z;
+                if (op.idx_range && (c0 >= op.idx_range || c1 >= op.idx_range)) range_err = true;
+                if (o == n_ops - 1) mx = max(mx, max(c0, c1));
+                if (q) { desc += c0 <= prv; eq += c0 == prv; }
+                desc += c1 <= c0; eq += c1 == c0;
             }
+        }
+        for (uint64_t p = 2 * n_pairs + t0; p < op.nnz; p += nt) {          // the odd last element / an unaligned array
+            const uint32_t cur = op.d[p].idx;
+            if (op.idx_range && cur >= op.idx_range) range_err = true;
+            if (o == n_ops - 1) mx = max(mx, cur);
+            if (p) { const uint32_t prv = op.d[p - 1].idx; desc += cur <= prv; eq += cur == prv; }
         }
         for (uint64_t r = t0; r < op.n_slices; r += nt) {
             const uint64_t s = op.pos[r], e = op.pos[r + 1];
@@ -233,7 +250,16 @@ k_validate(const ValidateOp op0, const ValidateOp op1, const int n_ops, DevScala
 // Also: row_bin[] (bin start of every row), the queues of long rows, the upper bound of nnz(C)
 // and the reference's row count rule numRows = maxRowId + 1 (SimOuterSPACE.cpp:49-53).
 // =====================================================================================
-constexpr int MT_CAP_SHIFT_MIN = 8, MT_CAP_SHIFT_MAX = 11;
+#ifndef OSP_CAP_SHIFT_MAX
+#define OSP_CAP_SHIFT_MAX 11
+#endif
+#ifndef OSP_MC_THREADS
+#define OSP_MC_THREADS 256
+#endif
+#ifndef OSP_MC_OCC
+#define OSP_MC_OCC 3
+#endif
+constexpr int MT_CAP_SHIFT_MIN = 8, MT_CAP_SHIFT_MAX = OSP_CAP_SHIFT_MAX;
 constexpr uint32_t MT_CAP = 1u << MT_CAP_SHIFT_MAX;   // partial products per tile (soft): one CTA merges a tile
 constexpr uint32_t MT_LONG = 512;      // longest row sorted in registers by one warp
 constexpr uint32_t MT_LONG_BM = 640;   // longest row merged by bitmap rank by one warp (small column ranges)
@@ -271,7 +297,7 @@ template <class RB>
 __global__ void __launch_bounds__(PLAN_BLOCK)
 k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *tile_row, uint32_t *long_list,
        uint32_t *xl_list, uint64_t *tile_state, DevScalars *sc, int ticket_slot, uint32_t long_thresh,
-       uint64_t *chain_state, TileStart *tile_start = nullptr, uint32_t cap_max = MT_CAP) {
+       uint64_t *chain_state, TileStart *tile_start = nullptr, uint32_t cap_max = MT_CAP, uint64_t cut_row = ~0ull) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[33];
     __shared__ uint64_t s_bound[PLAN_BLOCK / 32];
@@ -303,7 +329,7 @@ k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *ti
         if (i < rows) {
             const uint64_t len = s[it + 1] - s[it];
             const uint64_t plen = s[it] - sp;
-            flag[it] = i == 0 || (i % MT_RMAX) == 0 || len > long_thresh || plen > long_thresh || (sp / cap) != (s[it] / cap);
+            flag[it] = i == 0 || (i % MT_RMAX) == 0 || len > long_thresh || plen > long_thresh || (sp / cap) != (s[it] / cap) || i == cut_row;
             row_bin[i] = s[it];
             if (len > MT_XL) xl_list[atomicAdd(&sc->n_xl, 1u)] = uint32_t(i);
             else if (len > long_thresh) long_list[atomicAdd(&sc->n_long, 1u)] = uint32_t(i);
@@ -349,6 +375,7 @@ k_plan(RB rb, uint64_t rows, uint64_t cols_hint, uint64_t *row_bin, uint32_t *ti
         if (flag[it]) {
             chain_state[o] = 0;                                                    // (look-back state of the merge chain)
             if (tile_start) tile_start[o] = TileStart{uint32_t(i0 + it), uint32_t(rb.task_begin(i0 + it)), s[it]};
+            if (i0 + it == cut_row) sc->cut_tile = uint32_t(o);             // a row block of the caller starts here
             tile_row[o++] = uint32_t(i0 + it);
         }
 }
@@ -502,7 +529,7 @@ k_multiply(Src src, uint64_t t0, uint64_t t1, const Elem *__restrict__ b_data, E
             }
 #pragma unroll
             for (int u = 0; u < 2; u++)
-                if (e[u] < total) b[u] = ld_gather(b_data + dbs_t[u] + e[u]);
+                if (e[u] < total) b[u] = ld_gather(b_data + uint32_t(dbs_t[u] + e[u]));    // (32-bit wrap-around: dbs = bs - excl may be "negative")
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 if (e[u] < total) {
@@ -623,7 +650,7 @@ constexpr uint32_t XL_EMPTY = 0xFFFFFFFFu;             // no column id (ids are 
 __global__ void __launch_bounds__(XL_THREADS)
 k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, uint32_t *uniq,
            const uint32_t *xl_list, const uint32_t *long_list, DevScalars *sc, float *acc_all, uint32_t *bits_all,
-           uint64_t cols_b, uint64_t row_lo, uint64_t row_hi, uint64_t sweep_min) {
+           uint64_t cols_b, uint64_t row_lo, uint64_t row_hi, uint64_t sweep_min, const uint64_t *__restrict__ kw_a_pos = nullptr) {
     __shared__ uint32_t key[XL_SLOTS];                 // column held by the slot
     __shared__ uint32_t owner[XL_SLOTS];               // lowest pending position of that column
     __shared__ uint32_t warp_sums[33];
@@ -644,8 +671,10 @@ k_merge_xl(const uint64_t *__restrict__ row_bin, uint64_t bin_base, Elem *bins, 
                 x = atomicAdd(&sc->xl_ticket, 1u);
                 if (x >= n_all) break;
                 const uint64_t r = x < n_xl ? xl_list[x] : long_list[x - n_xl];
-                // rows of sweep_min partial products or more belong to the fused band sweep (~0: none)
-                if (r >= row_lo && r < row_hi && row_bin[r + 1] - row_bin[r] < sweep_min) break;
+                // rows of sweep_min partial products or more belong to the fused band sweep (~0: none); rows of few long
+                // ways to the k-way merge (kw_a_pos: CSR(A)'s row pointer, null when that kernel is off)
+                if (r >= row_lo && r < row_hi && row_bin[r + 1] - row_bin[r] < sweep_min &&
+                    !(kw_a_pos && x < n_xl && kway_takes(row_bin[r + 1] - row_bin[r], kw_a_pos[r + 1] - kw_a_pos[r]))) break;
             }
             s_x = x;
         }
@@ -1109,9 +1138,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // HBM traffic = the algorithmic minimum of the merge: 8 P read + 8 nnz(C) + 8 (m+1) written.
 // K = uint32_t when col << 9 fits 32 bits (cols <= 2^23), else uint64_t.
 // =====================================================================================
-constexpr int MC_THREADS = 256;
-constexpr int MC_OCC = 3;                              // resident CTAs per SM (shared memory: 3 stages each)
-static_assert(MT_RMAX == MC_THREADS, "one thread per row of a tile");
+constexpr int MC_THREADS = OSP_MC_THREADS;
+constexpr int MC_OCC = OSP_MC_OCC;                              // resident CTAs per SM (shared memory: 3 stages each)
+static_assert(MT_RMAX <= MC_THREADS, "one thread per row of a tile");
 constexpr uint32_t MC_STAGE_ELEMS = MT_STAGE + 16;     // + alignment shift, rounded for the swizzle groups
 template <bool BM>
 struct __align__(16) MergeChainSmem {
@@ -1675,6 +1704,19 @@ __global__ void k_pick_u64(const uint64_t *src, const uint64_t *index, uint32_t 
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[index[i]];
 }
+// The record a rank contributes to the call's one all-gather: words 0 .. G = the offsets of the owners' first rows in
+// this rank's local row-major order (row_bin at the rows `words_in` names), then the words the host put there
+// (capacities, host status), and in the last word what the device found (first error of the symbolic pass / validation).
+__global__ void k_dist_record(const uint64_t *row_bin, const uint64_t *words_in, uint32_t G, uint32_t W, const DevScalars *sc,
+                              uint64_t *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W) return;
+    if (i <= G) out[i] = row_bin[words_in[i]];
+    else if (i + 1 == W) {
+        const bool unsorted = sc->v_desc - sc->v_eq != sc->v_bdesc - sc->v_beq;
+        out[i] = sc->v_bad_pos || unsorted ? 1u : sc->v_eq != sc->v_beq ? 233u : sc->err;      // OSP_ERR_INVALID / _DUPLICATE / device code
+    } else out[i] = words_in[i];
+}
 // lens[s * RL + i] read in (i, s) order
 struct TransposedIn {
     const uint32_t *lens;
@@ -1695,11 +1737,12 @@ struct RowBinStrided {         // row i of the owner starts at dst_off[i * G]
 // lane copies whatever the segment lengths are (at G = 8 a segment is a single run of ~8 partial products) --
 // and find the segment of an element by comparing its position with the scanned segment lengths.
 __global__ void k_regroup(const Elem *__restrict__ recv, const uint64_t *__restrict__ src_off, const uint64_t *__restrict__ dst_off,
-                          const uint32_t *__restrict__ lens, uint64_t RL, uint32_t G, Elem *__restrict__ bins) {
+                          const uint32_t *__restrict__ lens, uint64_t RL, uint32_t G, Elem *__restrict__ bins, uint64_t row_lo,
+                          uint64_t row_hi) {
     const unsigned int lane = lane_id();
     uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
     uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
-    for (uint64_t i = warp; i < RL; i += nwarps) {
+    for (uint64_t i = row_lo + warp; i < row_hi; i += nwarps) {
         uint32_t l = 0;
         uint64_t so = 0;
         if (lane < G) { l = lens[uint64_t(lane) * RL + i]; so = src_off[uint64_t(lane) * RL + i]; }
@@ -1733,29 +1776,43 @@ struct PeerDst {
 // The warp-flat multiply of k_multiply with every run going to the GPU that owns its output row: 8-byte stores
 // over NVLink that are contiguous from run to run.  The exchange of the k-sharded path IS this kernel's store
 // stream: nothing is staged or sent.
+struct PeerRows { uint64_t lo[MAX_PEERS], hi[MAX_PEERS]; };      // rows of A whose runs this launch sends, per owner
 __global__ void __launch_bounds__(256)
 k_multiply_peer(const Elem *__restrict__ a_data, const uint64_t *__restrict__ run_off, const uint32_t *__restrict__ task_bs,
-                uint64_t t1, const Elem *__restrict__ b_data, const PeerDst dst, const uint64_t *__restrict__ a_pos,
-                uint64_t first_row) {
+                const Elem *__restrict__ b_data, const PeerDst dst, const uint64_t *__restrict__ a_pos, const uint64_t m_a,
+                const PeerRows rows, const int first_owner) {
     __shared__ Elem *s_base[MAX_PEERS];
+    __shared__ uint64_t s_tb[MAX_PEERS], s_cum[MAX_PEERS + 1];
     if (threadIdx.x < MAX_PEERS) s_base[threadIdx.x] = dst.base[threadIdx.x];
+    if (threadIdx.x == 0) {
+        // the launch's tasks: for every owner the non-zeros of A of its rows [lo, hi), owners taken from `first_owner` on and
+        // round: at any moment the G sources are writing to G different owners instead of all to the same one
+        uint64_t cum = 0;
+        for (int j = 0; j < dst.world; j++) {
+            const int r = (first_owner + j) % dst.world;
+            const uint64_t tb = a_pos[min(rows.lo[r], m_a)], te = a_pos[min(rows.hi[r], m_a)];
+            s_tb[j] = tb; s_cum[j] = cum;
+            cum += te - tb;
+        }
+        s_cum[dst.world] = cum;
+    }
     __syncthreads();
     const unsigned int lane = lane_id();
     const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
     const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
-    // The sweep over the tasks starts at `first_row` (the first row of the NEXT rank's block) and wraps round:
-    // at any moment the G sources are writing to G different owners instead of all to the same one.
-    const uint64_t rot = a_pos[first_row];
+    const uint64_t t1 = s_cum[dst.world];
     for (uint64_t base = warp * 32; base < t1; base += nwarps * 32) {
         uint32_t bs = 0, len = 0, owner = 0; float a = 0.f; uint64_t off = 0;
         if (base + lane < t1) {
-            uint64_t i = base + lane + rot;
-            if (i >= t1) i -= t1;
+            const uint64_t f = base + lane;
+            int j = 0;
+            while (j + 1 < dst.world && f >= s_cum[j + 1]) j++;
+            const uint64_t i = s_tb[j] + (f - s_cum[j]);
+            owner = uint32_t((first_owner + j) % dst.world);
             a = a_data[i].val;
             const uint64_t o = run_off[i];
             len = uint32_t(run_off[i + 1] - o);
             bs = task_bs[i];
-            for (int r = 1; r < dst.world; r++) owner += o >= dst.bound[r];      // rows are owned in ascending blocks
             off = o + uint64_t(dst.delta[owner]);
         }
         const uint32_t incl = warp_inclusive_scan(len);
@@ -1763,8 +1820,12 @@ k_multiply_peer(const Elem *__restrict__ a_data, const uint64_t *__restrict__ ru
         const uint32_t excl = incl - len;
         const uint32_t dbs = bs - excl;                       // B index of element e of this task: dbs + e
         const uint64_t doff = off - excl;                     // landing index of element e of this task: doff + e (mod 2^64)
-        for (uint32_t e0 = 0; e0 < total; e0 += 64) {          // two independent 32-element chunks per turn
-            const uint32_t e[2] = {e0 + lane, e0 + 32 + lane};
+        // The walk starts `shift` elements early so that every 32-lane store covers two whole 128-byte lines of the
+        // owner's landing buffer (the destination of the warp's runs is one contiguous stream per owner): NVLink
+        // moves full lines instead of a line and two fragments per store.
+        const uint32_t shift = uint32_t(__shfl_sync(FULL, doff, 0)) & 15u;
+        for (uint32_t e0 = 0; e0 < total + shift; e0 += 64) {  // two independent 32-element chunks per turn
+            const uint32_t e[2] = {e0 + lane - shift, e0 + 32 + lane - shift};     // (wraps below 0 for the first lanes: >= total)
             uint32_t t[2] = {0, 0};                            // number of tasks that end at or before e
 #pragma unroll
             for (int step = 16; step > 0; step >>= 1) {
@@ -1784,7 +1845,7 @@ k_multiply_peer(const Elem *__restrict__ a_data, const uint64_t *__restrict__ ru
             }
 #pragma unroll
             for (int u = 0; u < 2; u++)
-                if (e[u] < total) b[u] = b_data[dbs_t[u] + e[u]];
+                if (e[u] < total) b[u] = ld_gather(b_data + uint32_t(dbs_t[u] + e[u]));    // (32-bit wrap-around: dbs = bs - excl may be "negative")
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 if (e[u] < total) {

@@ -61,6 +61,8 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     return cudaSuccess;
 }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new cusimStream{0}; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { *s = new cusimStream{0}; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = 0; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }

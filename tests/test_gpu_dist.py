@@ -66,6 +66,28 @@ for name, sd in (("er16k", 4), ("rmat20", 256)):
     r0, r1 = deng.rows(dims["rows"])
     lo, hi = int(want.pos[r0]), int(want.pos[r1])
     assert_bit_exact(got, pack(want.pos[r0:r1 + 1] - want.pos[r0], want.data[lo:hi]), f"{name} rank {rank}")
+# one rank's bad shard (a k index beyond its inner dimension; an unsorted row) must come back as an error on EVERY rank --
+# nobody may be left waiting in a collective -- and the communicator must still work afterwards
+a, b, dims = synth.build_workload("er16k", 8)
+k0, k1 = osd.k_ranges(a, b, dims["n_k"], world)[rank]
+a_g, b_g = osd.shard_operands(a, b, k0, k1)
+for what in ("index", "unsorted"):
+    bad = osp.CSRMatrix(a_g.pos.copy(), a_g.data.copy())
+    if rank == world - 1:
+        if what == "index":
+            bad.data["idx"][0] = k1 - k0 + 7
+        else:
+            p0 = int(np.flatnonzero(np.diff(bad.pos.astype(np.int64)) >= 2)[0])
+            s0 = int(bad.pos[p0]); bad.data[[s0, s0 + 1]] = bad.data[[s0 + 1, s0]]
+    try:
+        deng.spgemm(bad, b_g, dims["rows"], dims["cols"])
+        raise SystemExit(f"rank {rank}: the bad shard ({what}) was accepted")
+    except osp.OspError as e:
+        want_code = {"index": osp.api.OSP_ERR_INDEX, "unsorted": osp.api.OSP_ERR_INVALID}[what] if rank == world - 1 else osp.api.OSP_ERR_INVALID
+        assert e.code == want_code, (rank, what, e.code, str(e))
+res = deng.spgemm(a_g, b_g, dims["rows"], dims["cols"])
+assert res.stats()["products"] > 0
+res.free()
 deng.close(); eng.close()
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")

@@ -373,6 +373,35 @@ def _row_lengths_case(rng, lens, cols, dup_rate):
     return A, B
 
 
+@pytest.mark.parametrize("cols,dup_rate", [(1 << 17, 0.0), (1 << 20, 0.4), ((1 << 24) + 5, 0.2)])
+def test_kway_merge_of_the_sorted_ways(engine, cols, dup_rate):
+    """rows of 4 097 .. 32 768 partial products made of a few long sorted ways are merged BY RANK
+    (k_merge_ways, the k-way merge of merge2way / mergeHardware, SimSpGEMM.cpp:306-327, 411-441) instead of through the
+    dense accumulator; rows outside that class (too short, too long) keep their kernels in the same call.  Same bits."""
+    rng = np.random.default_rng(cols % 977 + int(dup_rate * 10))
+    lens = [4096, 4097, 5000, 9000, 20000, 32768, 32769, 40000, 700, 12, 0, 300, 6000] * 2
+    rng.shuffle(lens)
+    A, B = _row_lengths_case(rng, lens, cols, dup_rate)
+    a_csc, a_csr, b_csr = operands(A, B)
+    want, prod = oracle_spgemm(a_csc, b_csr)
+    for flags in (api.OSP_KWAY_MERGE, 0):
+        res = engine.spgemm(a_csr, b_csr, a_is_csr=True, cols_b=cols, flags=flags | api.OSP_PROFILE_KERNELS)
+        got = res.to_host(); names = {n for n, _ in res.kernel_times()}; res.free()
+        assert any("k_merge_ways" in n for n in names) == bool(flags), names
+        assert_bit_exact(got, want, f"k-way merge cols={cols} dup={dup_rate} flags={flags}")
+        check_csr_invariants(got, cols)
+    # in row blocks (the ways of a row never straddle a block) and through the CSC hand-over
+    eng = osp.Engine(0)
+    try:
+        eng.set_workspace_limit(60000 * 8)
+        res = eng.spgemm(a_csc, b_csr, a_is_csr=False, cols_b=cols, flags=api.OSP_KWAY_MERGE)
+        got = res.to_host(); st = res.stats(); res.free()
+        assert st["row_chunks"] > 1
+        assert_bit_exact(got, want, "k-way merge in row blocks")
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("cols,dup_rate", [(1 << 14, 0.0), (1 << 14, 0.3), (1 << 20, 0.0), (1 << 20, 0.3), ((1 << 24) + 5, 0.2)])
 def test_every_row_length_class(engine, cols, dup_rate):
     """Rows of every size class of the merge chain (0, 1, 2..8, ..., 257..512, long rows) side by side in the same

@@ -80,7 +80,8 @@ def run_check(workload, scale_down=1, iters=2, sample_rows=256, heavy_rows=4, ke
 
     def up(x):
         return torch.from_numpy(x.view(np.uint8).reshape(-1)).to(dev)
-    t = [up(a.pos), up(a.data), up(b.pos), up(b.data)]
+    t = [up(a.pos), up(a.data)]
+    t += t if b is a else [up(b.pos), up(b.data)]          # C = A*A: both operands are the same arrays in HBM
     torch.cuda.synchronize()
     free_b, total_b = torch.cuda.mem_get_info(0)
     log(json.dumps(dict(hbm_total_gb=round(total_b / 1e9, 1), hbm_free_gb=round(free_b / 1e9, 1))))
