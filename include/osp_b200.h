@@ -51,16 +51,17 @@ extern "C" {
                                     bins, same result bit for bit (DESIGN.md "multiply order") */
 #define OSP_NO_FUSED_DENSE  64u  /* keep the bins even when every row is long over a small column range (see
                                     DESIGN.md "fused dense rows"): multiply -> bins -> k_merge_dense */
-#define OSP_LONGROW_SWEEP  128u  /* EXPERIMENTAL, off by default, not yet run on a B200 (validated on the CPU emulation
-                                    of tests/cusim only): rows of more than 4096 partial products over more than 16384
+#define OSP_LONGROW_SWEEP  128u  /* opt-in (round 2: bit-exact on a B200, not faster than the default on config 3,
+                                    profiles/r02_optin_paths.md): rows of more than 4096 partial products over more than 16384
                                     columns skip the bins -- a fused band sweep (k_long_fill)
                                     computes and merges them in shared memory.  Same bits.  Ignored with
                                     OSP_KSLICE_ORDER.  Environment: OSP_LONGROW_SWEEP=1 turns it on for every call of a
                                     context, OSP_LONGROW_SWEEP_MIN=<partial products> raises the row threshold */
-#define OSP_FUSED_SHORT    256u  /* EXPERIMENTAL, off by default, not yet run on a B200 (CPU emulation only): the tiles of short
-                                    rows never go through the bins -- the merge chain computes a tile's partial products
-                                    straight into its shared-memory stage (k_merge_chain_fused), k_multiply only serves the
-                                    long rows.  Same bits.  Ignored with OSP_KSLICE_ORDER.  Environment: OSP_FUSED_SHORT=1 */
+#define OSP_FUSED_SHORT    256u  /* opt-in (round 2: bit-exact on a B200, slower than the default, profiles/r02_chain2.md): the
+                                    tiles of short rows never go through the bins -- the warp-specialised k_chain2
+                                    (osp_chain2.cuh) gathers the rows of B straight into its shared-memory stages with
+                                    asynchronous copies while other warps sort; k_multiply only serves the long rows.
+                                    Same bits.  Ignored with OSP_KSLICE_ORDER.  Environment: OSP_FUSED_SHORT=1 */
 #define OSP_NO_VALIDATE    512u  /* the caller vouches for the operand preconditions (slices ascending and duplicate-free,
                                     every column id of B below cols_b): skips the validation pass (one streaming read of
                                     both operands, k_validate).  By default a violation returns OSP_ERR_INVALID (unsorted

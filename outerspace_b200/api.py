@@ -34,8 +34,8 @@ OSP_DEVICE_POINTERS = 2
 OSP_ROWWISE_ORDER = 4
 OSP_KSLICE_ORDER = 32
 OSP_NO_FUSED_DENSE = 64
-OSP_LONGROW_SWEEP = 128     # experimental, off by default (include/osp_b200.h)
-OSP_FUSED_SHORT = 256       # experimental, off by default (include/osp_b200.h)
+OSP_LONGROW_SWEEP = 128     # opt-in: verified on a B200, not faster (include/osp_b200.h)
+OSP_FUSED_SHORT = 256       # opt-in: verified on a B200, slower (include/osp_b200.h)
 OSP_NO_VALIDATE = 512       # the caller vouches for sorted, duplicate-free slices and in-range column ids
 OSP_KWAY_MERGE = 1024       # k-way merge of the pre-sorted ways for rows of 4097..32768 partial products in <= 64 ways
 OSP_PROFILE_PHASES = 8
