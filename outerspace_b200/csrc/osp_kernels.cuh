@@ -41,34 +41,35 @@ k_scan(In in, Out out, uint64_t n, uint64_t *tile_state, unsigned int *ticket) {
     __syncthreads();
     const uint32_t tile = s_tile;
     const unsigned int lane = lane_id(), warp = threadIdx.x >> 5;
-    // BLOCKED layout: a thread owns SCAN_ITEMS consecutive items, sums them in registers and only the thread totals go
-    // through a warp scan (the first version scanned every item across the warp: 80 shuffles per thread instead of 10).
-    // The items of a thread are 64 contiguous bytes of the input and of the output: whole sectors per thread, lines per warp.
-    const uint64_t tbase = uint64_t(tile) * SCAN_TILE + uint64_t(threadIdx.x) * SCAN_ITEMS;
+    const uint64_t wbase = uint64_t(tile) * SCAN_TILE + uint64_t(warp) * (32 * SCAN_ITEMS);
 
-    uint64_t own[SCAN_ITEMS];
+    uint64_t excl[SCAN_ITEMS], own[SCAN_ITEMS];
+    uint64_t running = 0;
     // two-stage input: all the first-level loads of a thread are issued before anything depends on them
     uint64_t key[SCAN_ITEMS];
 #pragma unroll
     for (int it = 0; it < SCAN_ITEMS; it++) {
-        const uint64_t idx = tbase + it;
+        const uint64_t idx = wbase + it * 32 + lane;
         key[it] = in.load(idx, idx < n);
     }
 #pragma unroll
     for (int it = 0; it < SCAN_ITEMS; it++) {
-        const uint64_t idx = tbase + it;
+        const uint64_t idx = wbase + it * 32 + lane;
         own[it] = in.value(key[it], idx, idx < n);
     }
-    uint64_t tsum = 0;
 #pragma unroll
-    for (int it = 0; it < SCAN_ITEMS; it++) tsum += own[it];
-    uint64_t incl = tsum;
+    for (int it = 0; it < SCAN_ITEMS; it++) {
+        uint64_t x = own[it];
+        uint64_t incl = x;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint64_t y = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += y;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t y = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += y;
+        }
+        excl[it] = running + incl - x;
+        running += __shfl_sync(FULL, incl, 31);
     }
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_warp[warp] = running;
     __syncthreads();
     if (warp == 0) {
         uint64_t w = lane < SCAN_BLOCK / 32 ? s_warp[lane] : 0;
@@ -88,12 +89,11 @@ k_scan(In in, Out out, uint64_t n, uint64_t *tile_state, unsigned int *ticket) {
         }
     }
     __syncthreads();
-    uint64_t run = s_tile_excl + s_warp[warp] + incl - tsum;      // exclusive prefix of this thread's first item
+    const uint64_t offset = s_tile_excl + s_warp[warp];
 #pragma unroll
     for (int it = 0; it < SCAN_ITEMS; it++) {
-        const uint64_t idx = tbase + it;
-        if (idx < n) out(idx, run, own[it]);
-        run += own[it];
+        uint64_t idx = wbase + it * 32 + lane;
+        if (idx < n) out(idx, offset + excl[it], own[it]);
     }
 }
 
@@ -1328,9 +1328,12 @@ merge_chain_body(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, 
         }
     };
     // Resolves the offset of tile `d` in C and streams its output stage out.
-    // (its offset was resolved into sm.base by warp 0 during the sort of the tile after it -- resolve_prev below --
-    // and a CTA barrier lies between that store and this call)
     auto retire_tile = [&](const TileDesc &d, uint32_t slot, uint32_t obuf) {
+        if (warp == 0) {
+            const uint64_t excl = lb_resolve(tile_state, d.idx, d.n_out, carry);
+            if (lane == 0) sm.base = excl;
+        }
+        __syncthreads();
         const uint64_t base = sm.base;
         if (tid == 0 && d.last) { c_pos[d.r0 + d.R] = base + d.n_out; sc->nnz_c[carry_slot ^ 1] = base + d.n_out; }
         if (d.is_long) {
@@ -1362,22 +1365,11 @@ merge_chain_body(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, 
         }
     };
 
-    TileDesc prev;
-    prev.idx = 0xFFFFFFFFu;
-    // The previous tile's offset in C: resolved by warp 0 at the START of the current tile's sort, while the other warps
-    // already pull batches (the batches are handed out dynamically, so nobody waits for warp 0).  Round 1 resolved it
-    // behind a CTA barrier right before the copy-out: 14 % of the kernel's stall samples sat on that barrier (ncu,
-    // config 4) -- the predecessors of a tile need more than one tile of slack to publish.
-    auto resolve_prev = [&]() {
-        if (warp == 0 && prev.idx != 0xFFFFFFFFu) {
-            const uint64_t excl = lb_resolve(tile_state, prev.idx, prev.n_out, carry);
-            if (lane == 0) sm.base = excl;
-        }
-    };
     uint32_t it = 0, n_tma = 0;                            // bulk copies awaited so far (mbarrier phase parity)
     if (warp == MC_THREADS / 32 - 1) prefetch_tile(0, 0);
     __syncthreads();
-    TileDesc cur = load_desc(0);
+    TileDesc cur = load_desc(0), prev;
+    prev.idx = 0xFFFFFFFFu;
     start_copy(cur);
     while (cur.idx < n_chain) {
         const uint32_t slot = it % 3, ob = it & 1;
@@ -1387,7 +1379,6 @@ merge_chain_body(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, 
         // ---- sort: stage -> ostage[ob], survivors per row ----
         if (cur.is_long) {
             cur.n_out = uniq[cur.r0];
-            resolve_prev();
             if (warp == MC_THREADS / 32 - 1) prefetch_tile((it + 1) % 3, (it + 1) & 1);
         } else {
             uint32_t *rstart = sm.rstart[slot], *rout = sm.rout[slot];
@@ -1426,8 +1417,7 @@ merge_chain_body(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, 
             if (my_len == 1) ostage[swz(rstart[tid])] = stage[rstart[tid]];
             __syncthreads();                                  // order[] is complete
             const uint32_t n_batches = sm.cls_b0[8];
-            resolve_prev();                                                               // warp 0; the others start on the batches
-            if (warp == MC_THREADS / 32 - 1) prefetch_tile((it + 1) % 3, (it + 1) & 1);   // the last warp likewise
+            if (warp == MC_THREADS / 32 - 1) prefetch_tile((it + 1) % 3, (it + 1) & 1);   // the others start on the batches
             while (true) {
                 uint32_t b = 0;
                 if (lane == 0) b = atomicAdd(&sm.next_batch, 1u);
@@ -1482,8 +1472,6 @@ merge_chain_body(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, 
         it++;
     }
     if (prev.idx != 0xFFFFFFFFu) {
-        __syncthreads();                                     // (sm.base of the tile before has been read by everybody)
-        resolve_prev();
         __syncthreads();
         retire_tile(prev, (it + 2) % 3, (it & 1) ^ 1);
     }
