@@ -233,12 +233,24 @@ int sync_scalars(osp_ctx *ctx) {
         static_assert(sizeof(DevScalars) % 8 == 0, "DevScalars is handed over in 8-byte words");
         unsigned long long spins = 0;
         for (int i = 0; i < PUBLISH_SLOTS; i++) {
+            bool drained = false;
             while (slots[2 * i + 1] != seq) {
                 if ((++spins & 0xFFF) == 0) {
                     cudaError_t q = cudaStreamQuery(ctx->stream);
                     if (q != cudaSuccess && q != cudaErrorNotReady) {
                         cudaGetLastError();
                         return fail(ctx, OSP_ERR_CUDA, std::string("device fault: ") + cudaGetErrorString(q));
+                    }
+                    if (q == cudaSuccess) {
+                        // the stream has drained: the stores are done.  A slot that still lacks the sequence number after
+                        // one more look was not delivered as one 16-byte write (a platform without that guarantee):
+                        // take the copy engine instead of spinning for ever
+                        if (drained) {
+                            CU(ctx, cudaMemcpyAsync(ctx->h_sc, ctx->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->stream));
+                            CU(ctx, cudaStreamSynchronize(ctx->stream));
+                            return OSP_OK;
+                        }
+                        drained = true;
                     }
                 }
             }
@@ -571,6 +583,7 @@ int osp_create(int device, osp_ctx **out) {
     if (device < 0 || device >= n) return fail(nullptr, OSP_ERR_INVALID, "osp_create: device index out of range");
     osp_ctx *ctx = new osp_ctx();
     ctx->device = device;
+    struct CtxGuard { osp_ctx *c; ~CtxGuard() { if (c) osp_destroy(c); } } ctx_guard{ctx};   // every early return below releases it
     CU(nullptr, cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(nullptr, cudaGetDeviceProperties(&prop, device));
@@ -668,6 +681,7 @@ int osp_create(int device, osp_ctx **out) {
         uint64_t mb = std::strtoull(env, nullptr, 10);
         if (mb) ctx->ws_limit = mb << 20;
     }
+    ctx_guard.c = nullptr;
     *out = ctx;
     return OSP_OK;
 }

@@ -204,9 +204,15 @@ unsigned host_threads(uint64_t bytes) {
 
 }  // namespace
 
+// No C++ exception crosses the C ABI: allocation failures become OSP_ERR_OOM, anything else OSP_ERR_INVALID.
+#define OSP_NOTHROW(expr)                                   \
+    try { return (expr); }                                  \
+    catch (const std::bad_alloc &) { return OSP_ERR_OOM; }  \
+    catch (...) { return OSP_ERR_INVALID; }
+
 extern "C" {
 
-int osp_readcoo_buffer(const char *text, uint64_t len, int symmetric, osp_coo **out) {
+static int osp_readcoo_buffer_impl(const char *text, uint64_t len, int symmetric, osp_coo **out) {
     if ((!text && len) || !out) return OSP_ERR_INVALID;
     *out = nullptr;
     // ---- header: the first line that is neither blank nor a comment (SimSpGEMM.cpp:66-88) ----
@@ -240,8 +246,16 @@ int osp_readcoo_buffer(const char *text, uint64_t len, int symmetric, osp_coo **
     std::vector<Piece> pieces(T);
     const size_t guess = size_t((symmetric ? 2 : 1) * hdr[2] / T + 16);
     auto work = [&](unsigned i) {
-        if (hdr[2] < (1ull << 32)) { pieces[i].rows.reserve(guess); pieces[i].cols.reserve(guess); pieces[i].vals.reserve(guess); }
-        parse_piece(cut[i], cut[i + 1], symmetric, pieces[i]);
+        try {            // (an exception must not leave a worker thread: std::terminate)
+            // the header's NNZ is untrusted: an entry takes at least four bytes of text ("1 1\n")
+            const size_t cap = std::min(guess, size_t((symmetric ? 2 : 1) * uint64_t(cut[i + 1] - cut[i]) / 4 + 16));
+            if (hdr[2] < (1ull << 32)) { pieces[i].rows.reserve(cap); pieces[i].cols.reserve(cap); pieces[i].vals.reserve(cap); }
+            parse_piece(cut[i], cut[i + 1], symmetric, pieces[i]);
+        } catch (const std::bad_alloc &) {
+            pieces[i].err = OSP_ERR_OOM;
+        } catch (...) {
+            pieces[i].err = OSP_ERR_INVALID;
+        }
     };
     if (T == 1) {
         work(0);
@@ -277,7 +291,7 @@ int osp_readcoo_buffer(const char *text, uint64_t len, int symmetric, osp_coo **
     return OSP_OK;
 }
 
-int osp_readcoo(const char *path, int symmetric, osp_coo **out) {
+static int osp_readcoo_impl(const char *path, int symmetric, osp_coo **out) {
     if (!path || !out) return OSP_ERR_INVALID;
     *out = nullptr;
     FILE *f = std::fopen(path, "rb");
@@ -303,7 +317,7 @@ int osp_coo_dims(const osp_coo *c, uint64_t *nrow, uint64_t *ncol, uint64_t *nnz
     return OSP_OK;
 }
 
-int osp_coo_copy(const osp_coo *c, uint32_t *rows, uint32_t *cols, float *vals) {
+static int osp_coo_copy_impl(const osp_coo *c, uint32_t *rows, uint32_t *cols, float *vals) {
     if (!c) return OSP_ERR_INVALID;
     size_t n = c->rows.size();
     if (n && (!rows || !cols || !vals)) return OSP_ERR_INVALID;
@@ -324,7 +338,7 @@ void osp_coo_free(osp_coo *c) { delete c; }
 //   sorted by (major, minor): no pass, the elements are copied in place            (CSR from a row-major file)
 //   sorted by (minor, major): one stable pass by major                             (CSC from a row-major file)
 //   anything else:            stable pass by minor, then stable pass by major
-int osp_coo2csr(uint64_t nnz, const uint32_t *rows, const uint32_t *cols, const float *vals, uint64_t N, int transpose,
+static int osp_coo2csr_impl(uint64_t nnz, const uint32_t *rows, const uint32_t *cols, const float *vals, uint64_t N, int transpose,
                 uint64_t *pos, void *data) {
     if (!pos || (nnz && (!rows || !cols || !vals || !data))) return OSP_ERR_INVALID;
     const uint32_t *major = transpose ? cols : rows;
@@ -372,11 +386,11 @@ int osp_coo2csr(uint64_t nnz, const uint32_t *rows, const uint32_t *cols, const 
 // ---- compact COO (CompactCOOMatrix, common.h:52-56) -------------------------------------------------------------
 // csr2compact (SimSpGEMM.cpp:154-219): group j holds the (j+1)-th non-zero of every slice that has one, slices in
 // ascending order; n_groups = the longest slice.  The reference counts the slices per length, suffix-sums the counts
-// and walks the slices with one cursor per group; here the suffix sum is the same and the scatter is a direct
-// computation of every element's place -- element j of slice i goes to group_pos[j] + (slices before i that hold
-// more than j non-zeros) -- found with one counting pass per group length class, no cursors.
+// and walks the slices with one cursor per group; here the suffix sum is the same and the scatter walks the slices in
+// ascending order with one cursor per group as well (fill[j]++): element j of slice i lands at group_pos[j] + (slices
+// before i that hold more than j non-zeros).
 // A matrix without any non-zero gives zero groups (the reference indexes statNNZR[-1] there: undefined behaviour).
-int osp_csr2compact(uint64_t n_major, const uint64_t *pos, const void *data, uint64_t *n_groups, uint64_t *group_pos,
+static int osp_csr2compact_impl(uint64_t n_major, const uint64_t *pos, const void *data, uint64_t *n_groups, uint64_t *group_pos,
                     uint32_t *rows, uint32_t *cols, float *vals) {
     if (!n_groups || (n_major && !pos)) return OSP_ERR_INVALID;
     uint64_t longest = 0;
@@ -412,7 +426,7 @@ int osp_csr2compact(uint64_t n_major, const uint64_t *pos, const void *data, uin
 
 // csc2rawcompact (SimSpGEMM.cpp:221-243): the COO view of a compressed matrix, one group per slice (group_pos = pos):
 // row = the element's index, col = the slice id.
-int osp_csc2rawcompact(uint64_t n_major, const uint64_t *pos, const void *data, uint32_t *rows, uint32_t *cols, float *vals) {
+static int osp_csc2rawcompact_impl(uint64_t n_major, const uint64_t *pos, const void *data, uint32_t *rows, uint32_t *cols, float *vals) {
     if (n_major && !pos) return OSP_ERR_INVALID;
     const uint64_t nnz = n_major ? pos[n_major] - pos[0] : 0;
     if (nnz && (!data || !rows || !cols || !vals)) return OSP_ERR_INVALID;
@@ -424,4 +438,24 @@ int osp_csc2rawcompact(uint64_t n_major, const uint64_t *pos, const void *data, 
     return OSP_OK;
 }
 
+int osp_readcoo_buffer(const char *text, uint64_t len, int symmetric, osp_coo **out) {
+    OSP_NOTHROW(osp_readcoo_buffer_impl(text, len, symmetric, out));
+}
+int osp_readcoo(const char *path, int symmetric, osp_coo **out) {
+    OSP_NOTHROW(osp_readcoo_impl(path, symmetric, out));
+}
+int osp_coo_copy(const osp_coo *c, uint32_t *rows, uint32_t *cols, float *vals) {
+    OSP_NOTHROW(osp_coo_copy_impl(c, rows, cols, vals));
+}
+int osp_coo2csr(uint64_t nnz, const uint32_t *rows, const uint32_t *cols, const float *vals, uint64_t N, int transpose,
+                uint64_t *pos, void *data) {
+    OSP_NOTHROW(osp_coo2csr_impl(nnz, rows, cols, vals, N, transpose, pos, data));
+}
+int osp_csr2compact(uint64_t n_major, const uint64_t *pos, const void *data, uint64_t *n_groups, uint64_t *group_pos,
+                    uint32_t *rows, uint32_t *cols, float *vals) {
+    OSP_NOTHROW(osp_csr2compact_impl(n_major, pos, data, n_groups, group_pos, rows, cols, vals));
+}
+int osp_csc2rawcompact(uint64_t n_major, const uint64_t *pos, const void *data, uint32_t *rows, uint32_t *cols, float *vals) {
+    OSP_NOTHROW(osp_csc2rawcompact_impl(n_major, pos, data, rows, cols, vals));
+}
 }  // extern "C"

@@ -17,4 +17,7 @@ def test_reference_arm_line():
     assert line["value"] > 0 and line["ms_per_step"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
-    assert "configs[1]" in line["config"]["workload"]
+    # both arms run the same headline workload at every N (configs[3]); the reference arm on a stated sample of it
+    assert "configs[3]" in line["config"]["workload"] and line["config"]["name"] == "er8m"
+    assert set(line["config"]) == {"workload", "name", "scale_down"} and line["scaling"] == "strong"
+    assert "1/64" in line["cpu_baseline"]["sample"]
