@@ -148,6 +148,9 @@ void osp_result_free(osp_result *r);
 /* Task-size lists the reference's timing models read from TaskProvider
  * (getMultiplyTasks/getMergeTasks, SimOuterSPACE.cpp:59-64; MultiplyTask/MergeTask :34-42):
  * per non-empty k-slice (nnzc, nnzr), and per output row (#ways, output nnz).
+ * (nnzc, nnzr) and #ways equal the as-written TaskProvider's; "output nnz" is the true number of non-zeros of the row
+ * of C (intended semantics) -- the as-written merge counts 1 + the adjacent equal position-index pairs there because of
+ * its inverted duplicate test (SimOuterSPACE.cpp:120), which this engine does not reproduce.
  * Two-call pattern: pass NULL arrays to obtain the counts. */
 int  osp_task_sizes(osp_ctx *ctx, const osp_spgemm_args *args, const osp_result *r,
                     uint64_t *n_multiply, uint32_t *multiply_nnzc_nnzr,

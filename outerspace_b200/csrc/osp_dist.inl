@@ -400,7 +400,9 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
     const uint64_t n_seg = RL * G;
     cudaStream_t main_stream = ctx->stream;
     const bool side = RL && !ctx->profile_kernels;               // (per-kernel event pairs assume one stream)
-    const int H = (direct && G > 1 && m >= uint64_t(4 * G) && !std::getenv("OSP_DIST_ONE_PHASE")) ? 2 : 1;
+    // (measured: worth 0.07 ms at G = 8, nothing at G = 2, where half of the products stay local and the multiply is not NVLink-bound)
+    const int H = (direct && G > 1 && (G >= 4 || std::getenv("OSP_DIST_TWO_PHASE")) && m >= uint64_t(4 * G) &&
+                   !std::getenv("OSP_DIST_ONE_PHASE")) ? 2 : 1;
     const uint64_t cut_local = H == 2 ? RL / 2 : ~0ull;          // first row (of this owner's block) of the second half
     if (RL) {
         if (side) {

@@ -323,7 +323,9 @@ int reserve_merge(osp_ctx *ctx, const MergeJob &job, unsigned int &xl_ctas) {
         const uint64_t budget = std::max<uint64_t>(ctx->total_mem / 16, 1ull << 28);
         const uint64_t max_ctas = budget / std::max<uint64_t>(per_cta, 1);
         if (max_ctas < 1) return fail(ctx, OSP_ERR_UNSUPPORTED, "long-row accumulator does not fit: column range too large");
-        xl_ctas = unsigned(std::min<uint64_t>({max_ctas, uint64_t(ctx->sm_count) * 4, n_acc_rows}));
+        uint64_t per_sm = 4;                                  // development knob: resident accumulators per SM
+        if (const char *env = std::getenv("OSP_XL_CTAS_PER_SM")) { const uint64_t v = std::strtoull(env, nullptr, 10); if (v) per_sm = v; }
+        xl_ctas = unsigned(std::min<uint64_t>({max_ctas, uint64_t(ctx->sm_count) * per_sm, n_acc_rows}));
         CU(ctx, ctx->xl_acc.reserve(uint64_t(xl_ctas) * job.idx_range * 4));
         CU(ctx, ctx->xl_bits.reserve(uint64_t(xl_ctas) * words * 4));
         CU(ctx, cudaMemsetAsync(ctx->xl_bits.p, 0, uint64_t(xl_ctas) * words * 4, ctx->stream));

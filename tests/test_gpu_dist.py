@@ -56,7 +56,11 @@ torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 eng = osp.Engine(rank)
 deng = osd.DistEngine.from_torch(eng)
-for name, sd in (("er16k", 4), ("rmat20", 256)):
+for name, sd, two_phase in (("er16k", 4, False), ("rmat20", 256, False), ("er16k", 4, True), ("rmat20", 256, True)):
+    # (the two-phase exchange -- owners merge the first half of their rows while the second is sent -- is the default from
+    # four ranks on; forced here so that two ranks cover it)
+    if two_phase: os.environ["OSP_DIST_TWO_PHASE"] = "1"
+    else: os.environ.pop("OSP_DIST_TWO_PHASE", None)
     a, b, dims = synth.build_workload(name, sd)
     k0, k1 = osd.k_ranges(a, b, dims["n_k"], world)[rank]
     a_g, b_g = osd.shard_operands(a, b, k0, k1)
@@ -65,7 +69,8 @@ for name, sd in (("er16k", 4), ("rmat20", 256)):
     want, _ = oracle_spgemm(synth.transpose_host(a, dims["n_k"]), b, rows_override=dims["rows"])
     r0, r1 = deng.rows(dims["rows"])
     lo, hi = int(want.pos[r0]), int(want.pos[r1])
-    assert_bit_exact(got, pack(want.pos[r0:r1 + 1] - want.pos[r0], want.data[lo:hi]), f"{name} rank {rank}")
+    assert_bit_exact(got, pack(want.pos[r0:r1 + 1] - want.pos[r0], want.data[lo:hi]), f"{name} rank {rank} two_phase={two_phase}")
+os.environ.pop("OSP_DIST_TWO_PHASE", None)
 # one rank's bad shard (a k index beyond its inner dimension; an unsorted row) must come back as an error on EVERY rank --
 # nobody may be left waiting in a collective -- and the communicator must still work afterwards
 a, b, dims = synth.build_workload("er16k", 8)
