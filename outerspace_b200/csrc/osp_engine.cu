@@ -323,7 +323,9 @@ int reserve_merge(osp_ctx *ctx, const MergeJob &job, unsigned int &xl_ctas) {
         const uint64_t budget = std::max<uint64_t>(ctx->total_mem / 16, 1ull << 28);
         const uint64_t max_ctas = budget / std::max<uint64_t>(per_cta, 1);
         if (max_ctas < 1) return fail(ctx, OSP_ERR_UNSUPPORTED, "long-row accumulator does not fit: column range too large");
-        uint64_t per_sm = 4;                                  // development knob: resident accumulators per SM
+        // accumulators in flight: four per SM while they are a few times L2 at most; two when they are far beyond it (config 3
+        // at full size, 4 MB each: 738 ms with two, 781 with four, 988 with one -- profiles/r02_experiments.md)
+        uint64_t per_sm = per_cta * uint64_t(ctx->sm_count) * 4 > 8 * uint64_t(ctx->l2_bytes) ? 2 : 4;
         if (const char *env = std::getenv("OSP_XL_CTAS_PER_SM")) { const uint64_t v = std::strtoull(env, nullptr, 10); if (v) per_sm = v; }
         xl_ctas = unsigned(std::min<uint64_t>({max_ctas, uint64_t(ctx->sm_count) * per_sm, n_acc_rows}));
         CU(ctx, ctx->xl_acc.reserve(uint64_t(xl_ctas) * job.idx_range * 4));
