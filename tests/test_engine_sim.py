@@ -71,6 +71,7 @@ test_rmat_small = gp.test_rmat_small
 test_mlp_batch_small = gp.test_mlp_batch_small
 test_every_row_length_class = gp.test_every_row_length_class
 test_kway_merge_of_the_sorted_ways = gp.test_kway_merge_of_the_sorted_ways
+test_config4_shape_spread_and_clustered_columns = gp.test_config4_shape_spread_and_clustered_columns
 
 
 def test_device_pointer_operands(engine):

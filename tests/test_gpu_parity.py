@@ -373,6 +373,31 @@ def _row_lengths_case(rng, lens, cols, dup_rate):
     return A, B
 
 
+@pytest.mark.parametrize("n,per_row,clustered", [(1 << 13, 8, False), (1 << 14, 6, False), (1 << 13, 10, True)])
+def test_config4_shape_spread_and_clustered_columns(engine, n, per_row, clustered):
+    """Config 4's shape at small scale, element-wise against the oracle: rows of C of 20-130 partial products over uniformly
+    spread columns; `clustered` packs the columns of every row of B into a few dense clumps plus outliers and adds repeated
+    columns, which force the k-ordered fold.  (Written for the bucket-rank merge experiment of round 2,
+    profiles/r02_experiments.md; kept as a parity test of the sorting network on this shape.)  Both operand forms."""
+    rng = np.random.default_rng(n + per_row)
+    a = synth.erdos_renyi(n, n, per_row * n, seed=n + per_row)
+    if clustered:
+        cols = a.data["idx"].astype(np.int64)
+        cols = np.where(rng.random(len(cols)) < 0.85, (cols % 97) + (cols // 4096) * 4096, cols)      # clumps of 97 columns + outliers
+        keys = np.unique(np.repeat(np.arange(n, dtype=np.int64), np.diff(a.pos.astype(np.int64))) * n + cols)
+        rows, c2 = keys // n, (keys % n).astype(np.uint32)
+        pos = np.zeros(n + 1, np.uint64); np.cumsum(np.bincount(rows, minlength=n), out=pos[1:])
+        a = osp.CSRMatrix.from_arrays(pos, c2, rng.standard_normal(len(c2)).astype(np.float32))
+    a_csc = synth.transpose_host(a, n)
+    want, prod = oracle_spgemm(a_csc, a)
+    for is_csr, op in ((True, a), (False, a_csc)):
+        res = engine.spgemm(op, a, a_is_csr=is_csr, cols_b=n)
+        got = res.to_host(); st = res.stats(); res.free()
+        assert st["products"] == prod
+        assert_bit_exact(got, want, f"config-4 shape n={n} per_row={per_row} clustered={clustered} csr={is_csr}")
+        check_csr_invariants(got, n)
+
+
 @pytest.mark.parametrize("cols,dup_rate", [(1 << 17, 0.0), (1 << 20, 0.4), ((1 << 24) + 5, 0.2)])
 def test_kway_merge_of_the_sorted_ways(engine, cols, dup_rate):
     """rows of 4 097 .. 32 768 partial products made of a few long sorted ways are merged BY RANK
