@@ -413,15 +413,8 @@ k_chain2(const TileStart *__restrict__ tiles, const uint64_t *__restrict__ row_b
                     if (c <= 6) u = merge_row_bitmap<16, MUL>(row_off, ost_off, rs, len, bm_wpl, scr_off, lane, ar);
                     else u = merge_row_bitmap<MT_LONG_BM / 32, MUL>(row_off, ost_off, rs, len, bm_wpl, scr_off, lane, ar);
                 } else
-                switch (c) {
-                    case 0: u = merge_rows_grouped<8, 0, K, MUL>(row_off, ost_off, rs, len, lane, ar); break;
-                    case 1: u = merge_rows_grouped<8, 1, K, MUL>(row_off, ost_off, rs, len, lane, ar); break;
-                    case 2: u = merge_rows_grouped<8, 2, K, MUL>(row_off, ost_off, rs, len, lane, ar); break;
-                    case 3: u = merge_rows_grouped<8, 3, K, MUL>(row_off, ost_off, rs, len, lane, ar); break;
-                    case 4: u = merge_rows_grouped<8, 4, K, MUL>(row_off, ost_off, rs, len, lane, ar); break;
-                    case 5: u = merge_rows_grouped<8, 5, K, MUL>(row_off, ost_off, rs, len, lane, ar); break;
-                    default: u = merge_rows_grouped<16, 5, K, MUL>(row_off, ost_off, rs, len, lane, ar); break;
-                }
+                if (c <= 5) u = merge_rows_grouped<8, K, MUL>(c, row_off, ost_off, rs, len, lane, ar);
+                else u = merge_rows_grouped<16, K, MUL>(5, row_off, ost_off, rs, len, lane, ar);
                 if (valid && (lane & ((1u << T) - 1)) == 0) rout[j] = u;
             }
         }

@@ -860,8 +860,8 @@ __device__ __forceinline__ void ce_inlane(K (&x)[E], const int a, const int b) {
     const K lo = min(x[a], x[b]), hi = max(x[a], x[b]);
     x[a] = lo; x[b] = hi;
 }
-template <int E, int T, class K>
-__device__ __forceinline__ void sort_grouped(K (&x)[E], const unsigned int lig) {
+template <int E, class K>
+__device__ __forceinline__ void sort_grouped(K (&x)[E], const unsigned int lig, const int T) {
 #pragma unroll
     for (int k = 2; k <= E; k <<= 1) {
 #pragma unroll
@@ -874,17 +874,22 @@ __device__ __forceinline__ void sort_grouped(K (&x)[E], const unsigned int lig) 
                 if ((e & j) == 0) ce_inlane<E, K>(x, e, e | j);
         }
     }
-#pragma unroll
+    // The cross-lane levels are a RUNTIME loop since round 2: one body for every row class.  Fully unrolled per class the
+    // merge chain was 134 KB of SASS, more than the instruction cache holds: warps sorting rows of different classes evicted
+    // each other's code (ncu: no_inst 15 % of the stall samples).  The element index stays a compile-time constant, so the
+    // keys never leave their registers.
+#pragma unroll 1
     for (int t = 1; t <= T; t++) {
         {   // flip stage: (lane, e) <-> (lane ^ (2^t - 1), E - 1 - e); the lane whose bit t-1 is clear keeps the minima
             const bool keep_min = ((lig >> (t - 1)) & 1u) == 0;
+            const int mask = (1 << t) - 1;
             K y[E];
 #pragma unroll
-            for (int e = 0; e < E; e++) y[e] = __shfl_xor_sync(FULL, x[E - 1 - e], (1 << t) - 1);
+            for (int e = 0; e < E; e++) y[e] = __shfl_xor_sync(FULL, x[E - 1 - e], mask);
 #pragma unroll
             for (int e = 0; e < E; e++) x[e] = keep_min ? min(x[e], y[e]) : max(x[e], y[e]);
         }
-#pragma unroll
+#pragma unroll 1
         for (int lj = (1 << t) >> 2; lj > 0; lj >>= 1) {
             const bool keep_min = (lig & lj) == 0;
 #pragma unroll
@@ -909,11 +914,11 @@ __device__ __forceinline__ void sort_grouped(K (&x)[E], const unsigned int lig) 
 // number of surviving entries.
 // MUL (k_chain2): the stage holds the raw elements of B; element p of the row is multiplied by the float at shared-memory
 // byte offset arow_off + 4 p (A(i,k) of the run it belongs to) when its value is read -- rounded on its own, no FMA.
-template <int E, int T, class K, bool MUL = false>
-__device__ __forceinline__ uint32_t merge_rows_grouped(const uint32_t row_off, const uint32_t ost_off, const uint32_t o0,
+template <int E, class K, bool MUL = false>
+__device__ __forceinline__ uint32_t merge_rows_grouped(const int T, const uint32_t row_off, const uint32_t ost_off, const uint32_t o0,
                                                        const uint32_t len, const unsigned int lane, const uint32_t arow_off = 0) {
     constexpr int LE = ILog2<E>::value;
-    constexpr uint32_t G = 1u << T, PB = LE + T, N = uint32_t(E) << T;
+    const uint32_t G = 1u << T, PB = LE + T, N = uint32_t(E) << T;       // (T is a run-time value: one body for all classes)
     const uint32_t lig = lane & (G - 1);
     K key[E];
     {
@@ -925,7 +930,7 @@ __device__ __forceinline__ uint32_t merge_rows_grouped(const uint32_t row_off, c
             key[e] = p < len ? k : ~K(0);
         }
     }
-    sort_grouped<E, T, K>(key, lig);
+    sort_grouped<E, K>(key, lig, T);
     // lane now holds the sorted positions lig*E .. lig*E+E-1 of its group's row
     uint32_t col[E];
     float v[E];
@@ -980,7 +985,6 @@ __device__ __forceinline__ uint32_t merge_rows_grouped(const uint32_t row_off, c
         }
     }
     uint32_t incl = nheads;                          // inclusive scan inside the group
-#pragma unroll
     for (uint32_t o = 1; o < G; o <<= 1) {
         const uint32_t y = __shfl_up_sync(FULL, incl, o);
         if (lig >= o) incl += y;
@@ -1441,15 +1445,8 @@ merge_chain_body(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, 
                     if (c <= 6) u = merge_row_bitmap<16>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);   // one hot body (instruction cache)
                     else u = merge_row_bitmap<MT_LONG_BM / 32>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);   // 513..640
                 } else
-                switch (c) {
-                    case 0: u = merge_rows_grouped<8, 0, K>(row_off, ost_off, s, len, lane); break;
-                    case 1: u = merge_rows_grouped<8, 1, K>(row_off, ost_off, s, len, lane); break;
-                    case 2: u = merge_rows_grouped<8, 2, K>(row_off, ost_off, s, len, lane); break;
-                    case 3: u = merge_rows_grouped<8, 3, K>(row_off, ost_off, s, len, lane); break;
-                    case 4: u = merge_rows_grouped<8, 4, K>(row_off, ost_off, s, len, lane); break;
-                    case 5: u = merge_rows_grouped<8, 5, K>(row_off, ost_off, s, len, lane); break;
-                    default: u = merge_rows_grouped<16, 5, K>(row_off, ost_off, s, len, lane); break;
-                }
+                if (c <= 5) u = merge_rows_grouped<8, K>(c, row_off, ost_off, s, len, lane);
+                else u = merge_rows_grouped<16, K>(5, row_off, ost_off, s, len, lane);
                 if (valid && (lane & ((1u << T) - 1)) == 0) rout[j] = u;
             }
             __syncthreads();
