@@ -28,7 +28,10 @@ namespace osp {
 //   Out: (idx, exclusive prefix, own contribution) for idx < n, and once (n, total, 0).
 // =====================================================================================
 constexpr int SCAN_BLOCK = 256;
-constexpr int SCAN_ITEMS = 8;
+#ifndef OSP_SCAN_ITEMS
+#define OSP_SCAN_ITEMS 8
+#endif
+constexpr int SCAN_ITEMS = OSP_SCAN_ITEMS;
 constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
 
 template <class In, class Out>
