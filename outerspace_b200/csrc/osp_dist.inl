@@ -520,7 +520,14 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
                 }
                 LAUNCH(ctx, k_regroup, grid_for(r_hi - r_lo, 8, unsigned(ctx->sm_count) * 32u), 256, 0, d->recv_buf.as<Elem>(),
                        d->src_off.as<uint64_t>(), d->dst_off.as<uint64_t>(), lens, RL, uint32_t(G), d->bins2.as<Elem>(), r_lo, r_hi);
-                return launch_merge(ctx, job, xl_ctas, d->bins2.as<Elem>(), 0, t_lo, t_hi, r_lo, r_hi, unsigned(h));
+                // the first half is merged while the peers' second multiply runs: three resident chain CTAs per SM hold every
+                // register of the SM and would lock that multiply out until the merge is over -- leave it room
+                MergeJob jb = job;
+                if (halves && h == 0 && side) {
+                    const char *env = std::getenv("OSP_DIST_CHAIN_OCC");
+                    jb.chain_ctas_per_sm = env ? std::atoi(env) : 2;
+                }
+                return launch_merge(ctx, jb, xl_ctas, d->bins2.as<Elem>(), 0, t_lo, t_hi, r_lo, r_hi, unsigned(h));
             }();
             if (rc) return bail(rc);
         }

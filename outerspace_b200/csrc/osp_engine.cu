@@ -296,6 +296,8 @@ struct MergeJob {
     bool fused_short = false;
     bool chain2 = false;                    // ... with k_chain2 (producer warps) instead of k_merge_chain_fused
     bool kway = false;                      // k_merge_ways takes the xl rows of few long ways (needs a_pos, run_off)
+    int chain_ctas_per_sm = 0;              // cap on the persistent chain's CTAs per SM (0: as many as are resident); the k-sharded
+                                            // path lowers it while a peer multiply shares the SMs (the chain's CTAs take every register)
     const uint64_t *run_off = nullptr;
     const uint32_t *task_bs = nullptr;
     uint64_t m_a = 0;
@@ -420,7 +422,8 @@ int launch_merge(osp_ctx *ctx, const MergeJob &job, unsigned int xl_ctas, Elem *
         else LAUNCH(ctx, (k_merge_chain_fused<uint64_t, false>), gridf, MC_THREADS, sizeof(MergeChainSmem<false>), MC_ARGS, fs);
         return OSP_OK;
     }
-    const unsigned int grid = std::min<unsigned>(n_chain, unsigned(ctx->sm_count) * unsigned(ctx->chain_occ[variant]));   // persistent CTAs
+    const int occ = job.chain_ctas_per_sm > 0 ? std::min(job.chain_ctas_per_sm, ctx->chain_occ[variant]) : ctx->chain_occ[variant];
+    const unsigned int grid = std::min<unsigned>(n_chain, unsigned(ctx->sm_count) * unsigned(occ));   // persistent CTAs
     if (variant == 2) LAUNCH(ctx, (k_merge_chain<uint32_t, true>), grid, MC_THREADS, sizeof(MergeChainSmem<true>), MC_ARGS);
     else if (variant == 0) LAUNCH(ctx, (k_merge_chain<uint32_t, false>), grid, MC_THREADS, sizeof(MergeChainSmem<false>), MC_ARGS);
     else LAUNCH(ctx, (k_merge_chain<uint64_t, false>), grid, MC_THREADS, sizeof(MergeChainSmem<false>), MC_ARGS);
