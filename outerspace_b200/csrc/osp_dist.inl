@@ -265,7 +265,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
         if (r) return r;
         run_off = ctx->run_off.as<uint64_t>(); task_bs = ctx->task_bs.as<uint32_t>(); row_bin = ctx->row_bin.as<uint64_t>();
         if (validate) {      // the shard's operands: ascending duplicate-free slices, column ids below cols_b (k < n_k: symbolic pass)
-            const ValidateOp opa{op.a_pos, op.a_data, m_a, op.nnz_a, 0}, opb{op.b_pos, op.b_data, n_k, op.nnz_b, cols_b};
+            const ValidateOp opa{op.a_pos, op.a_data, m_a, op.nnz_a, 0, nullptr}, opb{op.b_pos, op.b_data, n_k, op.nnz_b, cols_b, nullptr};
             r = launch_validate(ctx, opa, opb, 2);
             if (r) return r;
         }
@@ -520,12 +520,13 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
                 }
                 LAUNCH(ctx, k_regroup, grid_for(r_hi - r_lo, 8, unsigned(ctx->sm_count) * 32u), 256, 0, d->recv_buf.as<Elem>(),
                        d->src_off.as<uint64_t>(), d->dst_off.as<uint64_t>(), lens, RL, uint32_t(G), d->bins2.as<Elem>(), r_lo, r_hi);
-                // the first half is merged while the peers' second multiply runs: three resident chain CTAs per SM hold every
-                // register of the SM and would lock that multiply out until the merge is over -- leave it room
+                // the first half is merged while the peers' second multiply runs.  Three resident chain CTAs per SM hold every
+                // register of the SM; capping them (OSP_DIST_CHAIN_OCC) lets that multiply in earlier but slows the merge by as
+                // much: both kernels are bound by the SMs at G = 4 (profiles/r02_dist.md)
                 MergeJob jb = job;
                 if (halves && h == 0 && side) {
                     const char *env = std::getenv("OSP_DIST_CHAIN_OCC");
-                    jb.chain_ctas_per_sm = env ? std::atoi(env) : 2;
+                    jb.chain_ctas_per_sm = env ? std::atoi(env) : 0;      // measured at G = 4: 3.92 ms with 3 or 2, 4.78 ms with 1 -- no cap
                 }
                 return launch_merge(ctx, jb, xl_ctas, d->bins2.as<Elem>(), 0, t_lo, t_hi, r_lo, r_hi, unsigned(h));
             }();

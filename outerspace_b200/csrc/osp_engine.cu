@@ -69,7 +69,7 @@ struct osp_ctx {
     DevBuf task_bs, run_off, row_bin, tile_row, tile_start, long_list, xl_list, uniq, col_ptr, tasks, tile_state, xl_acc, xl_bits;
     DevBuf bins;
     // fused band sweep of the long rows (opt-in, osp_longrows.cuh): task bitmap for the multiply, band index of B
-    DevBuf swept, lr_bands, kw_scratch;
+    DevBuf swept, lr_bands, kw_scratch, vbits;
     bool kway_env = false;                  // OSP_KWAY=1: rows of 4097 .. 32768 partial products in <= 64 ways go to k_merge_ways
     bool sweep_ok = false;                  // the device accepted the kernel's shared-memory size
     bool sweep_env = false;                 // OSP_LONGROW_SWEEP=1
@@ -550,9 +550,17 @@ int launch_multiply(osp_ctx *ctx, Src src, uint64_t t0, uint64_t t1, uint64_t pr
 
 // Operand preconditions (k_validate): launched into the current arena; check_operands() reads the verdict after the next
 // hand-over of the device scalars.
-int launch_validate(osp_ctx *ctx, const ValidateOp &op0, const ValidateOp &op1, int n_ops) {
-    const uint64_t work = std::max<uint64_t>({op0.nnz, op0.n_slices, n_ops > 1 ? op1.nnz : 0, n_ops > 1 ? op1.n_slices : 0, 1});
-    LAUNCH(ctx, k_validate, grid_for(work, 1024, unsigned(ctx->sm_count) * 8u), 256, 0, op0, op1, n_ops, ctx->d_sc);
+int launch_validate(osp_ctx *ctx, ValidateOp op0, ValidateOp op1, int n_ops) {
+    // one bit per element position (does it open a slice?), both operands back to back in ctx->vbits
+    const uint64_t w0 = (op0.nnz + 31) / 32 + 1, w1 = n_ops > 1 ? (op1.nnz + 31) / 32 + 1 : 0;
+    CU(ctx, ctx->vbits.reserve((w0 + w1) * 4));
+    CU(ctx, cudaMemsetAsync(ctx->vbits.p, 0, (w0 + w1) * 4, ctx->stream));
+    op0.start_bits = ctx->vbits.as<uint32_t>();
+    op1.start_bits = ctx->vbits.as<uint32_t>() + (n_ops > 1 ? w0 : 0);
+    const uint64_t slices = std::max<uint64_t>({op0.n_slices, n_ops > 1 ? op1.n_slices : 0, 1});
+    const uint64_t elems = std::max<uint64_t>({op0.nnz, n_ops > 1 ? op1.nnz : 0, 1});
+    LAUNCH(ctx, k_validate_starts, grid_for(slices, 512, unsigned(ctx->sm_count) * 8u), 256, 0, op0, op1, n_ops, ctx->d_sc);
+    LAUNCH(ctx, k_validate, grid_for(elems, 1024, unsigned(ctx->sm_count) * 8u), 256, 0, op0, op1, n_ops, ctx->d_sc);
     return OSP_OK;
 }
 int check_operands(osp_ctx *ctx, const char *who) {
@@ -700,7 +708,7 @@ void osp_destroy(osp_ctx *ctx) {
     for (DevBuf *b : {&ctx->arena, &ctx->op_a_pos, &ctx->op_a_data, &ctx->op_b_pos, &ctx->op_b_data, &ctx->conv_pos,
                       &ctx->conv_data, &ctx->conv_tmp, &ctx->conv_chk, &ctx->task_bs, &ctx->run_off, &ctx->row_bin, &ctx->tile_row,
                       &ctx->tile_start, &ctx->long_list, &ctx->xl_list, &ctx->uniq, &ctx->col_ptr, &ctx->tasks, &ctx->tile_state,
-                      &ctx->xl_acc, &ctx->xl_bits, &ctx->bins, &ctx->swept, &ctx->lr_bands, &ctx->kw_scratch})
+                      &ctx->xl_acc, &ctx->xl_bits, &ctx->bins, &ctx->swept, &ctx->lr_bands, &ctx->kw_scratch, &ctx->vbits})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
@@ -769,7 +777,7 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         rc = prepare_arena(ctx, st0, 0, ar0);
         if (rc) return rc;
         if (validate) {             // also leaves the largest row id in max_idx
-            const ValidateOp opa{dA_pos, dA_data, args->a_slices, nnz_a, args->rows_c};
+            const ValidateOp opa{dA_pos, dA_data, args->a_slices, nnz_a, args->rows_c, nullptr};
             rc = launch_validate(ctx, opa, opa, 1);
             if (rc) return rc;
         } else if (nnz_a) LAUNCH(ctx, k_max_idx, grid_for(nnz_a, 1024, unsigned(ctx->sm_count) * 8u), 256, 0, dA_data, nnz_a, ctx->d_sc);
@@ -816,8 +824,8 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
         // B: ascending, duplicate-free rows, column ids below cols_b (or their maximum when cols_b is to be derived);
         // A in row-compressed form: ascending rows (k < n_k is the symbolic pass's check).  A converted on the device a
         // moment ago is sorted by construction; A == B (C = A*A on the same arrays) is read once.
-        const ValidateOp opb{dB_pos, dB_data, n_k, nnz_b, cols_b};
-        const ValidateOp opa{dA_pos, dA_data, m_a, nnz_a, 0};
+        const ValidateOp opb{dB_pos, dB_data, n_k, nnz_b, cols_b, nullptr};
+        const ValidateOp opa{dA_pos, dA_data, m_a, nnz_a, 0, nullptr};
         const bool same = a_is_csr && dA_pos == dB_pos && dA_data == dB_data && m_a == n_k;
         rc = a_is_csr && !same ? launch_validate(ctx, opa, opb, 2) : launch_validate(ctx, opb, opb, 1);
         if (rc) return rc;
