@@ -86,6 +86,27 @@ def test_device_pointer_operands(engine):
     assert all(res.device_pointers())
     res.free()
     assert_bit_exact(got, want, "device operands")
+    # data arrays that are only 8-byte aligned (an element into a larger allocation): the validation's 128-bit loads
+    # must step aside; an unsorted row behind such a pointer is still caught
+    def shifted(m):
+        buf = np.zeros(len(m.data) + 3, dtype=osp.ELEM)
+        base = buf.ctypes.data
+        off = 1 if (base // 8) % 2 == 0 else 2            # make (base + 8 * off) % 16 == 8
+        buf[off:off + len(m.data)] = m.data
+        return buf, base + 8 * off
+    keep_a, pa = shifted(a_csr); keep_b, pb = shifted(b_csr)
+    assert pa % 16 == 8 and pb % 16 == 8
+    res = engine.spgemm_device(a_csr.NRow(), a_csr.pos.ctypes.data, pa, b_csr.NRow(), b_csr.pos.ctypes.data, pb, a_is_csr=True,
+                               cols_b=180)
+    got = res.to_host(); res.free()
+    assert_bit_exact(got, want, "device operands, 8-byte aligned data")
+    r = int(np.flatnonzero(np.diff(b_csr.pos.astype(np.int64)) >= 2)[0]); s0 = int(b_csr.pos[r])
+    view = np.frombuffer(keep_b, dtype=osp.ELEM)          # (same memory)
+    i0 = (pb - keep_b.ctypes.data) // 8 + s0
+    keep_b[[i0, i0 + 1]] = keep_b[[i0 + 1, i0]]
+    with pytest.raises(osp.OspError) as ei:
+        engine.spgemm_device(a_csr.NRow(), a_csr.pos.ctypes.data, pa, b_csr.NRow(), b_csr.pos.ctypes.data, pb, a_is_csr=True, cols_b=180)
+    assert ei.value.code == api.OSP_ERR_INVALID
 
 
 # ---- the opt-in long-row sweep (OSP_LONGROW_SWEEP), end to end: the tests a B200 will run with OSP_TEST_SWEEP=1 ------
