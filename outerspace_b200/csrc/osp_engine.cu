@@ -514,22 +514,27 @@ int stage_operands(osp_ctx *ctx, const osp_spgemm_args *args, Operands &op) {
     } else {
         op.nnz_a = args->a_pos[args->a_slices];
         op.nnz_b = args->b_pos[n_k];
+        // C = A*A on the caller's one CSRMatrix (the same arrays as both operands): staged once
+        const bool same = args->b_pos == args->a_pos && args->b_data == args->a_data && args->a_slices == n_k;
         CU(ctx, ctx->op_a_pos.reserve((args->a_slices + 1) * 8));
-        CU(ctx, ctx->op_b_pos.reserve((n_k + 1) * 8));
         CU(ctx, ctx->op_a_data.reserve(std::max<uint64_t>(op.nnz_a, 1) * 8));
-        CU(ctx, ctx->op_b_data.reserve(std::max<uint64_t>(op.nnz_b, 1) * 8));
+        if (!same) {
+            CU(ctx, ctx->op_b_pos.reserve((n_k + 1) * 8));
+            CU(ctx, ctx->op_b_data.reserve(std::max<uint64_t>(op.nnz_b, 1) * 8));
+        }
         cudaEvent_t e0 = next_event(ctx);
         CU(ctx, cudaMemcpyAsync(ctx->op_a_pos.p, args->a_pos, (args->a_slices + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(ctx->op_b_pos.p, args->b_pos, (n_k + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (!same) CU(ctx, cudaMemcpyAsync(ctx->op_b_pos.p, args->b_pos, (n_k + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
         if (op.nnz_a && args->a_data)
             CU(ctx, cudaMemcpyAsync(ctx->op_a_data.p, args->a_data, op.nnz_a * 8, cudaMemcpyHostToDevice, ctx->stream));
-        if (op.nnz_b && args->b_data)
+        if (!same && op.nnz_b && args->b_data)
             CU(ctx, cudaMemcpyAsync(ctx->op_b_data.p, args->b_data, op.nnz_b * 8, cudaMemcpyHostToDevice, ctx->stream));
         cudaEvent_t e1 = next_event(ctx);
         CU(ctx, cudaEventSynchronize(e1));
         cudaEventElapsedTime(&op.ms_h2d, e0, e1);
-        op.a_pos = ctx->op_a_pos.as<uint64_t>(); op.b_pos = ctx->op_b_pos.as<uint64_t>();
-        op.a_data = ctx->op_a_data.as<Elem>(); op.b_data = ctx->op_b_data.as<Elem>();
+        op.a_pos = ctx->op_a_pos.as<uint64_t>(); op.a_data = ctx->op_a_data.as<Elem>();
+        op.b_pos = same ? op.a_pos : ctx->op_b_pos.as<uint64_t>();
+        op.b_data = same ? op.a_data : ctx->op_b_data.as<Elem>();
     }
     if ((op.nnz_a && !args->a_data) || (op.nnz_b && !args->b_data))
         return fail(ctx, OSP_ERR_INVALID, "osp_spgemm: NULL data array");
