@@ -27,7 +27,10 @@ namespace osp {
 //        first-level loads of all the items of a thread are in flight together).
 //   Out: (idx, exclusive prefix, own contribution) for idx < n, and once (n, total, 0).
 // =====================================================================================
-constexpr int SCAN_BLOCK = 256;
+#ifndef OSP_SCAN_BLOCK
+#define OSP_SCAN_BLOCK 256
+#endif
+constexpr int SCAN_BLOCK = OSP_SCAN_BLOCK;
 #ifndef OSP_SCAN_ITEMS
 #define OSP_SCAN_ITEMS 8
 #endif
