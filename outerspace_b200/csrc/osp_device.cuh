@@ -63,6 +63,7 @@ struct DevScalars {
     unsigned long long v_bad_pos;      // pos[] entries that decrease or exceed nnz
     unsigned int kw_ticket;            // dynamic row ids of k_merge_ways (zeroed before every launch)
     unsigned int cut_tile;             // k_plan: index of the tile that starts at the requested cut row (k-sharded path: two halves)
+    unsigned long long fl_quads;       // k_fl_count: quads (4 groups of 32 slots) handed out to the rows of B (osp_fusedlanes.cuh)
 };
 
 constexpr unsigned int FULL = 0xffffffffu;

@@ -6,6 +6,7 @@
 #include "osp_kernels.cuh"
 #include "osp_longrows.cuh"
 #include "osp_chain2.cuh"
+#include "osp_fusedlanes.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -70,6 +71,8 @@ struct osp_ctx {
     DevBuf bins;
     // fused band sweep of the long rows (opt-in, osp_longrows.cuh): task bitmap for the multiply, band index of B
     DevBuf swept, lr_bands, kw_scratch, vbits;
+    DevBuf fl_meta, fl_vals, fl_colb;     // B regrouped by shared-memory bank (osp_fusedlanes.cuh)
+    int fused_lanes_mode = 1;               // OSP_FUSED_LANES: 0 band kernel (k_fused_dense), 1 automatic, 2 bank-aligned kernel whatever B's regrouped size
     bool kway_env = false;                  // OSP_KWAY=1: rows of 4097 .. 32768 partial products in <= 64 ways go to k_merge_ways
     bool sweep_ok = false;                  // the device accepted the kernel's shared-memory size
     bool sweep_env = false;                 // OSP_LONGROW_SWEEP=1
@@ -631,6 +634,8 @@ int osp_create(int device, osp_ctx **out) {
     CU(nullptr, cudaFuncSetAttribute(k_merge_long, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LONG_SMEM)));
     CU(nullptr, cudaFuncSetAttribute(k_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dense_smem(DENSE_MAX_COLS))));
     CU(nullptr, cudaFuncSetAttribute(k_fused_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_dense_smem(DENSE_MAX_COLS))));
+    CU(nullptr, cudaFuncSetAttribute(k_fused_lanes<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_lanes_smem(FL_MAX_COLS, 1))));
+    CU(nullptr, cudaFuncSetAttribute(k_fused_lanes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_lanes_smem(FL_MAX_COLS, 1))));
     CU(nullptr, cudaFuncSetAttribute(k_bias_relu, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DENSE_MAX_COLS * 4 + 256)));
     {
         auto k32 = k_merge_chain<uint32_t, false>;
@@ -656,6 +661,7 @@ int osp_create(int device, osp_ctx **out) {
         ctx->sweep_env = env && env[0] && env[0] != '0';
         const char *kw = std::getenv("OSP_KWAY");
         ctx->kway_env = kw && kw[0] && kw[0] != '0';
+        if (const char *fl = std::getenv("OSP_FUSED_LANES")) ctx->fused_lanes_mode = fl[0] == '0' ? 0 : fl[0] == '2' ? 2 : 1;
         if (const char *m = std::getenv("OSP_LONGROW_SWEEP_MIN")) ctx->sweep_min = std::strtoull(m, nullptr, 10);
     }
     {   // OSP_FUSED_SHORT: opt-in as well
@@ -713,7 +719,8 @@ void osp_destroy(osp_ctx *ctx) {
     for (DevBuf *b : {&ctx->arena, &ctx->op_a_pos, &ctx->op_a_data, &ctx->op_b_pos, &ctx->op_b_data, &ctx->conv_pos,
                       &ctx->conv_data, &ctx->conv_tmp, &ctx->conv_chk, &ctx->task_bs, &ctx->run_off, &ctx->row_bin, &ctx->tile_row,
                       &ctx->tile_start, &ctx->long_list, &ctx->xl_list, &ctx->uniq, &ctx->col_ptr, &ctx->tasks, &ctx->tile_state,
-                      &ctx->xl_acc, &ctx->xl_bits, &ctx->bins, &ctx->swept, &ctx->lr_bands, &ctx->kw_scratch, &ctx->vbits})
+                      &ctx->xl_acc, &ctx->xl_bits, &ctx->bins, &ctx->swept, &ctx->lr_bands, &ctx->kw_scratch, &ctx->vbits,
+                      &ctx->fl_meta, &ctx->fl_vals, &ctx->fl_colb})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
@@ -1052,9 +1059,47 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     if (fused) {
         rc = [&]() -> int {
             ev_blocks.push_back(next_event(ctx));
+            CU(ctx, ctx->tile_state.reserve((m_plan + 1) * 8));
+            // bank-aligned variant (osp_fusedlanes.cuh): B regrouped so that a warp's accumulator accesses never conflict;
+            // kept off when the regrouped B would be much larger than B (many columns of a row in one bank, or rows of
+            // B too short to fill a quad of groups).  OSP_FUSED_LANES=0: band kernel, =2: bank-aligned whatever the size.
+            if (cols_b <= FL_MAX_COLS && ctx->fused_lanes_mode != 0) {
+                CU(ctx, ctx->fl_meta.reserve(std::max<uint64_t>(n_k, 1) * sizeof(FlMeta)));
+                FlMeta *meta = ctx->fl_meta.as<FlMeta>();
+                const unsigned prep_grid = grid_for(n_k, FL_PREP_WARPS, unsigned(ctx->sm_count) * 8u);
+                LAUNCH(ctx, k_fl_count, prep_grid, 32 * FL_PREP_WARPS, 0, dB_pos, dB_data, n_k, meta, ctx->d_sc);
+                int rc2 = sync_scalars(ctx);
+                if (rc2) return rc2;
+                const uint64_t quads = ctx->h_sc->fl_quads;
+                if (quads < (1ull << 32) && (ctx->fused_lanes_mode == 2 || quads * 128 <= uint64_t(FL_MAX_BLOWUP) * nnz_b)) {
+                    CU(ctx, ctx->fl_vals.reserve(std::max<uint64_t>(quads, 1) * 128 * 4));
+                    CU(ctx, ctx->fl_colb.reserve(std::max<uint64_t>(quads, 1) * 32 * 4));
+                    float *vals = ctx->fl_vals.as<float>();
+                    uint32_t *colb = ctx->fl_colb.as<uint32_t>();
+                    CU(ctx, cudaMemsetAsync(colb, fused_lanes_empty_byte(cols_b), std::max<uint64_t>(quads, 1) * 32 * 4, ctx->stream));   // every slot empty
+                    LAUNCH(ctx, k_fl_fill, prep_grid, 32 * FL_PREP_WARPS, 0, dB_pos, dB_data, n_k, meta, vals, colb);
+                    CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, (m_plan + 1) * 8, ctx->stream));
+                    CU(ctx, cudaMemsetAsync(&ctx->d_sc->tile_ticket, 0, 4, ctx->stream));
+                    ev_blocks.push_back(next_event(ctx));
+                    const int warps = fused_lanes_smem(cols_b, 2) <= 14336 ? 2 : 1;     // narrow rows: two per CTA (32 CTAs per SM at most)
+                    const size_t sm = fused_lanes_smem(cols_b, warps);
+                    int occ = 1;
+                    if (warps == 2) { CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_lanes<2>, 64, sm)); }
+                    else { CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_lanes<1>, 32, sm)); }
+                    const unsigned grid = unsigned(std::min<uint64_t>((m_plan + warps - 1) / warps, uint64_t(ctx->sm_count) * std::max(occ, 1)));
+                    if (warps == 2) {
+                        LAUNCH(ctx, k_fused_lanes<2>, grid, 64, sm, dA_pos, dA_data, m_a, meta, vals, colb, uint32_t(cols_b), m_plan,
+                               ctx->tile_state.as<uint64_t>(), ctx->d_sc, job.c_pos, job.c_data);
+                    } else {
+                        LAUNCH(ctx, k_fused_lanes<1>, grid, 32, sm, dA_pos, dA_data, m_a, meta, vals, colb, uint32_t(cols_b), m_plan,
+                               ctx->tile_state.as<uint64_t>(), ctx->d_sc, job.c_pos, job.c_data);
+                    }
+                    ev_blocks.push_back(next_event(ctx));
+                    return OSP_OK;
+                }
+            }
             const uint32_t band = uint32_t((cols_b + FD_WARPS - 1) / FD_WARPS);
             CU(ctx, ctx->tasks.reserve(n_k * (FD_WARPS + 1) * 4));                  // the band index of B
-            CU(ctx, ctx->tile_state.reserve((m_plan + 1) * 8));
             uint32_t *bandptr = ctx->tasks.as<uint32_t>();
             LAUNCH(ctx, k_band_ptr, grid_for(n_k * (FD_WARPS + 1), 256, 1u << 30), 256, 0, dB_pos, dB_data, n_k, band, bandptr);
             CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, (m_plan + 1) * 8, ctx->stream));

@@ -884,6 +884,19 @@ __device__ __forceinline__ void ce_inlane(K (&x)[E], const int a, const int b) {
     const K lo = min(x[a], x[b]), hi = max(x[a], x[b]);
     x[a] = lo; x[b] = hi;
 }
+// Cross-lane compare-exchange: the lane keeps the smaller or the larger of its key and its partner's.
+// OSP_CE_SEL=1 (experiment): compare + select instead of min-or-max under a predicate.
+#ifndef OSP_CE_SEL
+#define OSP_CE_SEL 0
+#endif
+template <class K>
+__device__ __forceinline__ K ce_cross(const K x, const K y, const bool keep_min) {
+#if OSP_CE_SEL
+    return ((x < y) == keep_min) ? x : y;
+#else
+    return keep_min ? min(x, y) : max(x, y);
+#endif
+}
 template <int E, class K>
 __device__ __forceinline__ void sort_grouped(K (&x)[E], const unsigned int lig, const int T) {
 #pragma unroll
@@ -911,7 +924,7 @@ __device__ __forceinline__ void sort_grouped(K (&x)[E], const unsigned int lig, 
 #pragma unroll
             for (int e = 0; e < E; e++) y[e] = __shfl_xor_sync(FULL, x[E - 1 - e], mask);
 #pragma unroll
-            for (int e = 0; e < E; e++) x[e] = keep_min ? min(x[e], y[e]) : max(x[e], y[e]);
+            for (int e = 0; e < E; e++) x[e] = ce_cross(x[e], y[e], keep_min);
         }
 #pragma unroll 1
         for (int lj = (1 << t) >> 2; lj > 0; lj >>= 1) {
@@ -919,7 +932,7 @@ __device__ __forceinline__ void sort_grouped(K (&x)[E], const unsigned int lig, 
 #pragma unroll
             for (int e = 0; e < E; e++) {
                 const K y = __shfl_xor_sync(FULL, x[e], lj);
-                x[e] = keep_min ? min(x[e], y) : max(x[e], y);
+                x[e] = ce_cross(x[e], y, keep_min);
             }
         }
 #pragma unroll
@@ -1166,6 +1179,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // HBM traffic = the algorithmic minimum of the merge: 8 P read + 8 nnz(C) + 8 (m+1) written.
 // K = uint32_t when col << 9 fits 32 bits (cols <= 2^23), else uint64_t.
 // =====================================================================================
+// Rows of class c (<= 8 << c partial products) are sorted 8 keys per lane by groups of 2^c lanes, from class MC_E16_FROM on
+// 16 keys per lane by groups of 2^(c-1) lanes (class 6, 257..512, has no other choice: 32 lanes x 16 keys).
+#ifndef OSP_E16_FROM
+#define OSP_E16_FROM 6
+#endif
+constexpr int MC_E16_FROM = OSP_E16_FROM;
+static_assert(MC_E16_FROM >= 1 && MC_E16_FROM <= 6, "class 0 has 8 keys at most; class 6 needs 16 keys per lane");
+__host__ __device__ constexpr uint32_t mc_group_bits(uint32_t c) { return c >= uint32_t(MC_E16_FROM) ? c - 1 : c; }
 constexpr int MC_THREADS = OSP_MC_THREADS;
 constexpr int MC_OCC = OSP_MC_OCC;                              // resident CTAs per SM (shared memory: 3 stages each)
 static_assert(MT_RMAX <= MC_THREADS, "one thread per row of a tile");
@@ -1432,7 +1453,8 @@ merge_chain_body(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, 
                     const uint32_t n = sm.cls_cnt[c];
                     sm.cls_off[c] = off; sm.cls_b0[c] = b;
                     off += n;
-                    b += c >= 6 || (BM && c == 5) ? n : (n + (32u >> c) - 1) >> (5 - c);
+                    const uint32_t T = mc_group_bits(uint32_t(c));
+                    b += c >= 6 || (BM && c == 5) ? n : (n + (32u >> T) - 1) >> (5 - T);
                 }
                 sm.cls_b0[8] = b;
             }
@@ -1453,8 +1475,8 @@ merge_chain_body(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, 
                 if (b >= n_batches) break;
                 int c = 7;
                 while (c > 0 && b >= sm.cls_b0[c - 1]) c--;     // cls_b0 ascends from class 6 down to class 0
-                const uint32_t T = c >= 6 ? 5u : uint32_t(c);
-                const uint32_t idx = c >= 6 || (BM && c == 5) ? b - sm.cls_b0[c] : ((b - sm.cls_b0[c]) << (5 - c)) + (lane >> T);
+                const uint32_t T = c >= 6 || (BM && c == 5) ? 5u : mc_group_bits(uint32_t(c));
+                const uint32_t idx = c >= 6 || (BM && c == 5) ? b - sm.cls_b0[c] : ((b - sm.cls_b0[c]) << (5 - T)) + (lane >> T);
                 const bool valid = idx < sm.cls_cnt[c];
                 uint32_t j = 0, s = 0, len = 0;
                 if (valid) {
@@ -1469,8 +1491,8 @@ merge_chain_body(const uint64_t *__restrict__ row_bin, const uint64_t bin_base, 
                     if (c <= 6) u = merge_row_bitmap<16>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);   // one hot body (instruction cache)
                     else u = merge_row_bitmap<MT_LONG_BM / 32>(row_off, ost_off, s, len, bm_wpl, scr_off, lane);   // 513..640
                 } else
-                if (c <= 5) u = merge_rows_grouped<8, K>(c, row_off, ost_off, s, len, lane);
-                else u = merge_rows_grouped<16, K>(5, row_off, ost_off, s, len, lane);
+                if (c < MC_E16_FROM) u = merge_rows_grouped<8, K>(c, row_off, ost_off, s, len, lane);
+                else u = merge_rows_grouped<16, K>(int(T), row_off, ost_off, s, len, lane);
                 if (valid && (lane & ((1u << T) - 1)) == 0) rout[j] = u;
             }
             __syncthreads();

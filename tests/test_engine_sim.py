@@ -33,7 +33,8 @@ def emulated_library(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("cusim_engine") / "libosp_b200_cusim.so")
     # CUSIM_ASAN=1 (with LD_PRELOAD=$(g++ -print-file-name=libasan.so) for the interpreter): AddressSanitizer build
     asan = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("CUSIM_ASAN") == "1" else []
-    cmd = ["g++", "-O1"] + asan + ["-std=c++17", "-x", "c++", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas",
+    defines = os.environ.get("CUSIM_DEFINES", "").split()      # e.g. "-DOSP_E16_FROM=3": experimental kernel variants on the emulation
+    cmd = ["g++", "-O1"] + asan + defines + ["-std=c++17", "-x", "c++", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas",
            "-Wno-unused-function", "-I", os.path.join(HERE, "cusim"), "-I", CSRC, "-o", out,
            os.path.join(HERE, "cusim", "engine_sim.cpp"), os.path.join(CSRC, "osp_host.cpp"), "-lpthread"]
     subprocess.run(cmd, check=True)
@@ -69,6 +70,8 @@ test_coo_ingest_on_device = gp.test_coo_ingest_on_device
 test_er_config2_scaled = gp.test_er_config2_scaled
 test_rmat_small = gp.test_rmat_small
 test_mlp_batch_small = gp.test_mlp_batch_small
+test_fused_lanes_bank_aligned_rows = gp.test_fused_lanes_bank_aligned_rows
+test_fused_lanes_keeps_the_band_kernel_for_short_rows_of_b = gp.test_fused_lanes_keeps_the_band_kernel_for_short_rows_of_b
 test_every_row_length_class = gp.test_every_row_length_class
 test_kway_merge_of_the_sorted_ways = gp.test_kway_merge_of_the_sorted_ways
 test_config4_shape_spread_and_clustered_columns = gp.test_config4_shape_spread_and_clustered_columns

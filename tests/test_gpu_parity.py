@@ -154,6 +154,84 @@ def test_mlp_batch_small(engine):
         assert_bit_exact(got, want2, f"fused dense 70x1000x999 flags={flags}")
 
 
+def _csr_from_rows(rows, n_cols, rng, explicit_zero_every=0):
+    """rows: list of sorted column lists -> CSRMatrix with N(0,3) values (optionally explicit +-0.0 entries)."""
+    pos = np.zeros(len(rows) + 1, dtype=np.uint64)
+    pos[1:] = np.cumsum([len(r) for r in rows])
+    idx = np.array([c for r in rows for c in r], dtype=np.uint32)
+    assert idx.size == 0 or idx.max() < n_cols
+    val = (rng.standard_normal(idx.size) * 3).astype(np.float32)
+    if explicit_zero_every:
+        val[::explicit_zero_every] = 0.0
+        val[1::2 * explicit_zero_every] = -0.0
+    return osp.CSRMatrix.from_arrays(pos, idx, val)
+
+
+@pytest.mark.parametrize("cols,mode", [(1024, "2"), (999, "2"), (4096, "1"), (8160, "2"), (100, "2"), (1024, "0")])
+def test_fused_lanes_bank_aligned_rows(monkeypatch, cols, mode):
+    """Fused dense rows, bank-aligned kernel (osp_fusedlanes.cuh; OSP_FUSED_LANES=2 forces it, 1 = automatic, 0 = the band
+    kernel): column ranges that are and are not multiples of 32, the one- and two-warp CTAs, rows of B whose columns pile
+    up in one shared-memory bank (more than 32 groups: a run applied in pieces), empty rows of A and of B, rows of C beyond
+    A's last row, explicit +0.0 / -0.0 entries (a column whose products are all -0.0 is still an entry), duplicates of a
+    column across runs summed in k order."""
+    monkeypatch.setenv("OSP_FUSED_LANES", mode)
+    rng = np.random.default_rng(cols * 7 + int(mode))
+    n_k = 96
+    dens = 0.7 if cols <= 128 else 0.25 if cols <= 1024 else 0.06
+    b_rows = []
+    for k in range(n_k):
+        if k % 17 == 5:
+            b_rows.append([])                                                # empty row of B
+        elif k % 13 == 3 and cols > 40 * 32:
+            b_rows.append(sorted(int(c) for c in (rng.choice(cols // 32, 40, replace=False) * 32 + 7)))   # 40 columns in bank 7
+        else:
+            b_rows.append(sorted(int(c) for c in np.nonzero(rng.random(cols) < dens)[0]))
+    b = _csr_from_rows(b_rows, cols, rng, explicit_zero_every=11)
+    m = 37
+    a_rows = []
+    for i in range(m):
+        if i % 9 == 4:
+            a_rows.append([])                                                # empty row of A
+        elif i == 7:
+            a_rows.append(list(range(n_k)))                                  # every k: more than 32 runs, the empty rows of B among them
+        else:
+            a_rows.append(sorted(int(k) for k in np.nonzero(rng.random(n_k) < 0.5)[0]))
+    a = _csr_from_rows(a_rows, n_k, rng, explicit_zero_every=13)
+    want, prod = oracle_spgemm(synth.transpose_host(a, n_k), b, rows_override=m + 3)
+    eng = osp.Engine(0)
+    try:
+        res = eng.spgemm(a, b, a_is_csr=True, rows_c=m + 3, cols_b=cols, flags=api.OSP_PROFILE_KERNELS)
+        got = res.to_host(); names = [n for n, _ in res.kernel_times()]; st = res.stats(); res.free()
+    finally:
+        eng.close()
+    assert st["products"] == prod
+    if mode == "0":
+        assert any("k_fused_dense" in n for n in names) and not any("k_fused_lanes" in n for n in names), names
+    else:
+        assert any("k_fused_lanes" in n for n in names), names
+    assert_bit_exact(got, want, f"fused lanes cols={cols} mode={mode}")
+    check_csr_invariants(got, cols)
+
+
+def test_fused_lanes_keeps_the_band_kernel_for_short_rows_of_b(monkeypatch):
+    """Automatic mode: a B whose rows are too short to fill their quads of groups (regrouped form > 6 slots per element)
+    stays with the band kernel; same bits either way."""
+    monkeypatch.setenv("OSP_FUSED_LANES", "1")
+    rng = np.random.default_rng(77)
+    n_k, cols, m = 3000, 512, 6
+    b = _csr_from_rows([sorted(int(c) for c in rng.choice(cols, 3, replace=False)) for _ in range(n_k)], cols, rng)
+    a = _csr_from_rows([sorted(int(k) for k in np.nonzero(rng.random(n_k) < 0.6)[0]) for _ in range(m)], n_k, rng)
+    want, prod = oracle_spgemm(synth.transpose_host(a, n_k), b)
+    eng = osp.Engine(0)
+    try:
+        res = eng.spgemm(a, b, a_is_csr=True, cols_b=cols, flags=api.OSP_PROFILE_KERNELS)
+        got = res.to_host(); names = [n for n, _ in res.kernel_times()]; res.free()
+    finally:
+        eng.close()
+    assert any("k_fused_dense" in n for n in names) and not any("k_fused_lanes<" in n for n in names), names
+    assert_bit_exact(got, want, "short rows of B")
+
+
 def test_row_chunking_gives_same_bits(engine):
     rng = np.random.default_rng(21)
     A, B = rand_sparse(rng, 400, 300, 0.05), rand_sparse(rng, 300, 350, 0.05)

@@ -14,6 +14,22 @@ import outerspace_b200 as osp  # noqa: E402
 from outerspace_b200 import api, synth  # noqa: E402
 
 
+def cached_workload(name, scale_down):
+    """Operands of a named workload through /dev/shm: several library variants are timed on one box without regenerating them."""
+    from outerspace_b200.formats import CSRMatrix
+    path = f"/dev/shm/osp_wl_{name}_{scale_down}.npz"
+    if os.path.exists(path):
+        z = np.load(path)
+        a = CSRMatrix(z["a_pos"], z["a_data"])
+        b = a if int(z["same"]) else CSRMatrix(z["b_pos"], z["b_data"])
+        return a, b, {k: int(v) for k, v in zip(("rows", "n_k", "cols"), z["dims"])}
+    a, b, dims = synth.build_workload(name, scale_down)
+    same = b is a
+    np.savez(path, a_pos=a.pos, a_data=a.data, b_pos=(a.pos[:1] if same else b.pos), b_data=(a.data[:1] if same else b.data),
+             same=np.int64(same), dims=np.array([dims["rows"], dims["n_k"], dims["cols"]], np.int64))
+    return a, b, dims
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="er16k")
@@ -23,9 +39,10 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--kernels", action="store_true", help="print per-kernel event times of the last iteration")
     ap.add_argument("--flush", action="store_true", help="flush L2 (256 MiB write) before every iteration")
+    ap.add_argument("--cache", action="store_true", help="keep the generated operands in /dev/shm for the next run of the same workload")
     args = ap.parse_args()
     t0 = time.time()
-    a, b, dims = synth.build_workload(args.workload, args.scale_down)
+    a, b, dims = cached_workload(args.workload, args.scale_down) if args.cache else synth.build_workload(args.workload, args.scale_down)
     print(f"built {args.workload}/{args.scale_down}: nnzA={a.nnz} nnzB={b.nnz} dims={dims} in {time.time()-t0:.1f}s", flush=True)
     dev = torch.device("cuda:0")
 
