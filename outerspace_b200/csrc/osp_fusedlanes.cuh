@@ -23,6 +23,8 @@
 //     counted and read back by its warp (128 conflict-free words per lane for 4096 columns).
 //   * The loads of a run (its column-byte words and values, up to 8 quads = 32 groups) are issued while the previous
 //     run is applied: two register sets, ~3.4 KB in flight per warp.
+//   * A finished row never waits for its place in C with the accumulator occupied: it is staged and leaves one row later
+//     (fl_retire).
 // Limits: cols <= FL_MAX_COLS (one byte of col / 32 per slot); a B whose regrouped form exceeds FL_MAX_BLOWUP slots
 // per element (many columns of a row in one bank) keeps the band kernel.  Selection: osp_engine.cu.
 #pragma once
@@ -104,28 +106,41 @@ struct FlRun {
     uint32_t groups;        // groups of this piece (<= 4 * FL_QUADS)
 };
 
+// Loads of a piece: whole quads behind one warp-uniform branch each (five loads, no per-group predicate); only the last,
+// partly filled quad tests its groups.  What lies past `groups` is never read by fl_apply.
 __device__ __forceinline__ void fl_load(FlRun &r, const float *__restrict__ vals, const uint32_t *__restrict__ colb, uint64_t quad0,
                                         uint32_t groups, float a, unsigned int lane) {
     r.a = a;
     r.groups = groups;
+    const uint32_t *cw = colb + quad0 * 32 + lane;
+    const float *vw = vals + quad0 * 128 + lane;
 #pragma unroll
     for (int q = 0; q < FL_QUADS; q++) {
-        r.w[q] = 0;
-        if (uint32_t(4 * q) < groups) r.w[q] = colb[(quad0 + q) * 32 + lane];
+        if (uint32_t(4 * q + 4) <= groups) {
+            r.w[q] = cw[q * 32];
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-            r.v[4 * q + g] = 0.f;
-            if (uint32_t(4 * q + g) < groups) r.v[4 * q + g] = vals[((quad0 + q) * 4 + g) * 32 + lane];
+            for (int g = 0; g < 4; g++) r.v[4 * q + g] = vw[(4 * q + g) * 32];
+        } else {
+            r.w[q] = 0;
+#pragma unroll
+            for (int g = 0; g < 4; g++) r.v[4 * q + g] = 0.f;
+            if (uint32_t(4 * q) < groups) {
+                r.w[q] = cw[q * 32];
+#pragma unroll
+                for (int g = 0; g < 3; g++)
+                    if (uint32_t(4 * q + g) < groups) r.v[4 * q + g] = vw[(4 * q + g) * 32];
+            }
         }
     }
 }
 
 // Shared-memory accesses of the accumulator by 32-bit shared-window address: one base computed per kernel, no generic
-// address arithmetic under the per-slot predicates.
+// address arithmetic under predicates.
 #ifdef OSP_CUSIM
 __device__ __forceinline__ uint32_t fl_smem_base() { return 0; }
 __device__ __forceinline__ uint32_t fl_lds(uint32_t addr) { return smem_u32_at(addr); }
 __device__ __forceinline__ void fl_sts(uint32_t addr, uint32_t v) { smem_u32_at(addr) = v; }
+__device__ __forceinline__ uint32_t fl_byte(uint32_t w, int g) { return (w >> (8 * g)) & 0xFFu; }
 #else
 __device__ __forceinline__ uint32_t fl_smem_base() { return uint32_t(__cvta_generic_to_shared(osp_smem)); }
 __device__ __forceinline__ uint32_t fl_lds(uint32_t addr) {
@@ -134,42 +149,69 @@ __device__ __forceinline__ uint32_t fl_lds(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void fl_sts(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-#endif
-
-#ifdef OSP_CUSIM
-__device__ __forceinline__ uint32_t fl_byte(uint32_t w, int g) { return (w >> (8 * g)) & 0xFFu; }
-#else
 __device__ __forceinline__ uint32_t fl_byte(uint32_t w, int g) { return __byte_perm(w, 0u, 0x4440u + uint32_t(g)); }
 #endif
 
 // Applies a loaded run to the warp's accumulator row; acc_lane = shared-window address of the lane's column `lane`
 // (column c of the row sits 4 * c bytes into the row: (c / 32) << 7 past acc_lane for the lane c % 32).  An empty slot
 // carries the column byte cpad / 32: it lands in the 32 dummy floats behind the row (one per lane, never emitted), so
-// the read-modify-write needs no validity test at all.  Only the last, partly filled quad of a run tests (uniformly)
-// which of its groups exist.
+// the read-modify-write needs no validity test at all.  Groups are applied FL_BLOCK at a time (all loads of the block,
+// then the adds, then the stores: the real columns of a lane within one run are distinct); only the last, partly filled
+// block of a run tests (uniformly) which of its groups exist.
+#ifndef OSP_FL_BLOCK
+#define OSP_FL_BLOCK 8
+#endif
+constexpr int FL_BLOCK = OSP_FL_BLOCK;
+static_assert(FL_BLOCK == 4 || FL_BLOCK == 8 || FL_BLOCK == 16, "whole quads");
 template <bool TAIL>
-__device__ __forceinline__ void fl_quad(const uint32_t w, const float (&v)[FL_QUADS * 4], const int q, const float a, const uint32_t groups,
-                                        const uint32_t acc_lane) {
-    uint32_t addr[4], old[4];
+__device__ __forceinline__ void fl_block(const FlRun &r, const int b0, const uint32_t acc_lane) {
+    uint32_t addr[FL_BLOCK], old[FL_BLOCK];
 #pragma unroll
-    for (int g = 0; g < 4; g++) {
-        addr[g] = acc_lane + fl_byte(w, g) * 128u;                              // PRMT + IMAD
-        old[g] = FL_EMPTY;
-        if (!TAIL || uint32_t(4 * q + g) < groups) old[g] = fl_lds(addr[g]);   // the (real) columns of a lane within one run are distinct
+    for (int u = 0; u < FL_BLOCK; u++) {
+        const int g = b0 + u;
+        addr[u] = acc_lane + fl_byte(r.w[g >> 2], g & 3) * 128u;                // PRMT + IMAD
+        old[u] = FL_EMPTY;
+        if (!TAIL || uint32_t(g) < r.groups) old[u] = fl_lds(addr[u]);
     }
 #pragma unroll
-    for (int g = 0; g < 4; g++) {
-        const float prod = __fmul_rn(a, v[4 * q + g]);                          // rounded on its own: no FMA
-        const float nv = old[g] == FL_EMPTY ? prod : __fadd_rn(__uint_as_float(old[g]), prod);
-        if (!TAIL || uint32_t(4 * q + g) < groups) fl_sts(addr[g], __float_as_uint(nv));
+    for (int u = 0; u < FL_BLOCK; u++) {
+        const int g = b0 + u;
+        const float prod = __fmul_rn(r.a, r.v[g]);                              // rounded on its own: no FMA
+        const float nv = old[u] == FL_EMPTY ? prod : __fadd_rn(__uint_as_float(old[u]), prod);
+        if (!TAIL || uint32_t(g) < r.groups) fl_sts(addr[u], __float_as_uint(nv));
     }
 }
 __device__ __forceinline__ void fl_apply(const FlRun &r, const uint32_t acc_lane) {
 #pragma unroll
-    for (int q = 0; q < FL_QUADS; q++) {
-        if (uint32_t(4 * q + 4) <= r.groups) fl_quad<false>(r.w[q], r.v, q, r.a, r.groups, acc_lane);       // warp-uniform branches
-        else if (uint32_t(4 * q) < r.groups) fl_quad<true>(r.w[q], r.v, q, r.a, r.groups, acc_lane);
+    for (int b = 0; b < 4 * FL_QUADS; b += FL_BLOCK) {
+        if (uint32_t(b + FL_BLOCK) <= r.groups) fl_block<false>(r, b, acc_lane);       // warp-uniform branches
+        else if (uint32_t(b) < r.groups) fl_block<true>(r, b, acc_lane);
     }
+}
+
+// Rows of C leave in two steps so that no warp ever waits with a full accumulator: the finished row is compacted into
+// one of the warp's two staging rows in global memory (ascending columns) and its count is published for the look-back
+// at once; its place in C is resolved and the staged row copied there one row LATER, when the warp has accumulated its
+// next row -- by then the predecessors have long published.  (Resolved right away, every row waited for the slowest
+// of the ~1900 rows in flight before it: 24 % of the executed instructions were look-back polls, ncu r02_call19.)
+__device__ __forceinline__ void fl_retire(const uint64_t row, const uint32_t total, const Elem *stage, uint64_t *tile_state,
+                                          DevScalars *sc, uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, const uint64_t rows,
+                                          const unsigned int lane) {
+    const uint64_t base = lb_resolve(tile_state, uint32_t(row), total, 0);
+    if (lane == 0) {
+        c_pos[row] = base;
+        if (row + 1 == rows) { c_pos[rows] = base + total; sc->nnz_c[1] = base + total; }
+    }
+    Elem *dst = c_data + base;
+    uint32_t i = lane;
+    for (; i + 96 < total; i += 128) {
+        Elem e[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) e[u] = stage[i + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 4; u++) dst[i + 32 * u] = e[u];
+    }
+    for (; i < total; i += 32) dst[i] = stage[i];
 }
 
 template <int WARPS>
@@ -177,13 +219,17 @@ __global__ void __launch_bounds__(32 * WARPS)
 k_fused_lanes(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data, const uint64_t m_a,
               const FlMeta *__restrict__ meta, const float *__restrict__ vals, const uint32_t *__restrict__ colb,
               const uint32_t cols, const uint64_t rows, uint64_t *tile_state, DevScalars *sc,
-              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data) {
+              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, Elem *stage_all) {
     const unsigned int lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t cpad = (cols + 31) & ~31u;
     const uint32_t acc_off = warp * (cpad + 32) * 4;
     const uint32_t acc_lane = fl_smem_base() + acc_off + lane * 4;
+    Elem *stage = stage_all + (uint64_t(blockIdx.x) * WARPS + warp) * 2 * cpad;       // two staging rows per warp
     for (uint32_t c = 0; c < cpad; c += 32) fl_sts(acc_lane + c * 4, FL_EMPTY);
     __syncwarp();
+    uint64_t pend_row = 0;
+    uint32_t pend_total = 0, cur = 0;
+    bool pending = false;
     while (true) {
         uint32_t t = 0;
         if (lane == 0) t = atomicAdd(&sc->tile_ticket, 1u);
@@ -226,48 +272,36 @@ k_fused_lanes(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_dat
                 fl_apply(rb, acc_lane);
             }
         }
-        // ---- count, chain, emit (ascending columns: word i of every lane, lanes in order) ----
+        // ---- compact the row into the staging row (ascending columns: word i of every lane, lanes in order), publish its count ----
+        Elem *st = stage + uint64_t(cur) * cpad;
         uint32_t total = 0;
         for (uint32_t c0 = 0; c0 < cpad; c0 += 128) {
             uint32_t bits[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
+                const uint32_t c = c0 + 32 * u;
                 bits[u] = FL_EMPTY;
-                if (c0 + 32 * u < cpad) bits[u] = fl_lds(acc_lane + (c0 + 32 * u) * 4);
+                if (c < cpad) { bits[u] = fl_lds(acc_lane + c * 4); fl_sts(acc_lane + c * 4, FL_EMPTY); }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) total += __popc(__ballot_sync(FULL, bits[u] != FL_EMPTY));
+            for (int u = 0; u < 4; u++) {
+                const bool hit = bits[u] != FL_EMPTY;
+                const unsigned int m = __ballot_sync(FULL, hit);
+                if (hit) {
+                    Elem e; e.idx = c0 + 32 * u + lane; e.val = __uint_as_float(bits[u]);
+                    st[total + __popc(m & ((1u << lane) - 1u))] = e;
+                }
+                total += __popc(m);
+            }
         }
         lb_publish(tile_state, uint32_t(row), total, 0);
-        const uint64_t base = lb_resolve(tile_state, uint32_t(row), total, 0);
-        if (lane == 0) {
-            c_pos[row] = base;
-            if (row + 1 == rows) { c_pos[rows] = base + total; sc->nnz_c[1] = base + total; }
-        }
-        if (total) {
-            uint64_t o = base;
-            for (uint32_t c0 = 0; c0 < cpad; c0 += 128) {
-                uint32_t bits[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t c = c0 + 32 * u;
-                    bits[u] = FL_EMPTY;
-                    if (c < cpad) { bits[u] = fl_lds(acc_lane + c * 4); fl_sts(acc_lane + c * 4, FL_EMPTY); }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const bool hit = bits[u] != FL_EMPTY;
-                    const unsigned int m = __ballot_sync(FULL, hit);
-                    if (hit) {
-                        Elem e; e.idx = c0 + 32 * u + lane; e.val = __uint_as_float(bits[u]);
-                        c_data[o + __popc(m & ((1u << lane) - 1u))] = e;
-                    }
-                    o += __popc(m);
-                }
-            }
-        }
-        __syncwarp();
+        __syncwarp();                                          // the staged row is visible to every lane of the warp
+        // ---- the row before this one leaves for C ----
+        if (pending) fl_retire(pend_row, pend_total, stage + uint64_t(cur ^ 1u) * cpad, tile_state, sc, c_pos, c_data, rows, lane);
+        pend_row = row; pend_total = total; pending = true;
+        cur ^= 1u;
     }
+    if (pending) fl_retire(pend_row, pend_total, stage + uint64_t(cur ^ 1u) * cpad, tile_state, sc, c_pos, c_data, rows, lane);
 }
 
 }  // namespace osp
