@@ -1075,8 +1075,10 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
                     CU(ctx, ctx->fl_vals.reserve(std::max<uint64_t>(quads, 1) * 128 * 4));
                     CU(ctx, ctx->fl_colb.reserve(std::max<uint64_t>(quads, 1) * 32 * 4));
                     float *vals = ctx->fl_vals.as<float>();
+                    const float4 *vals4 = ctx->fl_vals.as<float4>();
                     uint32_t *colb = ctx->fl_colb.as<uint32_t>();
                     CU(ctx, cudaMemsetAsync(colb, fused_lanes_empty_byte(cols_b), std::max<uint64_t>(quads, 1) * 32 * 4, ctx->stream));   // every slot empty
+                    CU(ctx, cudaMemsetAsync(vals, 0, std::max<uint64_t>(quads, 1) * 128 * 4, ctx->stream));                                  // (the unused slots of a quad are loaded with it)
                     LAUNCH(ctx, k_fl_fill, prep_grid, 32 * FL_PREP_WARPS, 0, dB_pos, dB_data, n_k, meta, vals, colb);
                     CU(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, (m_plan + 1) * 8, ctx->stream));
                     CU(ctx, cudaMemsetAsync(&ctx->d_sc->tile_ticket, 0, 4, ctx->stream));
@@ -1087,13 +1089,13 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
                     if (warps == 2) { CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_lanes<2>, 64, sm)); }
                     else { CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_lanes<1>, 32, sm)); }
                     const unsigned grid = unsigned(std::min<uint64_t>((m_plan + warps - 1) / warps, uint64_t(ctx->sm_count) * std::max(occ, 1)));
-                    CU(ctx, ctx->fl_stage.reserve(uint64_t(grid) * warps * 2 * ((cols_b + 31) & ~31ull) * sizeof(Elem)));   // two staging rows per warp
+                    if (FL_STAGE) { CU(ctx, ctx->fl_stage.reserve(uint64_t(grid) * warps * 2 * ((cols_b + 31) & ~31ull) * sizeof(Elem))); }   // two staging rows per warp
                     Elem *stage = ctx->fl_stage.as<Elem>();
                     if (warps == 2) {
-                        LAUNCH(ctx, k_fused_lanes<2>, grid, 64, sm, dA_pos, dA_data, m_a, meta, vals, colb, uint32_t(cols_b), m_plan,
+                        LAUNCH(ctx, k_fused_lanes<2>, grid, 64, sm, dA_pos, dA_data, m_a, meta, vals4, colb, uint32_t(cols_b), m_plan,
                                ctx->tile_state.as<uint64_t>(), ctx->d_sc, job.c_pos, job.c_data, stage);
                     } else {
-                        LAUNCH(ctx, k_fused_lanes<1>, grid, 32, sm, dA_pos, dA_data, m_a, meta, vals, colb, uint32_t(cols_b), m_plan,
+                        LAUNCH(ctx, k_fused_lanes<1>, grid, 32, sm, dA_pos, dA_data, m_a, meta, vals4, colb, uint32_t(cols_b), m_plan,
                                ctx->tile_state.as<uint64_t>(), ctx->d_sc, job.c_pos, job.c_data, stage);
                     }
                     ev_blocks.push_back(next_event(ctx));

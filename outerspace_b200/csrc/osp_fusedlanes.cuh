@@ -23,8 +23,6 @@
 //     counted and read back by its warp (128 conflict-free words per lane for 4096 columns).
 //   * The loads of a run (its column-byte words and values, up to 8 quads = 32 groups) are issued while the previous
 //     run is applied: two register sets, ~3.4 KB in flight per warp.
-//   * A finished row never waits for its place in C with the accumulator occupied: it is staged and leaves one row later
-//     (fl_retire).
 // Limits: cols <= FL_MAX_COLS (one byte of col / 32 per slot); a B whose regrouped form exceeds FL_MAX_BLOWUP slots
 // per element (many columns of a row in one bank) keeps the band kernel.  Selection: osp_engine.cu.
 #pragma once
@@ -74,7 +72,8 @@ k_fl_count(const uint64_t *__restrict__ b_pos, const Elem *__restrict__ b_data, 
 }
 
 // Pass 2 over B: every element into its slot.  colb was preset to the byte that marks an empty slot
-// (cpad / 32: the dummy floats behind an accumulator row).
+// (cpad / 32: the dummy floats behind an accumulator row).  Values lie lane-interleaved, the four groups of a quad side by
+// side -- vals[(quad * 32 + lane) * 4 + group] -- so that a lane fetches its four values of a quad with one 16-byte load.
 __global__ void __launch_bounds__(32 * FL_PREP_WARPS)
 k_fl_fill(const uint64_t *__restrict__ b_pos, const Elem *__restrict__ b_data, uint64_t n_k, const FlMeta *__restrict__ meta,
           float *__restrict__ vals, uint32_t *__restrict__ colb) {
@@ -90,9 +89,9 @@ k_fl_fill(const uint64_t *__restrict__ b_pos, const Elem *__restrict__ b_data, u
             const Elem e = b_data[p];
             const uint32_t b = e.idx & 31u;
             const uint32_t j = atomicAdd(&hist[warp][b], 1u);      // any order inside a bank: the columns of a row are distinct
-            const uint64_t q = q0 + (j >> 2);
-            vals[(q * 4 + (j & 3u)) * 32 + b] = e.val;
-            colbytes[(q * 32 + b) * 4 + (j & 3u)] = static_cast<unsigned char>(e.idx >> 5);
+            const uint64_t slot = ((q0 + (j >> 2)) * 32 + b) * 4 + (j & 3u);
+            vals[slot] = e.val;
+            colbytes[slot] = static_cast<unsigned char>(e.idx >> 5);
         }
         __syncwarp();
     }
@@ -101,35 +100,25 @@ k_fl_fill(const uint64_t *__restrict__ b_pos, const Elem *__restrict__ b_data, u
 // The registers of (up to FL_QUADS quads of) one run: column-byte words, values, multiplier.
 struct FlRun {
     uint32_t w[FL_QUADS];
-    float v[FL_QUADS * 4];
+    float4 v[FL_QUADS];
     float a;
     uint32_t groups;        // groups of this piece (<= 4 * FL_QUADS)
 };
 
-// Loads of a piece: whole quads behind one warp-uniform branch each (five loads, no per-group predicate); only the last,
-// partly filled quad tests its groups.  What lies past `groups` is never read by fl_apply.
-__device__ __forceinline__ void fl_load(FlRun &r, const float *__restrict__ vals, const uint32_t *__restrict__ colb, uint64_t quad0,
+// Loads of a piece: two loads per quad and lane (4 + 16 bytes), predicated quad by quad -- no branch: with three warps per
+// scheduler every unresolved branch is exposed.  Quads past `groups` stay unset (fl_apply never reads them); the unused
+// groups of the last quad are loaded with it (the storage is allocated in whole quads, their column bytes say "empty").
+__device__ __forceinline__ void fl_load(FlRun &r, const float4 *__restrict__ vals4, const uint32_t *__restrict__ colb, uint64_t quad0,
                                         uint32_t groups, float a, unsigned int lane) {
     r.a = a;
     r.groups = groups;
     const uint32_t *cw = colb + quad0 * 32 + lane;
-    const float *vw = vals + quad0 * 128 + lane;
+    const float4 *vw = vals4 + quad0 * 32 + lane;
 #pragma unroll
     for (int q = 0; q < FL_QUADS; q++) {
-        if (uint32_t(4 * q + 4) <= groups) {
+        if (uint32_t(4 * q) < groups) {
             r.w[q] = cw[q * 32];
-#pragma unroll
-            for (int g = 0; g < 4; g++) r.v[4 * q + g] = vw[(4 * q + g) * 32];
-        } else {
-            r.w[q] = 0;
-#pragma unroll
-            for (int g = 0; g < 4; g++) r.v[4 * q + g] = 0.f;
-            if (uint32_t(4 * q) < groups) {
-                r.w[q] = cw[q * 32];
-#pragma unroll
-                for (int g = 0; g < 3; g++)
-                    if (uint32_t(4 * q + g) < groups) r.v[4 * q + g] = vw[(4 * q + g) * 32];
-            }
+            r.v[q] = vw[q * 32];
         }
     }
 }
@@ -163,6 +152,7 @@ __device__ __forceinline__ uint32_t fl_byte(uint32_t w, int g) { return __byte_p
 #endif
 constexpr int FL_BLOCK = OSP_FL_BLOCK;
 static_assert(FL_BLOCK == 4 || FL_BLOCK == 8 || FL_BLOCK == 16, "whole quads");
+__device__ __forceinline__ float fl_f4(const float4 &v, const int g) { return g == 0 ? v.x : g == 1 ? v.y : g == 2 ? v.z : v.w; }
 template <bool TAIL>
 __device__ __forceinline__ void fl_block(const FlRun &r, const int b0, const uint32_t acc_lane) {
     uint32_t addr[FL_BLOCK], old[FL_BLOCK];
@@ -171,14 +161,14 @@ __device__ __forceinline__ void fl_block(const FlRun &r, const int b0, const uin
         const int g = b0 + u;
         addr[u] = acc_lane + fl_byte(r.w[g >> 2], g & 3) * 128u;                // PRMT + IMAD
         old[u] = FL_EMPTY;
-        if (!TAIL || uint32_t(g) < r.groups) old[u] = fl_lds(addr[u]);
+        if (!TAIL || uint32_t(g & ~3) < r.groups) old[u] = fl_lds(addr[u]);     // (whole quads: the missing groups of a quad are empty slots)
     }
 #pragma unroll
     for (int u = 0; u < FL_BLOCK; u++) {
         const int g = b0 + u;
-        const float prod = __fmul_rn(r.a, r.v[g]);                              // rounded on its own: no FMA
+        const float prod = __fmul_rn(r.a, fl_f4(r.v[g >> 2], g & 3));           // rounded on its own: no FMA
         const float nv = old[u] == FL_EMPTY ? prod : __fadd_rn(__uint_as_float(old[u]), prod);
-        if (!TAIL || uint32_t(g) < r.groups) fl_sts(addr[u], __float_as_uint(nv));
+        if (!TAIL || uint32_t(g & ~3) < r.groups) fl_sts(addr[u], __float_as_uint(nv));
     }
 }
 __device__ __forceinline__ void fl_apply(const FlRun &r, const uint32_t acc_lane) {
@@ -189,11 +179,15 @@ __device__ __forceinline__ void fl_apply(const FlRun &r, const uint32_t acc_lane
     }
 }
 
-// Rows of C leave in two steps so that no warp ever waits with a full accumulator: the finished row is compacted into
-// one of the warp's two staging rows in global memory (ascending columns) and its count is published for the look-back
-// at once; its place in C is resolved and the staged row copied there one row LATER, when the warp has accumulated its
-// next row -- by then the predecessors have long published.  (Resolved right away, every row waited for the slowest
-// of the ~1900 rows in flight before it: 24 % of the executed instructions were look-back polls, ncu r02_call19.)
+// OSP_FL_STAGE=1 (experiment, measured slower: profiles/r02_fusedlanes.md): rows of C leave in two steps so that no warp
+// waits with a full accumulator -- the finished row is compacted into one of the warp's two staging rows in global memory
+// and its count published at once; its place in C is resolved and the staged row copied there one row LATER, when the
+// predecessors have long published.  (Resolved right away, a row waits for the slowest of the ~1900 rows in flight before
+// it: 9 % of the warp samples asleep in the look-back, ncu r02_call19.)  The copy costs more than the wait.
+#ifndef OSP_FL_STAGE
+#define OSP_FL_STAGE 0
+#endif
+constexpr bool FL_STAGE = OSP_FL_STAGE != 0;
 __device__ __forceinline__ void fl_retire(const uint64_t row, const uint32_t total, const Elem *stage, uint64_t *tile_state,
                                           DevScalars *sc, uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, const uint64_t rows,
                                           const unsigned int lane) {
@@ -217,14 +211,14 @@ __device__ __forceinline__ void fl_retire(const uint64_t row, const uint32_t tot
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS)
 k_fused_lanes(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data, const uint64_t m_a,
-              const FlMeta *__restrict__ meta, const float *__restrict__ vals, const uint32_t *__restrict__ colb,
+              const FlMeta *__restrict__ meta, const float4 *__restrict__ vals, const uint32_t *__restrict__ colb,
               const uint32_t cols, const uint64_t rows, uint64_t *tile_state, DevScalars *sc,
               uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, Elem *stage_all) {
     const unsigned int lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t cpad = (cols + 31) & ~31u;
     const uint32_t acc_off = warp * (cpad + 32) * 4;
     const uint32_t acc_lane = fl_smem_base() + acc_off + lane * 4;
-    Elem *stage = stage_all + (uint64_t(blockIdx.x) * WARPS + warp) * 2 * cpad;       // two staging rows per warp
+    Elem *stage = FL_STAGE ? stage_all + (uint64_t(blockIdx.x) * WARPS + warp) * 2 * cpad : nullptr;       // two staging rows per warp
     for (uint32_t c = 0; c < cpad; c += 32) fl_sts(acc_lane + c * 4, FL_EMPTY);
     __syncwarp();
     uint64_t pend_row = 0;
@@ -272,36 +266,78 @@ k_fused_lanes(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_dat
                 fl_apply(rb, acc_lane);
             }
         }
-        // ---- compact the row into the staging row (ascending columns: word i of every lane, lanes in order), publish its count ----
-        Elem *st = stage + uint64_t(cur) * cpad;
-        uint32_t total = 0;
-        for (uint32_t c0 = 0; c0 < cpad; c0 += 128) {
-            uint32_t bits[4];
+        if (FL_STAGE) {
+            // ---- compact the row into the staging row (ascending columns: word i of every lane, lanes in order), publish its count ----
+            Elem *st = stage + uint64_t(cur) * cpad;
+            uint32_t total = 0;
+            for (uint32_t c0 = 0; c0 < cpad; c0 += 128) {
+                uint32_t bits[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t c = c0 + 32 * u;
-                bits[u] = FL_EMPTY;
-                if (c < cpad) { bits[u] = fl_lds(acc_lane + c * 4); fl_sts(acc_lane + c * 4, FL_EMPTY); }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const bool hit = bits[u] != FL_EMPTY;
-                const unsigned int m = __ballot_sync(FULL, hit);
-                if (hit) {
-                    Elem e; e.idx = c0 + 32 * u + lane; e.val = __uint_as_float(bits[u]);
-                    st[total + __popc(m & ((1u << lane) - 1u))] = e;
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t c = c0 + 32 * u;
+                    bits[u] = FL_EMPTY;
+                    if (c < cpad) { bits[u] = fl_lds(acc_lane + c * 4); fl_sts(acc_lane + c * 4, FL_EMPTY); }
                 }
-                total += __popc(m);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool hit = bits[u] != FL_EMPTY;
+                    const unsigned int m = __ballot_sync(FULL, hit);
+                    if (hit) {
+                        Elem e; e.idx = c0 + 32 * u + lane; e.val = __uint_as_float(bits[u]);
+                        st[total + __popc(m & ((1u << lane) - 1u))] = e;
+                    }
+                    total += __popc(m);
+                }
             }
+            lb_publish(tile_state, uint32_t(row), total, 0);
+            __syncwarp();                                          // the staged row is visible to every lane of the warp
+            // ---- the row before this one leaves for C ----
+            if (pending) fl_retire(pend_row, pend_total, stage + uint64_t(cur ^ 1u) * cpad, tile_state, sc, c_pos, c_data, rows, lane);
+            pend_row = row; pend_total = total; pending = true;
+            cur ^= 1u;
+        } else {
+            // ---- count, chain, emit (ascending columns: word i of every lane, lanes in order) ----
+            uint32_t total = 0;
+            for (uint32_t c0 = 0; c0 < cpad; c0 += 128) {
+                uint32_t bits[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    bits[u] = FL_EMPTY;
+                    if (c0 + 32 * u < cpad) bits[u] = fl_lds(acc_lane + (c0 + 32 * u) * 4);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) total += __popc(__ballot_sync(FULL, bits[u] != FL_EMPTY));
+            }
+            lb_publish(tile_state, uint32_t(row), total, 0);
+            const uint64_t base = lb_resolve(tile_state, uint32_t(row), total, 0);
+            if (lane == 0) {
+                c_pos[row] = base;
+                if (row + 1 == rows) { c_pos[rows] = base + total; sc->nnz_c[1] = base + total; }
+            }
+            uint64_t o = base;
+            for (uint32_t c0 = 0; c0 < cpad; c0 += 128) {
+                uint32_t bits[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t c = c0 + 32 * u;
+                    bits[u] = FL_EMPTY;
+                    if (c < cpad) { bits[u] = fl_lds(acc_lane + c * 4); fl_sts(acc_lane + c * 4, FL_EMPTY); }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool hit = bits[u] != FL_EMPTY;
+                    const unsigned int m = __ballot_sync(FULL, hit);
+                    if (hit) {
+                        Elem e; e.idx = c0 + 32 * u + lane; e.val = __uint_as_float(bits[u]);
+                        c_data[o + __popc(m & ((1u << lane) - 1u))] = e;
+                    }
+                    o += __popc(m);
+                }
+            }
+            __syncwarp();
         }
-        lb_publish(tile_state, uint32_t(row), total, 0);
-        __syncwarp();                                          // the staged row is visible to every lane of the warp
-        // ---- the row before this one leaves for C ----
-        if (pending) fl_retire(pend_row, pend_total, stage + uint64_t(cur ^ 1u) * cpad, tile_state, sc, c_pos, c_data, rows, lane);
-        pend_row = row; pend_total = total; pending = true;
-        cur ^= 1u;
     }
-    if (pending) fl_retire(pend_row, pend_total, stage + uint64_t(cur ^ 1u) * cpad, tile_state, sc, c_pos, c_data, rows, lane);
+    if (FL_STAGE && pending) fl_retire(pend_row, pend_total, stage + uint64_t(cur ^ 1u) * cpad, tile_state, sc, c_pos, c_data, rows, lane);
 }
 
 }  // namespace osp

@@ -52,6 +52,7 @@ inline dim3 blockDim, gridDim;
 struct uint2 { unsigned x, y; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct alignas(16) ulonglong2 { unsigned long long x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
 inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
