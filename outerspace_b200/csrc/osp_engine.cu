@@ -71,7 +71,8 @@ struct osp_ctx {
     DevBuf bins;
     // fused band sweep of the long rows (opt-in, osp_longrows.cuh): task bitmap for the multiply, band index of B
     DevBuf swept, lr_bands, kw_scratch, vbits;
-    DevBuf fl_meta, fl_vals, fl_colb, fl_stage;     // B regrouped by shared-memory bank, staging rows of the warps (osp_fusedlanes.cuh)
+    DevBuf fl_meta, fl_vals, fl_colb, fl_stage, fl_cnt, fl_pos2;     // B regrouped by shared-memory bank, staging rows of the warps (osp_fusedlanes.cuh)
+    bool fused_lanes_direct = true;         // OSP_FL_DIRECT=0: rows of C chained by the look-back instead of written at the prefix of their bounds
     int fused_lanes_mode = 1;               // OSP_FUSED_LANES: 0 band kernel (k_fused_dense), 1 automatic, 2 bank-aligned kernel whatever B's regrouped size
     bool kway_env = false;                  // OSP_KWAY=1: rows of 4097 .. 32768 partial products in <= 64 ways go to k_merge_ways
     bool sweep_ok = false;                  // the device accepted the kernel's shared-memory size
@@ -662,6 +663,7 @@ int osp_create(int device, osp_ctx **out) {
         const char *kw = std::getenv("OSP_KWAY");
         ctx->kway_env = kw && kw[0] && kw[0] != '0';
         if (const char *fl = std::getenv("OSP_FUSED_LANES")) ctx->fused_lanes_mode = fl[0] == '0' ? 0 : fl[0] == '2' ? 2 : 1;
+        if (const char *fd = std::getenv("OSP_FL_DIRECT")) ctx->fused_lanes_direct = fd[0] != '0';
         if (const char *m = std::getenv("OSP_LONGROW_SWEEP_MIN")) ctx->sweep_min = std::strtoull(m, nullptr, 10);
     }
     {   // OSP_FUSED_SHORT: opt-in as well
@@ -720,7 +722,7 @@ void osp_destroy(osp_ctx *ctx) {
                       &ctx->conv_data, &ctx->conv_tmp, &ctx->conv_chk, &ctx->task_bs, &ctx->run_off, &ctx->row_bin, &ctx->tile_row,
                       &ctx->tile_start, &ctx->long_list, &ctx->xl_list, &ctx->uniq, &ctx->col_ptr, &ctx->tasks, &ctx->tile_state,
                       &ctx->xl_acc, &ctx->xl_bits, &ctx->bins, &ctx->swept, &ctx->lr_bands, &ctx->kw_scratch, &ctx->vbits,
-                      &ctx->fl_meta, &ctx->fl_vals, &ctx->fl_colb, &ctx->fl_stage})
+                      &ctx->fl_meta, &ctx->fl_vals, &ctx->fl_colb, &ctx->fl_stage, &ctx->fl_cnt, &ctx->fl_pos2})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
@@ -828,7 +830,8 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     }
     // ---- symbolic pass, merge plan, CSR->CSC task list: launched back to back -------------------
     Arena ar;
-    const uint64_t st[4] = {scan_tiles(std::max<uint64_t>(nnz_a, 1)), plan_tiles(m_plan), scan_tiles(std::max<uint64_t>(n_k, 1)), 0};
+    const uint64_t st[4] = {scan_tiles(std::max<uint64_t>(nnz_a, 1)), plan_tiles(m_plan), scan_tiles(std::max<uint64_t>(n_k, 1)),
+                            fused ? scan_tiles(m_plan + 1) : 0};          // (the fourth: prefix of the row bounds / counts, osp_fusedlanes.cuh)
     rc = prepare_arena(ctx, st, rowwise ? 0 : n_k, ar);
     if (rc) return rc;
     uint64_t cols_b = args->cols_b;
@@ -1091,12 +1094,44 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
                     const unsigned grid = unsigned(std::min<uint64_t>((m_plan + warps - 1) / warps, uint64_t(ctx->sm_count) * std::max(occ, 1)));
                     if (FL_STAGE) { CU(ctx, ctx->fl_stage.reserve(uint64_t(grid) * warps * 2 * ((cols_b + 31) & ~31ull) * sizeof(Elem))); }   // two staging rows per warp
                     Elem *stage = ctx->fl_stage.as<Elem>();
+                    // rows of C at the prefix of their bounds (no chain); C was allocated at the bound
+                    const bool direct = ctx->fused_lanes_direct && !FL_STAGE && job.c_cap >= cap_bound;
+                    uint32_t *row_cnt = nullptr;
+                    if (direct) {
+                        CU(ctx, ctx->fl_cnt.reserve(m_plan * 4));
+                        row_cnt = ctx->fl_cnt.as<uint32_t>();
+                        LAUNCH(ctx, (k_scan<RowCapIn, U64Out>), unsigned(st[3]), SCAN_BLOCK, 0, RowCapIn{ctx->row_bin.as<uint64_t>(), cols_b},
+                               U64Out{job.c_pos}, m_plan, ar.state[3], &ctx->d_sc->scan_ticket[3]);
+                    }
                     if (warps == 2) {
                         LAUNCH(ctx, k_fused_lanes<2>, grid, 64, sm, dA_pos, dA_data, m_a, meta, vals4, colb, uint32_t(cols_b), m_plan,
-                               ctx->tile_state.as<uint64_t>(), ctx->d_sc, job.c_pos, job.c_data, stage);
+                               ctx->tile_state.as<uint64_t>(), ctx->d_sc, job.c_pos, job.c_data, stage, row_cnt);
                     } else {
                         LAUNCH(ctx, k_fused_lanes<1>, grid, 32, sm, dA_pos, dA_data, m_a, meta, vals4, colb, uint32_t(cols_b), m_plan,
-                               ctx->tile_state.as<uint64_t>(), ctx->d_sc, job.c_pos, job.c_data, stage);
+                               ctx->tile_state.as<uint64_t>(), ctx->d_sc, job.c_pos, job.c_data, stage, row_cnt);
+                    }
+                    if (direct) {
+                        rc2 = sync_scalars(ctx);
+                        if (rc2) return rc2;
+                        const uint64_t nnz = ctx->h_sc->nnz_c[1];
+                        if (nnz != cap_bound) {
+                            // some row is not full: exact C.pos from the counts, rows moved into an exactly sized C
+                            CU(ctx, ctx->fl_pos2.reserve((m_plan + 1) * 8));
+                            uint64_t *pos2 = ctx->fl_pos2.as<uint64_t>();
+                            CU(ctx, cudaMemsetAsync(ar.state[3], 0, st[3] * 8, ctx->stream));
+                            CU(ctx, cudaMemsetAsync(&ctx->d_sc->scan_ticket[3], 0, 4, ctx->stream));
+                            LAUNCH(ctx, (k_scan<U32In, U64Out>), unsigned(st[3]), SCAN_BLOCK, 0, U32In{row_cnt}, U64Out{pos2}, m_plan, ar.state[3],
+                                   &ctx->d_sc->scan_ticket[3]);
+                            Elem *c2 = nullptr;
+                            if (cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&c2), std::max<uint64_t>(nnz, 1) * 8, ctx->stream); e != cudaSuccess) {
+                                cudaGetLastError();
+                                return fail(ctx, OSP_ERR_OOM, std::string("result allocation (exact size): ") + cudaGetErrorString(e));
+                            }
+                            LAUNCH(ctx, k_fl_compact, grid_for(m_plan * 32, 256, unsigned(ctx->sm_count) * 16u), 256, 0, job.c_pos, pos2, job.c_data, c2, m_plan);
+                            CU(ctx, cudaMemcpyAsync(job.c_pos, pos2, (m_plan + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+                            CU(ctx, cudaFreeAsync(res->d_data, ctx->stream));
+                            res->d_data = c2; job.c_data = c2; job.c_cap = std::max<uint64_t>(nnz, 1);
+                        }
                     }
                     ev_blocks.push_back(next_event(ctx));
                     return OSP_OK;

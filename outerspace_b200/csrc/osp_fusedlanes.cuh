@@ -97,6 +97,31 @@ k_fl_fill(const uint64_t *__restrict__ b_pos, const Elem *__restrict__ b_data, u
     }
 }
 
+// ---- rows of C without a chain --------------------------------------------------------------------------------------
+// The plan's bound of a row, min(partial products, cols), is EXACT for a row that fills the column range -- which the rows of
+// this path do more often than not (config 5: every row of C is dense).  So the rows are written at the prefix sum of
+// their bounds, which is known before the multiply: no look-back, no row ever waits for the rows before it (with the
+// look-back, 9 % of the warp samples were asleep waiting for the slowest of the ~1900 rows in flight, ncu r02_call19).
+// If the counts then add up to the bound, C.pos = that prefix and C is final; otherwise the rows are moved left into an
+// exactly sized C (k_fl_compact) behind a scan of the counts.
+struct RowCapIn {          // k_scan input: bound of row i
+    const uint64_t *row_bin;
+    uint64_t cols;
+    __device__ uint64_t load(uint64_t i, bool valid) const { return valid ? row_bin[i + 1] - row_bin[i] : 0; }
+    __device__ uint64_t value(uint64_t v, uint64_t, bool) const { return v < cols ? v : cols; }
+};
+
+__global__ void __launch_bounds__(256)
+k_fl_compact(const uint64_t *__restrict__ pos_bound, const uint64_t *__restrict__ pos_exact, const Elem *__restrict__ src,
+             Elem *__restrict__ dst, uint64_t rows) {
+    const unsigned int lane = lane_id();
+    for (uint64_t row = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < rows; row += (uint64_t(gridDim.x) * blockDim.x) >> 5) {
+        const uint64_t s0 = pos_bound[row], d0 = pos_exact[row];
+        const uint32_t n = uint32_t(pos_exact[row + 1] - d0);
+        for (uint32_t i = lane; i < n; i += 32) dst[d0 + i] = src[s0 + i];
+    }
+}
+
 // The registers of (up to FL_QUADS quads of) one run: column-byte words, values, multiplier.
 struct FlRun {
     uint32_t w[FL_QUADS];
@@ -213,7 +238,7 @@ __global__ void __launch_bounds__(32 * WARPS)
 k_fused_lanes(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data, const uint64_t m_a,
               const FlMeta *__restrict__ meta, const float4 *__restrict__ vals, const uint32_t *__restrict__ colb,
               const uint32_t cols, const uint64_t rows, uint64_t *tile_state, DevScalars *sc,
-              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, Elem *stage_all) {
+              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, Elem *stage_all, uint32_t *__restrict__ row_cnt) {
     const unsigned int lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t cpad = (cols + 31) & ~31u;
     const uint32_t acc_off = warp * (cpad + 32) * 4;
@@ -266,7 +291,35 @@ k_fused_lanes(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_dat
                 fl_apply(rb, acc_lane);
             }
         }
-        if (FL_STAGE) {
+        if (row_cnt) {
+            // ---- no chain: the row goes to the prefix of the bounds (c_pos holds it), its count is recorded ----
+            const uint64_t base = c_pos[row];
+            uint32_t total = 0;
+            for (uint32_t c0 = 0; c0 < cpad; c0 += 128) {
+                uint32_t bits[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t c = c0 + 32 * u;
+                    bits[u] = FL_EMPTY;
+                    if (c < cpad) { bits[u] = fl_lds(acc_lane + c * 4); fl_sts(acc_lane + c * 4, FL_EMPTY); }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool hit = bits[u] != FL_EMPTY;
+                    const unsigned int m = __ballot_sync(FULL, hit);
+                    if (hit) {
+                        Elem e; e.idx = c0 + 32 * u + lane; e.val = __uint_as_float(bits[u]);
+                        c_data[base + total + __popc(m & ((1u << lane) - 1u))] = e;
+                    }
+                    total += __popc(m);
+                }
+            }
+            if (lane == 0) {
+                row_cnt[row] = total;
+                atomicAdd(&sc->nnz_c[1], static_cast<unsigned long long>(total));
+            }
+            __syncwarp();
+        } else if (FL_STAGE) {
             // ---- compact the row into the staging row (ascending columns: word i of every lane, lanes in order), publish its count ----
             Elem *st = stage + uint64_t(cur) * cpad;
             uint32_t total = 0;

@@ -167,14 +167,23 @@ def _csr_from_rows(rows, n_cols, rng, explicit_zero_every=0):
     return osp.CSRMatrix.from_arrays(pos, idx, val)
 
 
-@pytest.mark.parametrize("cols,mode", [(1024, "2"), (999, "2"), (4096, "1"), (8160, "2"), (100, "2"), (1024, "0")])
-def test_fused_lanes_bank_aligned_rows(monkeypatch, cols, mode):
+def _row_partials(a, b):
+    blen = np.diff(b.pos.astype(np.int64))
+    per_elem = blen[a.data["idx"]]
+    return np.add.reduceat(np.concatenate([per_elem, [0]]), np.minimum(a.pos[:-1].astype(np.int64), per_elem.size)) * (np.diff(a.pos.astype(np.int64)) > 0)
+
+
+@pytest.mark.parametrize("cols,mode,direct", [(1024, "2", "1"), (999, "2", "1"), (4096, "1", "1"), (8160, "2", "1"), (100, "2", "1"), (1024, "0", "1"),
+                                              (999, "2", "0"), (4096, "2", "0")])
+def test_fused_lanes_bank_aligned_rows(monkeypatch, cols, mode, direct):
     """Fused dense rows, bank-aligned kernel (osp_fusedlanes.cuh; OSP_FUSED_LANES=2 forces it, 1 = automatic, 0 = the band
     kernel): column ranges that are and are not multiples of 32, the one- and two-warp CTAs, rows of B whose columns pile
     up in one shared-memory bank (more than 32 groups: a run applied in pieces), empty rows of A and of B, rows of C beyond
     A's last row, explicit +0.0 / -0.0 entries (a column whose products are all -0.0 is still an entry), duplicates of a
-    column across runs summed in k order."""
+    column across runs summed in k order.  direct = "1": rows of C written at the prefix of their bounds and moved into an
+    exactly sized C when some row is not full (k_fl_compact); "0": rows chained by the look-back."""
     monkeypatch.setenv("OSP_FUSED_LANES", mode)
+    monkeypatch.setenv("OSP_FL_DIRECT", direct)
     rng = np.random.default_rng(cols * 7 + int(mode))
     n_k = 96
     dens = 0.7 if cols <= 128 else 0.25 if cols <= 1024 else 0.06
@@ -209,7 +218,9 @@ def test_fused_lanes_bank_aligned_rows(monkeypatch, cols, mode):
         assert any("k_fused_dense" in n for n in names) and not any("k_fused_lanes" in n for n in names), names
     else:
         assert any("k_fused_lanes" in n for n in names), names
-    assert_bit_exact(got, want, f"fused lanes cols={cols} mode={mode}")
+        # (the empty rows of A alone make the counts fall short of the bounds... no: their bound is 0; row 7 and the sparse rows do)
+        assert any("k_fl_compact" in n for n in names) == (direct == "1" and got.nnz != sum(min(int(p), cols) for p in _row_partials(a, b))), names
+    assert_bit_exact(got, want, f"fused lanes cols={cols} mode={mode} direct={direct}")
     check_csr_invariants(got, cols)
 
 
