@@ -34,7 +34,13 @@ constexpr uint32_t FL_MAX_COLS = 255u * 32u;       // col / 32 and the empty mar
 constexpr uint32_t FL_EMPTY = 0xFFFFFFFFu;          // accumulator not touched yet
 constexpr uint32_t FL_MAX_BLOWUP = 6;               // slots per element of B beyond which the band kernel is kept
 constexpr int FL_PREP_WARPS = 8;
-constexpr int FL_QUADS = 8;                         // quads (of four groups) of one run held in registers at a time
+#ifndef OSP_FL_QUADS
+#define OSP_FL_QUADS 8
+#endif
+#ifndef OSP_FL_DEPTH
+#define OSP_FL_DEPTH 2                              // register sets of the load pipeline (2 or 3)
+#endif
+constexpr int FL_QUADS = OSP_FL_QUADS;              // quads (of four groups) of one run held in registers at a time
 
 struct FlMeta {                                     // per row k of B
     uint32_t quad0;                                 // first quad of the row in vals / colb
@@ -176,7 +182,7 @@ __device__ __forceinline__ uint32_t fl_byte(uint32_t w, int g) { return __byte_p
 #define OSP_FL_BLOCK 8
 #endif
 constexpr int FL_BLOCK = OSP_FL_BLOCK;
-static_assert(FL_BLOCK == 4 || FL_BLOCK == 8 || FL_BLOCK == 16, "whole quads");
+static_assert((FL_BLOCK == 4 || FL_BLOCK == 8 || FL_BLOCK == 16) && (4 * FL_QUADS) % FL_BLOCK == 0, "whole quads, whole blocks");
 __device__ __forceinline__ float fl_f4(const float4 &v, const int g) { return g == 0 ? v.x : g == 1 ? v.y : g == 2 ? v.z : v.w; }
 template <bool TAIL>
 __device__ __forceinline__ void fl_block(const FlRun &r, const int b0, const uint32_t acc_lane) {
@@ -275,8 +281,28 @@ k_fused_lanes(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_dat
                 fl_load(dst, vals, colb, q0 + (g0 >> 2), min(ng - g0, uint32_t(4 * FL_QUADS)), a, lane);
                 g0 += 4 * FL_QUADS;
             };
-            FlRun ra, rb;
             skip_empty();
+#if OSP_FL_DEPTH == 3
+            // three register sets: the loads of a piece are issued two pieces ahead of its use
+            FlRun ra, rb, rc;
+            bool have_a = r < n_runs, have_b = false, have_c = false;
+            if (have_a) { load_piece(ra); skip_empty(); have_b = r < n_runs; }
+            if (have_b) load_piece(rb);
+            while (have_a) {
+                if (have_b) { skip_empty(); have_c = r < n_runs; } else have_c = false;
+                if (have_c) load_piece(rc);
+                fl_apply(ra, acc_lane);
+                if (!have_b) break;
+                if (have_c) { skip_empty(); have_a = r < n_runs; } else have_a = false;
+                if (have_a) load_piece(ra);
+                fl_apply(rb, acc_lane);
+                if (!have_c) break;
+                if (have_a) { skip_empty(); have_b = r < n_runs; } else have_b = false;
+                if (have_b) load_piece(rb);
+                fl_apply(rc, acc_lane);
+            }
+#else
+            FlRun ra, rb;
             bool have_a = r < n_runs, have_b = false;
             if (have_a) load_piece(ra);
             while (have_a) {
@@ -290,6 +316,7 @@ k_fused_lanes(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_dat
                 if (have_a) load_piece(ra);
                 fl_apply(rb, acc_lane);
             }
+#endif
         }
         if (row_cnt) {
             // ---- no chain: the row goes to the prefix of the bounds (c_pos holds it), its count is recorded ----
