@@ -21,7 +21,7 @@
 //   * A never-touched accumulator holds the bit pattern 0xFFFFFFFF (device arithmetic only produces the canonical
 //     NaN 0x7FFFFFFF), the first product of a column is stored as it is: no `seen` array; the row is
 //     counted and read back by its warp (128 conflict-free words per lane for 4096 columns).
-//   * The loads of a run (its column-byte words and values, up to 8 quads = 32 groups) are issued while the previous
+//   * The loads of a run (its column-byte words and values, up to 6 quads = 24 groups) are issued while the previous
 //     run is applied: two register sets, ~3.4 KB in flight per warp.
 // Limits: cols <= FL_MAX_COLS (one byte of col / 32 per slot); a B whose regrouped form exceeds FL_MAX_BLOWUP slots
 // per element (many columns of a row in one bank) keeps the band kernel.  Selection: osp_engine.cu.
@@ -35,7 +35,7 @@ constexpr uint32_t FL_EMPTY = 0xFFFFFFFFu;          // accumulator not touched y
 constexpr uint32_t FL_MAX_BLOWUP = 6;               // slots per element of B beyond which the band kernel is kept
 constexpr int FL_PREP_WARPS = 8;
 #ifndef OSP_FL_QUADS
-#define OSP_FL_QUADS 8
+#define OSP_FL_QUADS 6                              // (8: 11.2 ms on config 5, 6: 10.8 ms -- fewer registers, less code; GPU call 23)
 #endif
 #ifndef OSP_FL_DEPTH
 #define OSP_FL_DEPTH 2                              // register sets of the load pipeline (2 or 3)
@@ -182,7 +182,7 @@ __device__ __forceinline__ uint32_t fl_byte(uint32_t w, int g) { return __byte_p
 #define OSP_FL_BLOCK 8
 #endif
 constexpr int FL_BLOCK = OSP_FL_BLOCK;
-static_assert((FL_BLOCK == 4 || FL_BLOCK == 8 || FL_BLOCK == 16) && (4 * FL_QUADS) % FL_BLOCK == 0, "whole quads, whole blocks");
+static_assert(FL_BLOCK % 4 == 0 && FL_BLOCK >= 4 && FL_BLOCK <= 16 && (4 * FL_QUADS) % FL_BLOCK == 0, "whole quads, whole blocks");
 __device__ __forceinline__ float fl_f4(const float4 &v, const int g) { return g == 0 ? v.x : g == 1 ? v.y : g == 2 ? v.z : v.w; }
 template <bool TAIL>
 __device__ __forceinline__ void fl_block(const FlRun &r, const int b0, const uint32_t acc_lane) {
