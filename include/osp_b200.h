@@ -50,7 +50,10 @@ extern "C" {
                                     built on the device) against row k of B (B streamed once, bins scattered).  Same
                                     bins, same result bit for bit (DESIGN.md "multiply order") */
 #define OSP_NO_FUSED_DENSE  64u  /* keep the bins even when every row is long over a small column range (see
-                                    DESIGN.md "fused dense rows"): multiply -> bins -> k_merge_dense */
+                                    DESIGN.md "fused dense rows"): multiply -> bins -> k_merge_dense.  Without it such a
+                                    product runs the bank-aligned fused kernel (k_fused_lanes; environment:
+                                    OSP_FUSED_LANES=0 keeps the round-1 band kernel, OSP_FL_DIRECT=0 chains the rows of C
+                                    by the look-back).  Same bits. */
 #define OSP_LONGROW_SWEEP  128u  /* opt-in (round 2: bit-exact on a B200, not faster than the default on config 3,
                                     profiles/r02_optin_paths.md): rows of more than 4096 partial products over more than 16384
                                     columns skip the bins -- a fused band sweep (k_long_fill)
