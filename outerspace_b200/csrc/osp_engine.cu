@@ -71,7 +71,7 @@ struct osp_ctx {
     DevBuf bins;
     // fused band sweep of the long rows (opt-in, osp_longrows.cuh): task bitmap for the multiply, band index of B
     DevBuf swept, lr_bands, kw_scratch, vbits;
-    DevBuf fl_meta, fl_vals, fl_colb, fl_stage, fl_cnt, fl_pos2;     // B regrouped by shared-memory bank, staging rows of the warps (osp_fusedlanes.cuh)
+    DevBuf fl_meta, fl_vals, fl_colb, fl_cnt, fl_pos2;     // B regrouped by shared-memory bank, staging rows of the warps (osp_fusedlanes.cuh)
     bool fused_lanes_direct = true;         // OSP_FL_DIRECT=0: rows of C chained by the look-back instead of written at the prefix of their bounds
     int fused_lanes_mode = 1;               // OSP_FUSED_LANES: 0 band kernel (k_fused_dense), 1 automatic, 2 bank-aligned kernel whatever B's regrouped size
     bool kway_env = false;                  // OSP_KWAY=1: rows of 4097 .. 32768 partial products in <= 64 ways go to k_merge_ways
@@ -722,7 +722,7 @@ void osp_destroy(osp_ctx *ctx) {
                       &ctx->conv_data, &ctx->conv_tmp, &ctx->conv_chk, &ctx->task_bs, &ctx->run_off, &ctx->row_bin, &ctx->tile_row,
                       &ctx->tile_start, &ctx->long_list, &ctx->xl_list, &ctx->uniq, &ctx->col_ptr, &ctx->tasks, &ctx->tile_state,
                       &ctx->xl_acc, &ctx->xl_bits, &ctx->bins, &ctx->swept, &ctx->lr_bands, &ctx->kw_scratch, &ctx->vbits,
-                      &ctx->fl_meta, &ctx->fl_vals, &ctx->fl_colb, &ctx->fl_stage, &ctx->fl_cnt, &ctx->fl_pos2})
+                      &ctx->fl_meta, &ctx->fl_vals, &ctx->fl_colb, &ctx->fl_cnt, &ctx->fl_pos2})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
@@ -1092,10 +1092,8 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
                     if (warps == 2) { CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_lanes<2>, 64, sm)); }
                     else { CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_lanes<1>, 32, sm)); }
                     const unsigned grid = unsigned(std::min<uint64_t>((m_plan + warps - 1) / warps, uint64_t(ctx->sm_count) * std::max(occ, 1)));
-                    if (FL_STAGE) { CU(ctx, ctx->fl_stage.reserve(uint64_t(grid) * warps * 2 * ((cols_b + 31) & ~31ull) * sizeof(Elem))); }   // two staging rows per warp
-                    Elem *stage = ctx->fl_stage.as<Elem>();
                     // rows of C at the prefix of their bounds (no chain); C was allocated at the bound
-                    const bool direct = ctx->fused_lanes_direct && !FL_STAGE && job.c_cap >= cap_bound;
+                    const bool direct = ctx->fused_lanes_direct && job.c_cap >= cap_bound;
                     uint32_t *row_cnt = nullptr;
                     if (direct) {
                         CU(ctx, ctx->fl_cnt.reserve(m_plan * 4));
@@ -1105,10 +1103,10 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
                     }
                     if (warps == 2) {
                         LAUNCH(ctx, k_fused_lanes<2>, grid, 64, sm, dA_pos, dA_data, m_a, meta, vals4, colb, uint32_t(cols_b), m_plan,
-                               ctx->tile_state.as<uint64_t>(), ctx->d_sc, job.c_pos, job.c_data, stage, row_cnt);
+                               ctx->tile_state.as<uint64_t>(), ctx->d_sc, job.c_pos, job.c_data, row_cnt);
                     } else {
                         LAUNCH(ctx, k_fused_lanes<1>, grid, 32, sm, dA_pos, dA_data, m_a, meta, vals4, colb, uint32_t(cols_b), m_plan,
-                               ctx->tile_state.as<uint64_t>(), ctx->d_sc, job.c_pos, job.c_data, stage, row_cnt);
+                               ctx->tile_state.as<uint64_t>(), ctx->d_sc, job.c_pos, job.c_data, row_cnt);
                     }
                     if (direct) {
                         rc2 = sync_scalars(ctx);

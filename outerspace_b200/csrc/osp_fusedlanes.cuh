@@ -37,9 +37,6 @@ constexpr int FL_PREP_WARPS = 8;
 #ifndef OSP_FL_QUADS
 #define OSP_FL_QUADS 6                              // (8: 11.2 ms on config 5, 6: 10.8 ms -- fewer registers, less code; GPU call 23)
 #endif
-#ifndef OSP_FL_DEPTH
-#define OSP_FL_DEPTH 2                              // register sets of the load pipeline (2 or 3)
-#endif
 constexpr int FL_QUADS = OSP_FL_QUADS;              // quads (of four groups) of one run held in registers at a time
 
 struct FlMeta {                                     // per row k of B
@@ -210,51 +207,18 @@ __device__ __forceinline__ void fl_apply(const FlRun &r, const uint32_t acc_lane
     }
 }
 
-// OSP_FL_STAGE=1 (experiment, measured slower: profiles/r02_fusedlanes.md): rows of C leave in two steps so that no warp
-// waits with a full accumulator -- the finished row is compacted into one of the warp's two staging rows in global memory
-// and its count published at once; its place in C is resolved and the staged row copied there one row LATER, when the
-// predecessors have long published.  (Resolved right away, a row waits for the slowest of the ~1900 rows in flight before
-// it: 9 % of the warp samples asleep in the look-back, ncu r02_call19.)  The copy costs more than the wait.
-#ifndef OSP_FL_STAGE
-#define OSP_FL_STAGE 0
-#endif
-constexpr bool FL_STAGE = OSP_FL_STAGE != 0;
-__device__ __forceinline__ void fl_retire(const uint64_t row, const uint32_t total, const Elem *stage, uint64_t *tile_state,
-                                          DevScalars *sc, uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, const uint64_t rows,
-                                          const unsigned int lane) {
-    const uint64_t base = lb_resolve(tile_state, uint32_t(row), total, 0);
-    if (lane == 0) {
-        c_pos[row] = base;
-        if (row + 1 == rows) { c_pos[rows] = base + total; sc->nnz_c[1] = base + total; }
-    }
-    Elem *dst = c_data + base;
-    uint32_t i = lane;
-    for (; i + 96 < total; i += 128) {
-        Elem e[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) e[u] = stage[i + 32 * u];
-#pragma unroll
-        for (int u = 0; u < 4; u++) dst[i + 32 * u] = e[u];
-    }
-    for (; i < total; i += 32) dst[i] = stage[i];
-}
-
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS)
 k_fused_lanes(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_data, const uint64_t m_a,
               const FlMeta *__restrict__ meta, const float4 *__restrict__ vals, const uint32_t *__restrict__ colb,
               const uint32_t cols, const uint64_t rows, uint64_t *tile_state, DevScalars *sc,
-              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, Elem *stage_all, uint32_t *__restrict__ row_cnt) {
+              uint64_t *__restrict__ c_pos, Elem *__restrict__ c_data, uint32_t *__restrict__ row_cnt) {
     const unsigned int lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t cpad = (cols + 31) & ~31u;
     const uint32_t acc_off = warp * (cpad + 32) * 4;
     const uint32_t acc_lane = fl_smem_base() + acc_off + lane * 4;
-    Elem *stage = FL_STAGE ? stage_all + (uint64_t(blockIdx.x) * WARPS + warp) * 2 * cpad : nullptr;       // two staging rows per warp
     for (uint32_t c = 0; c < cpad; c += 32) fl_sts(acc_lane + c * 4, FL_EMPTY);
     __syncwarp();
-    uint64_t pend_row = 0;
-    uint32_t pend_total = 0, cur = 0;
-    bool pending = false;
     while (true) {
         uint32_t t = 0;
         if (lane == 0) t = atomicAdd(&sc->tile_ticket, 1u);
@@ -282,26 +246,6 @@ k_fused_lanes(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_dat
                 g0 += 4 * FL_QUADS;
             };
             skip_empty();
-#if OSP_FL_DEPTH == 3
-            // three register sets: the loads of a piece are issued two pieces ahead of its use
-            FlRun ra, rb, rc;
-            bool have_a = r < n_runs, have_b = false, have_c = false;
-            if (have_a) { load_piece(ra); skip_empty(); have_b = r < n_runs; }
-            if (have_b) load_piece(rb);
-            while (have_a) {
-                if (have_b) { skip_empty(); have_c = r < n_runs; } else have_c = false;
-                if (have_c) load_piece(rc);
-                fl_apply(ra, acc_lane);
-                if (!have_b) break;
-                if (have_c) { skip_empty(); have_a = r < n_runs; } else have_a = false;
-                if (have_a) load_piece(ra);
-                fl_apply(rb, acc_lane);
-                if (!have_c) break;
-                if (have_a) { skip_empty(); have_b = r < n_runs; } else have_b = false;
-                if (have_b) load_piece(rb);
-                fl_apply(rc, acc_lane);
-            }
-#else
             FlRun ra, rb;
             bool have_a = r < n_runs, have_b = false;
             if (have_a) load_piece(ra);
@@ -316,7 +260,6 @@ k_fused_lanes(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_dat
                 if (have_a) load_piece(ra);
                 fl_apply(rb, acc_lane);
             }
-#endif
         }
         if (row_cnt) {
             // ---- no chain: the row goes to the prefix of the bounds (c_pos holds it), its count is recorded ----
@@ -346,35 +289,6 @@ k_fused_lanes(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_dat
                 atomicAdd(&sc->nnz_c[1], static_cast<unsigned long long>(total));
             }
             __syncwarp();
-        } else if (FL_STAGE) {
-            // ---- compact the row into the staging row (ascending columns: word i of every lane, lanes in order), publish its count ----
-            Elem *st = stage + uint64_t(cur) * cpad;
-            uint32_t total = 0;
-            for (uint32_t c0 = 0; c0 < cpad; c0 += 128) {
-                uint32_t bits[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t c = c0 + 32 * u;
-                    bits[u] = FL_EMPTY;
-                    if (c < cpad) { bits[u] = fl_lds(acc_lane + c * 4); fl_sts(acc_lane + c * 4, FL_EMPTY); }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const bool hit = bits[u] != FL_EMPTY;
-                    const unsigned int m = __ballot_sync(FULL, hit);
-                    if (hit) {
-                        Elem e; e.idx = c0 + 32 * u + lane; e.val = __uint_as_float(bits[u]);
-                        st[total + __popc(m & ((1u << lane) - 1u))] = e;
-                    }
-                    total += __popc(m);
-                }
-            }
-            lb_publish(tile_state, uint32_t(row), total, 0);
-            __syncwarp();                                          // the staged row is visible to every lane of the warp
-            // ---- the row before this one leaves for C ----
-            if (pending) fl_retire(pend_row, pend_total, stage + uint64_t(cur ^ 1u) * cpad, tile_state, sc, c_pos, c_data, rows, lane);
-            pend_row = row; pend_total = total; pending = true;
-            cur ^= 1u;
         } else {
             // ---- count, chain, emit (ascending columns: word i of every lane, lanes in order) ----
             uint32_t total = 0;
@@ -417,7 +331,6 @@ k_fused_lanes(const uint64_t *__restrict__ a_pos, const Elem *__restrict__ a_dat
             __syncwarp();
         }
     }
-    if (FL_STAGE && pending) fl_retire(pend_row, pend_total, stage + uint64_t(cur ^ 1u) * cpad, tile_state, sc, c_pos, c_data, rows, lane);
 }
 
 }  // namespace osp
