@@ -2,8 +2,8 @@
 //
 // Same job as k_fused_dense (osp_kernels.cuh): C(i,:) = sum_k A(i,k) * B(k,:) accumulated in a dense shared-memory
 // row, every column summed in ascending k with separately rounded products and adds (the multiplyPhase / mergePhase
-// pair of simulator/SimOuterSPACE.cpp:77-132 without ever materialising a partial product), rows of C chained by the
-// decoupled look-back and written once.  k_fused_dense is bound by shared-memory wavefronts (ncu, profiles/r02_ncu/
+// pair of simulator/SimOuterSPACE.cpp:77-132 without ever materialising a partial product), rows of C written once.
+// k_fused_dense is bound by shared-memory wavefronts (ncu, profiles/r02_ncu/
 // mlp8_fused_raw.csv: L1 data pipe 85 % busy, 44 % of the shared wavefronts are bank conflicts): a warp applies ~25
 // elements of a row of B at random columns of its band, so every read-modify-write of the accumulator replays ~3
 // times, a `seen` byte is stored beside it, and the three shuffles + bounds per (run, band) are paid for 25 products.
@@ -12,7 +12,8 @@
 //   * B is regrouped once per call (k_fl_count / k_fl_fill, one warp per row of B): the elements of row k are dealt
 //     into groups of at most 32 in which every element sits in the lane equal to its shared-memory bank,
 //     lane = col % 32.  Element j of bank b goes to group j, so row k needs max_b(multiplicity of b) groups; a slot
-//     holds the value (4 bytes) and col / 32 (1 byte; cpad / 32 = empty: it points at 32 dummy floats behind the row), four groups per 32-bit word of column bytes.
+//     holds the value (4 bytes) and col / 32 (1 byte; cpad / 32 = empty: it points at 32 dummy floats behind the
+//     row), four groups (a quad) per 32-bit word of column bytes and per 16-byte vector of values.
 //     For config 5 (410 elements per row of B, 4096 columns) that is 21 groups per row, 61 % of the slots filled,
 //     5 bytes per slot: the bytes read per partial product stay what the 8-byte elements cost.
 //   * ONE WARP owns an output row: acc[col] lives in its 4 * cols bytes of shared memory, lane l only ever touches
@@ -23,6 +24,9 @@
 //     counted and read back by its warp (128 conflict-free words per lane for 4096 columns).
 //   * The loads of a run (its column-byte words and values, up to 6 quads = 24 groups) are issued while the previous
 //     run is applied: two register sets, ~3.4 KB in flight per warp.
+//   * Rows of C go to the prefix sum of the plan's bounds min(partial products, cols) -- no chain between the rows -- and
+//     are moved into an exactly sized C only when some row is not full (below: "rows of C without a chain").
+// Measured, version by version: profiles/r02_fusedlanes.md (config 5: 26.8 -> 11.2 ms per call).
 // Limits: cols <= FL_MAX_COLS (one byte of col / 32 per slot); a B whose regrouped form exceeds FL_MAX_BLOWUP slots
 // per element (many columns of a row in one bank) keeps the band kernel.  Selection: osp_engine.cu.
 #pragma once
