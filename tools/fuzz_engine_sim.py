@@ -49,7 +49,46 @@ def draw_wide_case(rng):
     return A, B, cols
 
 
+DENSE_SHARE = 0.15
+
+
+def draw_dense_case(rng):
+    """Long rows over a small column range: the fused dense paths (bank-aligned k_fused_lanes, band kernel k_fused_dense).
+    Rows of B pile up in few shared-memory banks now and then (runs of more than one piece), some are empty, some rows of A
+    are empty; explicit +-0.0 values."""
+    cols = int(rng.choice([rng.integers(1, 33), rng.integers(33, 1800), rng.integers(1800, 4097), rng.integers(4097, 8161), rng.integers(8161, 16385)]))
+    k = int(rng.integers(8, 120))
+    m = int(rng.integers(1, 40))
+    b_rows, b_cols = [], []
+    per_row = min(cols, int(rng.choice([40, 120, 400])))
+    for r in range(k):
+        kind = rng.random()
+        if kind < 0.08:
+            c = np.zeros(0, np.int64)
+        elif kind < 0.2 and cols >= 64:
+            bank = int(rng.integers(0, 32))                      # many columns of one bank: more groups than a piece holds
+            c = np.unique(rng.integers(0, (cols - bank + 31) // 32, size=int(rng.integers(20, 70)))) * 32 + bank
+            c = c[c < cols]
+        else:
+            c = np.nonzero(rng.random(cols) < per_row / cols)[0]
+        b_rows += [r] * len(c)
+        b_cols += c.tolist()
+    vals = (rng.standard_normal(len(b_rows)) * 2).astype(np.float32)
+    vals[::17] = 0.0
+    vals[5::29] = -0.0
+    B = sp.csr_matrix((vals, (b_rows, b_cols)), shape=(k, cols))
+    dens = float(rng.choice([0.3, 0.7, 1.0]))
+    mask = rng.random((m, k)) < dens
+    mask[rng.random(m) < 0.1] = False                          # empty rows of A
+    av = (rng.standard_normal((m, k)) * 3).astype(np.float32)
+    av[av == 0] = 1
+    A = sp.csr_matrix(np.where(mask, av, 0).astype(np.float32))
+    return A, B, cols
+
+
 def draw_case(rng):
+    if rng.random() < DENSE_SHARE:
+        return draw_dense_case(rng)
     if rng.random() < 0.1:
         return draw_wide_case(rng)
     cols = int(rng.choice([rng.integers(1, 64), rng.integers(64, 4096), rng.integers(4096, 16385), rng.integers(16385, 200000),
@@ -85,11 +124,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--dense-share", type=float, default=0.15, help="share of cases drawn for the fused dense paths (small column range, long rows)")
     ap.add_argument("--schedule", default="")
     ap.add_argument("--asan", action="store_true", help="AddressSanitizer build: every access of a kernel or of the host code outside an "
                     "allocation of the emulated device aborts the run (re-executes itself with libasan preloaded)")
     ap.add_argument("--resident", type=int, default=1, help="blocks resident at a time (CUSIM_RESIDENT = CUSIM_SMS): > 1 runs them on OS threads")
     args = ap.parse_args()
+    global DENSE_SHARE
+    DENSE_SHARE = args.dense_share
     if args.asan and "libasan" not in os.environ.get("LD_PRELOAD", ""):
         asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True, check=True).stdout.strip()
         env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1")
@@ -107,7 +149,7 @@ def main():
     api._LIB_PATH, api._lib = lib, None
     rng = np.random.default_rng(args.seed)
     t0 = time.time()
-    seen = {"sweep": 0, "blocks": 0, "fused": 0, "xl": 0, "long": 0, "products": 0, "fused_short": 0}
+    seen = {"sweep": 0, "blocks": 0, "fused": 0, "xl": 0, "long": 0, "products": 0, "fused_short": 0, "lanes": 0, "compact": 0}
     for case in range(args.cases):
         A, B, cols = draw_case(rng)
         a_csc, a_csr, b_csr = operands(A, B)
@@ -115,6 +157,8 @@ def main():
         flags = int(rng.choice([0, api.OSP_KSLICE_ORDER, api.OSP_ROWWISE_ORDER, api.OSP_LONGROW_SWEEP, api.OSP_LONGROW_SWEEP, api.OSP_NO_FUSED_DENSE,
                                 api.OSP_FUSED_SHORT, api.OSP_FUSED_SHORT | api.OSP_LONGROW_SWEEP, api.OSP_FUSED_SHORT | api.OSP_NO_FUSED_DENSE]))
         as_csr = bool(rng.integers(0, 2))
+        os.environ["OSP_FUSED_LANES"] = str(rng.choice(["1", "2", "2"]))      # read at osp_create: automatic / bank-aligned whatever B's regrouped size
+        os.environ["OSP_FL_DIRECT"] = str(rng.choice(["0", "1", "1"]))        # rows of C chained by the look-back / at the prefix of their bounds
         eng = osp.Engine(0)
         try:
             if rng.random() < 0.3 and prod > 64:
@@ -134,6 +178,8 @@ def main():
             assert_bit_exact(got, want, what)
             seen["sweep"] += any("k_long_fill" in n for n in names)
             seen["fused"] += any("k_fused_dense" in n for n in names)
+            seen["lanes"] += any("k_fused_lanes" in n for n in names)
+            seen["compact"] += any("k_fl_compact" in n for n in names)
             seen["fused_short"] += any("k_merge_chain_fused" in n for n in names)
             seen["blocks"] += st["row_chunks"] > 1
             seen["xl"] += st["rows_long"] > 0
@@ -142,7 +188,7 @@ def main():
         finally:
             eng.close()
     print(f"fuzz ok: {args.cases} cases, seed {args.seed}, schedule '{args.schedule or 'forward'}', {args.resident} resident block(s){', AddressSanitizer' if args.asan else ''}, {time.time() - t0:.0f} s; "
-          f"calls with sweep {seen['sweep']}, fused short rows {seen['fused_short']}, fused dense {seen['fused']}, row blocks {seen['blocks']}, xl rows {seen['xl']}, "
+          f"calls with sweep {seen['sweep']}, fused short rows {seen['fused_short']}, fused dense (band kernel) {seen['fused']}, bank-aligned {seen['lanes']} (of which with compaction {seen['compact']}), row blocks {seen['blocks']}, xl rows {seen['xl']}, "
           f"medium rows {seen['long']}; {seen['products']} partial products in total")
 
 
