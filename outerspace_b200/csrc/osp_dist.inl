@@ -270,7 +270,7 @@ int osp_dist_spgemm(osp_dist *d, const osp_spgemm_args *args, osp_result **out) 
             if (r) return r;
         }
         if (op.nnz_a)
-            LAUNCH(ctx, (k_scan<SymIn, RunOffOut>), unsigned(st[0]), SCAN_BLOCK, 0, SymIn{op.a_data, op.b_pos, n_k, nullptr, ctx->d_sc, task_bs},
+            LAUNCH(ctx, (k_scan<SymIn, RunOffOut>), unsigned(st[0]), SCAN_BLOCK, 0, SymIn{op.a_data, op.b_pos, n_k, nullptr, ctx->d_sc, task_bs, nullptr},
                    RunOffOut{run_off, ctx->d_sc, op.nnz_a}, op.nnz_a, ar.state[0], &ctx->d_sc->scan_ticket[0]);
         else
             CU(ctx, cudaMemsetAsync(run_off, 0, 8, ctx->stream));

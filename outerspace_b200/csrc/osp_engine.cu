@@ -71,7 +71,9 @@ struct osp_ctx {
     DevBuf bins;
     // fused band sweep of the long rows (opt-in, osp_longrows.cuh): task bitmap for the multiply, band index of B
     DevBuf swept, lr_bands, kw_scratch, vbits;
-    DevBuf fl_meta, fl_vals, fl_colb, fl_cnt, fl_pos2;     // B regrouped by shared-memory bank, staging rows of the warps (osp_fusedlanes.cuh)
+    DevBuf fl_meta, fl_vals, fl_colb, fl_cnt, fl_pos2;
+    DevBuf bpos32;                        // B.pos narrowed to 32 bits for the symbolic pass
+    uint64_t bpos32_min = 0;              // OSP_BPOS32_MIN_KB: a B.pos of at least that many KiB is narrowed (0 = never)     // B regrouped by shared-memory bank, staging rows of the warps (osp_fusedlanes.cuh)
     bool fused_lanes_direct = true;         // OSP_FL_DIRECT=0: rows of C chained by the look-back instead of written at the prefix of their bounds
     int fused_lanes_mode = 1;               // OSP_FUSED_LANES: 0 band kernel (k_fused_dense), 1 automatic, 2 bank-aligned kernel whatever B's regrouped size
     bool kway_env = false;                  // OSP_KWAY=1: rows of 4097 .. 32768 partial products in <= 64 ways go to k_merge_ways
@@ -664,6 +666,7 @@ int osp_create(int device, osp_ctx **out) {
         ctx->kway_env = kw && kw[0] && kw[0] != '0';
         if (const char *fl = std::getenv("OSP_FUSED_LANES")) ctx->fused_lanes_mode = fl[0] == '0' ? 0 : fl[0] == '2' ? 2 : 1;
         if (const char *fd = std::getenv("OSP_FL_DIRECT")) ctx->fused_lanes_direct = fd[0] != '0';
+        if (const char *bp = std::getenv("OSP_BPOS32_MIN_KB")) ctx->bpos32_min = std::strtoull(bp, nullptr, 10) << 10;
         if (const char *m = std::getenv("OSP_LONGROW_SWEEP_MIN")) ctx->sweep_min = std::strtoull(m, nullptr, 10);
     }
     {   // OSP_FUSED_SHORT: opt-in as well
@@ -722,7 +725,7 @@ void osp_destroy(osp_ctx *ctx) {
                       &ctx->conv_data, &ctx->conv_tmp, &ctx->conv_chk, &ctx->task_bs, &ctx->run_off, &ctx->row_bin, &ctx->tile_row,
                       &ctx->tile_start, &ctx->long_list, &ctx->xl_list, &ctx->uniq, &ctx->col_ptr, &ctx->tasks, &ctx->tile_state,
                       &ctx->xl_acc, &ctx->xl_bits, &ctx->bins, &ctx->swept, &ctx->lr_bands, &ctx->kw_scratch, &ctx->vbits,
-                      &ctx->fl_meta, &ctx->fl_vals, &ctx->fl_colb, &ctx->fl_cnt, &ctx->fl_pos2})
+                      &ctx->fl_meta, &ctx->fl_vals, &ctx->fl_colb, &ctx->fl_cnt, &ctx->fl_pos2, &ctx->bpos32})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
@@ -852,7 +855,14 @@ int osp_spgemm(osp_ctx *ctx, const osp_spgemm_args *args, osp_result **out) {
     uint32_t *task_bs = ctx->task_bs.as<uint32_t>();
     uint32_t *col_cnt = rowwise ? nullptr : ar.counters;
     if (nnz_a) {
-        LAUNCH(ctx, (k_scan<SymIn, RunOffOut>), unsigned(st[0]), SCAN_BLOCK, 0, SymIn{dA_data, dB_pos, n_k, col_cnt, ctx->d_sc, task_bs},
+        const uint32_t *b_pos32 = nullptr;
+        if (ctx->bpos32_min && (n_k + 1) * 8 >= ctx->bpos32_min && nnz_b < (1ull << 32)) {
+            // B.pos beyond what the L2 keeps under the pass's streams: a 32-bit copy for its random reads
+            CU(ctx, ctx->bpos32.reserve((n_k + 1) * 4));
+            LAUNCH(ctx, k_narrow_pos, grid_for(n_k + 1, 256, unsigned(ctx->sm_count) * 8u), 256, 0, dB_pos, n_k + 1, ctx->bpos32.as<uint32_t>());
+            b_pos32 = ctx->bpos32.as<uint32_t>();
+        }
+        LAUNCH(ctx, (k_scan<SymIn, RunOffOut>), unsigned(st[0]), SCAN_BLOCK, 0, SymIn{dA_data, dB_pos, n_k, col_cnt, ctx->d_sc, task_bs, b_pos32},
                RunOffOut{run_off, ctx->d_sc, nnz_a}, nnz_a, ar.state[0], &ctx->d_sc->scan_ticket[0]);
     } else {
         CU(ctx, cudaMemsetAsync(run_off, 0, 8, ctx->stream));

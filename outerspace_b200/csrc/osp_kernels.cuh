@@ -116,18 +116,24 @@ struct SymIn {
     uint32_t *col_cnt;
     DevScalars *sc;
     uint32_t *task_bs;     // [nnzA] offset of row k_p of B inside B's data array, or null
+    const uint32_t *b_pos32;   // B.pos narrowed to 32 bits (k_narrow_pos), or null: half the footprint of the random reads
     __device__ uint64_t load(uint64_t p, bool valid) const { return valid ? a[p].idx : ~0ull; }
     __device__ uint64_t value(uint64_t k, uint64_t p, bool valid) const {
         if (!valid) return 0;
         if (k >= n_k) { atomicMax(&sc->err, 4u); return 0; }   // OSP_ERR_INDEX
-        const uint64_t bs = b_pos[k];
-        const uint64_t len = b_pos[k + 1] - bs;
+        const uint64_t bs = b_pos32 ? b_pos32[k] : b_pos[k];
+        const uint64_t len = (b_pos32 ? b_pos32[k + 1] : b_pos[k + 1]) - bs;
         if (task_bs) task_bs[p] = uint32_t(bs);                // the row-order multiply reads it back as a stream
         if (col_cnt) atomicAdd(&col_cnt[k], 1u);
         if (len >> TASK_LEN_BITS) { atomicMax(&sc->err, 6u); return 0; }   // OSP_ERR_UNSUPPORTED
         return len;
     }
 };
+// B.pos as 32-bit offsets for the symbolic pass (operands have < 2^32 non-zeros): the pass reads B.pos[k], B.pos[k+1] at the
+// random k of A's elements, and an array that fits one L2 partition is served from L2 where the 64-bit one is not.
+__global__ void k_narrow_pos(const uint64_t *__restrict__ pos, uint64_t n, uint32_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) out[i] = uint32_t(pos[i]);
+}
 struct RunOffOut {
     uint64_t *run_off;   // [nnzA+1]
     DevScalars *sc;
