@@ -73,7 +73,7 @@ struct osp_ctx {
     DevBuf swept, lr_bands, kw_scratch, vbits;
     DevBuf fl_meta, fl_vals, fl_colb, fl_cnt, fl_pos2;
     DevBuf bpos32;                        // B.pos narrowed to 32 bits for the symbolic pass
-    uint64_t bpos32_min = 0;              // OSP_BPOS32_MIN_KB: a B.pos of at least that many KiB is narrowed (0 = never)     // B regrouped by shared-memory bank, staging rows of the warps (osp_fusedlanes.cuh)
+    uint64_t bpos32_min = 32ull << 20;    // a B.pos of at least 32 MiB is narrowed (config 4: scan 0.848 -> 0.711 + 0.023 ms); OSP_BPOS32_MIN_KB overrides, 0 = never     // B regrouped by shared-memory bank, staging rows of the warps (osp_fusedlanes.cuh)
     bool fused_lanes_direct = true;         // OSP_FL_DIRECT=0: rows of C chained by the look-back instead of written at the prefix of their bounds
     int fused_lanes_mode = 1;               // OSP_FUSED_LANES: 0 band kernel (k_fused_dense), 1 automatic, 2 bank-aligned kernel whatever B's regrouped size
     bool kway_env = false;                  // OSP_KWAY=1: rows of 4097 .. 32768 partial products in <= 64 ways go to k_merge_ways
